@@ -1,0 +1,87 @@
+"""ctypes binding of libaqualora_b200.so (the C ABI in include/aqualora_b200.h).
+
+The library is the product: there is no Python / CPU fallback.  If it is missing or a call fails, callers get
+an exception that names the failing entry point and `aq_last_error()`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libaqualora_b200.so"
+
+
+class AqualoraError(RuntimeError):
+    pass
+
+
+_SIGNATURES = {
+    "aq_version": ([], c_int),
+    "aq_arch": ([], c_int),
+    "aq_last_error": ([], c_char_p),
+    "aq_sm_count": ([], c_int),
+    "aq_lora_set_tuning": ([c_int, c_int], c_int),
+    "aq_lora_linear_fwd": (
+        [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+         c_int, c_int, c_int, c_void_p],
+        c_int,
+    ),
+    "aq_lora_linear_bwd_workspace_bytes": ([c_int64, c_int], c_size_t),
+    "aq_lora_linear_bwd": (
+        [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+         c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p],
+        c_int,
+    ),
+    "aq_wgrad_tn": ([c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p], c_int),
+    "aq_mapper_fwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    "aq_mapper_bwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    "aq_cast_transpose_bf16": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),
+    "aq_transpose_bf16": ([c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),
+    "aq_flat_sumsq": ([c_void_p, c_int64, c_void_p, c_void_p], c_int),
+    "aq_flat_clip_adamw": (
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
+         c_float, c_int, c_void_p],
+        c_int,
+    ),
+}
+
+_lib = None
+
+
+def exported_symbols() -> list[str]:
+    """Every symbol include/aqualora_b200.h declares (kept in sync by tests/test_abi.py)."""
+    return sorted(_SIGNATURES)
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise AqualoraError(
+            f"{LIB_PATH} is missing: build it with `python -m aqualora_b200.build` (needs nvcc). "
+            "aqualora_b200 has no CPU or PyTorch fallback for its kernels."
+        )
+    lib = ctypes.CDLL(os.fspath(LIB_PATH))
+    for name, (argtypes, restype) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().aq_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise AqualoraError(f"{what} failed with code {rc}: {last_error()}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)

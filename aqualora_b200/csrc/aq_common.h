@@ -1,0 +1,39 @@
+// Host-side shared declarations for libaqualora_b200.so (error handling, TMA descriptor factory).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/aqualora_b200.h"
+
+namespace aq {
+
+// thread-local error string returned by aq_last_error()
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#define AQ_CHECK_CUDA(expr)                                                                     \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return ::aq::fail(AQ_ERR_LAUNCH, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                    \
+  } while (0)
+
+#define AQ_REQUIRE(cond, code, ...)                  \
+  do {                                               \
+    if (!(cond)) return ::aq::fail(code, __VA_ARGS__); \
+  } while (0)
+
+enum TmaSwizzle { kSwzNone = 0, kSwz32 = 1, kSwz64 = 2, kSwz128 = 3 };
+
+// Encode a tiled bf16 / fp32 tensor map (rank 2 or 3).  dims/box are innermost-first; strides are in
+// BYTES for dims 1..rank-1.  Returns AQ_OK or an error code (aq_last_error() explains).
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, TmaSwizzle swz);
+
+int sm_count();  // SMs of the current device (cached)
+int check_arch();  // AQ_OK iff the current device is sm_100
+
+}  // namespace aq

@@ -1,0 +1,30 @@
+// Internal launch interface of the fused projection + LoRA kernel (lora_gemm.cu) and the weight-gradient
+// contraction (lora_wgrad.cu).
+#pragma once
+#include "aq_common.h"
+
+namespace aq {
+
+struct LoraGemmArgs {
+  const void* a; int64_t lda;       // [M, K] bf16
+  const void* w;                    // [N, K] bf16
+  const void* bias;                 // [N] bf16 or null
+  const void* dn;                   // [r, K] bf16 or null (null: plain projection)
+  const void* up;                   // [N, r] bf16
+  const float* scale;               // [num_samples, r] fp32
+  void* y; int64_t ldy;             // [M, N] bf16 (unused when has_main == 0)
+  void* aux_out0;                   // mode 0: H [M, r] (optional);  mode 1: dH [M, r]
+  void* aux_out1;                   // mode 1: Hs [M, r]
+  const void* h_in;                 // mode 1: H [M, r] saved by the forward
+  float* g_scale;                   // mode 1: [num_samples, r] accumulated (optional)
+  int64_t M, tokens; int K, N, r;
+  int mode;                         // 0 forward, 1 backward
+  int has_main;                     // 0: H phase + mid epilogue only
+  int force_bn, force_group;        // 0 = heuristic
+};
+
+int launch_lora_gemm(const LoraGemmArgs& a, cudaStream_t stream);
+int launch_wgrad(const void* pm, int64_t ldp, const void* qm, int64_t ldq, float* c, int64_t ldc, int64_t M, int I, int J,
+                 int transpose_out, cudaStream_t stream);
+
+}  // namespace aq

@@ -1,0 +1,177 @@
+"""Tensor-level wrappers over the C ABI: argument checking, stream plumbing, workspace handling.
+
+PyTorch is used for device memory and streams only; every function here launches hand-written sm_100a kernels
+from libaqualora_b200.so and raises if the library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_BF16 = torch.bfloat16
+_F32 = torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str, ndim: int | None = None) -> None:
+    if not t.is_cuda:
+        raise _lib.AqualoraError(f"{name} must be a CUDA tensor (aqualora_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.AqualoraError(f"{name} must be {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise _lib.AqualoraError(f"{name} must be {ndim}-D, got shape {tuple(t.shape)}")
+
+
+def _rows(t: torch.Tensor, name: str) -> int:
+    """Leading dimension (in elements) of a 2-D row-major view."""
+    if t.stride(1) != 1:
+        raise _lib.AqualoraError(f"{name} must be row-major (unit inner stride), got strides {t.stride()}")
+    return t.stride(0) if t.shape[0] > 1 else t.shape[1]
+
+
+def set_tuning(block_n: int = 0, group_size: int = 0) -> None:
+    _lib.call("aq_lora_set_tuning", block_n, group_size)
+
+
+def lora_linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, down: torch.Tensor | None,
+                    up: torch.Tensor | None, scale: torch.Tensor | None, tokens_per_sample: int, save_h: bool = False,
+                    out: torch.Tensor | None = None):
+    """y = x @ w.T + bias + ((x @ down.T) * scale[row // tokens]) @ up.T ; returns (y, h or None).
+
+    x [M, din] bf16, w [dout, din] bf16, bias [dout] bf16|None, down [r, din] bf16|None, up [dout, r] bf16,
+    scale [M // tokens, r] fp32.  (utils/lora_modules.py:9-26,56-62)
+    """
+    _need(x, _BF16, "x", 2)
+    _need(w, _BF16, "w", 2)
+    M, din = x.shape
+    dout = w.shape[0]
+    if w.shape[1] != din or not w.is_contiguous():
+        raise _lib.AqualoraError(f"w must be contiguous [dout, {din}], got {tuple(w.shape)}")
+    r = 0
+    h = None
+    if down is not None:
+        _need(down, _BF16, "down", 2)
+        _need(up, _BF16, "up", 2)
+        _need(scale, _F32, "scale", 2)
+        r = down.shape[0]
+        if tuple(down.shape) != (r, din) or tuple(up.shape) != (dout, r) or not down.is_contiguous() or not up.is_contiguous():
+            raise _lib.AqualoraError(f"down/up must be contiguous [r, din]/[dout, r], got {tuple(down.shape)}/{tuple(up.shape)}")
+        nsamp = (M + tokens_per_sample - 1) // tokens_per_sample
+        if tuple(scale.shape) != (nsamp, r) or not scale.is_contiguous():
+            raise _lib.AqualoraError(f"scale must be contiguous [{nsamp}, {r}], got {tuple(scale.shape)}")
+        if save_h:
+            h = torch.empty((M, r), dtype=_BF16, device=x.device)
+    if bias is not None:
+        _need(bias, _BF16, "bias", 1)
+    y = out if out is not None else torch.empty((M, dout), dtype=_BF16, device=x.device)
+    _lib.call("aq_lora_linear_fwd", x.data_ptr(), _rows(x, "x"), w.data_ptr(), _ptr(bias), _ptr(down), _ptr(up), _ptr(scale),
+              y.data_ptr(), _rows(y, "y"), _ptr(h), M, max(int(tokens_per_sample), 1), din, dout, r, _stream())
+    return y, h
+
+
+def lora_linear_bwd(gy: torch.Tensor, x: torch.Tensor, w_t: torch.Tensor | None, down_t: torch.Tensor, up_t: torch.Tensor,
+                    scale: torch.Tensor, h: torch.Tensor, g_down: torch.Tensor, g_up: torch.Tensor,
+                    g_scale: torch.Tensor | None, tokens_per_sample: int):
+    """Backward of lora_linear_fwd.  Accumulates into g_down [r, din], g_up [dout, r], g_scale [B, r] (fp32) and returns
+    gx [M, din] bf16 (None when w_t is None)."""
+    _need(gy, _BF16, "gy", 2)
+    _need(x, _BF16, "x", 2)
+    _need(h, _BF16, "h", 2)
+    _need(down_t, _BF16, "down_t", 2)
+    _need(up_t, _BF16, "up_t", 2)
+    _need(scale, _F32, "scale", 2)
+    _need(g_down, _F32, "g_down", 2)
+    _need(g_up, _F32, "g_up", 2)
+    M, dout = gy.shape
+    din = x.shape[1]
+    r = h.shape[1]
+    if tuple(down_t.shape) != (din, r) or tuple(up_t.shape) != (r, dout):
+        raise _lib.AqualoraError(f"down_t/up_t must be [din, r]/[r, dout], got {tuple(down_t.shape)}/{tuple(up_t.shape)}")
+    if tuple(g_down.shape) != (r, din) or tuple(g_up.shape) != (dout, r):
+        raise _lib.AqualoraError("g_down/g_up must be [r, din]/[dout, r]")
+    for t, n in ((down_t, "down_t"), (up_t, "up_t"), (h, "h"), (g_down, "g_down"), (g_up, "g_up"), (scale, "scale")):
+        if not t.is_contiguous():
+            raise _lib.AqualoraError(f"{n} must be contiguous")
+    gx = None
+    if w_t is not None:
+        _need(w_t, _BF16, "w_t", 2)
+        if tuple(w_t.shape) != (din, dout) or not w_t.is_contiguous():
+            raise _lib.AqualoraError(f"w_t must be contiguous [{din}, {dout}]")
+        gx = torch.empty((M, din), dtype=_BF16, device=gy.device)
+    if g_scale is not None:
+        _need(g_scale, _F32, "g_scale", 2)
+    nbytes = _lib.load().aq_lora_linear_bwd_workspace_bytes(M, r)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=gy.device)
+    _lib.call("aq_lora_linear_bwd", gy.data_ptr(), _rows(gy, "gy"), x.data_ptr(), _rows(x, "x"), _ptr(w_t), down_t.data_ptr(),
+              up_t.data_ptr(), scale.data_ptr(), h.data_ptr(), _ptr(gx), din if gx is not None else 0, g_down.data_ptr(),
+              g_up.data_ptr(), _ptr(g_scale), M, int(tokens_per_sample), din, dout, r, ws.data_ptr(), nbytes, _stream())
+    return gx
+
+
+def wgrad_tn(p: torch.Tensor, q: torch.Tensor, c: torch.Tensor, transpose_out: bool = False) -> None:
+    """c[i, j] += sum_m p[m, i] * q[m, j]   (c is [J, I] when transpose_out)."""
+    _need(p, _BF16, "p", 2)
+    _need(q, _BF16, "q", 2)
+    _need(c, _F32, "c", 2)
+    M, I = p.shape
+    J = q.shape[1]
+    _lib.call("aq_wgrad_tn", p.data_ptr(), _rows(p, "p"), q.data_ptr(), _rows(q, "q"), c.data_ptr(), c.stride(0), M, I, J,
+              int(transpose_out), _stream())
+
+
+def mapper_fwd(msg: torch.Tensor, emb: torch.Tensor, round_bf16: bool = True) -> torch.Tensor:
+    _need(msg, _F32, "msg", 2)
+    _need(emb, _F32, "emb", 2)
+    B, bits = msg.shape
+    r = emb.shape[1]
+    out = torch.empty((B, r), dtype=_F32, device=msg.device)
+    _lib.call("aq_mapper_fwd", msg.contiguous().data_ptr(), emb.contiguous().data_ptr(), out.data_ptr(), B, bits, r,
+              int(round_bf16), _stream())
+    return out
+
+
+def mapper_bwd(msg: torch.Tensor, g_scale: torch.Tensor, g_emb: torch.Tensor) -> None:
+    _need(msg, _F32, "msg", 2)
+    _need(g_scale, _F32, "g_scale", 2)
+    _need(g_emb, _F32, "g_emb", 2)
+    B, bits = msg.shape
+    r = g_scale.shape[1]
+    _lib.call("aq_mapper_bwd", msg.contiguous().data_ptr(), g_scale.contiguous().data_ptr(), g_emb.data_ptr(), B, bits, r,
+              _stream())
+
+
+def cast_transpose_bf16(src: torch.Tensor, dst: torch.Tensor | None, dst_t: torch.Tensor | None) -> None:
+    _need(src, _F32, "src", 2)
+    rows, cols = src.shape
+    _lib.call("aq_cast_transpose_bf16", src.data_ptr(), _ptr(dst), _ptr(dst_t), rows, cols, _stream())
+
+
+def transpose_bf16(src: torch.Tensor) -> torch.Tensor:
+    _need(src, _BF16, "src", 2)
+    rows, cols = src.shape
+    dst = torch.empty((cols, rows), dtype=_BF16, device=src.device)
+    _lib.call("aq_transpose_bf16", src.contiguous().data_ptr(), dst.data_ptr(), rows, cols, _stream())
+    return dst
+
+
+def flat_sumsq(g: torch.Tensor, out: torch.Tensor) -> None:
+    _need(g, _F32, "g", 1)
+    _need(out, _F32, "norm_sq")
+    _lib.call("aq_flat_sumsq", g.data_ptr(), g.numel(), out.data_ptr(), _stream())
+
+
+def flat_clip_adamw(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, norm_sq: torch.Tensor, *,
+                    grad_scale: float, max_norm: float, lr: float, beta1: float, beta2: float, eps: float,
+                    weight_decay: float, step: int) -> None:
+    for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _need(t, _F32, n, 1)
+    _lib.call("aq_flat_clip_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), norm_sq.data_ptr(),
+              grad_scale, max_norm, lr, beta1, beta2, eps, weight_decay, step, _stream())

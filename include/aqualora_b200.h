@@ -1,0 +1,114 @@
+/*
+ * libaqualora_b200.so -- C ABI of the B200-native AquaLoRA hot paths.
+ *
+ * Every entry point replaces one piece of the reference's Python hot path (file:line cited per function,
+ * relative to the AquaLoRA repository).  Conventions:
+ *   - plain C, all pointers are DEVICE pointers owned by the caller unless a name ends in `_host`;
+ *   - the library never allocates user-visible memory; scratch comes in through `ws` (query the size with
+ *     the matching `*_workspace_bytes`);
+ *   - every call is asynchronous and ordered on `stream` (a cudaStream_t passed as void*);
+ *   - returns 0 (AQ_OK) or a negative AQ_ERR_* code, never throws; aq_last_error() returns a thread-local
+ *     explanation of the last failure on the calling thread;
+ *   - bf16 tensors are raw uint16 bfloat16 bit patterns, row-major, with explicit leading dimensions (in
+ *     elements) where a view is allowed.
+ */
+#ifndef AQUALORA_B200_H_
+#define AQUALORA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AQ_OK 0
+#define AQ_ERR_BAD_SHAPE (-1)
+#define AQ_ERR_BAD_DTYPE (-2)
+#define AQ_ERR_BAD_ALIGN (-3)
+#define AQ_ERR_ARCH (-4)
+#define AQ_ERR_LAUNCH (-5)
+#define AQ_ERR_WORKSPACE (-6)
+
+int aq_version(void);               /* ABI version, bumped on any signature change */
+int aq_arch(void);                  /* 100: the only architecture this library is built for (sm_100a) */
+const char* aq_last_error(void);    /* thread-local, never NULL */
+int aq_sm_count(void);              /* SM count of the current device, or <0 */
+
+/* ------------------------------------------------------------------------------------------------
+ * (i) watermark-LoRA projection.  Replaces utils/lora_modules.py:9-26 (CustomLoRALinearLayerforward)
+ * fused with the base op of utils/lora_modules.py:56-62 (CustomLoRACompatibleLinearforward):
+ *
+ *      H  = X Dn^T                       [M, r]
+ *      Y  = X W^T + bias + (H (.) scale[row / tokens_per_sample, :]) Up^T        [M, dout]
+ *
+ * x      [M, din]   bf16, row stride ldx          w     [dout, din] bf16 (nn.Linear.weight)
+ * bias   [dout]     bf16 or NULL                  down  [r, din]    bf16 (lora_layer.down.weight) or NULL
+ * up     [dout, r]  bf16 (lora_layer.up.weight)   scale [M/tokens_per_sample, r] fp32 -- the EFFECTIVE
+ *        diagonal: mapper(msg) for a tensor scale, the float multiplier broadcast for a float scale, times
+ *        network_alpha/rank when set (lora_modules.py:15-25).
+ * y      [M, dout]  bf16, row stride ldy          h_save [M, r] bf16 or NULL: H before scaling (kept for
+ *        the backward).
+ * down == NULL runs the plain base projection (lora_layer is None, lora_modules.py:57-59).
+ * Constraints: din % 8 == 0, dout % 8 == 0, r % 8 == 0, 8 <= r <= 64, 16-byte aligned pointers.
+ * One kernel: TMA-staged tiles, tcgen05 MMA with TMEM accumulators; H never leaves the SM on its way
+ * into the second contraction.
+ * ---------------------------------------------------------------------------------------------- */
+int aq_lora_linear_fwd(const void* x, int64_t ldx, const void* w, const void* bias, const void* down,
+                       const void* up, const float* scale, void* y, int64_t ldy, void* h_save, int64_t M,
+                       int64_t tokens_per_sample, int din, int dout, int r, void* stream);
+
+/* Test / tuning hook: pin the column-tile width (64, 128, 160 or 192) and the number of column tiles per work
+ * item for the calling thread's next aq_lora_linear_* launches; (0, 0) restores the built-in heuristics. */
+int aq_lora_set_tuning(int block_n, int group_size);
+
+/* Backward of the above (what autograd derives from utils/lora_modules.py:9-26,56-62; closed form in
+ * DESIGN.md):
+ *      dHs = G Up            dH = dHs (.) scale        dX  = G W + dH Dn
+ *      dUp += G^T (H (.) scale)      dDn += dH^T X      dscale[b] += sum_n dHs (.) H
+ * gy [M, dout] bf16 (ldgy); x [M, din] bf16 (ldx); h_save [M, r] bf16 from the forward.
+ * w_t [din, dout] bf16 = W^T (cached once, W is frozen) -- NULL skips dX (inputs that need no gradient,
+ * e.g. the text context of attn2.to_k / to_v); down_t [din, r] bf16 = Dn^T; up_t [r, dout] bf16 = Up^T.
+ * gx [M, din] bf16 (ldgx) or NULL.  g_down [r, din], g_up [dout, r], g_scale [B, r] are fp32 and are
+ * ACCUMULATED into (the caller zeroes the flat gradient buffer once per step); g_scale may be NULL.
+ * ws: aq_lora_linear_bwd_workspace_bytes(M, r) bytes of scratch. */
+size_t aq_lora_linear_bwd_workspace_bytes(int64_t M, int r);
+int aq_lora_linear_bwd(const void* gy, int64_t ldgy, const void* x, int64_t ldx, const void* w_t,
+                       const void* down_t, const void* up_t, const float* scale, const void* h_save, void* gx,
+                       int64_t ldgx, float* g_down, float* g_up, float* g_scale, int64_t M,
+                       int64_t tokens_per_sample, int din, int dout, int r, void* ws, size_t ws_bytes,
+                       void* stream);
+
+/* Skinny weight-gradient contraction used by the backward:  C[i, j] (+)= sum_m P[m, i] * Q[m, j]
+ * P [M, I] bf16 (ldp), Q [M, J] bf16 (ldq, J <= 64), C fp32 [I, J] (transpose_out = 0) or [J, I] (= 1),
+ * accumulated with fp32 reductions in L2.  Exposed for tests and for create_wm_lora/merge tooling. */
+int aq_wgrad_tn(const void* p, int64_t ldp, const void* q, int64_t ldq, float* c, int64_t ldc, int64_t M, int I,
+                int J, int transpose_out, void* stream);
+
+/* MapperNet (utils/models.py:98-115):  scale[b, :] = 1 + (msg[b, :] @ E) / sqrt(bits);  E [bits, r] fp32.
+ * out_bf16_rounded != 0 rounds the result to bf16 precision (train/ppft_train.py:990 casts to weight dtype). */
+int aq_mapper_fwd(const float* msg, const float* emb, float* scale, int B, int bits, int r, int out_bf16_rounded,
+                  void* stream);
+/* g_emb[i, :] += sum_b msg[b, i] * g_scale[b, :] / sqrt(bits) */
+int aq_mapper_bwd(const float* msg, const float* g_scale, float* g_emb, int B, int bits, int r, void* stream);
+
+/* fp32 master LoRA parameters -> the bf16 operand copies the kernels consume.  src [rows, cols] fp32;
+ * dst [rows, cols] bf16 and (optional) dst_t [cols, rows] bf16. */
+int aq_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int rows, int cols, void* stream);
+/* bf16 [rows, cols] -> bf16 [cols, rows] (frozen W -> W^T cache for the dX contraction) */
+int aq_transpose_bf16(const void* src, void* dst, int rows, int cols, void* stream);
+
+/* Fused global-norm clip + AdamW over the flat fp32 LoRA parameter/gradient buffers
+ * (train/ppft_train.py:1059-1068: clip_grad_norm_(1.0), AdamW step, zero_grad).
+ * Pass 1 (aq_flat_sumsq) accumulates sum(g^2) into norm_sq[0] (caller zeroes it);  pass 2 applies
+ * g *= min(1, max_norm / (sqrt(norm_sq * grad_scale^2) + 1e-6)) * grad_scale, the decoupled-weight-decay Adam
+ * update, and zeroes g. */
+int aq_flat_sumsq(const float* g, int64_t n, float* norm_sq, void* stream);
+int aq_flat_clip_adamw(float* p, float* g, float* m, float* v, int64_t n, const float* norm_sq, float grad_scale,
+                       float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
+                       int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AQUALORA_B200_H_ */
