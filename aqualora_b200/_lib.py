@@ -36,6 +36,8 @@ _SIGNATURES = {
         c_int,
     ),
     "aq_wgrad_tn": ([c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p], c_int),
+    "aq_secret_encoder_workspace_bytes": ([c_int, c_int], c_size_t),
+    "aq_secret_encoder_fwd": ([c_void_p] * 8 + [c_int] * 6 + [c_void_p, c_void_p], c_int),
     "aq_mapper_fwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "aq_mapper_bwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     "aq_cast_transpose_bf16": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),

@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) lora_gemm_kernel(const __grid_con
       const int nt_end = min(nt_begin + p.group_size, p.num_n_tiles);
       const long long grow = (long long)m0 + row_in_tile;
       const bool row_ok = grow < p.M;
+      const bool aux_owner = row_ok && grp == 0;   // side outputs (H / dH / Hs / dscale) are emitted once per row block
       for (int nt = nt_begin; nt < nt_end; ++nt) {
         const int n0 = nt * BN;
         const bool first = (nt == nt_begin) && p.has_lora;
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) lora_gemm_kernel(const __grid_con
                 to_smem.y = pack_bf16x2(hb[2] * s[2], hb[3] * s[3]);
                 to_smem.z = pack_bf16x2(hb[4] * s[4], hb[5] * s[5]);
                 to_smem.w = pack_bf16x2(hb[6] * s[6], hb[7] * s[7]);
-                if (row_ok && p.aux_out0 != nullptr) {
+                if (aux_owner && p.aux_out0 != nullptr) {
                   uint4 hraw;
                   hraw.x = pack_bf16x2(hb[0], hb[1]);
                   hraw.y = pack_bf16x2(hb[2], hb[3]);
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) lora_gemm_kernel(const __grid_con
                 to_smem.y = pack_bf16x2(hb[2] * s[2], hb[3] * s[3]);
                 to_smem.z = pack_bf16x2(hb[4] * s[4], hb[5] * s[5]);
                 to_smem.w = pack_bf16x2(hb[6] * s[6], hb[7] * s[7]);
-                if (row_ok) {
+                if (aux_owner) {
                   *reinterpret_cast<uint4*>(p.aux_out0 + aux_off + j8 * 8) = to_smem;  // dH
                   uint4 hs;
                   hs.x = pack_bf16x2(hval[0] * s[0], hval[1] * s[1]);
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) lora_gemm_kernel(const __grid_con
           tc_fence_before();
           fence_proxy_async_smem();   // generic-proxy SMEM writes -> visible to the tensor-core (async) proxy
           mbar_arrive(hs_ready_bar);
-          if (p.mode == 1 && p.g_scale != nullptr) {
+          if (p.mode == 1 && p.g_scale != nullptr && grp == 0) {
             // dscale[b, j] += sum over this tile's rows of dHs * H
             const long long first_row = (long long)m0 + q * 32;
             const bool uniform = (p.tokens % 32 == 0) && (first_row + 32 <= p.M);

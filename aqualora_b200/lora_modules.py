@@ -1,0 +1,409 @@
+"""Drop-in replacement for the reference's `utils/lora_modules.py` (the plugin boundary).
+
+The four `Custom*forward` functions keep the reference's names, signatures and semantics
+(utils/lora_modules.py:9-62) and are meant to be monkey-patched onto diffusers' `LoRACompatibleLinear/Conv` and
+`LoRALinearLayer/LoRAConv2dLayer` exactly as `train/ppft_train.py:681-689` does:
+
+    module.forward = types.MethodType(CustomLoRACompatibleLinearforward, module)
+
+They only read the attributes the reference reads (`weight`, `bias`, `lora_layer`, `down.weight`, `up.weight`,
+`network_alpha`, `rank`, conv `stride/padding/dilation/groups`).  Behind them sits ONE fused sm_100a kernel per
+projection (csrc/lora_gemm.cu) plus the backward kernels; there is no PyTorch fallback: CPU tensors, missing
+library or unsupported dtypes raise `AqualoraError`.
+
+`diffusers` is not required: minimal container classes with the diffusers field names are defined here for the
+in-repo U-Net harness (aqualora_b200/unet.py) and for tests.
+"""
+from __future__ import annotations
+
+import contextlib
+import types
+from typing import Dict, Iterable, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from ._lib import AqualoraError
+
+# ------------------------------------------------------------------------------------------------
+# operand caches: bf16 (+ transposed) copies of fp32 master LoRA weights, W^T of frozen projections
+# ------------------------------------------------------------------------------------------------
+_PACK_CACHE: Dict[int, tuple] = {}
+_WT_CACHE: Dict[int, tuple] = {}
+_PACK_EPOCH = 0          # bumped by invalidate_packed(): kernels that update parameters in place bypass `_version`
+_LORA_DISABLED = False
+
+
+def invalidate_packed() -> None:
+    """Mark every cached bf16 operand copy stale (call after an in-place optimizer step on the flat buffers)."""
+    global _PACK_EPOCH
+    _PACK_EPOCH += 1
+
+
+@contextlib.contextmanager
+def lora_disabled():
+    """Run the patched modules as if `lora_layer is None` (utils/lora_modules.py:47-52,57-59).  Used for the PPFT
+    clean pass, whose all-zero scale makes the LoRA branch contribute exactly 0 (train/ppft_train.py:1026-1029)."""
+    global _LORA_DISABLED
+    prev, _LORA_DISABLED = _LORA_DISABLED, True
+    try:
+        yield
+    finally:
+        _LORA_DISABLED = prev
+
+
+def _packed(param: torch.Tensor, rows: int, cols: int):
+    """(bf16 [rows, cols], bf16 [cols, rows]) of a fp32/bf16 parameter, refreshed when the parameter changes."""
+    key = id(param)
+    ver = (param._version, param.data_ptr(), _PACK_EPOCH)
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    src = param.detach().reshape(rows, cols)
+    if hit is not None and hit[1].shape == (rows, cols):
+        d, dt = hit[1], hit[2]                       # reuse the buffers (stable addresses, CUDA-graph friendly)
+    else:
+        d = torch.empty((rows, cols), dtype=torch.bfloat16, device=param.device)
+        dt = torch.empty((cols, rows), dtype=torch.bfloat16, device=param.device)
+    if src.dtype == torch.float32:
+        ops.cast_transpose_bf16(src.contiguous(), d, dt)
+    elif src.dtype == torch.bfloat16:
+        d.copy_(src)
+        dt.copy_(ops.transpose_bf16(src))
+    else:
+        raise AqualoraError(f"LoRA weights must be fp32 or bf16, got {src.dtype}")
+    _PACK_CACHE[key] = (ver, d, dt)
+    return d, dt
+
+
+def _weight_t(weight: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    """W^T [cols, rows] bf16 of a frozen projection weight (needed by the dX contraction), cached."""
+    key = id(weight)
+    ver = (weight._version, weight.data_ptr())
+    hit = _WT_CACHE.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    wt = ops.transpose_bf16(weight.detach().reshape(rows, cols))
+    _WT_CACHE[key] = (ver, wt)
+    return wt
+
+
+def clear_caches() -> None:
+    _PACK_CACHE.clear()
+    _WT_CACHE.clear()
+
+
+def _grad_target(tgt, shape, device) -> tuple[torch.Tensor, bool]:
+    """fp32 buffer the backward kernels accumulate into.  A parameter may carry `_aq_grad` (a view of a flat
+    gradient buffer, see aqualora_b200/ppft.py): then gradients are accumulated there and autograd gets None."""
+    if tgt is not None:
+        return tgt.view(shape), True
+    return torch.zeros(shape, dtype=torch.float32, device=device), False
+
+
+class _FusedLoraProjection(torch.autograd.Function):
+    """y = x W^T + b + ((x Dn^T) (.) s) Up^T  on [M, din] bf16 rows; see include/aqualora_b200.h."""
+
+    @staticmethod
+    def forward(ctx, x2d, weight, bias, down, up, scale_eff, tokens):
+        dout, din = weight.shape[0], x2d.shape[1]
+        w2d = weight.reshape(dout, din)
+        need_grad = any(ctx.needs_input_grad)     # (grad mode itself is off inside Function.forward)
+        if down is not None:
+            r = down.shape[0]
+            dn16, _ = _packed(down, r, din)
+            up16, _ = _packed(up, dout, r)
+            y, h = ops.lora_linear_fwd(x2d, w2d, bias, dn16, up16, scale_eff.detach(), tokens, save_h=need_grad)
+        else:
+            y, h = ops.lora_linear_fwd(x2d, w2d, bias, None, None, None, tokens)
+        ctx.tokens = tokens
+        ctx.has_lora = down is not None
+        # python-side handles: `_aq_grad` (direct accumulation target) lives on the caller's tensor objects
+        ctx.grad_targets = tuple(getattr(t, "_aq_grad", None) for t in (down, up, scale_eff))
+        ctx.save_for_backward(x2d, weight, down, up, scale_eff, h)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2d, weight, down, up, scale_eff, h = ctx.saved_tensors
+        dout, din = weight.shape[0], x2d.shape[1]
+        gy = gy if gy.stride(1) == 1 and gy.stride(0) % 8 == 0 else gy.contiguous()
+        need_dx = ctx.needs_input_grad[0]
+        w_t = _weight_t(weight, dout, din) if need_dx else None
+        if not ctx.has_lora:
+            gx = None
+            if need_dx:
+                gx, _ = ops.lora_linear_fwd(gy, w_t, None, None, None, None, ctx.tokens)
+            return gx, None, None, None, None, None, None
+        r = down.shape[0]
+        _, dn16_t = _packed(down, r, din)
+        _, up16_t = _packed(up, dout, r)
+        t_down, t_up, t_scale = ctx.grad_targets
+        g_down, down_direct = _grad_target(t_down, (r, din), gy.device)
+        g_up, up_direct = _grad_target(t_up, (dout, r), gy.device)
+        g_scale, scale_direct = None, False
+        if ctx.needs_input_grad[5]:
+            g_scale, scale_direct = _grad_target(t_scale, tuple(scale_eff.shape), gy.device)
+        gx = ops.lora_linear_bwd(gy, x2d, w_t, dn16_t, up16_t, scale_eff.detach(), h, g_down, g_up, g_scale, ctx.tokens)
+        return (gx, None, None,
+                None if down_direct else g_down.view_as(down).to(down.dtype),
+                None if up_direct else g_up.view_as(up).to(up.dtype),
+                None if (g_scale is None or scale_direct) else g_scale, None)
+
+
+def _effective_scale(scale, lora_layer, nsamples: int, r: int, device, compute_dtype) -> torch.Tensor:
+    """[B, r] fp32 diagonal the kernel applies between down and up (utils/lora_modules.py:15-25): the tensor scale
+    (rounded to the compute dtype, as the reference's `.to(weight_dtype)` + autocast matmul do), or the float
+    multiplier broadcast, times network_alpha / rank."""
+    a = 1.0
+    if getattr(lora_layer, "network_alpha", None) is not None:
+        a = float(lora_layer.network_alpha) / float(lora_layer.rank)
+    if isinstance(scale, torch.Tensor):
+        if scale.dim() != 2 or scale.shape[1] != r:
+            raise AqualoraError(f"tensor scale must be [batch, rank={r}], got {tuple(scale.shape)}")
+        if getattr(scale, "_aq_grad", None) is not None and scale.dtype == torch.float32 and a == 1.0:
+            return scale                                       # pre-rounded leaf managed by the PPFT harness
+        s = scale.to(compute_dtype).to(torch.float32)
+        return s * a if a != 1.0 else s
+    return torch.full((1, r), float(scale) * a, dtype=torch.float32, device=device)
+
+
+def _check_input(x: torch.Tensor, what: str) -> None:
+    if not x.is_cuda:
+        raise AqualoraError(f"{what}: CPU tensor passed; aqualora_b200 runs on sm_100a only and has no CPU fallback "
+                            "(patch oracle.lora_oracle forwards in tests that need a CPU reference)")
+    if x.dtype != torch.bfloat16:
+        raise AqualoraError(f"{what}: activations must be bf16 (the BASELINE precision), got {x.dtype}")
+
+
+def _rows_view(x: torch.Tensor, din: int) -> torch.Tensor:
+    x2d = x.reshape(-1, din)
+    if x2d.stride(1) != 1 or (x2d.shape[0] > 1 and x2d.stride(0) % 8 != 0) or x2d.data_ptr() % 16 != 0:
+        x2d = x2d.contiguous()
+    return x2d
+
+
+def _project_rows(x2d, weight, bias, down, up, lora_meta, scale, compute_dtype):
+    """Shared tail of the four forwards: x2d [M, din] bf16 rows -> [M, dout] through the fused kernel."""
+    M = x2d.shape[0]
+    if weight.dtype != torch.bfloat16:
+        raise AqualoraError("frozen projection weights must be bf16 (train/ppft_train.py:569-581 casts them)")
+    if down is None:
+        return _FusedLoraProjection.apply(x2d, weight, bias, None, None, None, M)
+    r = down.shape[0]
+    if isinstance(scale, torch.Tensor):
+        nsamp = scale.shape[0]
+        if M % nsamp != 0:
+            raise AqualoraError(f"{M} rows cannot be split over a scale batch of {nsamp}")
+        tokens = M // nsamp
+    else:
+        nsamp, tokens = 1, M
+    s_eff = _effective_scale(scale, lora_meta, nsamp, r, x2d.device, compute_dtype)
+    return _FusedLoraProjection.apply(x2d, weight, bias, down, up, s_eff, tokens)
+
+
+_ZERO_BASE: Dict[tuple, torch.Tensor] = {}
+
+
+def _zero_base(dout: int, din: int, device) -> torch.Tensor:
+    """Zero base weight for a stand-alone LoRA layer call (the fused kernel always carries a base operand)."""
+    key = (dout, din, str(device))
+    if key not in _ZERO_BASE:
+        _ZERO_BASE[key] = torch.zeros((dout, din), dtype=torch.bfloat16, device=device)
+    return _ZERO_BASE[key]
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's four forwards (names and signatures: utils/lora_modules.py:9,28,46,56)
+# ------------------------------------------------------------------------------------------------
+def CustomLoRALinearLayerforward(self, hidden_states: torch.Tensor, scale: float = 1.0):
+    """up(diag(scale) down(x)) [* alpha/rank] [* float scale]  -- utils/lora_modules.py:9-26.
+    Stand-alone call (the compatible-linear forward below fuses this into the base projection instead)."""
+    _check_input(hidden_states, "LoRALinearLayer")
+    down, up = self.down.weight, self.up.weight
+    x2d = _rows_view(hidden_states, hidden_states.shape[-1])
+    y = _project_rows(x2d, _zero_base(up.shape[0], down.shape[1], x2d.device), None, down, up, self, scale, hidden_states.dtype)
+    return y.view(*hidden_states.shape[:-1], up.shape[0])
+
+
+def CustomLoRACompatibleLinearforward(self, hidden_states: torch.Tensor, scale: float = 1.0):
+    """Linear(x) [+ lora_layer(x, scale)]  -- utils/lora_modules.py:56-62, as one fused kernel."""
+    _check_input(hidden_states, "LoRACompatibleLinear")
+    x2d = _rows_view(hidden_states, hidden_states.shape[-1])
+    lora = None if _LORA_DISABLED else self.lora_layer
+    if lora is None:
+        y = _project_rows(x2d, self.weight, self.bias, None, None, None, scale, hidden_states.dtype)
+    else:
+        y = _project_rows(x2d, self.weight, self.bias, lora.down.weight, lora.up.weight, lora, scale, hidden_states.dtype)
+    return y.view(*hidden_states.shape[:-1], self.weight.shape[0])
+
+
+def _conv_as_rows(hidden_states: torch.Tensor):
+    B, C, H, W = hidden_states.shape
+    x = hidden_states.contiguous(memory_format=torch.channels_last)      # no-op inside the channels_last U-Net
+    return _rows_view(x.permute(0, 2, 3, 1).reshape(B * H * W, C), C), (B, H, W)
+
+
+def _is_pointwise(conv) -> bool:
+    def one(v, want):
+        return all(int(t) == want for t in (v if isinstance(v, (tuple, list)) else (v, v)))
+
+    return one(conv.kernel_size, 1) and one(conv.stride, 1) and one(conv.padding, 0) and one(conv.dilation, 1) and conv.groups == 1
+
+
+def CustomLoRAConv2dLayerforward(self, hidden_states: torch.Tensor, scale: float = 1.0):
+    """up(down(x) * scale[:, :, None, None])  -- utils/lora_modules.py:28-44 (1x1 down only: the SD1.5 proj_in/out).
+    A pointwise conv over NCHW is the row projection over the channels_last view [B*H*W, C]."""
+    if not _is_pointwise(self.down):
+        raise AqualoraError("LoRAConv2dLayer: only 1x1 stride-1 down convolutions are implemented (the unet_keys.json targets)")
+    _check_input(hidden_states, "LoRAConv2dLayer")
+    x2d, (B, H, W) = _conv_as_rows(hidden_states)
+    down, up = self.down.weight, self.up.weight
+    y = _project_rows(x2d, _zero_base(up.shape[0], down.shape[1], x2d.device), None, down, up, self, scale, hidden_states.dtype)
+    return y.view(B, H, W, -1).permute(0, 3, 1, 2)
+
+
+def CustomLoRACompatibleConvforward(self, hidden_states: torch.Tensor, scale: float = 1.0):
+    """conv2d(x) [+ lora_layer(x, scale)]  -- utils/lora_modules.py:46-54."""
+    if self.lora_layer is None or (_LORA_DISABLED and not _is_pointwise(self)):
+        return F.conv2d(hidden_states, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+    if _LORA_DISABLED:
+        _check_input(hidden_states, "LoRACompatibleConv")
+        x2d, (B, H, W) = _conv_as_rows(hidden_states)
+        y = _project_rows(x2d, self.weight, self.bias, None, None, None, scale, hidden_states.dtype)
+        return y.view(B, H, W, -1).permute(0, 3, 1, 2)
+    if not (_is_pointwise(self) and _is_pointwise(self.lora_layer.down)):
+        raise AqualoraError("LoRACompatibleConv with a LoRA layer: only 1x1 stride-1 convolutions are implemented "
+                            "(proj_in / proj_out, the only conv targets in utils/unet_keys.json)")
+    _check_input(hidden_states, "LoRACompatibleConv")
+    x2d, (B, H, W) = _conv_as_rows(hidden_states)
+    lora = self.lora_layer
+    # [Co, C, 1, 1] / [r, C, 1, 1] / [Co, r, 1, 1] are row-major matrices already: the kernel reads them in place
+    y = _project_rows(x2d, self.weight, self.bias, lora.down.weight, lora.up.weight, lora, scale, hidden_states.dtype)
+    return y.view(B, H, W, -1).permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# diffusers-shaped containers (field names per diffusers 0.24 models/lora.py, which the reference relies on)
+# ------------------------------------------------------------------------------------------------
+class LoRALinearLayer(nn.Module):
+    def __init__(self, in_features: int, out_features: int, rank: int = 4, network_alpha: Optional[float] = None,
+                 device=None, dtype=None):
+        super().__init__()
+        self.down = nn.Linear(in_features, rank, bias=False, device=device, dtype=dtype)
+        self.up = nn.Linear(rank, out_features, bias=False, device=device, dtype=dtype)
+        self.network_alpha = network_alpha
+        self.rank = rank
+        self.in_features, self.out_features = in_features, out_features
+        nn.init.normal_(self.down.weight, std=1 / rank)
+        nn.init.zeros_(self.up.weight)
+
+    forward = CustomLoRALinearLayerforward
+
+
+class LoRAConv2dLayer(nn.Module):
+    def __init__(self, in_features: int, out_features: int, rank: int = 4, kernel_size=(1, 1), stride=(1, 1), padding=0,
+                 network_alpha: Optional[float] = None):
+        super().__init__()
+        self.down = nn.Conv2d(in_features, rank, kernel_size=kernel_size, stride=stride, padding=padding, bias=False)
+        self.up = nn.Conv2d(rank, out_features, kernel_size=(1, 1), stride=(1, 1), bias=False)
+        self.network_alpha = network_alpha
+        self.rank = rank
+        nn.init.normal_(self.down.weight, std=1 / rank)
+        nn.init.zeros_(self.up.weight)
+
+    forward = CustomLoRAConv2dLayerforward
+
+
+class LoRACompatibleLinear(nn.Linear):
+    def __init__(self, *args, lora_layer: Optional[LoRALinearLayer] = None, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.lora_layer = lora_layer
+
+    def set_lora_layer(self, lora_layer):
+        self.lora_layer = lora_layer
+
+    forward = CustomLoRACompatibleLinearforward
+
+
+class LoRACompatibleConv(nn.Conv2d):
+    def __init__(self, *args, lora_layer: Optional[LoRAConv2dLayer] = None, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.lora_layer = lora_layer
+
+    def set_lora_layer(self, lora_layer):
+        self.lora_layer = lora_layer
+
+    forward = CustomLoRACompatibleConvforward
+
+
+# ------------------------------------------------------------------------------------------------
+# injection / patching / state-dict naming (train/ppft_train.py:443-471, :620-689)
+# ------------------------------------------------------------------------------------------------
+def resolve(root: nn.Module, key: str) -> nn.Module:
+    mod = root
+    for sub in key.split("."):
+        mod = getattr(mod, sub)
+    return mod
+
+
+def inject_lora(unet: nn.Module, keys: Iterable[str], rank: int, network_alpha: Optional[float] = None):
+    """Build one LoRA layer per target module and attach it (train/ppft_train.py:635-678).  Returns the list of
+    (key, target_module, lora_layer)."""
+    out = []
+    for key in keys:
+        target = resolve(unet, key)
+        if isinstance(target, nn.Conv2d):
+            lora = LoRAConv2dLayer(target.in_channels, target.out_channels, rank=rank, kernel_size=target.kernel_size,
+                                   stride=target.stride, padding=target.padding, network_alpha=network_alpha)
+        elif isinstance(target, nn.Linear):
+            lora = LoRALinearLayer(target.in_features, target.out_features, rank, network_alpha=network_alpha)
+        else:
+            raise ValueError(f"Module {key} is not a LoRACompatibleConv or LoRACompatibleLinear module.")
+        lora.to(target.weight.device)
+        target.set_lora_layer(lora) if hasattr(target, "set_lora_layer") else setattr(target, "lora_layer", lora)
+        out.append((key, target, lora))
+    return out
+
+
+def patch_unet(unet: nn.Module, linear_cls=None, conv_cls=None, linear_layer_cls=None, conv_layer_cls=None) -> int:
+    """Monkey-patch every LoRA-compatible module and its lora_layer (train/ppft_train.py:681-689).  With no class
+    arguments this patches the in-repo containers; pass diffusers' classes to patch a diffusers U-Net."""
+    linear_cls = linear_cls or LoRACompatibleLinear
+    conv_cls = conv_cls or LoRACompatibleConv
+    n = 0
+    for _, module in unet.named_modules():
+        if isinstance(module, conv_cls):
+            module.forward = types.MethodType(CustomLoRACompatibleConvforward, module)
+            if module.lora_layer is not None:
+                module.lora_layer.forward = types.MethodType(CustomLoRAConv2dLayerforward, module.lora_layer)
+            n += 1
+        elif isinstance(module, linear_cls):
+            module.forward = types.MethodType(CustomLoRACompatibleLinearforward, module)
+            if module.lora_layer is not None:
+                module.lora_layer.forward = types.MethodType(CustomLoRALinearLayerforward, module.lora_layer)
+            n += 1
+    return n
+
+
+def lora_state_dict_key(key: str) -> str:
+    """Module path -> key stem inside pytorch_lora_weights.safetensors (train/ppft_train.py:459-467)."""
+    k = key.replace(".proj_in", ".proj_in.lora").replace(".proj_out", ".proj_out.lora")
+    k = k.replace(".to_q", ".processor.to_q_lora").replace(".to_k", ".processor.to_k_lora")
+    k = k.replace(".to_v", ".processor.to_v_lora").replace(".to_out.0", ".processor.to_out_lora")
+    if "ff" in k:
+        k = k + ".lora"
+    return k
+
+
+def unet_attn_processors_state_dict(unet: nn.Module, keys: Iterable[str]) -> Dict[str, torch.Tensor]:
+    """train/ppft_train.py:443-471: {'<renamed key>.down.weight' / '.up.weight': tensor} for every target."""
+    out: Dict[str, torch.Tensor] = {}
+    for key in keys:
+        target = resolve(unet, key)
+        for pk, p in target.state_dict().items():
+            if "lora_layer" in pk:
+                out[f"{lora_state_dict_key(key)}.{pk.replace('lora_layer.', '')}"] = p
+    return out

@@ -175,3 +175,23 @@ def flat_clip_adamw(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.
         _need(t, _F32, n, 1)
     _lib.call("aq_flat_clip_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), norm_sq.data_ptr(),
               grad_scale, max_norm, lr, beta1, beta2, eps, weight_decay, step, _stream())
+
+
+def secret_encoder_fwd(msg: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, wc: torch.Tensor, bc: torch.Tensor,
+                       x: torch.Tensor | None, hw: tuple[int, int], base: int = 32, res: int = 64):
+    """SecretEncoder forward (utils/models.py:74-81): returns (x + c or None, c), c [B, 4, H, W] fp32."""
+    for t, n in ((msg, "msg"), (w1, "w1"), (b1, "b1"), (wc, "wc"), (bc, "bc")):
+        _need(t, _F32, n)
+    B, bits = msg.shape
+    H, W = hw
+    c = torch.empty((B, 4, H, W), dtype=_F32, device=msg.device)
+    xo = None
+    if x is not None:
+        _need(x, _F32, "x", 4)
+        x = x.contiguous()
+        xo = torch.empty_like(x)
+    ws = torch.empty(_lib.load().aq_secret_encoder_workspace_bytes(B, res), dtype=torch.uint8, device=msg.device)
+    _lib.call("aq_secret_encoder_fwd", msg.contiguous().data_ptr(), w1.contiguous().data_ptr(), b1.contiguous().data_ptr(),
+              wc.contiguous().data_ptr(), bc.contiguous().data_ptr(), _ptr(x), c.data_ptr(), _ptr(xo), B, bits, base, res, H, W,
+              ws.data_ptr(), _stream())
+    return xo, c

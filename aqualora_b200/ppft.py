@@ -1,0 +1,208 @@
+"""Prior-preserving fine-tuning (PPFT) step around the fused watermark-LoRA kernels.
+
+Mirrors the loop body of train/ppft_train.py:987-1068 on one GPU per process:
+
+    msg -> scale = mapper(msg)                         (:989-990)      aq_mapper_fwd
+    x_clean / x_wm = add_noise(z), add_noise(z + wm)   (:1010-1011)
+    clean_pred = unet(x_clean, scale = 0).detach()     (:1026-1029)    LoRA skipped: scale 0 is bit-identical to the base op
+    model_pred = unet(x_wm, scale)                     (:1032-1035)    192 fused projection+LoRA kernels
+    loss = mse(model_pred, clean_pred); backward       (:1051-1058)    fused dX / weight-grad kernels
+    DDP gradient allreduce over the LoRA (+mapper) gradients only      one NCCL allreduce of the flat fp32 buffer
+    clip_grad_norm_(lora, 1.0); AdamW; zero_grad       (:1065-1068)    aq_flat_sumsq + aq_flat_clip_adamw
+
+All trainable state lives in four flat fp32 buffers (param / grad / exp_avg / exp_avg_sq): the 384 LoRA matrices in
+`unet_keys.json` order (down then up per target), then the mapper's bit embeddings.  The backward kernels accumulate
+straight into the flat gradient buffer (`param._aq_grad` views), so the data-parallel exchange is ONE allreduce.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import lora_modules, ops
+from .unet import UNet2DConditionModel, UNetConfig, lora_target_keys
+
+
+@dataclass
+class PPFTConfig:
+    rank: int = 64
+    msg_bits: int = 48
+    learning_rate: float = 1e-4
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    adam_weight_decay: float = 1e-2
+    adam_epsilon: float = 1e-8
+    max_grad_norm: float = 1.0
+    lr_warmup_steps: int = 0
+    max_train_steps: int = 1000
+    lr_end: float = 0.0
+    prediction_type: str = "epsilon"      # "v_prediction" for SD 2.x (train/ppft_train.py:1047-1049)
+    scaling_factor: float = 0.18215       # vae.config.scaling_factor
+
+
+def scaled_linear_alphas_cumprod(num_steps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012) -> torch.Tensor:
+    """DDPM `scaled_linear` schedule used by Stable Diffusion (scripts/lib/model_util.py:14-16)."""
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_steps, dtype=torch.float32) ** 2
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+def add_noise(alphas_cumprod: torch.Tensor, x: torch.Tensor, noise: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    """DDPMScheduler.add_noise: sqrt(a_t) x + sqrt(1 - a_t) noise."""
+    a = alphas_cumprod.to(device=x.device, dtype=x.dtype)[t]
+    return a.sqrt().view(-1, 1, 1, 1) * x + (1 - a).sqrt().view(-1, 1, 1, 1) * noise
+
+
+def velocity_to_epsilon(alphas_cumprod: torch.Tensor, v: torch.Tensor, noisy: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    """utils/cschedulers.py:56-72."""
+    a = alphas_cumprod.to(device=t.device)[t]
+    return (1 - a).sqrt()[:, None, None, None] * noisy + a.sqrt()[:, None, None, None] * v
+
+
+def cosine_lr_factor(step: int, warmup: int, total: int, lr_end: float = 0.0, num_cycles: float = 0.5) -> float:
+    """utils/misc.py:24-34 (get_cosine_schedule_with_warmup_lr_end)."""
+    if step < warmup:
+        return float(step) / float(max(1, warmup))
+    progress = float(step - warmup) / float(max(1, total - warmup))
+    return max(lr_end, 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress)))
+
+
+class FlatLoraState:
+    """Flat fp32 buffers holding every trainable tensor; parameters are views, `_aq_grad` points into `grad`."""
+
+    def __init__(self, lora_layers, mapper_emb: torch.Tensor, device):
+        shapes = []
+        for _, _, lora in lora_layers:
+            shapes.append(lora.down.weight.shape)
+            shapes.append(lora.up.weight.shape)
+        self.n_lora = sum(math.prod(s) for s in shapes)
+        self.n_lora_pad = (self.n_lora + 3) // 4 * 4
+        self.n_mapper = mapper_emb.numel()
+        total = self.n_lora_pad + (self.n_mapper + 3) // 4 * 4
+        self.param = torch.zeros(total, dtype=torch.float32, device=device)
+        self.grad = torch.zeros_like(self.param)
+        self.exp_avg = torch.zeros_like(self.param)
+        self.exp_avg_sq = torch.zeros_like(self.param)
+        self.norm_sq = torch.zeros(1, dtype=torch.float32, device=device)
+        off = 0
+        self.params = []
+        for _, _, lora in lora_layers:
+            for lin in (lora.down, lora.up):
+                n = lin.weight.numel()
+                view = self.param[off:off + n].view(lin.weight.shape)
+                view.copy_(lin.weight.detach().to(device=device, dtype=torch.float32))
+                p = nn.Parameter(view, requires_grad=True)
+                p._aq_grad = self.grad[off:off + n]
+                lin.weight = p
+                self.params.append(p)
+                off += n
+        self.mapper_off = self.n_lora_pad
+        mview = self.param[self.mapper_off:self.mapper_off + self.n_mapper].view(mapper_emb.shape)
+        mview.copy_(mapper_emb.detach().to(device=device, dtype=torch.float32))
+        self.mapper_emb = mview
+        self.mapper_grad = self.grad[self.mapper_off:self.mapper_off + self.n_mapper].view(mapper_emb.shape)
+
+    @property
+    def lora_param(self):
+        return self.param[:self.n_lora_pad]
+
+    def region(self, buf: torch.Tensor, which: str) -> torch.Tensor:
+        return buf[:self.n_lora_pad] if which == "lora" else buf[self.mapper_off:]
+
+
+class PPFTTrainer:
+    """One process = one GPU.  `step()` runs one PPFT iteration on a synthetic or real latent batch."""
+
+    def __init__(self, unet: UNet2DConditionModel, cfg: PPFTConfig, mapper_emb: torch.Tensor, device,
+                 lora_up_std: Optional[float] = None, seed: int = 0):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.unet = unet
+        unet.requires_grad_(False)
+        self.keys = lora_target_keys(unet)
+        self.lora_layers = lora_modules.inject_lora(unet, self.keys, cfg.rank)
+        if lora_up_std is not None:
+            # benchmarking / gradient-parity init: a zero `up` makes dDn and dscale vanish
+            g = torch.Generator().manual_seed(seed)
+            for _, _, lora in self.lora_layers:
+                lora.up.weight.data.copy_(torch.randn(lora.up.weight.shape, generator=g) * lora_up_std)
+        self.state = FlatLoraState(self.lora_layers, mapper_emb, self.device)
+        self.alphas_cumprod = scaled_linear_alphas_cumprod().to(self.device)
+        self.global_step = 0
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.g_scale = None
+
+    # -- pieces of the step ------------------------------------------------------------------
+    def mapper(self, msg: torch.Tensor) -> torch.Tensor:
+        """scale [B, r]: fp32 values rounded to bf16 (`.to(dtype=weight_dtype)`, train/ppft_train.py:990); a leaf whose
+        gradient the projection kernels accumulate into `self.g_scale`."""
+        scale = ops.mapper_fwd(msg, self.state.mapper_emb, round_bf16=True)
+        if self.g_scale is None or self.g_scale.shape != scale.shape:
+            self.g_scale = torch.zeros_like(scale)
+        else:
+            self.g_scale.zero_()
+        scale.requires_grad_(True)
+        scale._aq_grad = self.g_scale
+        return scale
+
+    def lr(self) -> float:
+        c = self.cfg
+        # accelerate steps the scheduler once per process (train/ppft_train.py:896-901 scales the horizon by num_processes)
+        return c.learning_rate * cosine_lr_factor(self.global_step * self.world, c.lr_warmup_steps * self.world,
+                                                  c.max_train_steps * self.world, c.lr_end)
+
+    def forward_backward(self, latents, wm_latent, noise, timesteps, ctx, msg):
+        c = self.cfg
+        scale = self.mapper(msg)
+        noisy = add_noise(self.alphas_cumprod, latents, noise, timesteps)
+        noisy_wm = add_noise(self.alphas_cumprod, latents + wm_latent, noise, timesteps)
+        with torch.no_grad(), lora_modules.lora_disabled():
+            clean_pred = self.unet(noisy, timesteps, ctx).sample
+        model_pred = self.unet(noisy_wm, timesteps, ctx, cross_attention_kwargs={"scale": scale}).sample
+        if c.prediction_type == "v_prediction":
+            model_pred = velocity_to_epsilon(self.alphas_cumprod, model_pred, noisy_wm, timesteps)
+            clean_pred = velocity_to_epsilon(self.alphas_cumprod, clean_pred, noisy, timesteps)
+        loss = F.mse_loss(model_pred.float(), clean_pred.float(), reduction="mean")
+        loss.backward()
+        ops.mapper_bwd(msg, self.g_scale, self.state.mapper_grad)
+        return loss.detach()
+
+    def optimizer_step(self):
+        c, st = self.cfg, self.state
+        if self.world > 1:
+            dist.all_reduce(st.grad)                                  # the only data-path collective: LoRA (+mapper) grads
+        gs = 1.0 / self.world
+        st.norm_sq.zero_()
+        ops.flat_sumsq(st.region(st.grad, "lora"), st.norm_sq)       # clip_grad_norm_ covers the U-Net LoRA params only
+        lr = self.lr()
+        self.global_step += 1
+        common = dict(grad_scale=gs, lr=lr, beta1=c.adam_beta1, beta2=c.adam_beta2, eps=c.adam_epsilon,
+                      weight_decay=c.adam_weight_decay, step=self.global_step)
+        ops.flat_clip_adamw(st.region(st.param, "lora"), st.region(st.grad, "lora"), st.region(st.exp_avg, "lora"),
+                            st.region(st.exp_avg_sq, "lora"), st.norm_sq, max_norm=c.max_grad_norm, **common)
+        ops.flat_clip_adamw(st.region(st.param, "mapper"), st.region(st.grad, "mapper"), st.region(st.exp_avg, "mapper"),
+                            st.region(st.exp_avg_sq, "mapper"), st.norm_sq, max_norm=0.0, **common)
+        lora_modules.invalidate_packed()                             # the bf16 operand copies are stale now
+
+    def step(self, latents, wm_latent, noise, timesteps, ctx, msg):
+        loss = self.forward_backward(latents, wm_latent, noise, timesteps, ctx, msg)
+        self.optimizer_step()
+        return loss
+
+
+def build_unet(cfg: UNetConfig, device, dtype=torch.bfloat16, seed: int = 0) -> UNet2DConditionModel:
+    """Random-init U-Net of the named architecture (no checkpoints exist offline), cast like ppft_train.py:569-581."""
+    torch.manual_seed(seed)
+    with torch.device(device):
+        unet = UNet2DConditionModel(cfg)
+    unet = unet.to(dtype=dtype)
+    if torch.device(device).type == "cuda":
+        unet = unet.to(memory_format=torch.channels_last)
+    unet.requires_grad_(False)
+    unet.eval()
+    return unet

@@ -1,0 +1,371 @@
+"""Stable-Diffusion U-Net harness around the watermark-LoRA projections (host plumbing, plain PyTorch).
+
+The hot path of this repository is the 192 LoRA-target projections (aqualora_b200/lora_modules.py -> CUDA).  This file
+is the CALLER on either side of it: a compact `UNet2DConditionModel` whose module paths and state-dict keys are the
+diffusers ones, so that `utils/unet_keys.json` (train/ppft_train.py:620-689) resolves on it and checkpoints /
+`pytorch_lora_weights.safetensors` keys (train/ppft_train.py:443-471) line up.  Everything that is not a LoRA target
+(3x3 convolutions, GroupNorm, attention core) is a library call and out of scope of the kernels.
+
+Topology follows the SD 1.5 / 2.1 configs quoted in scripts/lib/original_unet.py:22-106; the golden test loads the
+same procedurally generated weights into the reference's vendored U-Net and into this one and compares outputs.
+Activations are kept channels_last so a Transformer2D block sees [B, H*W, C] token-major memory without copies.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .lora_modules import LoRACompatibleConv, LoRACompatibleLinear
+
+
+@dataclass
+class UNetConfig:
+    sample_size: int = 64
+    in_channels: int = 4
+    out_channels: int = 4
+    block_out_channels: Sequence[int] = (320, 640, 1280, 1280)
+    layers_per_block: int = 2
+    attention_head_dim: Sequence[int] | int = 8      # SD1.5: number of heads (diffusers' historical misnomer)
+    cross_attention_dim: int = 768
+    use_linear_projection: bool = False
+    upcast_attention: bool = False
+    norm_num_groups: int = 32
+    norm_eps: float = 1e-5
+    down_has_attn: Sequence[bool] = (True, True, True, False)
+    time_embed_dim: int = field(default=0)
+
+    def heads(self, level: int) -> int:
+        if isinstance(self.attention_head_dim, int):
+            return self.attention_head_dim
+        return self.attention_head_dim[level]
+
+    @staticmethod
+    def sd15(sample_size: int = 64) -> "UNetConfig":
+        return UNetConfig(sample_size=sample_size)
+
+    @staticmethod
+    def sd21(sample_size: int = 96) -> "UNetConfig":
+        return UNetConfig(sample_size=sample_size, attention_head_dim=(5, 10, 20, 20), cross_attention_dim=1024,
+                          use_linear_projection=True, upcast_attention=True)
+
+    @staticmethod
+    def tiny(sample_size: int = 16) -> "UNetConfig":
+        """Same topology, narrow channels: CPU-sized for tests (not a BASELINE config)."""
+        return UNetConfig(sample_size=sample_size, block_out_channels=(32, 64, 128, 128), attention_head_dim=4,
+                          cross_attention_dim=64, norm_num_groups=8)
+
+
+def timestep_embedding(timesteps: torch.Tensor, dim: int) -> torch.Tensor:
+    """Sinusoidal embedding, flip_sin_to_cos=True, freq_shift=0 (scripts/lib/original_unet.py:323-362)."""
+    half = dim // 2
+    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=timesteps.device) / half
+    emb = timesteps[:, None].float() * torch.exp(exponent)[None, :]
+    return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, in_dim: int, dim: int):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_dim, dim)
+        self.linear_2 = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        return self.linear_2(F.silu(self.linear_1(x)))
+
+
+class ResnetBlock2D(nn.Module):
+    def __init__(self, cin: int, cout: int, temb_dim: int, groups: int, eps: float):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=eps)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_dim, cout)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=eps)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+
+    def forward(self, x, temb):
+        h = self.conv1(F.silu(self.norm1(x)))
+        h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
+        h = self.conv2(F.silu(self.norm2(h)))
+        if self.conv_shortcut is not None:
+            x = self.conv_shortcut(x)
+        return x + h
+
+
+class Attention(nn.Module):
+    """diffusers `Attention` / kohya `CrossAttention`: q/k/v/out are the LoRA targets (utils/unet_keys.json)."""
+
+    def __init__(self, query_dim: int, context_dim: Optional[int], heads: int, upcast: bool):
+        super().__init__()
+        context_dim = context_dim or query_dim
+        self.heads = heads
+        self.upcast = upcast
+        self.to_q = LoRACompatibleLinear(query_dim, query_dim, bias=False)
+        self.to_k = LoRACompatibleLinear(context_dim, query_dim, bias=False)
+        self.to_v = LoRACompatibleLinear(context_dim, query_dim, bias=False)
+        self.to_out = nn.ModuleList([LoRACompatibleLinear(query_dim, query_dim)])
+
+    def forward(self, x, context=None, scale=1.0):
+        ctx = x if context is None else context.to(x.dtype)
+        q = self.to_q(x, scale)
+        k = self.to_k(ctx, scale)
+        v = self.to_v(ctx, scale)
+        B, N, C = q.shape
+        h = self.heads
+        q = q.view(B, N, h, C // h).transpose(1, 2)
+        k = k.view(B, k.shape[1], h, C // h).transpose(1, 2)
+        v = v.view(B, v.shape[1], h, C // h).transpose(1, 2)
+        if self.upcast:
+            o = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).to(v.dtype)
+        else:
+            o = F.scaled_dot_product_attention(q, k, v)
+        o = o.transpose(1, 2).reshape(B, N, C)
+        return self.to_out[0](o, scale)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in: int, dim_out: int):
+        super().__init__()
+        self.proj = LoRACompatibleLinear(dim_in, dim_out * 2)
+
+    def forward(self, x, scale=1.0):
+        h, gate = self.proj(x, scale).chunk(2, dim=-1)
+        return h * F.gelu(gate)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * 4), nn.Identity(), LoRACompatibleLinear(dim * 4, dim)])
+
+    def forward(self, x, scale=1.0):
+        return self.net[2](self.net[0](x, scale), scale)
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim: int, heads: int, context_dim: int, upcast: bool):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn1 = Attention(dim, None, heads, upcast)
+        self.norm2 = nn.LayerNorm(dim)
+        self.attn2 = Attention(dim, context_dim, heads, upcast)
+        self.norm3 = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+
+    def forward(self, x, context, scale=1.0):
+        x = self.attn1(self.norm1(x), None, scale) + x
+        x = self.attn2(self.norm2(x), context, scale) + x
+        return self.ff(self.norm3(x), scale) + x
+
+
+class Transformer2DModel(nn.Module):
+    def __init__(self, channels: int, heads: int, context_dim: int, groups: int, linear_proj: bool, upcast: bool):
+        super().__init__()
+        self.linear_proj = linear_proj
+        self.norm = nn.GroupNorm(groups, channels, eps=1e-6)
+        if linear_proj:
+            self.proj_in = LoRACompatibleLinear(channels, channels)
+            self.proj_out = LoRACompatibleLinear(channels, channels)
+        else:
+            self.proj_in = LoRACompatibleConv(channels, channels, kernel_size=1)
+            self.proj_out = LoRACompatibleConv(channels, channels, kernel_size=1)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(channels, heads, context_dim, upcast)])
+
+    def forward(self, x, context, scale=1.0):
+        B, C, H, W = x.shape
+        res = x
+        h = self.norm(x)
+        if self.linear_proj:
+            h = self.proj_in(h.permute(0, 2, 3, 1).reshape(B, H * W, C), scale)
+        else:
+            h = self.proj_in(h, scale).permute(0, 2, 3, 1).reshape(B, H * W, C)
+        for blk in self.transformer_blocks:
+            h = blk(h, context, scale)
+        if self.linear_proj:
+            h = self.proj_out(h, scale).reshape(B, H, W, C).permute(0, 3, 1, 2)
+        else:
+            h = self.proj_out(h.reshape(B, H, W, C).permute(0, 3, 1, 2), scale)
+        return h + res
+
+
+class Downsample2D(nn.Module):
+    def __init__(self, ch: int):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, stride=2, padding=1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class Upsample2D(nn.Module):
+    def __init__(self, ch: int):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, padding=1)
+
+    def forward(self, x, size=None):
+        if size is None:
+            x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+        else:
+            x = F.interpolate(x, size=size, mode="nearest")
+        return self.conv(x)
+
+
+class DownBlock(nn.Module):
+    def __init__(self, cfg: UNetConfig, cin: int, cout: int, level: int, has_attn: bool, add_down: bool):
+        super().__init__()
+        self.resnets = nn.ModuleList()
+        self.attentions = nn.ModuleList() if has_attn else None
+        for j in range(cfg.layers_per_block):
+            self.resnets.append(ResnetBlock2D(cin if j == 0 else cout, cout, cfg.time_embed_dim, cfg.norm_num_groups, cfg.norm_eps))
+            if has_attn:
+                self.attentions.append(Transformer2DModel(cout, cfg.heads(level), cfg.cross_attention_dim, cfg.norm_num_groups,
+                                                          cfg.use_linear_projection, cfg.upcast_attention))
+        self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if add_down else None
+
+    def forward(self, x, temb, context, scale):
+        outs = []
+        for j, res in enumerate(self.resnets):
+            x = res(x, temb)
+            if self.attentions is not None:
+                x = self.attentions[j](x, context, scale)
+            outs.append(x)
+        if self.downsamplers is not None:
+            x = self.downsamplers[0](x)
+            outs.append(x)
+        return x, outs
+
+
+class MidBlock(nn.Module):
+    def __init__(self, cfg: UNetConfig, ch: int):
+        super().__init__()
+        mk = lambda: ResnetBlock2D(ch, ch, cfg.time_embed_dim, cfg.norm_num_groups, cfg.norm_eps)
+        self.resnets = nn.ModuleList([mk(), mk()])
+        # the vendored reference does not forward upcast_attention to the mid block (original_unet.py:1372-1377)
+        self.attentions = nn.ModuleList([Transformer2DModel(ch, cfg.heads(len(cfg.block_out_channels) - 1), cfg.cross_attention_dim,
+                                                            cfg.norm_num_groups, cfg.use_linear_projection, False)])
+
+    def forward(self, x, temb, context, scale):
+        x = self.resnets[0](x, temb)
+        x = self.attentions[0](x, context, scale)
+        return self.resnets[1](x, temb)
+
+
+class UpBlock(nn.Module):
+    def __init__(self, cfg: UNetConfig, cin: int, cout: int, cprev: int, level: int, has_attn: bool, add_up: bool):
+        super().__init__()
+        self.resnets = nn.ModuleList()
+        self.attentions = nn.ModuleList() if has_attn else None
+        n = cfg.layers_per_block + 1
+        for j in range(n):
+            skip = cin if j == n - 1 else cout
+            rin = cprev if j == 0 else cout
+            self.resnets.append(ResnetBlock2D(rin + skip, cout, cfg.time_embed_dim, cfg.norm_num_groups, cfg.norm_eps))
+            if has_attn:
+                self.attentions.append(Transformer2DModel(cout, cfg.heads(level), cfg.cross_attention_dim, cfg.norm_num_groups,
+                                                          cfg.use_linear_projection, cfg.upcast_attention))
+        self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_up else None
+
+    def forward(self, x, skips, temb, context, scale, up_size=None):
+        for j, res in enumerate(self.resnets):
+            x = res(torch.cat([x, skips.pop()], dim=1), temb)
+            if self.attentions is not None:
+                x = self.attentions[j](x, context, scale)
+        if self.upsamplers is not None:
+            x = self.upsamplers[0](x, up_size)
+        return x
+
+
+class UNetOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+
+class UNet2DConditionModel(nn.Module):
+    def __init__(self, cfg: UNetConfig):
+        super().__init__()
+        ch = list(cfg.block_out_channels)
+        cfg.time_embed_dim = ch[0] * 4
+        self.cfg = cfg
+        self.conv_in = nn.Conv2d(cfg.in_channels, ch[0], 3, padding=1)
+        self.time_embedding = TimestepEmbedding(ch[0], cfg.time_embed_dim)
+        self.down_blocks = nn.ModuleList()
+        cout = ch[0]
+        for i in range(len(ch)):
+            cin, cout = cout, ch[i]
+            self.down_blocks.append(DownBlock(cfg, cin, cout, i, cfg.down_has_attn[i], add_down=i < len(ch) - 1))
+        self.mid_block = MidBlock(cfg, ch[-1])
+        self.up_blocks = nn.ModuleList()
+        rev = ch[::-1]
+        rev_attn = list(cfg.down_has_attn)[::-1]
+        cout = rev[0]
+        for i in range(len(ch)):
+            cprev, cout = cout, rev[i]
+            cin = rev[min(i + 1, len(ch) - 1)]
+            self.up_blocks.append(UpBlock(cfg, cin, cout, cprev, len(ch) - 1 - i, rev_attn[i], add_up=i < len(ch) - 1))
+        self.conv_norm_out = nn.GroupNorm(cfg.norm_num_groups, ch[0], eps=cfg.norm_eps)
+        self.conv_out = nn.Conv2d(ch[0], cfg.out_channels, 3, padding=1)
+
+    @property
+    def dtype(self):
+        return self.conv_in.weight.dtype
+
+    def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, cross_attention_kwargs=None,
+                return_dict: bool = True):
+        scale = 1.0 if cross_attention_kwargs is None else cross_attention_kwargs.get("scale", 1.0)
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([timestep], device=sample.device)
+        timestep = timestep.reshape(-1).expand(sample.shape[0])
+        temb = self.time_embedding(timestep_embedding(timestep, self.cfg.block_out_channels[0]).to(self.dtype))
+        if sample.is_cuda:
+            sample = sample.contiguous(memory_format=torch.channels_last)
+        x = self.conv_in(sample)
+        skips = [x]
+        for blk in self.down_blocks:
+            x, outs = blk(x, temb, encoder_hidden_states, scale)
+            skips.extend(outs)
+        x = self.mid_block(x, temb, encoder_hidden_states, scale)
+        n_up = len(self.up_blocks)
+        odd = any(s % (2 ** (n_up - 1)) for s in sample.shape[-2:])
+        for i, blk in enumerate(self.up_blocks):
+            n_res = len(blk.resnets)
+            up_size = None
+            if odd and i < n_up - 1:
+                up_size = skips[-n_res - 1].shape[2:]
+            x = blk(x, skips, temb, encoder_hidden_states, scale, up_size)
+        x = self.conv_out(F.silu(self.conv_norm_out(x)))
+        return UNetOutput(x) if return_dict else (x,)
+
+
+def lora_target_keys(unet: UNet2DConditionModel) -> list[str]:
+    """The ordered list the reference ships as utils/unet_keys.json (192 entries for SD 1.5 / 2.1): every
+    Transformer2D proj_in/proj_out, attn{1,2}.to_{k,out.0,q,v} and ff.net.{0.proj,2}, block by block in the file's order
+    (alphabetical inside a transformer)."""
+    keys: list[str] = []
+
+    def add(prefix: str, blocks):
+        for i, blk in enumerate(blocks):
+            if getattr(blk, "attentions", None) is None:
+                continue
+            for j in range(len(blk.attentions)):
+                base = f"{prefix}.{i}.attentions.{j}"
+                keys.extend([f"{base}.proj_in", f"{base}.proj_out"])
+                tb = f"{base}.transformer_blocks.0"
+                for attn in ("attn1", "attn2"):
+                    keys.extend([f"{tb}.{attn}.to_k", f"{tb}.{attn}.to_out.0", f"{tb}.{attn}.to_q", f"{tb}.{attn}.to_v"])
+                keys.extend([f"{tb}.ff.net.0.proj", f"{tb}.ff.net.2"])
+
+    add("down_blocks", unet.down_blocks)
+    base = "mid_block.attentions.0"
+    mid: list[str] = [f"{base}.proj_in", f"{base}.proj_out"]
+    tb = f"{base}.transformer_blocks.0"
+    for attn in ("attn1", "attn2"):
+        mid.extend([f"{tb}.{attn}.to_k", f"{tb}.{attn}.to_out.0", f"{tb}.{attn}.to_q", f"{tb}.{attn}.to_v"])
+    mid.extend([f"{tb}.ff.net.0.proj", f"{tb}.ff.net.2"])
+    keys.extend(mid)
+    add("up_blocks", unet.up_blocks)
+    return keys

@@ -108,6 +108,17 @@ int aq_flat_clip_adamw(float* p, float* g, float* m, float* v, int64_t n, const 
                        float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
                        int step, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (ii) latent watermark encoder.  SecretEncoder.forward / encode (utils/models.py:70-81, layers :57-64):
+ *   c = bilinear_resize(Conv3x3(nearest_up(repeat4(view(SiLU(Linear(msg))))))), x_out = x + c.
+ * msg [B, bits] fp32; w1 [base*base, bits], b1 [base*base] (secret_scaler.0); wc [4, 4, 3, 3], bc [4]
+ * (secret_scaler.5); x, c_out, x_out [B, 4, H, W] fp32 NCHW (x / x_out may both be NULL: encode only).
+ * base = 32, res = 64 in the reference.  ws: aq_secret_encoder_workspace_bytes(B, res). */
+size_t aq_secret_encoder_workspace_bytes(int B, int res);
+int aq_secret_encoder_fwd(const float* msg, const float* w1, const float* b1, const float* wc, const float* bc,
+                          const float* x, float* c_out, float* x_out, int B, int bits, int base, int res, int H, int W,
+                          void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,221 @@
+"""Generate tests/golden/* by executing the REFERENCE's own Python (read-only, /root/reference) on seeded inputs.
+
+Runs only in the build container (the GPU box has no /root/reference).  The reference modules are imported
+unchanged; the only shims are `sys.modules` placeholders for packages that are absent here and that the hot-path
+functions never call (`diffusers`, `lpips`, `timm` -- see SURVEY.md 8(c)).
+
+    python tools/gen_golden.py            # rewrites tests/golden/*.pt
+"""
+from __future__ import annotations
+
+import importlib.util
+import json
+import sys
+import types
+from pathlib import Path
+
+import torch
+import torch.nn as nn
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def _stub_modules():
+    d = types.ModuleType("diffusers")
+    dl = types.ModuleType("diffusers.loaders")
+    dm = types.ModuleType("diffusers.models")
+    dml = types.ModuleType("diffusers.models.lora")
+
+    class LoraLoaderMixin:  # placeholder base class, never exercised
+        pass
+
+    class LoRACompatibleLinear(nn.Linear):
+        def __init__(self, *a, lora_layer=None, **k):
+            super().__init__(*a, **k)
+            self.lora_layer = lora_layer
+
+    class LoRACompatibleConv(nn.Conv2d):
+        def __init__(self, *a, lora_layer=None, **k):
+            super().__init__(*a, **k)
+            self.lora_layer = lora_layer
+
+    class LoRALinearLayer(nn.Module):
+        def __init__(self, in_features, out_features, rank=4, network_alpha=None):
+            super().__init__()
+            self.down = nn.Linear(in_features, rank, bias=False)
+            self.up = nn.Linear(rank, out_features, bias=False)
+            self.network_alpha = network_alpha
+            self.rank = rank
+
+    class LoRAConv2dLayer(nn.Module):
+        def __init__(self, in_features, out_features, rank=4, kernel_size=(1, 1), stride=(1, 1), padding=0, network_alpha=None):
+            super().__init__()
+            self.down = nn.Conv2d(in_features, rank, kernel_size=kernel_size, stride=stride, padding=padding, bias=False)
+            self.up = nn.Conv2d(rank, out_features, kernel_size=(1, 1), stride=(1, 1), bias=False)
+            self.network_alpha = network_alpha
+            self.rank = rank
+
+    dl.LoraLoaderMixin = LoraLoaderMixin
+    dml.text_encoder_attn_modules = lambda *a, **k: []
+    dml.text_encoder_mlp_modules = lambda *a, **k: []
+    dml.PatchedLoraProjection = type("PatchedLoraProjection", (nn.Module,), {})
+    dml.LoRALinearLayer = LoRALinearLayer
+    dml.LoRAConv2dLayer = LoRAConv2dLayer
+    dml.LoRACompatibleConv = LoRACompatibleConv
+    dml.LoRACompatibleLinear = LoRACompatibleLinear
+    d.loaders = dl
+    d.models = dm
+    dm.lora = dml
+    sys.modules.update({"diffusers": d, "diffusers.loaders": dl, "diffusers.models": dm, "diffusers.models.lora": dml})
+    for name in ("lpips", "timm"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    return dml
+
+
+def _load(name: str, path: Path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def gen_lora(dml, ref_lora):
+    import types as _t
+
+    g = torch.Generator().manual_seed(20240517)
+    cases = []
+    # (B, N, din, dout, r, bias, alpha, scale_kind)
+    specs = [
+        (2, 24, 32, 48, 8, True, None, "tensor"),
+        (3, 16, 64, 32, 16, False, None, "tensor"),
+        (2, 10, 40, 40, 8, True, 4.0, "tensor"),
+        (2, 12, 32, 64, 8, True, None, "float"),
+        (2, 12, 32, 64, 8, True, 2.0, "float"),
+        (2, 77, 96, 40, 64, False, None, "tensor"),
+        (2, 8, 32, 32, 8, True, None, "zero"),
+    ]
+    for (B, N, din, dout, r, bias, alpha, kind) in specs:
+        lin = dml.LoRACompatibleLinear(din, dout, bias=bias)
+        lora = dml.LoRALinearLayer(din, dout, rank=r, network_alpha=alpha)
+        with torch.no_grad():
+            lin.weight.copy_(torch.randn(dout, din, generator=g) * din ** -0.5)
+            if bias:
+                lin.bias.copy_(torch.randn(dout, generator=g) * 0.1)
+            lora.down.weight.copy_(torch.randn(r, din, generator=g) / r)
+            lora.up.weight.copy_(torch.randn(dout, r, generator=g) * 0.05)
+        lin.lora_layer = lora
+        lin.forward = _t.MethodType(ref_lora.CustomLoRACompatibleLinearforward, lin)
+        lora.forward = _t.MethodType(ref_lora.CustomLoRALinearLayerforward, lora)
+        x = torch.randn(B, N, din, generator=g, requires_grad=True)
+        if kind == "tensor":
+            scale = (1 + 0.7 * torch.randn(B, r, generator=g)).requires_grad_(True)
+        elif kind == "zero":
+            scale = torch.zeros(B, r, requires_grad=True)
+        else:
+            scale = 0.75
+        y = lin(x, scale)
+        gy = torch.randn(y.shape, generator=g)
+        y.backward(gy)
+        rec = {
+            "B": B, "N": N, "din": din, "dout": dout, "r": r, "alpha": alpha, "kind": kind,
+            "x": x.detach().clone(), "w": lin.weight.detach().clone(), "b": None if not bias else lin.bias.detach().clone(),
+            "down": lora.down.weight.detach().clone(), "up": lora.up.weight.detach().clone(),
+            "scale": scale.detach().clone() if isinstance(scale, torch.Tensor) else scale,
+            "gy": gy, "y": y.detach().clone(), "gx": x.grad.clone(), "g_down": lora.down.weight.grad.clone(),
+            "g_up": lora.up.weight.grad.clone(),
+            "g_scale": scale.grad.clone() if isinstance(scale, torch.Tensor) else None,
+        }
+        # the lora_layer is None branch (lora_modules.py:57-59)
+        lin.lora_layer = None
+        rec["y_base"] = lin(x.detach(), scale).detach().clone()
+        cases.append(rec)
+    torch.save(cases, OUT / "lora_linear.pt")
+
+    # conv 1x1 (proj_in / proj_out of SD1.5: lora_modules.py:28-54)
+    conv_cases = []
+    for (B, C, Co, H, W, r, alpha, kind) in [(2, 32, 32, 8, 8, 8, None, "tensor"), (2, 48, 24, 6, 10, 16, 8.0, "tensor"),
+                                             (1, 32, 32, 4, 4, 8, None, "float")]:
+        conv = dml.LoRACompatibleConv(C, Co, kernel_size=1)
+        lora = dml.LoRAConv2dLayer(C, Co, rank=r, kernel_size=(1, 1), network_alpha=alpha)
+        with torch.no_grad():
+            conv.weight.copy_(torch.randn(Co, C, 1, 1, generator=g) * C ** -0.5)
+            conv.bias.copy_(torch.randn(Co, generator=g) * 0.1)
+            lora.down.weight.copy_(torch.randn(r, C, 1, 1, generator=g) / r)
+            lora.up.weight.copy_(torch.randn(Co, r, 1, 1, generator=g) * 0.05)
+        conv.lora_layer = lora
+        conv.forward = _t.MethodType(ref_lora.CustomLoRACompatibleConvforward, conv)
+        lora.forward = _t.MethodType(ref_lora.CustomLoRAConv2dLayerforward, lora)
+        x = torch.randn(B, C, H, W, generator=g, requires_grad=True)
+        scale = (1 + 0.7 * torch.randn(B, r, generator=g)).requires_grad_(True) if kind == "tensor" else 1.25
+        y = conv(x, scale)
+        gy = torch.randn(y.shape, generator=g)
+        y.backward(gy)
+        conv_cases.append({
+            "x": x.detach().clone(), "w": conv.weight.detach().clone(), "b": conv.bias.detach().clone(),
+            "down": lora.down.weight.detach().clone(), "up": lora.up.weight.detach().clone(), "alpha": alpha, "r": r,
+            "scale": scale.detach().clone() if isinstance(scale, torch.Tensor) else scale, "gy": gy, "y": y.detach().clone(),
+            "gx": x.grad.clone(), "g_down": lora.down.weight.grad.clone(), "g_up": lora.up.weight.grad.clone(),
+            "g_scale": scale.grad.clone() if isinstance(scale, torch.Tensor) else None,
+        })
+    torch.save(conv_cases, OUT / "lora_conv1x1.pt")
+
+
+def gen_models(ref_models):
+    g = torch.Generator().manual_seed(7)
+    torch.manual_seed(11)
+    out = {}
+    # MapperNet (utils/models.py:98-115)
+    mapper = ref_models.MapperNet(input_size=48, output_size=64)
+    msg = torch.randint(0, 2, (5, 48), generator=g).float()
+    out["mapper"] = {"emb": mapper.bit_embeddings.weight.detach().clone(), "msg": msg, "scale": mapper(msg).detach().clone()}
+    # SecretEncoder (utils/models.py:51-81); the conv is zero-initialised, re-initialise it so the output is informative
+    enc = ref_models.SecretEncoder(48)
+    with torch.no_grad():
+        enc.secret_scaler[-1].weight.normal_(0, 0.02, generator=g)
+        enc.secret_scaler[-1].bias.normal_(0, 0.02, generator=g)
+    for hw in ((64, 64), (96, 96), (40, 56)):
+        x = torch.randn(2, 4, *hw, generator=g)
+        m = torch.randint(0, 2, (2, 48), generator=g).float()
+        xo, c = enc(x, m)
+        out[f"encoder_{hw[0]}x{hw[1]}"] = {"x": x, "msg": m, "x_out": xo.detach().clone(), "c": c.detach().clone()}
+    out["encoder_state"] = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+    enc0 = ref_models.SecretEncoder(48)
+    out["encoder_zero_init_is_zero"] = bool((enc0(torch.zeros(1, 4, 64, 64), torch.ones(1, 48))[1] == 0).all())
+    torch.save(out, OUT / "models_small.pt")
+
+
+def gen_jpeg():
+    sys.path.insert(0, str(REF))
+    from utils.noise_layers.jpeg_compression import JpegCompression  # imports with no stubs
+
+    g = torch.Generator().manual_seed(99)
+    jp = JpegCompression("cpu")
+    out = []
+    for shape in ((2, 3, 64, 64), (1, 3, 40, 72), (1, 3, 37, 50)):
+        x = torch.rand(shape, generator=g) * 2 - 1
+        y = jp([x.clone(), None])[0]
+        out.append({"x": x, "y": y.clone()})
+    torch.save(out, OUT / "jpeg_small.pt")
+
+
+def gen_keys():
+    keys = json.load(open(REF / "utils" / "unet_keys.json"))
+    (OUT / "unet_keys.json").write_text(json.dumps(keys, indent=0))
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    dml = _stub_modules()
+    ref_lora = _load("ref_lora_modules", REF / "utils" / "lora_modules.py")
+    gen_lora(dml, ref_lora)
+    ref_models = _load("ref_models", REF / "utils" / "models.py")
+    gen_models(ref_models)
+    gen_jpeg()
+    gen_keys()
+    for f in sorted(OUT.glob("*")):
+        print(f.name, f.stat().st_size)
+
+
+if __name__ == "__main__":
+    main()
