@@ -23,6 +23,7 @@ _SIGNATURES = {
     "aq_arch": ([], c_int),
     "aq_last_error": ([], c_char_p),
     "aq_sm_count": ([], c_int),
+    "aq_launch_count": ([], ctypes.c_longlong),
     "aq_lora_set_tuning": ([c_int, c_int], c_int),
     "aq_lora_linear_fwd": (
         [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,

@@ -21,6 +21,13 @@ int fail(int code, const char* fmt, ...);
                         __FILE__, __LINE__);                                                    \
   } while (0)
 
+// after every kernel launch: bump the process-wide launch counter (aq_launch_count) and surface launch errors
+#define AQ_LAUNCHED()                      \
+  do {                                     \
+    ::aq::count_launch();                  \
+    AQ_CHECK_CUDA(cudaGetLastError());     \
+  } while (0)
+
 #define AQ_REQUIRE(cond, code, ...)                  \
   do {                                               \
     if (!(cond)) return ::aq::fail(code, __VA_ARGS__); \
@@ -33,6 +40,7 @@ enum TmaSwizzle { kSwzNone = 0, kSwz32 = 1, kSwz64 = 2, kSwz128 = 3 };
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, TmaSwizzle swz);
 
+void count_launch();
 int sm_count();  // SMs of the current device (cached)
 int check_arch();  // AQ_OK iff the current device is sm_100
 

@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "aq_common.h"
@@ -76,6 +77,10 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
   return AQ_OK;
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -110,4 +115,5 @@ int aq_version(void) { return 1; }
 int aq_arch(void) { return 100; }
 const char* aq_last_error(void) { return aq::g_err; }
 int aq_sm_count(void) { return aq::sm_count(); }
+long long aq_launch_count(void) { return aq::launch_count(); }
 }

@@ -147,7 +147,7 @@ int aq_mapper_fwd(const float* msg, const float* emb, float* scale, int B, int b
   if (rc) return rc;
   const int n = B * r;
   mapper_fwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(msg, emb, scale, B, bits, r, out_bf16_rounded);
-  AQ_CHECK_CUDA(cudaGetLastError());
+  AQ_LAUNCHED();
   return AQ_OK;
 }
 
@@ -157,7 +157,7 @@ int aq_mapper_bwd(const float* msg, const float* g_scale, float* g_emb, int B, i
   if (rc) return rc;
   const int n = bits * r;
   mapper_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(msg, g_scale, g_emb, B, bits, r);
-  AQ_CHECK_CUDA(cudaGetLastError());
+  AQ_LAUNCHED();
   return AQ_OK;
 }
 
@@ -167,7 +167,7 @@ int aq_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int rows, i
   if (rc) return rc;
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   cast_transpose_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_t, rows, cols);
-  AQ_CHECK_CUDA(cudaGetLastError());
+  AQ_LAUNCHED();
   return AQ_OK;
 }
 
@@ -177,7 +177,7 @@ int aq_transpose_bf16(const void* src, void* dst, int rows, int cols, void* stre
   if (rc) return rc;
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   cast_transpose_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, nullptr, (__nv_bfloat16*)dst, rows, cols);
-  AQ_CHECK_CUDA(cudaGetLastError());
+  AQ_LAUNCHED();
   return AQ_OK;
 }
 
@@ -187,7 +187,7 @@ int aq_flat_sumsq(const float* g, int64_t n, float* norm_sq, void* stream) {
   int rc = check_arch();
   if (rc) return rc;
   flat_sumsq_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(g, n, norm_sq);
-  AQ_CHECK_CUDA(cudaGetLastError());
+  AQ_LAUNCHED();
   return AQ_OK;
 }
 
@@ -205,7 +205,7 @@ int aq_flat_clip_adamw(float* p, float* g, float* m, float* v, int64_t n, const 
   a.bc1 = 1.f - powf(beta1, (float)step);
   a.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   flat_clip_adamw_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, norm_sq, a);
-  AQ_CHECK_CUDA(cudaGetLastError());
+  AQ_LAUNCHED();
   return AQ_OK;
 }
 

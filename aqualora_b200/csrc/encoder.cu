@@ -110,14 +110,14 @@ int aq_secret_encoder_fwd(const float* msg, const float* w1, const float* b1, co
   dim3 grid((res + 7) / 8, B);
   const size_t smem = (size_t)(8 / up + 3) * base * sizeof(float);
   secret_encoder_map_kernel<<<grid, 256, smem, st>>>(msg, w1, b1, wc, bc, c_res, bits, base, res);
-  AQ_CHECK_CUDA(cudaGetLastError());
+  AQ_LAUNCHED();
   if (c_res != c_out) {
     const long long n = (long long)B * 4 * H * W;
     int blocks = (int)((n + 255) / 256);
     const int cap = (sm_count() > 0 ? sm_count() : 148) * 8;
     if (blocks > cap) blocks = cap;
     secret_encoder_resize_add_kernel<<<blocks, 256, 0, st>>>(c_res, x, c_out, x_out, B * 4, res, H, W);
-    AQ_CHECK_CUDA(cudaGetLastError());
+    AQ_LAUNCHED();
   }
   return AQ_OK;
 }

@@ -525,7 +525,7 @@ static int launch_bn(const LoraGemmArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   lora_gemm_kernel<BN><<<grid, kThreads, L::kTotal, stream>>>(p);
-  AQ_CHECK_CUDA(cudaGetLastError());
+  AQ_LAUNCHED();
   return AQ_OK;
 }
 

@@ -192,7 +192,7 @@ int launch_wgrad(const void* pm, int64_t ldp, const void* qm, int64_t ldq, float
   }
   dim3 grid(i_tiles, splits);
   lora_wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, stream>>>(p);
-  AQ_CHECK_CUDA(cudaGetLastError());
+  AQ_LAUNCHED();
   return AQ_OK;
 }
 

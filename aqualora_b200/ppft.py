@@ -172,11 +172,17 @@ class PPFTTrainer:
         ops.mapper_bwd(msg, self.g_scale, self.state.mapper_grad)
         return loss.detach()
 
+    def exchange_gradients(self) -> float:
+        """The only data-path collective of the PPFT step: ONE sum-allreduce of the flat LoRA (+mapper) gradient buffer over
+        NVLink (what DDP does bucket by bucket for the 385 trainable tensors, train/ppft_train.py:906-912).  Returns the factor
+        that turns the sum into DDP's mean; it is folded into the clip/AdamW kernel instead of a separate pass."""
+        if self.world > 1:
+            dist.all_reduce(self.state.grad)
+        return 1.0 / self.world
+
     def optimizer_step(self):
         c, st = self.cfg, self.state
-        if self.world > 1:
-            dist.all_reduce(st.grad)                                  # the only data-path collective: LoRA (+mapper) grads
-        gs = 1.0 / self.world
+        gs = self.exchange_gradients()
         st.norm_sq.zero_()
         ops.flat_sumsq(st.region(st.grad, "lora"), st.norm_sq)       # clip_grad_norm_ covers the U-Net LoRA params only
         lr = self.lr()

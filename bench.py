@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""Headline benchmark: PPFT images/sec, SD1.5 512x512 (64x64 latents), LoRA rank 64, 48-bit messages, bf16, per-GPU batch 16
+(BASELINE.json configs[1]; configs[2] is the same step at N = 2/4/8 with one NCCL allreduce of the flat LoRA gradients).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                    # this repository's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]              # the reference op sequence on the host CPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one synthetic batch: mapper -> clean U-Net forward (LoRA skipped) ->
+watermarked U-Net forward (192 fused projection+LoRA kernels) -> MSE -> backward (fused dX / weight-grad kernels) ->
+[allreduce] -> clip + AdamW over the flat buffers (train/ppft_train.py:987-1068).  VAE / text encoder are outside the
+north-star path and have no weights offline: latents and text context are synthetic.
+
+Prints ONE JSON line (rank 0).  `value` = images/s with the batch already resident in HBM; `e2e` = the same step through the
+public API with the batch in pinned host memory (H2D copies and the D2H read of the loss inside the timed region).
+`roofline` describes the dominant kernel (aq::lora_gemm_kernel, the fused base-GEMM + LoRA contraction): algorithmic FLOPs
+per launch / CUDA-event duration per launch, measured live on the launching stream in instrumented steps that follow the
+timed region, against MEASURED_PEAKS.json.  `cpu_baseline` = the oracle's PyTorch-eager restatement of the reference step
+on the host cores (bounded sample: B=1).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "ppft_images_per_sec"
+UNIT = "images/s"
+RANK_R = 64
+BITS = 48
+PER_GPU_BATCH = 16
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# synthetic PPFT batch: generator seed = 1234 + step (+ rank)
+# --------------------------------------------------------------------------------------------------------------------
+def synth_batch(B, cfg, seed, encoder_state=None):
+    g = torch.Generator().manual_seed(seed)
+    s = cfg.sample_size
+    lat = torch.randn(B, 4, s, s, generator=g) * 0.18215
+    noise = torch.randn(B, 4, s, s, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    ctx = torch.randn(B, 77, cfg.cross_attention_dim, generator=g)
+    msg = torch.randint(0, 2, (B, BITS), generator=g).float()
+    return lat, noise, t, ctx, msg
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ts, line in self.rows:
+            if not (t0 <= ts <= t1 + 0.2):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# roofline instrumentation: CUDA events around every aq_lora_linear_* launch, on the launching stream
+# --------------------------------------------------------------------------------------------------------------------
+class GemmProbe:
+    """Wraps ops.lora_linear_fwd (the fused kernel: forward, plain projection, and the backward's plain dX) and
+    ops.lora_linear_bwd (fused dX + 2 weight-grad launches) with CUDA events + algorithmic FLOP/byte counts."""
+
+    def __init__(self, ops):
+        self.ops = ops
+        self.records = []   # (kind, flops, bytes, ev0, ev1, shape)
+        self._fwd, self._bwd = ops.lora_linear_fwd, ops.lora_linear_bwd
+
+    def __enter__(self):
+        ops = self.ops
+
+        def fwd(x, w, bias, down, up, scale, tokens, save_h=False, out=None):
+            M, K = x.shape
+            N = w.shape[0]
+            r = 0 if down is None else down.shape[0]
+            flops = 2.0 * M * K * N + 2.0 * M * r * (K + N)
+            byts = 2.0 * M * (K + N) + 2.0 * (K * N + r * (K + N)) + (2.0 * M * r if save_h else 0.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = self._fwd(x, w, bias, down, up, scale, tokens, save_h=save_h, out=out)
+            e1.record()
+            self.records.append(("gemm_fwd" if r else "gemm_plain", flops, byts, e0, e1, (M, K, N, r)))
+            return res
+
+        def bwd(gy, x, w_t, down_t, up_t, scale, h, g_down, g_up, g_scale, tokens):
+            M, N = gy.shape      # N = dout
+            K = x.shape[1]       # K = din
+            r = h.shape[1]
+            dx = w_t is not None
+            flops = (2.0 * M * K * N if dx else 0.0) + 2.0 * M * r * N + (2.0 * M * r * K if dx else 0.0) + 2.0 * M * r * (K + N)
+            byts = 2.0 * M * (N + K + r) + (2.0 * M * K if dx else 0.0) + 2.0 * (K * N + r * (K + N)) + 8.0 * r * (K + N)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = self._bwd(gy, x, w_t, down_t, up_t, scale, h, g_down, g_up, g_scale, tokens)
+            e1.record()
+            self.records.append(("bwd_dx_wgrad", flops, byts, e0, e1, (M, K, N, r)))
+            return res
+
+        ops.lora_linear_fwd, ops.lora_linear_bwd = fwd, bwd
+        return self
+
+    def __exit__(self, *exc):
+        self.ops.lora_linear_fwd, self.ops.lora_linear_bwd = self._fwd, self._bwd
+
+    def summary(self, steps: int):
+        torch.cuda.synchronize()
+        agg = {}
+        per_shape = {}
+        for kind, fl, by, e0, e1, shape in self.records:
+            ms = e0.elapsed_time(e1)
+            a = agg.setdefault(kind, [0.0, 0.0, 0.0, 0])
+            a[0] += fl; a[1] += by; a[2] += ms; a[3] += 1
+            s = per_shape.setdefault((kind,) + shape, [0.0, 0.0, 0])
+            s[0] += fl; s[1] += ms; s[2] += 1
+        out = {}
+        for kind, (fl, by, ms, n) in agg.items():
+            out[kind] = {"launch_groups_per_step": n // steps, "ms_per_step": ms / steps, "tflops": fl / ms / 1e9 if ms else 0.0,
+                         "gbs": by / ms / 1e6 if ms else 0.0, "flops_per_step": fl / steps, "bytes_per_step": by / steps}
+        shapes = [{"kind": k[0], "M": k[1], "K": k[2], "N": k[3], "r": k[4], "calls_per_step": v[2] // steps,
+                   "us_per_call": v[1] / v[2] * 1e3, "tflops": v[0] / v[1] / 1e9} for k, v in sorted(per_shape.items())]
+        return out, shapes
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# the CUDA arm
+# --------------------------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
+                         "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this repository has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from aqualora_b200 import _lib, build, ops, ppft
+    from aqualora_b200.models import MapperNet, SecretEncoder
+    from aqualora_b200.unet import UNetConfig
+
+    if not _lib.LIB_PATH.exists():
+        if rank == 0:
+            build.build()
+        if world > 1:
+            dist.barrier()
+    lib = _lib.load()
+
+    B = args.batch
+    cfg = UNetConfig.sd15(64) if args.model == "sd15" else UNetConfig.sd21(96)
+    unet = ppft.build_unet(cfg, dev, seed=0)
+    torch.manual_seed(5)
+    mapper = MapperNet(BITS, RANK_R)
+    pcfg = ppft.PPFTConfig(rank=RANK_R, msg_bits=BITS, max_train_steps=10_000,
+                           prediction_type="epsilon" if args.model == "sd15" else "v_prediction")
+    trainer = ppft.PPFTTrainer(unet, pcfg, mapper.bit_embeddings.weight.data, dev, lora_up_std=0.02, seed=1)
+    torch.manual_seed(0)
+    enc = SecretEncoder(BITS).to(dev)
+    torch.nn.init.normal_(enc.secret_scaler[5].weight, std=0.02)   # the reference zero-inits this conv; trained value assumed
+
+    def to_dev(batch, non_blocking=False):
+        lat, noise, t, ctx, msg = batch
+        f = lambda x: x.to(dev, non_blocking=non_blocking)
+        return f(lat), f(noise), f(t), f(ctx), f(msg)
+
+    def step_from_device(lat, noise, t, ctx, msg):
+        # train/ppft_train.py:994-996: secret residual from the encoder (no_grad), scaled like the latents
+        wm = enc.encode(msg) * pcfg.scaling_factor
+        bf = torch.bfloat16
+        return trainer.step(lat.to(bf), wm.to(bf), noise.to(bf), t, ctx.to(bf), msg)
+
+    n_pool = 4
+    host = [tuple(x.pin_memory() for x in synth_batch(B, cfg, 1234 + i + 1000 * rank)) for i in range(n_pool)]
+    resident = [to_dev(b) for b in host]
+    h2d_bytes = sum(x.numel() * x.element_size() for x in host[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up --------------------------------------------------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        loss = step_from_device(*resident[i % n_pool])
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM -------------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = lib.aq_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        loss = step_from_device(*resident[i % n_pool])
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = lib.aq_launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    final_loss = float(loss)
+
+    # ---- timed region 2: end to end from pinned host memory -------------------------------------------------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        batch = to_dev(host[i % n_pool], non_blocking=True)
+        loss_host = float(step_from_device(*batch))       # D2H read of the step's result
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = ms2.item()
+
+    # ---- roofline pass (instrumented, after the timed regions) ----------------------------------------------------
+    roof = None
+    extra = {}
+    if rank == 0:
+        pk = peaks()
+        probe_steps = 2
+        with GemmProbe(ops) as probe:
+            for i in range(probe_steps):
+                step_from_device(*resident[i % n_pool])
+            kinds, shapes = probe.summary(probe_steps)
+        dom = kinds.get("gemm_fwd")
+        if dom:
+            peak = pk["bf16_tflops_sustained"]     # the kernel is timed inside a long step
+            roof = {"bound": "tensor", "kernel": "aq::lora_gemm_kernel (fused base GEMM + watermark LoRA, forward launches)",
+                    "achieved": round(dom["tflops"], 1), "peak": peak, "unit": "TFLOP/s", "frac": round(dom["tflops"] / peak, 4),
+                    "peak_kind": f"bf16_tflops_sustained of {pk['source']}", "traffic": None,
+                    "launches_per_step": dom["launch_groups_per_step"], "kernel_ms_per_step": round(dom["ms_per_step"], 3),
+                    "flops_per_step": dom["flops_per_step"], "frac_of_burst": round(dom["tflops"] / pk["bf16_tflops"], 4),
+                    "method": "CUDA events around each launch on the launching stream, 2 instrumented steps after the timed region"}
+        extra = {"kernel_groups": {k: {kk: (round(vv, 3) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kinds.items()}}
+        if args.shapes_out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.shapes_out)), exist_ok=True)
+            json.dump({"kinds": kinds, "shapes": shapes}, open(args.shapes_out, "w"), indent=1)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_arm(args.model, steps=1, warmup=0, budget_s=60.0)
+
+    if rank == 0:
+        gb = B * world
+        ms_step = ms_total / args.steps
+        line = {
+            "metric": METRIC, "value": round(gb / ms_step * 1e3, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{'SD1.5' if args.model == 'sd15' else 'SD2.1-base'} PPFT step, LoRA rank {RANK_R} on the 192 "
+                                   f"unet_keys.json targets, {BITS}-bit messages, {cfg.sample_size * 8}x{cfg.sample_size * 8} "
+                                   f"({cfg.sample_size}x{cfg.sample_size} latents), random-init U-Net, VAE/text-encoder excluded",
+                       "per_gpu_batch": B, "global_batch": gb, "parallelism": f"dp{world}",
+                       "l2": "each step streams > 126 MB (1.7 GB bf16 U-Net weights + activations), inputs rotate over 4 batches",
+                       "final_loss": final_loss},
+            "e2e": {"value": round(gb / (e2e_ms / args.steps) * 1e3, 3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms / args.steps, 3)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# the reference arm: the reference's op sequence (oracle restatement, PyTorch eager) on the host CPU
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_reference_arm(model: str, steps: int, warmup: int, budget_s: float | None = None):
+    """PPFT step exactly as train/ppft_train.py:987-1068 issues it (clean forward WITH the zero-scale LoRA branch, watermarked
+    forward, MSE, backward, clip, AdamW), with the reference's unfused LoRA forwards (oracle/lora_oracle.py, pinned to the
+    reference's own utils/lora_modules.py by tests/golden) on the PyTorch-eager U-Net, fp32, B = 1, all host threads."""
+    from aqualora_b200 import lora_modules, ppft
+    from aqualora_b200.unet import UNetConfig, lora_target_keys
+    from oracle import lora_oracle as O
+    from oracle import models_oracle as MO
+    from oracle.patch import patch_with_oracle
+
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    cfg = UNetConfig.sd15(64) if model == "sd15" else UNetConfig.sd21(96)
+    B = 1
+    unet = ppft.build_unet(cfg, "cpu", dtype=torch.float32, seed=0)
+    layers = lora_modules.inject_lora(unet, lora_target_keys(unet), RANK_R)
+    g = torch.Generator().manual_seed(1)
+    params = []
+    for _, _, l in layers:
+        l.up.weight.data.copy_(torch.randn(l.up.weight.shape, generator=g) * 0.02)
+        for p in (l.down.weight, l.up.weight):
+            p.requires_grad_(True)
+            params.append(p)
+    patch_with_oracle(unet)
+    emb = O.mapper_init(BITS, RANK_R, generator=torch.Generator().manual_seed(5)).requires_grad_(True)
+    torch.manual_seed(0)
+    enc_sd = {"secret_scaler.0.weight": torch.randn(1024, BITS) * BITS ** -0.5, "secret_scaler.0.bias": torch.zeros(1024),
+              "secret_scaler.5.weight": torch.randn(4, 4, 3, 3) * 0.02, "secret_scaler.5.bias": torch.zeros(4)}
+    opt = torch.optim.AdamW([{"params": params}, {"params": [emb]}], lr=1e-4, weight_decay=1e-2)
+    ac = ppft.scaled_linear_alphas_cumprod()
+    v_pred = model != "sd15"
+
+    def step(i):
+        lat, noise, t, ctx, msg = synth_batch(B, cfg, 1234 + i)
+        scale = O.mapper_forward(msg, emb)
+        with torch.no_grad():
+            wm = MO.secret_encoder_forward(lat, msg, enc_sd)[1] * 0.18215
+        noisy = ppft.add_noise(ac, lat, noise, t)
+        noisy_wm = ppft.add_noise(ac, lat + wm, noise, t)
+        clean = unet(noisy, t, ctx, cross_attention_kwargs={"scale": torch.zeros_like(scale)}).sample.detach()
+        pred = unet(noisy_wm, t, ctx, cross_attention_kwargs={"scale": scale}).sample
+        if v_pred:
+            pred = ppft.velocity_to_epsilon(ac, pred, noisy_wm, t)
+            clean = ppft.velocity_to_epsilon(ac, clean, noisy, t)
+        loss = torch.nn.functional.mse_loss(pred.float(), clean.float())
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        opt.zero_grad()
+        return float(loss)
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.time()
+    done = 0
+    for i in range(steps):
+        step(warmup + i)
+        done += 1
+        if budget_s is not None and time.time() - t0 > budget_s:
+            break
+    dt = time.time() - t0
+    return {"value": round(B * done / dt, 5), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{done} PPFT step(s) at B=1 (full {model} U-Net, fp32, PyTorch eager + the reference's unfused LoRA forwards), "
+                      f"{dt:.1f} s on {cores} threads", "seconds": round(dt, 2), "steps_done": done}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    res = cpu_reference_arm(args.model, steps=args.steps, warmup=min(args.warmup, 1), budget_s=args.budget)
+    ms_step = res["seconds"] / max(res["steps_done"], 1) * 1e3
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": res["steps_done"],
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SD1.5 PPFT step, LoRA rank 64 on the 192 unet_keys.json targets, 48-bit messages, 512x512 (64x64 "
+                                   "latents), random-init U-Net, VAE/text-encoder excluded" if args.model == "sd15" else "SD2.1-base PPFT step",
+                       "per_gpu_batch": 1, "global_batch": 1, "parallelism": "cpu",
+                       "note": "reference op sequence (oracle port of utils/lora_modules.py on a PyTorch-eager U-Net) on host cores; "
+                               "bounded sample B=1 per step"},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": round(time.time() - t0, 1)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--model", default="sd15", choices=["sd15", "sd21"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--budget", type=float, default=240.0, help="--impl reference: stop after this many seconds of timed CPU steps")
+    ap.add_argument("--shapes-out", default=None, help="write the per-shape kernel table (JSON) here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,7 @@ int aq_version(void);               /* ABI version, bumped on any signature chan
 int aq_arch(void);                  /* 100: the only architecture this library is built for (sm_100a) */
 const char* aq_last_error(void);    /* thread-local, never NULL */
 int aq_sm_count(void);              /* SM count of the current device, or <0 */
+long long aq_launch_count(void);    /* kernels this library has launched in this process (bench.py: gpu_launches) */
 
 /* ------------------------------------------------------------------------------------------------
  * (i) watermark-LoRA projection.  Replaces utils/lora_modules.py:9-26 (CustomLoRALinearLayerforward)

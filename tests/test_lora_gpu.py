@@ -1,0 +1,377 @@
+"""Hot path (i) on a B200: the fused projection + watermark-LoRA kernels, called through the drop-in modules and the
+C ABI (ctypes -> libaqualora_b200.so), against
+
+  * the golden vectors produced by the REFERENCE's own utils/lora_modules.py (tests/golden/lora_*.pt),
+  * the CPU oracle (oracle/lora_oracle.py) on seeded inputs, including the reference's bf16-autocast arithmetic,
+  * size-independent properties at the BASELINE shapes (zero scale == base bit-for-bit, linearity in the message scale,
+    a plain PyTorch fp32 matmul of the same operands on the device).
+
+Tolerance: activations are bf16 (8-bit mantissa, the precision the reference trains in: train/ppft_train.py:569-581).
+A bf16-rounded output of an fp32-accumulated contraction differs from the fp32 result by <= 2^-8 relative per rounding;
+the kernel rounds H, Hs and Y (the reference's autocast rounds the same three plus the base output and the LoRA output
+separately), so |y - y_fp32| <= 2e-2 * max|y| is the stated bound for y / gx, and 2e-2 relative (Frobenius) for the fp32
+weight gradients accumulated from bf16 operands.
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 2e-2
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _max_rel(got, want):
+    want = want.float()
+    return ((got.float().cpu() - want.cpu()).abs().max() / (want.abs().max() + 1e-12)).item()
+
+
+def _fro_rel(got, want):
+    want = want.float().cpu()
+    return ((got.float().cpu() - want).norm() / (want.norm() + 1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def lm(cuda_device):
+    from aqualora_b200 import _lib, lora_modules
+
+    assert _lib.load().aq_arch() == 100
+    return lora_modules
+
+
+def _build_linear(lm, c, dev):
+    dout, din = c["w"].shape
+    lin = lm.LoRACompatibleLinear(din, dout, bias=c["b"] is not None)
+    lin.weight.data.copy_(c["w"])
+    if c["b"] is not None:
+        lin.bias.data.copy_(c["b"])
+    lin = lin.to(dev, torch.bfloat16)
+    lin.requires_grad_(False)
+    lora = lm.LoRALinearLayer(din, dout, c["r"], network_alpha=c["alpha"])
+    lora.down.weight.data.copy_(c["down"])
+    lora.up.weight.data.copy_(c["up"])
+    lora = lora.to(dev)           # fp32 master weights, as in train/ppft_train.py:651-666
+    lin.set_lora_layer(lora)
+    return lin, lora
+
+
+def test_linear_golden_forward_backward(lm, cuda_device, golden_dir):
+    """Reference outputs/grads (fp32) vs the CUDA path on the bf16-rounded operands."""
+    dev = cuda_device
+    for c in _load(golden_dir, "lora_linear.pt"):
+        lin, lora = _build_linear(lm, c, dev)
+        x = c["x"].to(dev, torch.bfloat16).requires_grad_(True)
+        scale = c["scale"]
+        if isinstance(scale, torch.Tensor):
+            scale = scale.to(dev).requires_grad_(True)
+        y = lin(x, scale)
+        assert y.dtype == torch.bfloat16 and tuple(y.shape) == tuple(c["y"].shape)
+        assert _max_rel(y, c["y"]) < BF16_TOL, c["kind"]
+        y.backward(c["gy"].to(dev, torch.bfloat16))
+        assert _max_rel(x.grad, c["gx"]) < BF16_TOL
+        assert _fro_rel(lora.down.weight.grad, c["g_down"]) < BF16_TOL
+        assert _fro_rel(lora.up.weight.grad, c["g_up"]) < BF16_TOL
+        if isinstance(scale, torch.Tensor):
+            assert _fro_rel(scale.grad, c["g_scale"]) < BF16_TOL
+        # lora_layer is None -> exact base op (utils/lora_modules.py:57-59)
+        lin.set_lora_layer(None)
+        yb = lin(x.detach(), 1.0)
+        assert _max_rel(yb, c["y_base"]) < BF16_TOL
+
+
+def test_conv1x1_golden_forward_backward(lm, cuda_device, golden_dir):
+    dev = cuda_device
+    for c in _load(golden_dir, "lora_conv1x1.pt"):
+        co, ci = c["w"].shape[:2]
+        conv = lm.LoRACompatibleConv(ci, co, kernel_size=1)
+        conv.weight.data.copy_(c["w"]); conv.bias.data.copy_(c["b"])
+        conv = conv.to(dev, torch.bfloat16)
+        conv.requires_grad_(False)
+        lora = lm.LoRAConv2dLayer(ci, co, rank=c["r"], network_alpha=c["alpha"])
+        lora.down.weight.data.copy_(c["down"]); lora.up.weight.data.copy_(c["up"])
+        lora = lora.to(dev)
+        conv.set_lora_layer(lora)
+        x = c["x"].to(dev, torch.bfloat16).requires_grad_(True)
+        scale = c["scale"].to(dev).requires_grad_(True) if isinstance(c["scale"], torch.Tensor) else c["scale"]
+        y = conv(x, scale)
+        assert tuple(y.shape) == tuple(c["y"].shape)
+        assert _max_rel(y, c["y"]) < BF16_TOL
+        y.backward(c["gy"].to(dev, torch.bfloat16))
+        assert _max_rel(x.grad, c["gx"]) < BF16_TOL
+        assert _fro_rel(lora.down.weight.grad, c["g_down"]) < BF16_TOL
+        assert _fro_rel(lora.up.weight.grad, c["g_up"]) < BF16_TOL
+        if isinstance(scale, torch.Tensor):
+            assert _fro_rel(scale.grad, c["g_scale"]) < BF16_TOL
+
+
+def test_standalone_lora_layer_matches_oracle(lm, cuda_device):
+    """CustomLoRALinearLayerforward called on its own (utils/lora_modules.py:9-26), float and tensor scale."""
+    from oracle import lora_oracle as O
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 40, 64, generator=g).bfloat16()
+    lora = lm.LoRALinearLayer(64, 96, 16, network_alpha=8.0)
+    lora.up.weight.data.copy_(torch.randn(96, 16, generator=g) * 0.1)
+    for scale in (0.5, torch.rand(2, 16, generator=g) + 0.5):
+        want = O.lora_linear_layer_forward(x.float(), lora.down.weight.data.bfloat16().float(), lora.up.weight.data.bfloat16().float(),
+                                           scale.bfloat16().float() if isinstance(scale, torch.Tensor) else scale, 8.0, 16)
+        got = lora.to(dev)(x.to(dev), scale.to(dev) if isinstance(scale, torch.Tensor) else scale)
+        assert _max_rel(got, want) < BF16_TOL
+        lora = lora.cpu()
+
+
+@pytest.mark.parametrize("M,K,N,r,tok", [
+    (128, 64, 64, 64, 128),          # one tile
+    (1000, 328, 200, 8, 500),        # ragged everything
+    (1232, 768, 320, 64, 77),        # cross-attention K/V: 77 tokens per sample, samples straddle row tiles
+    (64 * 16, 1280, 1280, 64, 64),   # mid block: 64 tokens per sample, 2 samples per 128-row tile
+    (4096, 320, 2560, 64, 1024),     # GEGLU projection, many column tiles per row block
+    (2048, 2560, 640, 32, 1024),     # long K
+])
+def test_forward_matches_autocast_oracle(cuda_device, M, K, N, r, tok):
+    """Against the reference's bf16-autocast arithmetic restated on CPU (oracle.bf16_autocast_linear)."""
+    from aqualora_b200 import ops
+    from oracle import lora_oracle as O
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(M + K + N)
+    B = M // tok
+    x = torch.randn(B, tok, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(N, generator=g).bfloat16()
+    dn = torch.randn(r, K, generator=g) * K ** -0.5
+    up = torch.randn(N, r, generator=g) * 0.1
+    sc = (1 + 0.7 * torch.randn(B, r, generator=g)).bfloat16()
+    want, h_want = O.bf16_autocast_linear(x, w, b, dn, up, sc)
+    y, h = ops.lora_linear_fwd(x.reshape(M, K).to(dev), w.to(dev), b.to(dev), dn.bfloat16().to(dev), up.bfloat16().to(dev),
+                               sc.float().to(dev), tok, save_h=True)
+    assert _max_rel(y, want.reshape(M, N)) < BF16_TOL
+    # H is a single fp32-accumulated contraction rounded once: at most 1 bf16 ulp from the oracle's rounding
+    assert _max_rel(h, h_want.reshape(M, r)) < 2 ** -7
+
+
+def test_zero_scale_is_bit_identical_to_base(cuda_device):
+    """scale = 0 -> the LoRA branch contributes exactly 0 (train/ppft_train.py:1026-1029 relies on it)."""
+    from aqualora_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(1)
+    for (M, K, N, r, tok) in [(4096, 320, 320, 64, 1024), (16 * 4096, 320, 320, 64, 4096), (1232, 768, 640, 64, 77)]:
+        x = torch.randn(M, K, generator=g).bfloat16().to(dev)
+        w = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16().to(dev)
+        b = torch.randn(N, generator=g).bfloat16().to(dev)
+        dn = (torch.randn(r, K, generator=g)).bfloat16().to(dev)
+        up = (torch.randn(N, r, generator=g)).bfloat16().to(dev)
+        zero = torch.zeros(M // tok, r, device=dev)
+        y0, _ = ops.lora_linear_fwd(x, w, b, dn, up, zero, tok)
+        yb, _ = ops.lora_linear_fwd(x, w, b, None, None, None, tok)
+        assert torch.equal(y0, yb)
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE shape (B=16, 4096 tokens, 320 -> 320, r = 64): device fp32 matmul reference + linearity in the scale."""
+    from aqualora_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(2)
+    B, tok, K, N, r = 16, 4096, 320, 320, 64
+    M = B * tok
+    x = torch.randn(M, K, generator=g, device=dev).bfloat16()
+    w = (torch.randn(N, K, generator=g, device=dev) * K ** -0.5).bfloat16()
+    dn = (torch.randn(r, K, generator=g, device=dev) * K ** -0.5).bfloat16()
+    up = (torch.randn(N, r, generator=g, device=dev) * 0.1).bfloat16()
+    s = (1 + 0.5 * torch.randn(B, r, generator=g, device=dev)).bfloat16().float()
+    y, h = ops.lora_linear_fwd(x, w, None, dn, up, s, tok, save_h=True)
+    h_ref = (x.float() @ dn.float().t()).bfloat16().float()
+    hs = (h_ref * s.repeat_interleave(tok, 0)).bfloat16().float()
+    ref = x.float() @ w.float().t() + hs @ up.float().t()
+    assert ((y.float() - ref).abs().max() / ref.abs().max()).item() < BF16_TOL
+    # linearity: y(2s) - y(0) == 2 (y(s) - y(0)) up to the bf16 roundings of Hs and Y
+    y2, _ = ops.lora_linear_fwd(x, w, None, dn, up, 2 * s, tok)
+    y0, _ = ops.lora_linear_fwd(x, w, None, dn, up, torch.zeros_like(s), tok)
+    lhs = (y2.float() - y0.float())
+    rhs = 2 * (y.float() - y0.float())
+    assert ((lhs - rhs).abs().max() / ref.abs().max()).item() < BF16_TOL
+    # every column tile width / grouping computes the same thing
+    from aqualora_b200 import ops as _ops
+    try:
+        for bn, grp in [(64, 1), (128, 2), (160, 1), (192, 2)]:
+            _ops.set_tuning(bn, grp)
+            yt, _ = _ops.lora_linear_fwd(x, w, None, dn, up, s, tok)
+            assert ((yt.float() - y.float()).abs().max() / ref.abs().max()).item() < 2 ** -7, (bn, grp)
+    finally:
+        _ops.set_tuning(0, 0)
+
+
+@pytest.mark.parametrize("M,K,N,r,tok,dx", [
+    (1024, 320, 320, 64, 256, True),
+    (1232, 768, 320, 64, 77, False),     # text-context input needs no gradient (attn2.to_k / to_v)
+    (2048, 640, 2560, 32, 1024, True),
+    (1000, 328, 200, 8, 250, True),
+])
+def test_backward_matches_closed_form_oracle(cuda_device, M, K, N, r, tok, dx):
+    from aqualora_b200 import ops
+    from oracle import lora_oracle as O
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(7 * M + r)
+    B = M // tok
+    x = torch.randn(B, tok, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16()
+    dn = (torch.randn(r, K, generator=g) * K ** -0.5).bfloat16()
+    up = (torch.randn(N, r, generator=g) * 0.1).bfloat16()
+    sc = (1 + 0.7 * torch.randn(B, r, generator=g)).bfloat16().float()
+    gy = (torch.randn(B, tok, N, generator=g) * 0.05).bfloat16()
+    dxr, ddr, dur, dsr = O.closed_form_linear_grads(x.float(), w.float(), dn.float(), up.float(), sc, gy.float())
+    xd, wd, dnd, upd, scd, gyd = (t.to(dev) for t in (x.reshape(M, K), w, dn, up, sc, gy.reshape(M, N)))
+    _, h = ops.lora_linear_fwd(xd, wd, None, dnd, upd, scd, tok, save_h=True)
+    g_dn = torch.zeros(r, K, device=dev); g_up = torch.zeros(N, r, device=dev); g_sc = torch.zeros(B, r, device=dev)
+    gx = ops.lora_linear_bwd(gyd, xd, wd.t().contiguous() if dx else None, dnd.t().contiguous(), upd.t().contiguous(), scd, h,
+                             g_dn, g_up, g_sc, tok)
+    if dx:
+        assert _max_rel(gx, dxr.reshape(M, K)) < BF16_TOL
+    else:
+        assert gx is None
+    assert _fro_rel(g_dn, ddr) < BF16_TOL and _fro_rel(g_up, dur) < BF16_TOL and _fro_rel(g_sc, dsr) < BF16_TOL
+    # gradients ACCUMULATE into the caller's buffers (flat gradient buffer contract)
+    ops.lora_linear_bwd(gyd, xd, wd.t().contiguous() if dx else None, dnd.t().contiguous(), upd.t().contiguous(), scd, h,
+                        g_dn, g_up, g_sc, tok)
+    assert _fro_rel(g_up, 2 * dur) < BF16_TOL
+
+
+def test_wgrad_contraction(cuda_device):
+    from aqualora_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    for (M, I, J, t) in [(1024, 320, 64, False), (5000, 1280, 64, True), (1232, 768, 16, True), (65536, 320, 64, False)]:
+        p = torch.randn(M, I, generator=g).bfloat16()
+        q = torch.randn(M, J, generator=g).bfloat16()
+        c = torch.zeros((J, I) if t else (I, J), device=dev)
+        ops.wgrad_tn(p.to(dev), q.to(dev), c, transpose_out=t)
+        ref = p.double().t() @ q.double()
+        assert _fro_rel(c, ref.t() if t else ref) < 1e-5      # fp32 accumulation of exact bf16 products
+
+
+def test_mapper_and_flat_adamw(cuda_device, golden_dir):
+    from aqualora_b200 import ops
+
+    dev = cuda_device
+    gm = _load(golden_dir, "models_small.pt")["mapper"]
+    got = ops.mapper_fwd(gm["msg"].to(dev), gm["emb"].to(dev), round_bf16=False)
+    torch.testing.assert_close(got.cpu(), gm["scale"], rtol=1e-6, atol=1e-6)
+    # backward: dE = msg^T ds / sqrt(bits)
+    ds = torch.randn(gm["msg"].shape[0], gm["emb"].shape[1], generator=torch.Generator().manual_seed(0))
+    ge = torch.zeros_like(gm["emb"]).to(dev)
+    ops.mapper_bwd(gm["msg"].to(dev), ds.to(dev), ge)
+    torch.testing.assert_close(ge.cpu(), gm["msg"].t() @ ds / gm["emb"].shape[0] ** 0.5, rtol=1e-5, atol=1e-6)
+
+    # clip_grad_norm_(1.0) + AdamW + zero_grad (train/ppft_train.py:1065-1068) vs torch on CPU
+    n = 100_003
+    g = torch.Generator().manual_seed(4)
+    p0 = torch.randn(n, generator=g); gr = torch.randn(n, generator=g) * 0.05
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([p_ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    pd, gd = p0.to(dev), torch.zeros(n, device=dev)
+    m, v, nsq = torch.zeros(n, device=dev), torch.zeros(n, device=dev), torch.zeros(1, device=dev)
+    for step in (1, 2, 3):
+        p_ref.grad = gr.clone() * step
+        torch.nn.utils.clip_grad_norm_([p_ref], 1.0)
+        opt.step()
+        gd.copy_(gr * step); nsq.zero_()
+        ops.flat_sumsq(gd, nsq)
+        ops.flat_clip_adamw(pd, gd, m, v, nsq, grad_scale=1.0, max_norm=1.0, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8,
+                            weight_decay=1e-2, step=step)
+        assert bool((gd == 0).all())
+    torch.testing.assert_close(pd.cpu(), p_ref.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_tiny_unet_ppft_step_matches_oracle(cuda_device):
+    """One PPFT step on the tiny U-Net: CUDA path (bf16) vs the reference op sequence on CPU in fp32 (oracle patch)."""
+    from aqualora_b200 import lora_modules, ppft
+    from aqualora_b200.unet import UNetConfig, lora_target_keys
+    from oracle import lora_oracle as O
+    from oracle.patch import patch_with_oracle
+
+    dev = cuda_device
+    cfg = UNetConfig.tiny(16)
+    rank, bits, B = 8, 48, 2
+    unet = ppft.build_unet(cfg, dev, seed=3)
+    emb = O.mapper_init(bits, rank, generator=torch.Generator().manual_seed(5))
+    tr = ppft.PPFTTrainer(unet, ppft.PPFTConfig(rank=rank, msg_bits=bits), emb, dev, lora_up_std=0.05, seed=1)
+    g = torch.Generator().manual_seed(11)
+    s = cfg.sample_size
+    lat = torch.randn(B, 4, s, s, generator=g) * 0.18215
+    wm = torch.randn(B, 4, s, s, generator=g) * 0.02 * 0.18215
+    noise = torch.randn(B, 4, s, s, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    ctx = torch.randn(B, 77, cfg.cross_attention_dim, generator=g)
+    msg = torch.randint(0, 2, (B, bits), generator=g).float()
+    bf = lambda x: x.to(dev, torch.bfloat16)
+    loss = tr.forward_backward(bf(lat), bf(wm), bf(noise), t.to(dev), bf(ctx), msg.to(dev))
+    g_flat = tr.state.grad.clone()
+
+    cpu_unet = ppft.build_unet(cfg, "cpu", dtype=torch.float32, seed=3)
+    layers = lora_modules.inject_lora(cpu_unet, lora_target_keys(cpu_unet), rank)
+    cpu_unet.load_state_dict({k: v.detach().float().cpu() for k, v in unet.state_dict().items()})
+    patch_with_oracle(cpu_unet)
+    for _, _, l in layers:
+        l.down.weight.requires_grad_(True); l.up.weight.requires_grad_(True)
+    E = tr.state.mapper_emb.detach().cpu().clone().requires_grad_(True)
+    r16 = lambda x: x.bfloat16().float()
+    scale = r16(O.mapper_forward(msg, E))
+    ac = ppft.scaled_linear_alphas_cumprod()
+    noisy = ppft.add_noise(ac, r16(lat), r16(noise), t)
+    noisy_wm = ppft.add_noise(ac, r16(lat) + r16(wm), r16(noise), t)
+    with torch.no_grad():
+        clean = cpu_unet(noisy, t, r16(ctx), cross_attention_kwargs={"scale": torch.zeros_like(scale)}).sample
+    pred = cpu_unet(noisy_wm, t, r16(ctx), cross_attention_kwargs={"scale": scale}).sample
+    loss_ref = torch.nn.functional.mse_loss(pred, clean)
+    loss_ref.backward()
+    g_ref = torch.cat([p.grad.reshape(-1) for _, _, l in layers for p in (l.down.weight, l.up.weight)])
+    g_got = g_flat[:g_ref.numel()].cpu()
+    cos = torch.nn.functional.cosine_similarity(g_got, g_ref, dim=0).item()
+    # whole-network bf16 (activations, attention, norms) vs fp32: direction must agree, magnitude within 10 %
+    assert cos > 0.995, cos
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 0.05
+    assert abs(g_got.norm().item() / g_ref.norm().item() - 1) < 0.1
+    ge = tr.state.mapper_grad.cpu().reshape(-1)
+    assert torch.nn.functional.cosine_similarity(ge, E.grad.reshape(-1), dim=0).item() > 0.995
+    tr.optimizer_step()
+    assert bool((tr.state.grad == 0).all())
+
+
+def test_secret_encoder_golden(cuda_device, golden_dir):
+    """SecretEncoder (utils/models.py:51-81) vs the reference's own outputs."""
+    from aqualora_b200.models import SecretEncoder
+
+    g = _load(golden_dir, "models_small.pt")
+    enc = SecretEncoder(48)
+    enc.load_state_dict(g["encoder_state"])
+    enc = enc.to(cuda_device)
+    for key in ("encoder_64x64", "encoder_96x96", "encoder_40x56"):
+        c = g[key]
+        xo, cm = enc(c["x"].to(cuda_device), c["msg"].to(cuda_device))
+        torch.testing.assert_close(cm.cpu(), c["c"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(xo.cpu(), c["x_out"], rtol=1e-5, atol=1e-6)
+
+
+def test_state_dict_keys_follow_reference(cuda_device):
+    """pytorch_lora_weights.safetensors key naming (train/ppft_train.py:443-471)."""
+    from aqualora_b200 import lora_modules, ppft
+    from aqualora_b200.unet import UNetConfig, lora_target_keys
+
+    unet = ppft.build_unet(UNetConfig.tiny(16), cuda_device, seed=0)
+    keys = lora_target_keys(unet)
+    lora_modules.inject_lora(unet, keys, 8)
+    sd = lora_modules.unet_attn_processors_state_dict(unet, keys)
+    assert len(sd) == 2 * 192
+    assert "down_blocks.0.attentions.0.transformer_blocks.0.attn1.processor.to_q_lora.down.weight" in sd
+    assert "down_blocks.0.attentions.0.proj_in.lora.up.weight" in sd
+    assert "mid_block.attentions.0.transformer_blocks.0.ff.net.0.proj.lora.down.weight" in sd
