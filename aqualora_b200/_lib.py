@@ -43,6 +43,11 @@ _SIGNATURES = {
     "aq_mapper_bwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     "aq_cast_transpose_bf16": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),
     "aq_transpose_bf16": ([c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),
+    "aq_noise_jpeg": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    "aq_noise_crop_resize": ([c_void_p, c_void_p] + [c_int] * 11 + [c_void_p], c_int),
+    "aq_noise_gauss_blur": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    "aq_noise_gauss_noise": ([c_void_p, c_void_p, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, c_void_p], c_int),
+    "aq_noise_color_jiggle": ([c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_int), c_int, c_int, c_int, c_void_p], c_int),
     "aq_flat_sumsq": ([c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "aq_flat_clip_adamw": (
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,

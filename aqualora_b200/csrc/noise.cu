@@ -64,8 +64,10 @@ __host__ __device__ constexpr int zz_rank(int a, int b) {
 __host__ __device__ constexpr int keep_count(int c) { return c == 0 ? 25 : 9; }   // yuv_keep_weights = (25, 9, 9)
 __host__ __device__ constexpr bool kept(int c, int a, int b) { return zz_rank(a, b) < keep_count(c); }
 // number of leading second-index values that hold any kept coefficient
-__host__ __device__ constexpr int kb_max(int c) { return c == 0 ? 7 : 4; }
-static_assert(kept(0, 0, 6) && !kept(0, 0, 7) && kept(1, 0, 3) && !kept(1, 0, 4) && !kept(1, 4, 0), "zig-zag table");
+__host__ __device__ constexpr int kb_max(int c) { return c == 0 ? 6 : 4; }
+static_assert(kept(0, 6, 0) && kept(0, 3, 3) && kept(0, 0, 5) && !kept(0, 0, 6) && !kept(0, 2, 4) && kept(1, 0, 3) && kept(1, 2, 1) &&
+                  !kept(1, 3, 0) && !kept(1, 0, 4),
+              "zig-zag table (jpeg_compression.py:31-41)");
 
 constexpr int kJpegBlocks = 64;                 // 8x8 blocks per CTA strip (512 columns)
 constexpr int kJpegCols = kJpegBlocks * 8;

@@ -195,3 +195,70 @@ def secret_encoder_fwd(msg: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, wc
               wc.contiguous().data_ptr(), bc.contiguous().data_ptr(), _ptr(x), c.data_ptr(), _ptr(xo), B, bits, base, res, H, W,
               ws.data_ptr(), _stream())
     return xo, c
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# noise_layers (utils/noise_layers/*): [B, 3, H, W] fp32 images in [-1, 1]
+# ------------------------------------------------------------------------------------------------------------------
+def _image(x: torch.Tensor, name: str = "image") -> torch.Tensor:
+    _need(x, _F32, name, 4)
+    if x.shape[1] != 3:
+        raise _lib.AqualoraError(f"{name} must be [B, 3, H, W], got {tuple(x.shape)}")
+    return x.contiguous()
+
+
+def noise_jpeg(x: torch.Tensor) -> torch.Tensor:
+    x = _image(x)
+    B, _, H, W = x.shape
+    y = torch.empty_like(x)
+    _lib.call("aq_noise_jpeg", x.data_ptr(), y.data_ptr(), B, H, W, _stream())
+    return y
+
+
+def noise_crop_resize(x: torch.Tensor, top: int, left: int, crop_h: int, crop_w: int, resize_h: int, resize_w: int,
+                      out_hw=(512, 512)) -> torch.Tensor:
+    x = _image(x)
+    B, _, H, W = x.shape
+    y = torch.empty((B, 3, out_hw[0], out_hw[1]), dtype=_F32, device=x.device)
+    _lib.call("aq_noise_crop_resize", x.data_ptr(), y.data_ptr(), B, H, W, int(top), int(left), int(crop_h), int(crop_w),
+              int(resize_h), int(resize_w), int(out_hw[0]), int(out_hw[1]), _stream())
+    return y
+
+
+def noise_gauss_blur(x: torch.Tensor, sigmas: torch.Tensor, ksize=(3, 9)) -> torch.Tensor:
+    x = _image(x)
+    _need(sigmas, _F32, "sigmas", 1)
+    B, _, H, W = x.shape
+    if sigmas.shape[0] != B:
+        raise _lib.AqualoraError(f"sigmas must have one entry per sample ({B}), got {tuple(sigmas.shape)}")
+    y = torch.empty_like(x)
+    _lib.call("aq_noise_gauss_blur", x.data_ptr(), y.data_ptr(), sigmas.contiguous().data_ptr(), B, H, W, int(ksize[0]),
+              int(ksize[1]), _stream())
+    return y
+
+
+def noise_gauss_noise(x: torch.Tensor | None, std: float, seed: int, offset: int = 0, shape=None, device=None) -> torch.Tensor:
+    """x + std * N(0, 1) with the in-kernel Philox stream (seed, offset); x = None returns std * noise of `shape`."""
+    if x is not None:
+        _need(x, _F32, "x")
+        x = x.contiguous()
+        y = torch.empty_like(x)
+    else:
+        y = torch.empty(shape, dtype=_F32, device=device)
+    _lib.call("aq_noise_gauss_noise", _ptr(x), y.data_ptr(), y.numel(), float(std), int(seed), int(offset), _stream())
+    return y
+
+
+def noise_color_jiggle(x: torch.Tensor, params: torch.Tensor, order) -> torch.Tensor:
+    """params [B, 4] = (brightness, contrast, saturation, hue); order = permutation of (0, 1, 2, 3)."""
+    import ctypes
+
+    x = _image(x)
+    _need(params, _F32, "params", 2)
+    B, _, H, W = x.shape
+    if tuple(params.shape) != (B, 4):
+        raise _lib.AqualoraError(f"params must be [{B}, 4], got {tuple(params.shape)}")
+    y = torch.empty_like(x)
+    arr = (ctypes.c_int * 4)(*[int(o) for o in order])
+    _lib.call("aq_noise_color_jiggle", x.data_ptr(), y.data_ptr(), params.contiguous().data_ptr(), arr, B, H, W, _stream())
+    return y

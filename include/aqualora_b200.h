@@ -120,6 +120,30 @@ int aq_secret_encoder_fwd(const float* msg, const float* w1, const float* b1, co
                           const float* x, float* c_out, float* x_out, int B, int bits, int base, int res, int H, int W,
                           void* ws, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (ii) noise_layers distortion stack (utils/noise_layers/*).  x, y: [B, 3, H, W] fp32 NCHW in [-1, 1]; y != x.
+ * Every quantity the reference layer samples internally is an explicit argument here (Noiser draws them on the
+ * host, aqualora_b200/noise_layers.py), so results are reproducible against the CPU oracle.
+ * ---------------------------------------------------------------------------------------------- */
+/* JpegCompression.forward (jpeg_compression.py:130-162): zero-pad to x8, RGB->YUV, 8x8 DCT, keep the first
+ * (25, 9, 9) zig-zag coefficients of (Y, U, V), IDCT, YUV->RGB, un-pad.  No quantisation. */
+int aq_noise_jpeg(const float* x, float* y, int B, int H, int W, void* stream);
+/* CropandResize.forward (noises.py:46-57): crop (top, left, crop_h, crop_w) -> bilinear (resize_h, resize_w) ->
+ * bilinear (out_h, out_w), align_corners = False, no antialias; one box for the whole batch.  y: [B, 3, out_h, out_w]. */
+int aq_noise_crop_resize(const float* x, float* y, int B, int H, int W, int top, int left, int crop_h, int crop_w,
+                         int resize_h, int resize_w, int out_h, int out_w, void* stream);
+/* GaussianBlur.forward (noises.py:67-70; kornia RandomGaussianBlur((ky, kx), sigma)): separable normalised Gaussian,
+ * reflect border, sigmas [B] fp32 on the device (one per sample, both axes). */
+int aq_noise_gauss_blur(const float* x, float* y, const float* sigmas, int B, int H, int W, int ky, int kx, void* stream);
+/* GaussianNoise.forward (noises.py:80-85): y = x + std * N(0, 1) over n elements; the normals are element e ->
+ * Philox4x32-10(key = seed, counter = offset + e / 4)[e % 4] through Box-Muller.  x == NULL writes std * noise only
+ * (std = 1 gives the exact noise tensor, which tests hand to the oracle). */
+int aq_noise_gauss_noise(const float* x, float* y, int64_t n, float std, uint64_t seed, uint64_t offset, void* stream);
+/* ColorJitter.forward (noises.py:95-104; kornia ColorJiggle): params [B, 4] fp32 on the device = (brightness,
+ * contrast, saturation, hue) per sample; order_host[4] = permutation of (0 brightness, 1 contrast, 2 saturation, 3 hue). */
+int aq_noise_color_jiggle(const float* x, float* y, const float* params, const int* order_host, int B, int H, int W,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif
