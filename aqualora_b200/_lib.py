@@ -48,6 +48,9 @@ _SIGNATURES = {
     "aq_noise_gauss_blur": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "aq_noise_gauss_noise": ([c_void_p, c_void_p, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, c_void_p], c_int),
     "aq_noise_color_jiggle": ([c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_int), c_int, c_int, c_int, c_void_p], c_int),
+    "aq_effnetb1_packed_floats": ([c_int], c_size_t),
+    "aq_effnetb1_workspace_bytes": ([c_int], c_size_t),
+    "aq_effnetb1_fwd": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p], c_int),
     "aq_flat_sumsq": ([c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "aq_flat_clip_adamw": (
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,

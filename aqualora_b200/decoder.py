@@ -1,0 +1,153 @@
+"""Drop-in `SecretDecoder` (utils/models.py:84-96, duplicated at evaluation/utils_eval.py:142-154).
+
+The reference wraps torchvision's `efficientnet_b1` and replaces its classifier by `Linear(1280, 2 * bits)`; checkpoints
+(`msgdecoder.pt`, the `sec_decoder` entry of the pretrain checkpoint) are that module's state-dict under `model.`.
+This class keeps exactly those parameter / buffer names (so `load_state_dict` of a reference checkpoint works unchanged)
+but owns no torchvision code: the forward is the fp32 NHWC kernel chain in csrc/decoder.cu with every BatchNorm folded
+into its convolution.  Eval-mode only (PPFT and evaluation run the decoder in eval(): train/ppft_train.py:974,
+evaluation/utils_eval.py:168); calling it in train mode or on CPU tensors raises -- there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import AqualoraError
+
+# (expand_ratio, kernel, stride, in_ch, out_ch, layers): torchvision efficientnet_b1 (width 1.0, depth 1.1)
+B1_STAGES = [
+    (1, 3, 1, 32, 16, 2),
+    (6, 3, 2, 16, 24, 3),
+    (6, 5, 2, 24, 40, 3),
+    (6, 3, 2, 40, 80, 4),
+    (6, 5, 1, 80, 112, 4),
+    (6, 5, 2, 112, 192, 5),
+    (6, 3, 1, 192, 320, 2),
+]
+BN_EPS = 1e-5
+
+
+def _conv_bn(cin, cout, k, stride=1, groups=1):
+    """torchvision Conv2dNormActivation: [0] conv (no bias), [1] BatchNorm2d, [2] activation (no parameters)."""
+    return nn.Sequential(nn.Conv2d(cin, cout, k, stride, (k - 1) // 2, groups=groups, bias=False), nn.BatchNorm2d(cout, eps=BN_EPS))
+
+
+class _SE(nn.Module):
+    def __init__(self, c, sq):
+        super().__init__()
+        self.fc1 = nn.Conv2d(c, sq, 1)
+        self.fc2 = nn.Conv2d(sq, c, 1)
+
+
+class _MBConv(nn.Module):
+    def __init__(self, cin, cout, expand, k, stride):
+        super().__init__()
+        cexp = cin * expand
+        layers = []
+        if expand != 1:
+            layers.append(_conv_bn(cin, cexp, 1))
+        layers.append(_conv_bn(cexp, cexp, k, stride, groups=cexp))
+        layers.append(_SE(cexp, max(1, cin // 4)))
+        layers.append(_conv_bn(cexp, cout, 1))
+        self.block = nn.Sequential(*layers)
+
+
+class _EfficientNetB1Params(nn.Module):
+    """Parameter container with torchvision's module paths: features.{0..8}, classifier.{0,1}."""
+
+    def __init__(self, out_features):
+        super().__init__()
+        feats = [_conv_bn(3, 32, 3, 2)]
+        for expand, k, stride, cin, cout, layers in B1_STAGES:
+            feats.append(nn.Sequential(*[_MBConv(cin if i == 0 else cout, cout, expand, k, stride if i == 0 else 1) for i in range(layers)]))
+        feats.append(_conv_bn(320, 1280, 1))
+        self.features = nn.Sequential(*feats)
+        self.classifier = nn.Sequential(nn.Dropout(0.2), nn.Linear(1280, out_features))
+
+
+def _fold(sd, conv_key, bn_key):
+    w = sd[conv_key + ".weight"].double()
+    g, b = sd[bn_key + ".weight"].double(), sd[bn_key + ".bias"].double()
+    mu, var = sd[bn_key + ".running_mean"].double(), sd[bn_key + ".running_var"].double()
+    s = g / torch.sqrt(var + BN_EPS)
+    return (w * s.view(-1, 1, 1, 1)).float(), (b - mu * s).float()
+
+
+def pack_state_dict(sd: dict, out_features: int, prefix: str = "model.") -> torch.Tensor:
+    """Fold every BatchNorm (eval) into its convolution and lay the fp32 parameters out in execution order, each segment
+    padded to a multiple of 4 floats -- the layout csrc/decoder.cu walks:
+        stem  w [(ky, kx, ci), 32], b [32]
+        block [expand: Wt [cin, cexp], b] , dw w [k*k, cexp], b , se w1 [sq, cexp], b1, w2 [cexp, sq], b2 , project Wt [cexp, cout], b
+        head  Wt [320, 1280], b ; fc w [out, 1280], b
+    The fold is computed in float64 and rounded once."""
+    out = []
+
+    def put(t):
+        t = t.reshape(-1).float()
+        padn = (-t.numel()) % 4
+        out.append(torch.cat([t, t.new_zeros(padn)]) if padn else t)
+
+    p = prefix + "features."
+    w, b = _fold(sd, p + "0.0", p + "0.1")
+    put(w.permute(2, 3, 1, 0)); put(b)
+    for si, (expand, k, stride, cin, cout, layers) in enumerate(B1_STAGES):
+        for li in range(layers):
+            q = f"{p}{si + 1}.{li}.block."
+            i = 0
+            if expand != 1:
+                w, b = _fold(sd, f"{q}{i}.0", f"{q}{i}.1")
+                put(w.flatten(1).t()); put(b)
+                i += 1
+            w, b = _fold(sd, f"{q}{i}.0", f"{q}{i}.1")
+            put(w.flatten(1).t()); put(b)                     # [cexp, 1, k, k] -> [k*k, cexp]
+            i += 1
+            put(sd[f"{q}{i}.fc1.weight"].flatten(1)); put(sd[f"{q}{i}.fc1.bias"])
+            put(sd[f"{q}{i}.fc2.weight"].flatten(1)); put(sd[f"{q}{i}.fc2.bias"])
+            i += 1
+            w, b = _fold(sd, f"{q}{i}.0", f"{q}{i}.1")
+            put(w.flatten(1).t()); put(b)
+    w, b = _fold(sd, p + "8.0", p + "8.1")
+    put(w.flatten(1).t()); put(b)
+    put(sd[prefix + "classifier.1.weight"]); put(sd[prefix + "classifier.1.bias"])
+    return torch.cat(out).contiguous()
+
+
+class SecretDecoder(nn.Module):
+    """`SecretDecoder(output_size)`: logits [B, output_size, 2] for images [B, 3, H, W] in [-1, 1] (resized to 512 x 512 with the
+    reference's bilinear interpolate when needed).  `decode_bits(x)` returns the argmax bits as uint8."""
+
+    def __init__(self, output_size=64):
+        super().__init__()
+        self.output_size = output_size
+        self.model = _EfficientNetB1Params(output_size * 2)
+        self._packed = None
+        self._packed_key = None
+
+    def _packed_weights(self, device):
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        if self._packed is None or self._packed_key != key:
+            sd = {k: v.detach() for k, v in self.state_dict().items()}
+            self._packed = pack_state_dict(sd, self.output_size * 2).to(device)
+            self._packed_key = key
+        return self._packed
+
+    def _run(self, x, want_bits):
+        if self.training:
+            raise AqualoraError("SecretDecoder: only eval() is implemented on the CUDA path (BatchNorm folded; PPFT / evaluation "
+                                "run the decoder in eval mode)")
+        if not x.is_cuda:
+            raise AqualoraError("SecretDecoder: CPU tensor passed; aqualora_b200 has no CPU fallback")
+        x = x.float()
+        if tuple(x.shape[-2:]) != (512, 512):
+            H, W = x.shape[-2:]
+            x = ops.noise_crop_resize(x, 0, 0, H, W, 512, 512, (512, 512))     # F.interpolate(x, (512, 512), 'bilinear')
+        with torch.no_grad():
+            logits, bits = ops.effnetb1_fwd(x, self._packed_weights(x.device), self.output_size * 2, want_bits)
+        return logits.view(-1, self.output_size, 2), bits
+
+    def forward(self, x):
+        return self._run(x, False)[0]
+
+    def decode_bits(self, x):
+        return self._run(x, True)[1]

@@ -262,3 +262,32 @@ def noise_color_jiggle(x: torch.Tensor, params: torch.Tensor, order) -> torch.Te
     arr = (ctypes.c_int * 4)(*[int(o) for o in order])
     _lib.call("aq_noise_color_jiggle", x.data_ptr(), y.data_ptr(), params.contiguous().data_ptr(), arr, B, H, W, _stream())
     return y
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# message decoder (EfficientNet-B1, utils/models.py:84-96)
+# ------------------------------------------------------------------------------------------------------------------
+_DECODER_WS: dict = {}
+
+
+def effnetb1_fwd(x: torch.Tensor, packed: torch.Tensor, out_features: int, want_bits: bool = True):
+    """x [B, 3, 512, 512] fp32 -> (logits [B, out_features] fp32, bits [B, out_features // 2] uint8 or None)."""
+    x = _image(x, "x")
+    _need(packed, _F32, "packed", 1)
+    B = x.shape[0]
+    if tuple(x.shape[2:]) != (512, 512):
+        raise _lib.AqualoraError(f"decoder input must be 512 x 512 (resize first), got {tuple(x.shape)}")
+    lib = _lib.load()
+    if packed.numel() != lib.aq_effnetb1_packed_floats(out_features):
+        raise _lib.AqualoraError(f"packed decoder weights: {packed.numel()} floats, expected {lib.aq_effnetb1_packed_floats(out_features)}")
+    nbytes = lib.aq_effnetb1_workspace_bytes(B)
+    key = (x.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _DECODER_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)   # reused across calls on the same stream
+        _DECODER_WS[key] = ws
+    logits = torch.empty((B, out_features), dtype=_F32, device=x.device)
+    bits = torch.empty((B, out_features // 2), dtype=torch.uint8, device=x.device) if want_bits else None
+    _lib.call("aq_effnetb1_fwd", x.data_ptr(), packed.data_ptr(), logits.data_ptr(), _ptr(bits), B, out_features, ws.data_ptr(),
+              ws.numel(), _stream())
+    return logits, bits

@@ -144,6 +144,20 @@ int aq_noise_gauss_noise(const float* x, float* y, int64_t n, float std, uint64_
 int aq_noise_color_jiggle(const float* x, float* y, const float* params, const int* order_host, int B, int H, int W,
                           void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (ii) message decoder.  SecretDecoder.forward (utils/models.py:91-96 == evaluation/utils_eval.py:149-154):
+ * torchvision EfficientNet-B1 (eval) with a Linear(1280, out_features) head; out_features = 2 * bits, viewed as
+ * [B, bits, 2]; bit = argmax over the pair (evaluation/utils_eval.py:194).
+ * x [B, 3, 512, 512] fp32 NCHW in [-1, 1] (resize other sizes first: aq_noise_crop_resize with a full-image crop is
+ * the reference's bilinear F.interpolate).  packed: aq_effnetb1_packed_floats(out_features) fp32 values, BatchNorm
+ * folded into the preceding conv, in execution order (layout: aqualora_b200/decoder.py:pack_state_dict).
+ * logits [B, out_features] fp32; bits [B, out_features / 2] u8 or NULL.  All arithmetic fp32 FFMA (no TF32).
+ * ---------------------------------------------------------------------------------------------- */
+size_t aq_effnetb1_packed_floats(int out_features);
+size_t aq_effnetb1_workspace_bytes(int B);
+int aq_effnetb1_fwd(const float* x, const float* packed, float* logits, unsigned char* bits, int B, int out_features,
+                    void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

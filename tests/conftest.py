@@ -9,6 +9,13 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+try:  # the CPU oracle runs on the cores this process may use, not on every core of the host (cgroup-limited GPU boxes)
+    import torch
+
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+except Exception:  # pragma: no cover
+    pass
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")

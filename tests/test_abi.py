@@ -73,3 +73,49 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_decoder_container_matches_torchvision_layout(lib):
+    """SecretDecoder keeps the reference checkpoint's names (torchvision efficientnet_b1 under `model.`), and the Python
+    packer and the C walker agree on the packed size."""
+    import torch
+
+    from aqualora_b200.decoder import SecretDecoder, pack_state_dict
+    from oracle import models_oracle as MO
+
+    sd, module = MO.make_decoder_state(48, seed=0)
+    dec = SecretDecoder(48)
+    assert list(dec.state_dict().keys()) == list(sd.keys())
+    assert all(dec.state_dict()[k].shape == v.shape for k, v in sd.items())
+    packed = pack_state_dict(sd, 96)
+    assert packed.dtype == torch.float32 and packed.numel() == lib.aq_effnetb1_packed_floats(96)
+    assert lib.aq_effnetb1_workspace_bytes(2) > 2 * 6291456 * 4
+
+
+def test_compat_shim_exports_reference_names(lib):
+    """compat/utils mirrors the module paths the reference scripts import (train/ppft_train.py:49-57,
+    train/latent_wm_pretrain.py:36)."""
+    import importlib
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "compat"))
+    saved = {k: v for k, v in sys.modules.items() if k == "utils" or k.startswith("utils.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        lm = importlib.import_module("utils.lora_modules")
+        for name in ("CustomLoraLoaderMixin", "CustomLoRAConv2dLayerforward", "CustomLoRACompatibleConvforward",
+                     "CustomLoRALinearLayerforward", "CustomLoRACompatibleLinearforward"):
+            assert hasattr(lm, name)
+        import inspect
+
+        assert list(inspect.signature(lm.CustomLoRALinearLayerforward).parameters) == ["self", "hidden_states", "scale"]
+        m = importlib.import_module("utils.models")
+        assert all(hasattr(m, n) for n in ("SecretEncoder", "SecretDecoder", "MapperNet"))
+        n = importlib.import_module("utils.noise_layers.noiser")
+        assert hasattr(n, "Noiser") and hasattr(n, "distorsion_unit")
+    finally:
+        sys.path.remove(os.path.join(ROOT, "compat"))
+        for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
