@@ -1,18 +1,23 @@
-// Fused base projection + watermark-LoRA contraction for sm_100a.
+// Fused base projection + watermark-LoRA contraction for sm_100a, CTA-pair (tcgen05 cta_group::2) edition.
 //
-//   H  = A Dn^T                                   (128 x 64 fp32 in TMEM, once per row block)
+//   H  = A Dn^T                                   (256 x 64 fp32 in the pair's TMEM, once per row block)
 //   Hs = bf16(bf16(H) * scale[sample(row), :])    (epilogue warps: TMEM -> registers -> swizzled SMEM)
-//   Y  = A W^T + bias + Hs Up^T                   (same TMEM accumulator; Hs is the A operand of a 65th k-block)
+//   Y  = A W^T + bias + Hs Up^T                   (same TMEM accumulator; Hs is the A operand of one extra k-block)
 //
 // Replaces the op sequence of utils/lora_modules.py:9-26 + :56-62 (Linear, down, diag_embed, bmm, up, add).
 // The backward's dX uses the same kernel with (A, W, Dn, Up) = (G, W^T, Up^T, Dn^T) and a mid-epilogue that
 // also emits dH, Hs and the per-sample dscale reduction (mode 1).
 //
-// Structure (one CTA per SM, persistent over work items = (row block, group of column tiles)):
-//   warp 0    TMA producer      global -> SMEM ring (A, W, Dn tiles; 128B swizzle; mbarrier complete_tx)
-//   warp 1    MMA issuer        one thread issues tcgen05.mma; tcgen05.commit releases ring slots
-//   warp 2    TMEM allocator
-//   warps 4-7 epilogue          tcgen05.ld -> bias/scale -> bf16 -> SMEM staging -> TMA store
+// Why pairs: measured on B200 the 1-CTA 128 x 160 version moved 36 KiB L2->SMEM per 2.6 MFLOP k-block and sat at the
+// ~11 TB/s L2->SMEM ceiling (profiles/r01_*).  A pair shares the W tile (each CTA loads half of it), so the same k-block
+// costs 26 KiB (BN=160) / 28 KiB (BN=192, 3.1 MFLOP) per CTA.
+//
+// Structure: cluster of 2 CTAs = one 256-row block, one CTA pair per SM pair, persistent over work items
+// (row block, group of column tiles); 320 threads per CTA:
+//   warps 0-7  epilogue          TMEM lane quadrant = warp % 4, column half = warp / 4:
+//                                tcgen05.ld -> bias -> bf16 -> padded SMEM transpose -> coalesced 16B global stores
+//   warp 8     TMA producer      both CTAs: own A rows, own half of W / Dn / Up; bytes signalled on the LEADER's barrier
+//   warp 9     TMEM allocator; in the leader CTA one thread issues every tcgen05.mma of the pair
 #include <stdio.h>
 #include <string.h>
 
@@ -21,33 +26,36 @@
 
 namespace aq {
 
-constexpr int kBlockM = 128;
+constexpr int kBlockM = 128;         // rows per CTA (the pair covers 256)
+constexpr int kPairM = 2 * kBlockM;
 constexpr int kBlockK = 64;          // 64 bf16 = 128 bytes = one 128B swizzle row
 constexpr int kRankPad = 64;         // H tile width (r <= 64, zero padded by TMA)
-constexpr int kThreads = 256;
-constexpr int kEpiThreads = 128;
-constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KiB
-constexpr int kDnTileBytes = kRankPad * kBlockK * 2; // 8 KiB
-constexpr int kHsBytes = kBlockM * kRankPad * 2;     // 16 KiB
-constexpr int kStgBytesPerBuf = 32 * 64;             // one warp: 32 rows x 32 bf16
-constexpr int kStgBytes = 4 * 2 * kStgBytesPerBuf;   // 4 warps x double buffer
+constexpr int kThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;          // 16 KiB
+constexpr int kDnHalfBytes = (kRankPad / 2) * kBlockK * 2;  // 4 KiB: this CTA's 32 rows of Dn
+constexpr int kHsBytes = kBlockM * kRankPad * 2;            // 16 KiB
+constexpr uint16_t kBothCtas = 0x3;
 
 struct LoraGemmParams {
-  CUtensorMap tmap_a;    // A  [M, K]   box {64, 128} swizzle 128B
-  CUtensorMap tmap_w;    // W  [N, K]   box {64, BN}  swizzle 128B
-  CUtensorMap tmap_dn;   // Dn [r, K]   box {64, 64}  swizzle 128B
-  CUtensorMap tmap_up;   // Up [N, r]   box {64, BN}  swizzle 128B
-  CUtensorMap tmap_y;    // Y  [M, N]   box {32, 32}  swizzle 64B (store)
+  CUtensorMap tmap_a;    // A  [M, K]   box {64, 128}    swizzle 128B
+  CUtensorMap tmap_w;    // W  [N, K]   box {64, BN/2}   swizzle 128B
+  CUtensorMap tmap_dn;   // Dn [r, K]   box {64, 32}     swizzle 128B
+  CUtensorMap tmap_up;   // Up [N, r]   box {64, BN/2}   swizzle 128B
   const __nv_bfloat16* bias;   // [N] or null
   const float* scale;          // [num_samples, r]
+  __nv_bfloat16* y;            // [M, ldy]
   __nv_bfloat16* aux_out0;     // mode 0: H [M, r] (may be null); mode 1: dH [M, r]
   __nv_bfloat16* aux_out1;     // mode 1: Hs [M, r]
   const __nv_bfloat16* h_in;   // mode 1: H [M, r] saved by the forward
   float* g_scale;              // mode 1: [num_samples, r] accumulated (may be null)
   long long tokens;            // rows per sample
+  long long ldy;
   int num_samples;
   int M, N, K, r;
-  int num_m_tiles, num_n_tiles, group_size, num_groups;
+  int num_m_pairs, num_n_tiles, group_size, num_groups;
   int mode;       // 0 forward, 1 backward (dX)
   int has_lora;   // 0: plain GEMM
   int has_main;   // 0: only the H phase + mid epilogue (backward of layers whose input needs no gradient)
@@ -55,24 +63,39 @@ struct LoraGemmParams {
 
 template <int BN>
 struct SmemLayout {
-  static constexpr int kWTileBytes = BN * kBlockK * 2;
-  static constexpr int kStageBytes = kATileBytes + kWTileBytes + kDnTileBytes;
+  static constexpr int kNC = BN / 2;                         // accumulator columns per epilogue warp
+  static constexpr int kWHalfBytes = (BN / 2) * kBlockK * 2;
+  static constexpr int kStageBytes = kATileBytes + kWHalfBytes + kDnHalfBytes;
+  static constexpr int kNCP = kNC / 2;                       // columns per epilogue pass (two passes per tile)
+  static constexpr int kStgStride16 = (kNCP / 8 + 1) | 1;    // row stride in 16B units, odd: conflict-free 16B accesses
+  static constexpr int kStgStride = kStgStride16 * 16;
+  static constexpr int kStgWarpBytes = 32 * kStgStride;
+  static constexpr int kStgBytes = kEpiWarps * kStgWarpBytes;
+  static constexpr int kBiasWarpBytes = 256;                 // this warp's slice of the bias row (kNC bf16 <= 192 B)
+  static constexpr int kBiasBytes = kEpiWarps * kBiasWarpBytes;
   static constexpr int kBudget = 232448 - 1024 /*alignment slack*/ - 512 /*barriers*/;
-  static constexpr int kStagesRaw = (kBudget - kHsBytes - kStgBytes) / kStageBytes;
+  static constexpr int kStagesRaw = (kBudget - kHsBytes - kStgBytes - kBiasBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kHsOff = kStages * kStageBytes;
   static constexpr int kStgOff = kHsOff + kHsBytes;
-  static constexpr int kBarOff = kStgOff + kStgBytes;
+  static constexpr int kBiasOff = kStgOff + kStgBytes;
+  static constexpr int kBarOff = kBiasOff + kBiasBytes;
   static constexpr int kTotal = kBarOff + 512 + 1024;
-  static_assert(kStages >= 2, "not enough shared memory for a pipeline");
-  static_assert(kWTileBytes % 1024 == 0, "W tile must keep 1024B alignment");
+  static_assert(kStages >= 3, "not enough shared memory for a pipeline");
+  static_assert(kWHalfBytes % 1024 == 0, "W tile must keep 1024B alignment");
+  static_assert(BN % 32 == 0, "two epilogue column halves of whole 16-column TMEM loads, each stored in two 8-column-aligned passes");
   static_assert(2 * BN + kRankPad <= 512, "TMEM budget");
+  static_assert((2 * kStages + 7) * 8 <= 512, "barrier block");
 };
 
-// 64 values per lane, 32 lanes -> lane L ends with the column sums of columns 2L and 2L+1 in v[0], v[1].
-__device__ __forceinline__ void warp_colsum64(float (&v)[64], int lane) {
+template <bool B>
+struct BoolC { static constexpr bool value = B; };
+
+// N values per lane, 32 lanes -> lane L ends with the column sums of columns L*N/32 ... in v[0 .. N/32).
+template <int N>
+__device__ __forceinline__ void warp_colsum(float (&v)[N], int lane) {
 #pragma unroll
-  for (int w = 32, bit = 16; w >= 2; w >>= 1, bit >>= 1) {
+  for (int w = N / 2, bit = 16; bit >= 1; w >>= 1, bit >>= 1) {
     const bool up = (lane & bit) != 0;
 #pragma unroll
     for (int i = 0; i < w; ++i) {
@@ -84,360 +107,443 @@ __device__ __forceinline__ void warp_colsum64(float (&v)[64], int lane) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1) lora_gemm_kernel(const __grid_constant__ LoraGemmParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_gemm_kernel(const __grid_constant__ LoraGemmParams p) {
   using L = SmemLayout<BN>;
   constexpr int kStages = L::kStages;
+  constexpr int NC = L::kNC;
   extern __shared__ uint8_t smem_raw[];
   // 1024B alignment: required by the 128B swizzle atoms referenced through UMMA descriptors
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
 
   const uint32_t bar_base = smem_base + L::kBarOff;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto acc_full_bar = [&](int b) { return bar_base + 8u * (2 * kStages + b); };
-  auto acc_empty_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 2 + b); };
-  const uint32_t h_full_bar = bar_base + 8u * (2 * kStages + 4);
-  const uint32_t hs_ready_bar = bar_base + 8u * (2 * kStages + 5);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // waited on in the leader only
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };          // both CTAs (multicast commit)
+  auto acc_full_bar = [&](int b) { return bar_base + 8u * (2 * kStages + b); };   // both CTAs (multicast commit)
+  auto acc_empty_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 2 + b); };  // leader: 16 warp arrivals
+  const uint32_t h_full_bar = bar_base + 8u * (2 * kStages + 4);                  // both CTAs (multicast commit)
+  const uint32_t hs_ready_bar = bar_base + 8u * (2 * kStages + 5);                // leader: 16 warp arrivals
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 6);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kBarOff + 8 * (2 * kStages + 6));
 
   auto a_tile = [&](int s) { return smem_base + s * L::kStageBytes; };
   auto w_tile = [&](int s) { return smem_base + s * L::kStageBytes + kATileBytes; };
-  auto dn_tile = [&](int s) { return smem_base + s * L::kStageBytes + kATileBytes + L::kWTileBytes; };
+  auto dn_tile = [&](int s) { return smem_base + s * L::kStageBytes + kATileBytes + L::kWHalfBytes; };
   const uint32_t hs_tile = smem_base + L::kHsOff;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
-    if (p.has_main) {
-      tma_prefetch_desc(&p.tmap_w);
-      tma_prefetch_desc(&p.tmap_y);
-    }
+    if (p.has_main) tma_prefetch_desc(&p.tmap_w);
     if (p.has_lora) {
       tma_prefetch_desc(&p.tmap_dn);
       if (p.has_main) tma_prefetch_desc(&p.tmap_up);
     }
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full_bar(b), 1);
-      mbar_init(acc_empty_bar(b), kEpiThreads);
+      mbar_init(acc_empty_bar(b), 2 * kEpiWarps);
     }
     mbar_init(h_full_bar, 1);
-    mbar_init(hs_ready_bar, kEpiThreads);
+    mbar_init(hs_ready_bar, 2 * kEpiWarps);
     fence_mbar_init();
   }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+  if (warp == kMmaWarp) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
-  const int total_items = p.num_m_tiles * p.num_groups;
+  const int total_items = p.num_m_pairs * p.num_groups;
+  const int item0 = blockIdx.x >> 1, item_step = gridDim.x >> 1;
 
-  if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int m_tile = item % p.num_m_tiles;
-        const int grp = item / p.num_m_tiles;
-        const int m0 = m_tile * kBlockM;
-        const int nt_begin = grp * p.group_size;
-        const int nt_end = min(nt_begin + p.group_size, p.num_n_tiles);
+  if (warp == kProducerWarp) {
+    // =========================== TMA producer (both CTAs; converged warp, one elected lane issues) ===========================
+    int stage = 0;
+    uint32_t phase = 0;
+    const int w_row_off = (int)cta_rank * (BN / 2);
+    const int dn_row_off = (int)cta_rank * (kRankPad / 2);
+    auto k_loads = [&](int m0, int n0, bool first) {
+      const uint32_t bytes = 2u * (kATileBytes + (p.has_main ? L::kWHalfBytes : 0) + (first ? kDnHalfBytes : 0));
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t fb = mapa_shared(full_bar(stage), 0);
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), bytes);
+          tma_load_2d_pair(a_tile(stage), &p.tmap_a, fb, kb * kBlockK, m0);
+          if (p.has_main) tma_load_2d_pair(w_tile(stage), &p.tmap_w, fb, kb * kBlockK, n0 + w_row_off);
+          if (first) tma_load_2d_pair(dn_tile(stage), &p.tmap_dn, fb, kb * kBlockK, dn_row_off);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    };
+    auto up_load = [&](int n0) {
+      // the rank-r extra k-block: only the Up tile travels; its A operand (Hs) is produced on chip
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      if (elect_one()) {
+        const uint32_t fb = mapa_shared(full_bar(stage), 0);
+        if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * L::kWHalfBytes);
+        tma_load_2d_pair(w_tile(stage), &p.tmap_up, fb, 0, n0 + w_row_off);
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    };
+    for (int item = item0; item < total_items; item += item_step) {
+      const int m_pair = item % p.num_m_pairs;
+      const int grp = item / p.num_m_pairs;
+      const int m0 = m_pair * kPairM + (int)cta_rank * kBlockM;
+      const int nt_begin = grp * p.group_size;
+      const int nt_end = min(nt_begin + p.group_size, p.num_n_tiles);
+      const bool fused = p.has_lora && p.has_main;
+      if (fused && nt_end - nt_begin >= 2) {
+        // deferred order: the Hs.Up k-blocks of the first two tiles follow the second tile's main loop
+        k_loads(m0, nt_begin * BN, true);
+        k_loads(m0, (nt_begin + 1) * BN, false);
+        up_load(nt_begin * BN);
+        up_load((nt_begin + 1) * BN);
+        for (int nt = nt_begin + 2; nt < nt_end; ++nt) {
+          k_loads(m0, nt * BN, false);
+          up_load(nt * BN);
+        }
+      } else {
         for (int nt = nt_begin; nt < nt_end; ++nt) {
-          const int n0 = nt * BN;
           const bool first = (nt == nt_begin) && p.has_lora;
-          if (p.has_main || first) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              const uint32_t bytes = kATileBytes + (p.has_main ? L::kWTileBytes : 0) + (first ? kDnTileBytes : 0);
-              mbar_arrive_expect_tx(full_bar(stage), bytes);
-              tma_load_2d(a_tile(stage), &p.tmap_a, full_bar(stage), kb * kBlockK, m0);
-              if (p.has_main) tma_load_2d(w_tile(stage), &p.tmap_w, full_bar(stage), kb * kBlockK, n0);
-              if (first) tma_load_2d(dn_tile(stage), &p.tmap_dn, full_bar(stage), kb * kBlockK, 0);
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
-            }
-          }
-          if (p.has_lora && p.has_main) {
-            // the rank-r "65th k-block": only the Up tile travels; its A operand (Hs) is produced on chip
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_arrive_expect_tx(full_bar(stage), L::kWTileBytes);
-            tma_load_2d(w_tile(stage), &p.tmap_up, full_bar(stage), 0, n0);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-          }
+          if (p.has_main || first) k_loads(m0, nt * BN, first);
+          if (fused) up_load(nt * BN);
         }
       }
     }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      const uint32_t idesc_main = make_idesc_bf16(kBlockM, BN, 0, 0);
-      const uint32_t idesc_h = make_idesc_bf16(kBlockM, kRankPad, 0, 0);
+  } else if (warp == kMmaWarp) {
+    // =========================== MMA issuer (leader CTA; converged warp, one elected lane issues) ===========================
+    if (leader) {
+      const uint32_t idesc_main = make_idesc_bf16(kPairM, BN, 0, 0);
+      const uint32_t idesc_h = make_idesc_bf16(kPairM, kRankPad, 0, 0);
       const uint32_t tmem_h = tmem_base + 2 * BN;
+      // K-major 128B-swizzled operand tile: LBO 16 B, SBO 1024 B (8 rows); a 16-element k-step advances the start by 32 B
+      constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      auto desc = [&](uint32_t addr) { return kDescHi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
       int stage = 0;
       uint32_t phase = 0;
       uint32_t acc_iter = 0, item_iter = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++item_iter) {
-        const int grp = item / p.num_m_tiles;
+      auto acquire_acc = [&](uint32_t it) {
+        mbar_wait(acc_empty_bar(it & 1u), ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+      };
+      auto commit = [&](uint32_t bar) {
+        if (elect_one()) umma_commit_pair(bar, kBothCtas);
+        __syncwarp();
+      };
+      auto k_mmas_t = [&](uint32_t tmem_acc, auto main_c, auto first_c) {
+        constexpr bool kMain = decltype(main_c)::value;
+        constexpr bool kFirst = decltype(first_c)::value;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = desc(a_tile(stage));
+            const uint64_t wd = desc(w_tile(stage));
+            const uint64_t dd = desc(dn_tile(stage));
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint32_t acc_flag = (kb | k) != 0 ? 1u : 0u;
+              if constexpr (kMain) umma_f16_pair(tmem_acc, ad + 2 * k, wd + 2 * k, idesc_main, acc_flag);
+              if constexpr (kFirst) umma_f16_pair(tmem_h, ad + 2 * k, dd + 2 * k, idesc_h, acc_flag);
+            }
+            umma_commit_pair(empty_bar(stage), kBothCtas);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      };
+      using TrueC = BoolC<true>;
+      using FalseC = BoolC<false>;
+      auto k_mmas = [&](uint32_t tmem_acc, bool first) {
+        if (!p.has_main) k_mmas_t(tmem_acc, FalseC{}, TrueC{});
+        else if (first) k_mmas_t(tmem_acc, TrueC{}, TrueC{});
+        else k_mmas_t(tmem_acc, TrueC{}, FalseC{});
+      };
+      auto up_mmas = [&](uint32_t tmem_acc) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = desc(hs_tile);
+          const uint64_t wd = desc(w_tile(stage));
+#pragma unroll
+          for (int k = 0; k < kRankPad / 16; ++k) umma_f16_pair(tmem_acc, ad + 2 * k, wd + 2 * k, idesc_main, 1u);
+          umma_commit_pair(empty_bar(stage), kBothCtas);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      };
+      for (int item = item0; item < total_items; item += item_step, ++item_iter) {
+        const int grp = item / p.num_m_pairs;
         const int nt_begin = grp * p.group_size;
         const int nt_end = min(nt_begin + p.group_size, p.num_n_tiles);
-        for (int nt = nt_begin; nt < nt_end; ++nt) {
-          const bool first = (nt == nt_begin) && p.has_lora;
-          const uint32_t buf = acc_iter & 1u;
-          const uint32_t tmem_acc = tmem_base + buf * BN;
-          if (p.has_main) {
-            mbar_wait(acc_empty_bar(buf), ((acc_iter >> 1) & 1u) ^ 1u);
-            tc_fence_after();
-          }
-          if (p.has_main || first) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-              mbar_wait(full_bar(stage), phase);
-              tc_fence_after();
-#pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                const uint64_t adesc = make_smem_desc(a_tile(stage) + k * 32, 16, 1024, 2);
-                const uint32_t acc_flag = (kb | k) != 0 ? 1u : 0u;
-                if (p.has_main) {
-                  const uint64_t bdesc = make_smem_desc(w_tile(stage) + k * 32, 16, 1024, 2);
-                  umma_f16(tmem_acc, adesc, bdesc, idesc_main, acc_flag);
-                }
-                if (first) {
-                  const uint64_t ddesc = make_smem_desc(dn_tile(stage) + k * 32, 16, 1024, 2);
-                  umma_f16(tmem_h, adesc, ddesc, idesc_h, acc_flag);
-                }
-              }
-              umma_commit(empty_bar(stage));
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
-            }
-          }
-          if (first) {
-            umma_commit(h_full_bar);                       // H accumulated -> wake the epilogue warps
-            mbar_wait(hs_ready_bar, item_iter & 1u);       // Hs (bf16, swizzled) is in SMEM
-            tc_fence_after();
-          }
-          if (p.has_lora && p.has_main) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < kRankPad / 16; ++k) {
-              const uint64_t adesc = make_smem_desc(hs_tile + k * 32, 16, 1024, 2);
-              const uint64_t bdesc = make_smem_desc(w_tile(stage) + k * 32, 16, 1024, 2);
-              umma_f16(tmem_acc, adesc, bdesc, idesc_main, 1u);
-            }
-            umma_commit(empty_bar(stage));
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-          }
-          if (p.has_main) {
-            umma_commit(acc_full_bar(buf));
+        const bool fused = p.has_lora && p.has_main;
+        if (fused && nt_end - nt_begin >= 2) {
+          const uint32_t it0 = acc_iter, it1 = acc_iter + 1;
+          const uint32_t acc0 = tmem_base + (it0 & 1u) * BN, acc1 = tmem_base + (it1 & 1u) * BN;
+          acquire_acc(it0);
+          k_mmas(acc0, true);
+          commit(h_full_bar);                                // H accumulated -> wake the epilogue warps of both CTAs
+          acquire_acc(it1);
+          k_mmas(acc1, false);                               // the tensor core stays busy while Hs is being produced
+          mbar_wait(hs_ready_bar, item_iter & 1u);           // Hs (bf16, swizzled) is in both CTAs' SMEM
+          tc_fence_after();
+          up_mmas(acc0);
+          commit(acc_full_bar(it0 & 1u));
+          up_mmas(acc1);
+          commit(acc_full_bar(it1 & 1u));
+          acc_iter += 2;
+          for (int nt = nt_begin + 2; nt < nt_end; ++nt) {
+            const uint32_t acc = tmem_base + (acc_iter & 1u) * BN;
+            acquire_acc(acc_iter);
+            k_mmas(acc, false);
+            up_mmas(acc);
+            commit(acc_full_bar(acc_iter & 1u));
             ++acc_iter;
+          }
+        } else {
+          for (int nt = nt_begin; nt < nt_end; ++nt) {
+            const bool first = (nt == nt_begin) && p.has_lora;
+            const uint32_t acc = tmem_base + (acc_iter & 1u) * BN;
+            if (p.has_main) acquire_acc(acc_iter);
+            if (p.has_main || first) k_mmas(acc, first);
+            if (first) {
+              commit(h_full_bar);
+              mbar_wait(hs_ready_bar, item_iter & 1u);
+              tc_fence_after();
+            }
+            if (fused) up_mmas(acc);
+            if (p.has_main) {
+              commit(acc_full_bar(acc_iter & 1u));
+              ++acc_iter;
+            }
           }
         }
       }
     }
-  } else if (warp >= 4) {
-    // =========================== epilogue warps ===========================
-    const int q = warp - 4;  // TMEM lane quadrant == warp_id % 4
+  } else {
+    // =========================== epilogue warps (both CTAs) ===========================
+    const int q = warp & 3;       // TMEM lane quadrant == warp_id % 4
+    const int half = warp >> 2;   // which half of the tile's columns (and of H's 64 columns)
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const uint32_t stg_base = smem_base + L::kStgOff + q * 2 * kStgBytesPerBuf;
     uint8_t* hs_gen = smem_gen + L::kHsOff;
-    uint8_t* stg_gen = smem_gen + L::kStgOff + q * 2 * kStgBytesPerBuf;
+    uint8_t* stg_gen = smem_gen + L::kStgOff + warp * L::kStgWarpBytes;
+    uint32_t* bias_sm = reinterpret_cast<uint32_t*>(smem_gen + L::kBiasOff + warp * L::kBiasWarpBytes);
     const int row_in_tile = q * 32 + lane;
-    uint32_t acc_iter = 0, item_iter = 0, store_iter = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++item_iter) {
-      const int m_tile = item % p.num_m_tiles;
-      const int grp = item / p.num_m_tiles;
-      const int m0 = m_tile * kBlockM;
+    const uint32_t acc_empty_remote[2] = {mapa_shared(acc_empty_bar(0), 0), mapa_shared(acc_empty_bar(1), 0)};
+    const uint32_t hs_ready_remote = mapa_shared(hs_ready_bar, 0);
+    uint32_t acc_iter = 0, item_iter = 0;
+    for (int item = item0; item < total_items; item += item_step, ++item_iter) {
+      const int m_pair = item % p.num_m_pairs;
+      const int grp = item / p.num_m_pairs;
+      const int m0 = m_pair * kPairM + (int)cta_rank * kBlockM;
       const int nt_begin = grp * p.group_size;
       const int nt_end = min(nt_begin + p.group_size, p.num_n_tiles);
       const long long grow = (long long)m0 + row_in_tile;
       const bool row_ok = grow < p.M;
       const bool aux_owner = row_ok && grp == 0;   // side outputs (H / dH / Hs / dscale) are emitted once per row block
-      for (int nt = nt_begin; nt < nt_end; ++nt) {
-        const int n0 = nt * BN;
-        const bool first = (nt == nt_begin) && p.has_lora;
-        if (first) {
-          // ---------------- mid epilogue: H (TMEM, fp32) -> Hs (SMEM, bf16, 128B-swizzled K-major) ----------------
-          long long sample = grow / p.tokens;
-          if (sample > p.num_samples - 1) sample = p.num_samples - 1;
-          const float* sp = p.scale + sample * p.r;
-          const size_t aux_off = (size_t)grow * p.r;
-          uint4 hin[8];
-          if (p.mode == 1) {
+      if (p.has_lora) {
+        // ---------------- mid epilogue: H (TMEM, fp32) -> Hs (SMEM, bf16, 128B-swizzled K-major) ----------------
+        // this warp: 32 rows x H columns [32 * half, 32 * half + 32)
+        const int hc0 = 32 * half;
+        long long sample = grow / p.tokens;
+        if (sample > p.num_samples - 1) sample = p.num_samples - 1;
+        const float* sp = p.scale + sample * p.r + hc0;
+        const size_t aux_off = (size_t)grow * p.r + hc0;
+        uint4 hin[4];
+        if (p.mode == 1) {
 #pragma unroll
-            for (int j8 = 0; j8 < 8; ++j8) {
-              hin[j8] = make_uint4(0, 0, 0, 0);
-              if (row_ok && j8 * 8 < p.r) hin[j8] = __ldg(reinterpret_cast<const uint4*>(p.h_in + aux_off + j8 * 8));
-            }
-          }
-          mbar_wait(h_full_bar, item_iter & 1u);
-          tc_fence_after();
-          float v[64];
-          {
-            uint32_t t0[32], t1[32];
-            tmem_ld_32x32(tmem_base + lane_base + 2 * BN, t0);
-            tmem_ld_32x32(tmem_base + lane_base + 2 * BN + 32, t1);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              v[i] = __uint_as_float(t0[i]);
-              v[32 + i] = __uint_as_float(t1[i]);
-            }
-          }
-#pragma unroll
-          for (int j8 = 0; j8 < 8; ++j8) {
-            uint4 to_smem = make_uint4(0, 0, 0, 0);
-            if (j8 * 8 < p.r) {
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp + j8 * 8));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(sp + j8 * 8 + 4));
-              const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-              float hb[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) hb[i] = bf16_round(v[j8 * 8 + i]);
-              if (p.mode == 0) {
-                to_smem.x = pack_bf16x2(hb[0] * s[0], hb[1] * s[1]);
-                to_smem.y = pack_bf16x2(hb[2] * s[2], hb[3] * s[3]);
-                to_smem.z = pack_bf16x2(hb[4] * s[4], hb[5] * s[5]);
-                to_smem.w = pack_bf16x2(hb[6] * s[6], hb[7] * s[7]);
-                if (aux_owner && p.aux_out0 != nullptr) {
-                  uint4 hraw;
-                  hraw.x = pack_bf16x2(hb[0], hb[1]);
-                  hraw.y = pack_bf16x2(hb[2], hb[3]);
-                  hraw.z = pack_bf16x2(hb[4], hb[5]);
-                  hraw.w = pack_bf16x2(hb[6], hb[7]);
-                  *reinterpret_cast<uint4*>(p.aux_out0 + aux_off + j8 * 8) = hraw;
-                }
-              } else {
-                // hb = dHs (bf16-rounded like the reference's bf16 matmul output); hin = saved H
-                const uint32_t hw[4] = {hin[j8].x, hin[j8].y, hin[j8].z, hin[j8].w};
-                float hval[8];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  hval[2 * i] = bf16_lo(hw[i]);
-                  hval[2 * i + 1] = bf16_hi(hw[i]);
-                }
-                to_smem.x = pack_bf16x2(hb[0] * s[0], hb[1] * s[1]);
-                to_smem.y = pack_bf16x2(hb[2] * s[2], hb[3] * s[3]);
-                to_smem.z = pack_bf16x2(hb[4] * s[4], hb[5] * s[5]);
-                to_smem.w = pack_bf16x2(hb[6] * s[6], hb[7] * s[7]);
-                if (aux_owner) {
-                  *reinterpret_cast<uint4*>(p.aux_out0 + aux_off + j8 * 8) = to_smem;  // dH
-                  uint4 hs;
-                  hs.x = pack_bf16x2(hval[0] * s[0], hval[1] * s[1]);
-                  hs.y = pack_bf16x2(hval[2] * s[2], hval[3] * s[3]);
-                  hs.z = pack_bf16x2(hval[4] * s[4], hval[5] * s[5]);
-                  hs.w = pack_bf16x2(hval[6] * s[6], hval[7] * s[7]);
-                  *reinterpret_cast<uint4*>(p.aux_out1 + aux_off + j8 * 8) = hs;       // Hs
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[j8 * 8 + i] = hb[i] * hval[i];  // dscale integrand
-              }
-            } else if (p.mode == 1) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[j8 * 8 + i] = 0.f;
-            }
-            *reinterpret_cast<uint4*>(hs_gen + row_in_tile * 128 + ((j8 ^ (row_in_tile & 7)) << 4)) = to_smem;
-          }
-          tc_fence_before();
-          fence_proxy_async_smem();   // generic-proxy SMEM writes -> visible to the tensor-core (async) proxy
-          mbar_arrive(hs_ready_bar);
-          if (p.mode == 1 && p.g_scale != nullptr && grp == 0) {
-            // dscale[b, j] += sum over this tile's rows of dHs * H
-            const long long first_row = (long long)m0 + q * 32;
-            const bool uniform = (p.tokens % 32 == 0) && (first_row + 32 <= p.M);
-            if (uniform) {
-              warp_colsum64(v, lane);
-              const int c = 2 * lane;
-              if (c < p.r) {
-                atomicAdd(p.g_scale + sample * p.r + c, v[0]);
-                atomicAdd(p.g_scale + sample * p.r + c + 1, v[1]);
-              }
-            } else if (row_ok) {
-#pragma unroll
-              for (int j = 0; j < 64; ++j)
-                if (j < p.r) atomicAdd(p.g_scale + sample * p.r + j, v[j]);
-            }
+          for (int j8 = 0; j8 < 4; ++j8) {
+            hin[j8] = make_uint4(0, 0, 0, 0);
+            if (row_ok && hc0 + j8 * 8 < p.r) hin[j8] = __ldg(reinterpret_cast<const uint4*>(p.h_in + aux_off + j8 * 8));
           }
         }
-        if (!p.has_main) continue;
-        // ---------------- tile epilogue: accumulator -> (+bias) -> bf16 -> staging -> TMA store ----------------
-        const uint32_t buf = acc_iter & 1u;
-        mbar_wait(acc_full_bar(buf), (acc_iter >> 1) & 1u);
+        float4 sc4[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          sc4[j4] = (hc0 + j4 * 4 < p.r) ? __ldg(reinterpret_cast<const float4*>(sp + j4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(h_full_bar, item_iter & 1u);
         tc_fence_after();
-        const int cols_left = p.N - n0;
-        const int nchunks = min(BN / 32, (cols_left + 31) / 32);
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t t[32];
-          tmem_ld_32x32(tmem_base + lane_base + buf * BN + c * 32, t);
+        float v[32];
+        {
+          uint32_t t0[32];
+          tmem_ld_32x16(tmem_base + lane_base + 2 * BN + hc0, t0);
+          tmem_ld_32x16(tmem_base + lane_base + 2 * BN + hc0 + 16, t0 + 16);
           tmem_wait_ld();
-          if (c == nchunks - 1) {
-            tc_fence_before();
-            mbar_arrive(acc_empty_bar(buf));   // accumulator drained -> MMA may start the tile after next
-          }
-          const int col0 = n0 + c * 32;
-          float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(t[i]);
-          if (p.bias != nullptr) {
-            if (col0 + 32 <= p.N) {
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(t0[i]);
+        }
 #pragma unroll
-              for (int i4 = 0; i4 < 4; ++i4) {
-                const uint4 bw = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + i4 * 8));
-                const uint32_t bb[4] = {bw.x, bw.y, bw.z, bw.w};
+        for (int j8 = 0; j8 < 4; ++j8) {
+          uint4 to_smem = make_uint4(0, 0, 0, 0);
+          if (hc0 + j8 * 8 < p.r) {
+            const float4 s0 = sc4[2 * j8], s1 = sc4[2 * j8 + 1];
+            const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            float hb[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  f[i4 * 8 + 2 * i] += bf16_lo(bb[i]);
-                  f[i4 * 8 + 2 * i + 1] += bf16_hi(bb[i]);
-                }
+            for (int i = 0; i < 8; ++i) hb[i] = bf16_round(v[j8 * 8 + i]);
+            to_smem.x = pack_bf16x2(hb[0] * s[0], hb[1] * s[1]);
+            to_smem.y = pack_bf16x2(hb[2] * s[2], hb[3] * s[3]);
+            to_smem.z = pack_bf16x2(hb[4] * s[4], hb[5] * s[5]);
+            to_smem.w = pack_bf16x2(hb[6] * s[6], hb[7] * s[7]);
+            if (p.mode == 0) {
+              if (aux_owner && p.aux_out0 != nullptr) {
+                uint4 hraw;
+                hraw.x = pack_bf16x2(hb[0], hb[1]);
+                hraw.y = pack_bf16x2(hb[2], hb[3]);
+                hraw.z = pack_bf16x2(hb[4], hb[5]);
+                hraw.w = pack_bf16x2(hb[6], hb[7]);
+                *reinterpret_cast<uint4*>(p.aux_out0 + aux_off + j8 * 8) = hraw;
               }
             } else {
+              // hb = dHs (bf16-rounded like the reference's bf16 matmul output); hin = saved H
+              const uint32_t hw[4] = {hin[j8].x, hin[j8].y, hin[j8].z, hin[j8].w};
+              float hval[8];
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) f[i] += __bfloat162float(p.bias[col0 + i]);
+              for (int i = 0; i < 4; ++i) {
+                hval[2 * i] = bf16_lo(hw[i]);
+                hval[2 * i + 1] = bf16_hi(hw[i]);
+              }
+              if (aux_owner) {
+                *reinterpret_cast<uint4*>(p.aux_out0 + aux_off + j8 * 8) = to_smem;  // dH
+                uint4 hs;
+                hs.x = pack_bf16x2(hval[0] * s[0], hval[1] * s[1]);
+                hs.y = pack_bf16x2(hval[2] * s[2], hval[3] * s[3]);
+                hs.z = pack_bf16x2(hval[4] * s[4], hval[5] * s[5]);
+                hs.w = pack_bf16x2(hval[6] * s[6], hval[7] * s[7]);
+                *reinterpret_cast<uint4*>(p.aux_out1 + aux_off + j8 * 8) = hs;       // Hs
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[j8 * 8 + i] = row_ok ? hb[i] * hval[i] : 0.f;  // dscale integrand
             }
-          }
-          const uint32_t sb = store_iter & 1u;
-          if (lane == 0) tma_store_wait_read<1>();   // the store that last used this buffer has read it
-          __syncwarp();
-          uint8_t* dst = stg_gen + sb * kStgBytesPerBuf + lane * 64;
+          } else if (p.mode == 1) {
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint4 o;
-            o.x = pack_bf16x2(f[ch * 8 + 0], f[ch * 8 + 1]);
-            o.y = pack_bf16x2(f[ch * 8 + 2], f[ch * 8 + 3]);
-            o.z = pack_bf16x2(f[ch * 8 + 4], f[ch * 8 + 5]);
-            o.w = pack_bf16x2(f[ch * 8 + 6], f[ch * 8 + 7]);
-            *reinterpret_cast<uint4*>(dst + ((ch ^ ((lane >> 1) & 3)) << 4)) = o;   // 64B swizzle
+            for (int i = 0; i < 8; ++i) v[j8 * 8 + i] = 0.f;
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&p.tmap_y, stg_base + sb * kStgBytesPerBuf, col0, m0 + q * 32);
-            tma_store_commit();
-          }
-          ++store_iter;
+          const int chunk = 4 * half + j8;   // 16-byte chunk inside the 128-byte swizzled row
+          *reinterpret_cast<uint4*>(hs_gen + row_in_tile * 128 + ((chunk ^ (row_in_tile & 7)) << 4)) = to_smem;
         }
+        tc_fence_before();
+        fence_proxy_async_smem();   // generic-proxy SMEM writes -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(hs_ready_remote);
+        if (p.mode == 1 && p.g_scale != nullptr && grp == 0) {
+          // dscale[b, j] += sum over this tile's rows of dHs * H
+          const long long first_row = (long long)m0 + q * 32;
+          const bool uniform = (p.tokens % 32 == 0) && (first_row + 32 <= p.M);
+          if (uniform) {
+            warp_colsum<32>(v, lane);
+            if (hc0 + lane < p.r) atomicAdd(p.g_scale + sample * p.r + hc0 + lane, v[0]);
+          } else if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (hc0 + j < p.r) atomicAdd(p.g_scale + sample * p.r + hc0 + j, v[j]);
+          }
+        }
+      }
+      if (!p.has_main) continue;
+      for (int nt = nt_begin; nt < nt_end; ++nt) {
+        // ---------------- tile epilogue: accumulator -> (+bias) -> bf16 -> SMEM transpose -> coalesced stores ----------------
+        const int col0 = nt * BN + half * NC;   // first global column of this warp's slice
+        const uint32_t buf = acc_iter & 1u;
+        // this warp's NC bias values: global loads issued before the accumulator wait, parked in SMEM after the TMEM loads
+        // are in flight (a dependent load between tcgen05.ld and the stores was 11-16 % of the epilogue's stall samples)
+        uint32_t bias_r[(NC / 2 + 31) / 32] = {};
+        if (p.bias != nullptr) {
+          const uint32_t* bw = reinterpret_cast<const uint32_t*>(p.bias + col0);
+#pragma unroll
+          for (int j = 0; j < (NC / 2 + 31) / 32; ++j) {
+            const int w = j * 32 + lane;
+            bias_r[j] = (w < NC / 2 && col0 + 2 * w < p.N) ? __ldg(bw + w) : 0u;
+          }
+        }
+        mbar_wait(acc_full_bar(buf), (acc_iter >> 1) & 1u);
+        tc_fence_after();
+        uint32_t t[NC];
+#pragma unroll
+        for (int c = 0; c < NC / 16; ++c) tmem_ld_32x16(tmem_base + lane_base + buf * BN + half * NC + c * 16, t + c * 16);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < (NC / 2 + 31) / 32; ++j) {
+            const int w = j * 32 + lane;
+            if (w < NC / 2) bias_sm[w] = bias_r[j];
+          }
+        }
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(acc_empty_remote[buf]);   // drained -> the MMA thread may reuse this accumulator
         ++acc_iter;
+        if (col0 >= p.N) continue;   // whole slice past the last column (partial last tile)
+        constexpr int NCP = L::kNCP;     // columns per pass
+        constexpr int kCpr = NCP / 8;    // 16-byte chunks per row and pass
+        const long long row_base = (long long)m0 + q * 32;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const int pcol0 = col0 + pass * NCP;
+#pragma unroll
+          for (int c8 = 0; c8 < kCpr; ++c8) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(t[pass * NCP + c8 * 8 + i]);
+            if (p.bias != nullptr) {
+              const uint4 bw = *reinterpret_cast<const uint4*>(bias_sm + (pass * NCP + c8 * 8) / 2);
+              const uint32_t bb[4] = {bw.x, bw.y, bw.z, bw.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                f[2 * i] += bf16_lo(bb[i]);
+                f[2 * i + 1] += bf16_hi(bb[i]);
+              }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]);
+            o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]);
+            o.w = pack_bf16x2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(stg_gen + lane * L::kStgStride + c8 * 16) = o;
+          }
+          __syncwarp();
+          // row-contiguous read-back: 32 consecutive 16-byte chunks per instruction -> each row's slice is one contiguous run
+          uint4 o[kCpr];
+#pragma unroll
+          for (int i = 0; i < kCpr; ++i) {
+            const int c = i * 32 + lane;
+            o[i] = *reinterpret_cast<const uint4*>(stg_gen + (c / kCpr) * L::kStgStride + (c % kCpr) * 16);
+          }
+#pragma unroll
+          for (int i = 0; i < kCpr; ++i) {
+            const int c = i * 32 + lane;
+            const int row = c / kCpr, col = pcol0 + (c % kCpr) * 8;
+            if (row_base + row < p.M && col < p.N)
+              *reinterpret_cast<uint4*>(p.y + (size_t)(row_base + row) * p.ldy + col) = o[i];
+          }
+          __syncwarp();
+        }
       }
     }
-    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  cluster_sync_all();   // no CTA leaves while its pair may still read its SMEM / signal its barriers
+  if (warp == kMmaWarp) tmem_dealloc_pair(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -459,31 +565,28 @@ static int launch_bn(const LoraGemmArgs& a, cudaStream_t stream) {
   if (a.has_main) {
     uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
     uint64_t str[1] = {(uint64_t)a.K * 2};
-    uint32_t box[2] = {kBlockK, (uint32_t)BN};
+    uint32_t box[2] = {kBlockK, (uint32_t)(BN / 2)};
     int rc = make_tmap(&p.tmap_w, a.w, 2, 2, dims, str, box, kSwz128);
-    if (rc) return rc;
-    uint64_t ydims[2] = {(uint64_t)a.N, (uint64_t)a.M};
-    uint64_t ystr[1] = {(uint64_t)a.ldy * 2};
-    uint32_t ybox[2] = {32, 32};
-    rc = make_tmap(&p.tmap_y, a.y, 2, 2, ydims, ystr, ybox, kSwz64);
     if (rc) return rc;
   }
   if (has_lora) {
     uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.r};
     uint64_t str[1] = {(uint64_t)a.K * 2};
-    uint32_t box[2] = {kBlockK, kRankPad};
+    uint32_t box[2] = {kBlockK, kRankPad / 2};
     int rc = make_tmap(&p.tmap_dn, a.dn, 2, 2, dims, str, box, kSwz128);
     if (rc) return rc;
     if (a.has_main) {
       uint64_t udims[2] = {(uint64_t)a.r, (uint64_t)a.N};
       uint64_t ustr[1] = {(uint64_t)a.r * 2};
-      uint32_t ubox[2] = {kRankPad, (uint32_t)BN};
+      uint32_t ubox[2] = {kRankPad, (uint32_t)(BN / 2)};
       rc = make_tmap(&p.tmap_up, a.up, 2, 2, udims, ustr, ubox, kSwz128);
       if (rc) return rc;
     }
   }
   p.bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
   p.scale = a.scale;
+  p.y = reinterpret_cast<__nv_bfloat16*>(a.y);
+  p.ldy = a.ldy;
   p.aux_out0 = reinterpret_cast<__nv_bfloat16*>(a.aux_out0);
   p.aux_out1 = reinterpret_cast<__nv_bfloat16*>(a.aux_out1);
   p.h_in = reinterpret_cast<const __nv_bfloat16*>(a.h_in);
@@ -492,11 +595,12 @@ static int launch_bn(const LoraGemmArgs& a, cudaStream_t stream) {
   p.num_samples = (int)((a.M + p.tokens - 1) / p.tokens);
   p.M = (int)a.M; p.N = a.N; p.K = a.K; p.r = a.r;
   p.mode = a.mode; p.has_lora = has_lora; p.has_main = a.has_main;
-  p.num_m_tiles = (int)((a.M + kBlockM - 1) / kBlockM);
+  p.num_m_pairs = (int)((a.M + kPairM - 1) / kPairM);
   p.num_n_tiles = a.has_main ? (a.N + BN - 1) / BN : 1;
 
   const int sms = sm_count();
-  if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
+  if (sms < 2) return fail(AQ_ERR_LAUNCH, "no CUDA device");
+  const int slots = sms / 2;   // CTA pairs resident at once
   // Column tiles per work item: the H phase is paid once per item, wave quantisation once per launch.
   int best_g = 1;
   if (a.force_group > 0) {
@@ -506,18 +610,20 @@ static int launch_bn(const LoraGemmArgs& a, cudaStream_t stream) {
     const double kb = (double)((a.K + kBlockK - 1) / kBlockK);
     for (int g = 1; g <= p.num_n_tiles; ++g) {
       const int groups = (p.num_n_tiles + g - 1) / g;
-      const long long items = (long long)groups * p.num_m_tiles;
-      const long long waves = (items + sms - 1) / sms;
-      // per item: g tiles of (kb + 1) k-blocks of width BN, plus the H phase (kb k-blocks of width 64) and its bubble
-      const double item_cost = g * (kb + (has_lora ? 1.0 : 0.0)) * BN + (has_lora ? kb * kRankPad + 6.0 * BN : 0.0);
+      const long long items = (long long)groups * p.num_m_pairs;
+      const long long waves = (items + slots - 1) / slots;
+      // per item: g tiles of (kb + 1) k-blocks of width BN, plus the H phase (kb k-blocks of width 64); a single-tile
+      // item cannot hide the H -> Hs round trip behind the next tile's main loop
+      const double bubble = has_lora ? (g == 1 ? 6.0 * BN : 1.0 * BN) : 0.0;
+      const double item_cost = g * (kb + (has_lora ? 1.0 : 0.0)) * BN + (has_lora ? kb * kRankPad : 0.0) + bubble;
       const double cost = (double)waves * item_cost;
       if (cost < best_cost - 1e-9) { best_cost = cost; best_g = g; }
     }
   }
   p.group_size = best_g;
   p.num_groups = (p.num_n_tiles + best_g - 1) / best_g;
-  const long long items = (long long)p.num_groups * p.num_m_tiles;
-  const int grid = (int)(items < sms ? items : sms);
+  const long long items = (long long)p.num_groups * p.num_m_pairs;
+  const int grid = 2 * (int)(items < slots ? items : slots);
 
   static bool attr_set = false;   // benign race: idempotent
   if (!attr_set) {
@@ -530,23 +636,20 @@ static int launch_bn(const LoraGemmArgs& a, cudaStream_t stream) {
 }
 
 static int pick_bn(int N) {
-  if (N % 160 == 0) return 160;
-  if (N % 192 == 0) return 192;
-  if (N % 128 == 0) return 128;
   if (N <= 64) return 64;
-  // least padded columns, prefer the wider tile on ties
-  int best = 192, best_pad = 1 << 30;
-  const int cand[4] = {192, 160, 128, 64};
-  for (int i = 0; i < 4; ++i) {
-    const int pad = (N + cand[i] - 1) / cand[i] * cand[i] - N;
-    if (pad < best_pad) { best_pad = pad; best = cand[i]; }
+  // fewest computed columns; ties go to the wider tile (more FLOPs per byte staged through SMEM)
+  int best = 192, best_cols = 1 << 30;
+  const int cand[3] = {192, 160, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int cols = (N + cand[i] - 1) / cand[i] * cand[i];
+    if (cols < best_cols) { best_cols = cols; best = cand[i]; }
   }
   return best;
 }
 
 int launch_lora_gemm(const LoraGemmArgs& a, cudaStream_t stream) {
   AQ_REQUIRE(a.M > 0 && a.K > 0, AQ_ERR_BAD_SHAPE, "lora_gemm: empty problem M=%lld K=%d", (long long)a.M, a.K);
-  AQ_REQUIRE(a.M < (1ll << 31), AQ_ERR_BAD_SHAPE, "lora_gemm: M=%lld exceeds 2^31-1 rows", (long long)a.M);
+  AQ_REQUIRE(a.M < (1ll << 31) - kPairM, AQ_ERR_BAD_SHAPE, "lora_gemm: M=%lld exceeds 2^31-1 rows", (long long)a.M);
   AQ_REQUIRE(a.K % 8 == 0, AQ_ERR_BAD_SHAPE, "lora_gemm: K=%d must be a multiple of 8", a.K);
   AQ_REQUIRE(!a.has_main || (a.N > 0 && a.N % 8 == 0), AQ_ERR_BAD_SHAPE, "lora_gemm: N=%d must be a positive multiple of 8", a.N);
   if (a.dn != nullptr) {
@@ -557,6 +660,7 @@ int launch_lora_gemm(const LoraGemmArgs& a, cudaStream_t stream) {
   }
   AQ_REQUIRE(a.has_main || a.dn != nullptr, AQ_ERR_BAD_SHAPE, "lora_gemm: nothing to compute");
   AQ_REQUIRE(a.lda % 8 == 0 && (!a.has_main || a.ldy % 8 == 0), AQ_ERR_BAD_ALIGN, "lora_gemm: leading dimensions must be multiples of 8 elements");
+  AQ_REQUIRE(!a.has_main || (reinterpret_cast<uintptr_t>(a.y) & 15u) == 0, AQ_ERR_BAD_ALIGN, "lora_gemm: y must be 16-byte aligned");
   int rc = check_arch();
   if (rc) return rc;
   const int bn = a.force_bn > 0 ? a.force_bn : pick_bn(a.has_main ? a.N : 64);

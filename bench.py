@@ -161,21 +161,32 @@ class GemmProbe:
         self.ops.lora_linear_fwd, self.ops.lora_linear_bwd = self._fwd, self._bwd
 
     def summary(self, steps: int):
+        """Per kind and per shape totals.  Each launch is bracketed by its own pair of CUDA events; a bracket also contains
+        any time the GPU waited for the host to issue that launch, so one host hiccup (GC, allocator) can add milliseconds
+        to a 15 us kernel.  Per shape we therefore report mean AND median, and the kind totals use median x count
+        (`ms_per_step`), with the raw mean-based total kept beside it (`ms_per_step_mean`)."""
         torch.cuda.synchronize()
-        agg = {}
         per_shape = {}
         for kind, fl, by, e0, e1, shape in self.records:
-            ms = e0.elapsed_time(e1)
-            a = agg.setdefault(kind, [0.0, 0.0, 0.0, 0])
-            a[0] += fl; a[1] += by; a[2] += ms; a[3] += 1
-            s = per_shape.setdefault((kind,) + shape, [0.0, 0.0, 0])
-            s[0] += fl; s[1] += ms; s[2] += 1
+            s = per_shape.setdefault((kind,) + shape, {"fl": fl, "by": by, "ms": []})
+            s["ms"].append(e0.elapsed_time(e1))
+        agg = {}
+        shapes = []
+        for k, v in sorted(per_shape.items()):
+            ms = sorted(v["ms"])
+            n = len(ms)
+            med = ms[n // 2] if n % 2 else 0.5 * (ms[n // 2 - 1] + ms[n // 2])
+            mean = sum(ms) / n
+            a = agg.setdefault(k[0], [0.0, 0.0, 0.0, 0.0, 0])
+            a[0] += v["fl"] * n; a[1] += v["by"] * n; a[2] += med * n; a[3] += mean * n; a[4] += n
+            shapes.append({"kind": k[0], "M": k[1], "K": k[2], "N": k[3], "r": k[4], "calls_per_step": n // steps,
+                           "us_per_call": med * 1e3, "us_per_call_mean": mean * 1e3, "us_min": ms[0] * 1e3, "us_max": ms[-1] * 1e3,
+                           "tflops": v["fl"] / med / 1e9})
         out = {}
-        for kind, (fl, by, ms, n) in agg.items():
-            out[kind] = {"launch_groups_per_step": n // steps, "ms_per_step": ms / steps, "tflops": fl / ms / 1e9 if ms else 0.0,
-                         "gbs": by / ms / 1e6 if ms else 0.0, "flops_per_step": fl / steps, "bytes_per_step": by / steps}
-        shapes = [{"kind": k[0], "M": k[1], "K": k[2], "N": k[3], "r": k[4], "calls_per_step": v[2] // steps,
-                   "us_per_call": v[1] / v[2] * 1e3, "tflops": v[0] / v[1] / 1e9} for k, v in sorted(per_shape.items())]
+        for kind, (fl, by, ms_med, ms_mean, n) in agg.items():
+            out[kind] = {"launch_groups_per_step": n // steps, "ms_per_step": ms_med / steps, "ms_per_step_mean": ms_mean / steps,
+                         "tflops": fl / ms_med / 1e9 if ms_med else 0.0, "gbs": by / ms_med / 1e6 if ms_med else 0.0,
+                         "flops_per_step": fl / steps, "bytes_per_step": by / steps}
         return out, shapes
 
 
@@ -287,7 +298,7 @@ def run_cuda(args):
     extra = {}
     if rank == 0:
         pk = peaks()
-        probe_steps = 2
+        probe_steps = 3
         with GemmProbe(ops) as probe:
             for i in range(probe_steps):
                 step_from_device(*resident[i % n_pool])
@@ -300,7 +311,9 @@ def run_cuda(args):
                     "peak_kind": f"bf16_tflops_sustained of {pk['source']}", "traffic": None,
                     "launches_per_step": dom["launch_groups_per_step"], "kernel_ms_per_step": round(dom["ms_per_step"], 3),
                     "flops_per_step": dom["flops_per_step"], "frac_of_burst": round(dom["tflops"] / pk["bf16_tflops"], 4),
-                    "method": "CUDA events around each launch on the launching stream, 2 instrumented steps after the timed region"}
+                    "kernel_ms_per_step_mean": round(dom["ms_per_step_mean"], 3),
+                    "method": "CUDA events around each launch on the launching stream, 3 instrumented steps after the timed region; "
+                              "per shape median x launch count (a bracket also holds host-issue gaps; the mean-based total is kernel_ms_per_step_mean)"}
         extra = {"kernel_groups": {k: {kk: (round(vv, 3) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kinds.items()}}
         if args.shapes_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.shapes_out)), exist_ok=True)

@@ -20,17 +20,28 @@ CASES = [
     "plain:M=256,K=128,N=128,bn=128",
     "plain:M=1024,K=320,N=320,bn=160",
     "plain:M=1000,K=328,N=200,bn=0",
+    "plain:M=128,K=320,N=320,bn=160",
+    "plain:M=384,K=640,N=640,bn=192",
+    "plain:M=40000,K=320,N=1280,bn=0",
     "fwd:M=128,K=64,N=64,r=64,tok=128,bn=64",
     "fwd:M=1024,K=320,N=320,r=64,tok=256,bn=160",
     "fwd:M=1232,K=768,N=320,r=64,tok=77,bn=160",
     "fwd:M=2048,K=640,N=5120,r=16,tok=1024,bn=0",
     "fwd:M=4096,K=1280,N=1280,r=64,tok=256,bn=192",
+    "fwd:M=4096,K=1280,N=1280,r=64,tok=256,bn=160,grp=1",
+    "fwd:M=4096,K=1280,N=1280,r=64,tok=256,bn=160,grp=3",
+    "fwd:M=4096,K=1280,N=1280,r=64,tok=256,bn=128,grp=10",
+    "fwd:M=384,K=320,N=320,r=8,tok=128,bn=0",
+    "fwd:M=65536,K=320,N=320,r=64,tok=4096,bn=0",
+    "fwd:M=20000,K=640,N=5120,r=64,tok=1000,bn=0",
     "wgrad:M=1024,I=320,J=64,t=0",
     "wgrad:M=5000,I=1280,J=64,t=1",
     "wgrad:M=1232,I=768,J=16,t=1",
     "bwd:M=1024,K=320,N=320,r=64,tok=256",
     "bwd:M=1232,K=768,N=320,r=64,tok=77,nodx=1",
     "bwd:M=2048,K=640,N=2560,r=32,tok=1024",
+    "bwd:M=16384,K=640,N=640,r=64,tok=1024",
+    "bwd:M=900,K=320,N=1280,r=64,tok=300",
     "time:M=65536,K=320,N=320,r=64,tok=4096",
     "time:M=65536,K=320,N=2560,r=64,tok=4096",
     "time:M=65536,K=1280,N=320,r=64,tok=4096",

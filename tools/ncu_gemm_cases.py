@@ -13,7 +13,10 @@ SHAPES = [(65536, 320, 320, 4096), (4096, 1280, 1280, 256), (16384, 640, 5120, 1
 def main():
     dev = torch.device("cuda:0")
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-    for (M, K, N, tok) in SHAPES:
+    shapes = SHAPES
+    if len(sys.argv) > 2:      # "M,K,N,tok;M,K,N,tok"
+        shapes = [tuple(int(v) for v in item.split(",")) for item in sys.argv[2].split(";")]
+    for (M, K, N, tok) in shapes:
         g = torch.Generator(device=dev).manual_seed(0)
         x = torch.randn(M, K, generator=g, device=dev).bfloat16()
         w = (torch.randn(N, K, generator=g, device=dev) * K ** -0.5).bfloat16()
