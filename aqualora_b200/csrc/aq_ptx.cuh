@@ -143,6 +143,17 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem desc] * B[smem desc]; tf32 inputs (fp32 bits, low 13 mantissa bits ignored), fp32 accumulate.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -275,6 +286,17 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t m, uint32_
   d |= 1u << 10;  // B format bf16
   d |= (a_major & 1u) << 15;
   d |= (b_major & 1u) << 16;
+  d |= ((n >> 3) & 0x3Fu) << 17;
+  d |= ((m >> 4) & 0x1Fu) << 24;
+  return d;
+}
+
+// kind::tf32 instruction descriptor: tf32 x tf32 -> fp32, dense, both operands K-major.
+__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t m, uint32_t n) {
+  uint32_t d = 0;
+  d |= 1u << 4;   // D format f32
+  d |= 2u << 7;   // A format tf32
+  d |= 2u << 10;  // B format tf32
   d |= ((n >> 3) & 0x3Fu) << 17;
   d |= ((m >> 4) & 0x1Fu) << 24;
   return d;

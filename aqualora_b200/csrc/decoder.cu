@@ -6,10 +6,13 @@
 //   head      1x1 (320 -> 1280) + SiLU + global average pool fused (the 1280-channel map is never written)
 //   fc        Linear(1280 -> 2 * bits), bit = argmax over each logit pair
 //
-// Arithmetic is plain fp32 FFMA (no TF32): with random-initialised weights the logit margins are tiny, and
-// the decoded bits must match the fp32 reference.  HBM-bound by design: activations make one round trip per layer, the
-// elementwise work (bias, SiLU, SE scale, residual, pooling) rides in the producing / consuming kernel.
+// Arithmetic is fp32-faithful: with random-initialised weights the logit margins are tiny and the decoded bits
+// must match the fp32 reference.  The pointwise convolutions (89 % of the FLOPs) run on the tensor cores as 3-term split-TF32
+// products with fp32 accumulation (decoder_pw.cu); stem, depthwise, SE and classifier are fp32 FFMA.  HBM-bound by design:
+// activations make one round trip per layer, the elementwise work (bias, SiLU, SE scale, residual, pooling) rides in the
+// producing / consuming kernel.
 #include "aq_common.h"
+#include "decoder_pw.h"
 
 namespace aq {
 
@@ -23,7 +26,9 @@ constexpr int kStemC = 32, kHeadC = 1280, kLastC = 320, kImg = 512;
 
 static inline size_t pad4(size_t n) { return (n + 3) & ~(size_t)3; }
 
-__device__ __forceinline__ float silu(float v) { return v / (1.f + expf(-v)); }
+__device__ __forceinline__ float silu(float v) { return v / (1.f + expf(-v)); }   // exact: SE MLP (tiny tensors)
+// SFU exponential + reciprocal (relative error ~1e-6): the activation maps, where the exact form cost more than the convolution
+__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // stem: [B, 3, 512, 512] NCHW -> [B, 256, 256, 32] NHWC.  w [27][32] ((ky, kx, ci) major), b [32]
@@ -62,7 +67,7 @@ __global__ void __launch_bounds__(kStemTile) stem_kernel(const float* __restrict
     }
   }
 #pragma unroll
-  for (int c = 0; c < 32; ++c) outs[threadIdx.x][c] = silu(acc[c]);
+  for (int c = 0; c < 32; ++c) outs[threadIdx.x][c] = silu_fast(acc[c]);
   __syncthreads();
   // coalesced NHWC store: the tile is 128 pixels x 32 channels = 4096 contiguous floats
   float* dst = y + (((size_t)n * Ho + oy) * Wo + (size_t)blockIdx.x * kStemTile) * 32;
@@ -72,193 +77,142 @@ __global__ void __launch_bounds__(kStemTile) stem_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// pointwise (1x1) convolution = row GEMM over NHWC pixels:  Y[m, n] = epi( sum_k (X[m, k] * se[m / hw, k]) * Wt[k, n] + b[n] )
-// X [M, K], Wt [K, N] (transposed at pack time), fp32 FFMA, 128 x BN x 16 tiles, 256 threads, 8 x TN register tiles
+// depthwise k x k stride s (+ folded BN) + SiLU, NHWC; squeeze sums for the SE block
+// x [B, H, W, C], w [k*k][C], b [C], y [B, Ho, Wo, C], pooled [B, C] += sum over pixels
+// One thread = V channels x R output rows, sliding along x over a segment of TW outputs with the (R-1)*S+k by k input window
+// and the k*k weights in registers: each step loads only the S new input columns (consecutive threads = consecutive channel
+// vectors -> coalesced), so an input element is fetched (R-1+k)/(R*S) times (L1 / L2 hits) instead of k*k/S^2 times.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kPwBM = 128, kPwBK = 16, kPwThreads = 256, kPwAStride = kPwBM + 4;
-enum PwEpilogue { kEpiNone = 0, kEpiSilu = 1, kEpiResidual = 2, kEpiSiluPool = 3 };
+template <int V>
+__device__ __forceinline__ void ldv(const float* p, float (&d)[V]) {
+  if constexpr (V == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+  } else {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    d[0] = t.x; d[1] = t.y;
+  }
+}
+template <int V>
+__device__ __forceinline__ void stv(float* p, const float (&d)[V]) {
+  if constexpr (V == 4) *reinterpret_cast<float4*>(p) = make_float4(d[0], d[1], d[2], d[3]);
+  else *reinterpret_cast<float2*>(p) = make_float2(d[0], d[1]);
+}
 
-struct PwArgs {
-  const float* x; const float* wt; const float* bias; const float* se;   // se [B, K] or null
-  const float* residual;                                                // [M, N] or null
-  float* y;                                                             // [M, N]   (kEpiSiluPool: pooled sums [B, N])
-  long long M; int K, N, hw, epi;
-};
+constexpr int kDwThreads = 128;
 
-template <int BN>
-__global__ void __launch_bounds__(kPwThreads) pointwise_kernel(const PwArgs a) {
-  constexpr int TN = BN / 16;
-  __shared__ __align__(16) float As[kPwBK][kPwAStride];
-  __shared__ __align__(16) float Bs[kPwBK][BN];
-  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-  const long long m0 = (long long)blockIdx.x * kPwBM;
-  const int n0 = blockIdx.y * BN;
-  float acc[8][TN];
+template <int KS, int S, int R, int V>
+__global__ void __launch_bounds__(kDwThreads, 3) depthwise_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                   const float* __restrict__ b, float* __restrict__ y,
+                                                                   float* __restrict__ pooled, int B, int H, int W, int C, int Ho, int Wo,
+                                                                   int TW) {
+  constexpr int P = (KS - 1) / 2, NR = (R - 1) * S + KS;
+  constexpr int kBad = -(1 << 30);   // offset of an out-of-image row / column: the sum of two offsets stays negative
+  const unsigned CV = (unsigned)(C / V);
+  const unsigned nseg = (unsigned)((Wo + TW - 1) / TW), nrg = (unsigned)((Ho + R - 1) / R);
+  unsigned idx = blockIdx.x * kDwThreads + threadIdx.x;   // < 2^32: B * Ho / R * Wo / TW * C / V threads
+  const unsigned cv = idx % CV; idx /= CV;
+  const unsigned seg = idx % nseg; idx /= nseg;
+  const unsigned rg = idx % nrg;
+  const unsigned n = idx / nrg;
+  if (n >= (unsigned)B) return;
+  const int c0 = (int)cv * V;
+  float wr[KS * KS][V], bias[V], pool[V];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < KS * KS; ++i) ldv<V>(w + i * C + c0, wr[i]);
+  ldv<V>(b + c0, bias);
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-
-  // A loader: 128 rows x 4 k-quads = 512 float4 -> 2 per thread;  B loader: 16 x BN/4 float4
-  const int a_row[2] = {t >> 2, (t >> 2) + 64};
-  const int a_kq = (t & 3) * 4;
-  for (int k0 = 0; k0 < a.K; k0 += kPwBK) {
-    float4 av[2];
+  for (int v = 0; v < V; ++v) pool[v] = 0.f;
+  const int oy0 = (int)rg * R, iy0 = oy0 * S - P;
+  const int ox_begin = (int)seg * TW, ox_end = min(Wo, ox_begin + TW);
+  const float* xn = x + (size_t)n * H * W * C + c0;                 // one 64-bit base per thread, 32-bit element offsets below
+  float* yn = y + ((size_t)n * Ho + oy0) * Wo * C + c0;
+  int roff[NR];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const long long m = m0 + a_row[h];
-      av[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < a.M && k0 + a_kq < a.K) {
-        av[h] = __ldg(reinterpret_cast<const float4*>(a.x + m * a.K + k0 + a_kq));
-        if (a.se != nullptr) {
-          const float4 s = __ldg(reinterpret_cast<const float4*>(a.se + (m / a.hw) * a.K + k0 + a_kq));
-          av[h].x *= s.x; av[h].y *= s.y; av[h].z *= s.z; av[h].w *= s.w;
+  for (int r = 0; r < NR; ++r) {
+    const int iy = iy0 + r;
+    roff[r] = (iy >= 0 && iy < H) ? iy * W * C : kBad;
+  }
+  float win[NR][KS][V];
+  auto load_col = [&](int ix, float (&dst)[NR][V]) {
+    const int coff = (ix >= 0 && ix < W) ? ix * C : kBad;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int off = roff[r] + coff;
+#pragma unroll
+      for (int v = 0; v < V; ++v) dst[r][v] = 0.f;
+      if (off >= 0) ldv<V>(xn + off, dst[r]);
+    }
+  };
+  {
+    float col[NR][V];
+#pragma unroll
+    for (int kx = 0; kx < KS; ++kx) {
+      load_col(ox_begin * S - P + kx, col);
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int v = 0; v < V; ++v) win[r][kx][v] = col[r][v];
+    }
+  }
+  const int WoC = Wo * C;
+  for (int ox = ox_begin; ox < ox_end; ++ox) {
+    // the S input columns the NEXT output needs are requested first: their latency overlaps this output's k*k*R FMAs
+    // (an unrolled, shift-free variant with rotating window slots was slower: its body no longer fits the instruction cache)
+    float nxt[S][NR][V];
+    const bool more = ox + 1 < ox_end;
+    if (more) {
+#pragma unroll
+      for (int s2 = 0; s2 < S; ++s2) load_col((ox + 1) * S - P + KS - S + s2, nxt[s2]);
+    }
+    const int yoff = ox * C;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float acc[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = bias[v];
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = fmaf(win[r * S + ky][kx][v], wr[ky * KS + kx][v], acc[v]);
+      if (oy0 + r < Ho) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          acc[v] = silu_fast(acc[v]);
+          pool[v] += acc[v];
         }
+        stv<V>(yn + (yoff + r * WoC), acc);
       }
     }
-    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int b_k = t / (BN / 4), b_n = (t % (BN / 4)) * 4;
-    if (t < kPwBK * (BN / 4) && k0 + b_k < a.K && n0 + b_n < a.N)
-      bv = __ldg(reinterpret_cast<const float4*>(a.wt + (size_t)(k0 + b_k) * a.N + n0 + b_n));
-    __syncthreads();   // previous tile fully consumed
+    if (more) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      As[a_kq + 0][a_row[h]] = av[h].x; As[a_kq + 1][a_row[h]] = av[h].y;
-      As[a_kq + 2][a_row[h]] = av[h].z; As[a_kq + 3][a_row[h]] = av[h].w;
-    }
-    if (t < kPwBK * (BN / 4)) *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = bv;
-    __syncthreads();
+      for (int r = 0; r < NR; ++r) {
 #pragma unroll
-    for (int k = 0; k < kPwBK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
-      const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      float br[TN];
-      if constexpr (TN == 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-        br[0] = b4.x; br[1] = b4.y; br[2] = b4.z; br[3] = b4.w;
-      } else {
-        const float2 b2 = *reinterpret_cast<const float2*>(&Bs[k][tx * 2]);
-        br[0] = b2.x; br[1] = b2.y;
-      }
+        for (int kx = 0; kx < KS - S; ++kx)
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+          for (int v = 0; v < V; ++v) win[r][kx][v] = win[r][kx + S][v];
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
-    }
-  }
-
-  const int nb = n0 + tx * TN;
-  if (nb >= a.N) {
-    if (a.epi != kEpiSiluPool) return;
-  }
-  float bias[TN];
+        for (int s2 = 0; s2 < S; ++s2)
 #pragma unroll
-  for (int j = 0; j < TN; ++j) bias[j] = nb + j < a.N ? __ldg(a.bias + nb + j) : 0.f;
-  if (a.epi == kEpiSiluPool) {
-    // column sums of SiLU(acc + b) over this tile's rows (all in one sample: hw % 128 == 0), then one atomic per column
-    __shared__ float red[16][BN];
-    float cs[TN];
-#pragma unroll
-    for (int j = 0; j < TN; ++j) cs[j] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const long long m = m0 + ty * 8 + i;
-      if (m < a.M) {
-#pragma unroll
-        for (int j = 0; j < TN; ++j) cs[j] += silu(acc[i][j] + bias[j]);
+          for (int v = 0; v < V; ++v) win[r][KS - S + s2][v] = nxt[s2][r][v];
       }
     }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < TN; ++j) red[ty][tx * TN + j] = cs[j];
-    __syncthreads();
-    if (t < BN && n0 + t < a.N) {
-      float s = 0.f;
-#pragma unroll
-      for (int r = 0; r < 16; ++r) s += red[r][t];
-      atomicAdd(a.y + (m0 / a.hw) * a.N + n0 + t, s);
-    }
-    return;
   }
+  float* pd = pooled + (size_t)n * C + c0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const long long m = m0 + ty * 8 + i;
-    if (m >= a.M) continue;
-    float o[TN];
-#pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      o[j] = acc[i][j] + bias[j];
-      if (a.epi == kEpiSilu) o[j] = silu(o[j]);
-    }
-    float* dst = a.y + m * a.N + nb;
-    if (a.epi == kEpiResidual) {
-      const float* rs = a.residual + m * a.N + nb;
-#pragma unroll
-      for (int j = 0; j < TN; ++j) o[j] += __ldg(rs + j);
-    }
-    if constexpr (TN == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-    else *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
-  }
+  for (int v = 0; v < V; ++v) atomicAdd(pd + v, pool[v]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// depthwise k x k stride s (+ folded BN) + SiLU, NHWC, 4 channels per thread; squeeze sums for the SE block
-// x [B, H, W, C], w [k*k][C], b [C], y [B, Ho, Wo, C], pooled [B, C] += sum over the tile's pixels
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kDwTileW = 16;
-
-template <int KS, int S>
-__global__ void __launch_bounds__(256) depthwise_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                         const float* __restrict__ b, float* __restrict__ y,
-                                                         float* __restrict__ pooled, int H, int W, int C, int Ho, int Wo) {
-  constexpr int P = (KS - 1) / 2;
-  const int n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * kDwTileW;
-  const int cq_count = C >> 2;
-  const float4* x4 = reinterpret_cast<const float4*>(x) + (size_t)n * H * W * cq_count;
-  const float4* w4 = reinterpret_cast<const float4*>(w);
-  float4* y4 = reinterpret_cast<float4*>(y) + ((size_t)n * Ho + oy) * Wo * cq_count;
-  for (int cq = threadIdx.x; cq < cq_count; cq += blockDim.x) {
-    const float4 bias = __ldg(reinterpret_cast<const float4*>(b) + cq);
-    float4 wreg[KS == 3 ? 9 : 1];
-    if (KS == 3) {
-#pragma unroll
-      for (int i = 0; i < 9; ++i) wreg[i] = __ldg(w4 + i * cq_count + cq);
-    }
-    float4 pool = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int dx = 0; dx < kDwTileW; ++dx) {
-      const int ox = ox0 + dx;
-      if (ox >= Wo) break;
-      float4 acc = bias;
-#pragma unroll
-      for (int ky = 0; ky < KS; ++ky) {
-        const int iy = oy * S - P + ky;
-        if (iy < 0 || iy >= H) continue;
-#pragma unroll
-        for (int kx = 0; kx < KS; ++kx) {
-          const int ix = ox * S - P + kx;
-          if (ix < 0 || ix >= W) continue;
-          const float4 v = __ldg(x4 + ((size_t)iy * W + ix) * cq_count + cq);
-          const float4 ww = KS == 3 ? wreg[ky * 3 + kx] : __ldg(w4 + (ky * KS + kx) * cq_count + cq);
-          acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
-          acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
-        }
-      }
-      acc.x = silu(acc.x); acc.y = silu(acc.y); acc.z = silu(acc.z); acc.w = silu(acc.w);
-      y4[(size_t)ox * cq_count + cq] = acc;
-      pool.x += acc.x; pool.y += acc.y; pool.z += acc.z; pool.w += acc.w;
-    }
-    float* pd = pooled + (size_t)n * C + cq * 4;
-    atomicAdd(pd + 0, pool.x); atomicAdd(pd + 1, pool.y); atomicAdd(pd + 2, pool.z); atomicAdd(pd + 3, pool.w);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// SqueezeExcitation MLP: scale[n, c] = sigmoid(b2[c] + sum_j w2[c, j] * silu(b1[j] + sum_c' w1[j, c'] * mean[n, c']))
-// one block per sample; pooled holds SUMS over hw pixels
+// SqueezeExcitation MLP: scale[n, c] = sigmoid(b2[c] + sum_j w2t[j, c] * silu(b1[j] + sum_c' w1[j, c'] * mean[n, c']))
+// grid (B, channel chunks of 256): every block recomputes the tiny squeeze vector s1 [SQ] (warp per row of w1, 4 independent
+// accumulators), then one thread per output channel walks w2t [SQ, C] (transposed at pack time -> coalesced).
+// pooled holds SUMS over hw pixels.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) se_kernel(const float* __restrict__ pooled, const float* __restrict__ w1,
-                                                  const float* __restrict__ b1, const float* __restrict__ w2,
+                                                  const float* __restrict__ b1, const float* __restrict__ w2t,
                                                   const float* __restrict__ b2, float* __restrict__ scale, int C, int SQ,
                                                   float inv_hw) {
   extern __shared__ float sm[];   // mean [C], s1 [SQ]
@@ -270,17 +224,33 @@ __global__ void __launch_bounds__(256) se_kernel(const float* __restrict__ poole
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int j = warp; j < SQ; j += 8) {
     const float* wr = w1 + (size_t)j * C;
-    float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(wr + c), mean[c], acc);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int c = lane;
+    for (; c + 96 < C; c += 128) {
+      a0 = fmaf(__ldg(wr + c), mean[c], a0);
+      a1 = fmaf(__ldg(wr + c + 32), mean[c + 32], a1);
+      a2 = fmaf(__ldg(wr + c + 64), mean[c + 64], a2);
+      a3 = fmaf(__ldg(wr + c + 96), mean[c + 96], a3);
+    }
+    for (; c < C; c += 32) a0 = fmaf(__ldg(wr + c), mean[c], a0);
+    float acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) s1[j] = silu(acc + b1[j]);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float* wr = w2 + (size_t)c * SQ;
-    float acc = b2[c];
-    for (int j = 0; j < SQ; ++j) acc = fmaf(__ldg(wr + j), s1[j], acc);
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c < C) {
+    float a0 = b2[c], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int j = 0;
+    for (; j + 3 < SQ; j += 4) {
+      a0 = fmaf(__ldg(w2t + (size_t)j * C + c), s1[j], a0);
+      a1 = fmaf(__ldg(w2t + (size_t)(j + 1) * C + c), s1[j + 1], a1);
+      a2 = fmaf(__ldg(w2t + (size_t)(j + 2) * C + c), s1[j + 2], a2);
+      a3 = fmaf(__ldg(w2t + (size_t)(j + 3) * C + c), s1[j + 3], a3);
+    }
+    for (; j < SQ; ++j) a0 = fmaf(__ldg(w2t + (size_t)j * C + c), s1[j], a0);
+    const float acc = (a0 + a1) + (a2 + a3);
     scale[(size_t)n * C + c] = 1.f / (1.f + expf(-acc));
   }
 }
@@ -335,13 +305,13 @@ static size_t packed_floats(int out_features) {
     const StageCfg& st = kStages[s];
     for (int l = 0; l < st.layers; ++l) {
       const int cin = l == 0 ? st.cin : st.cout, cexp = cin * st.expand, sq = cin / 4 > 1 ? cin / 4 : 1;
-      if (st.expand != 1) { wk.take((size_t)cin * cexp); wk.take(cexp); }
+      if (st.expand != 1) { wk.take((size_t)cin * cexp); wk.take((size_t)cin * cexp); wk.take(cexp); }
       wk.take((size_t)st.k * st.k * cexp); wk.take(cexp);
       wk.take((size_t)sq * cexp); wk.take(sq); wk.take((size_t)cexp * sq); wk.take(cexp);
-      wk.take((size_t)cexp * st.cout); wk.take(st.cout);
+      wk.take((size_t)cexp * st.cout); wk.take((size_t)cexp * st.cout); wk.take(st.cout);
     }
   }
-  wk.take((size_t)kLastC * kHeadC); wk.take(kHeadC);
+  wk.take((size_t)kLastC * kHeadC); wk.take((size_t)kLastC * kHeadC); wk.take(kHeadC);
   wk.take((size_t)out_features * kHeadC); wk.take(out_features);
   return wk.off;
 }
@@ -372,24 +342,18 @@ static Buffers buffer_plan() {
   return bf;
 }
 
-static int launch_pointwise(const PwArgs& a, cudaStream_t st) {
-  const int bn = a.N <= 32 ? 32 : 64;
-  dim3 grid((unsigned)((a.M + kPwBM - 1) / kPwBM), (a.N + bn - 1) / bn);
-  if (bn == 32) pointwise_kernel<32><<<grid, kPwThreads, 0, st>>>(a);
-  else pointwise_kernel<64><<<grid, kPwThreads, 0, st>>>(a);
-  AQ_LAUNCHED();
-  return AQ_OK;
-}
-
 static int launch_depthwise(const float* x, const float* w, const float* b, float* y, float* pooled, int B, int H, int C, int k,
                             int stride, int Ho, cudaStream_t st) {
-  int threads = ((C / 4) + 31) / 32 * 32;
-  if (threads > 256) threads = 256;
-  dim3 grid((Ho + kDwTileW - 1) / kDwTileW, Ho, B);
-  if (k == 3 && stride == 1) depthwise_kernel<3, 1><<<grid, threads, 0, st>>>(x, w, b, y, pooled, H, H, C, Ho, Ho);
-  else if (k == 3 && stride == 2) depthwise_kernel<3, 2><<<grid, threads, 0, st>>>(x, w, b, y, pooled, H, H, C, Ho, Ho);
-  else if (k == 5 && stride == 1) depthwise_kernel<5, 1><<<grid, threads, 0, st>>>(x, w, b, y, pooled, H, H, C, Ho, Ho);
-  else if (k == 5 && stride == 2) depthwise_kernel<5, 2><<<grid, threads, 0, st>>>(x, w, b, y, pooled, H, H, C, Ho, Ho);
+  const int R = 2;   // output rows per thread
+  const int TW = Ho >= 64 ? 32 : 16;
+  const int V = k == 3 ? 4 : 2;
+  const long long threads = (long long)B * ((Ho + R - 1) / R) * ((Ho + TW - 1) / TW) * (C / V);
+  AQ_REQUIRE(threads < (1ll << 32), AQ_ERR_BAD_SHAPE, "depthwise: %lld work items exceed 2^32", threads);
+  const unsigned grid = (unsigned)((threads + kDwThreads - 1) / kDwThreads);
+  if (k == 3 && stride == 1) depthwise_kernel<3, 1, 2, 4><<<grid, kDwThreads, 0, st>>>(x, w, b, y, pooled, B, H, H, C, Ho, Ho, TW);
+  else if (k == 3 && stride == 2) depthwise_kernel<3, 2, 2, 4><<<grid, kDwThreads, 0, st>>>(x, w, b, y, pooled, B, H, H, C, Ho, Ho, TW);
+  else if (k == 5 && stride == 1) depthwise_kernel<5, 1, 2, 2><<<grid, kDwThreads, 0, st>>>(x, w, b, y, pooled, B, H, H, C, Ho, Ho, TW);
+  else if (k == 5 && stride == 2) depthwise_kernel<5, 2, 2, 2><<<grid, kDwThreads, 0, st>>>(x, w, b, y, pooled, B, H, H, C, Ho, Ho, TW);
   else return fail(AQ_ERR_BAD_SHAPE, "depthwise: unsupported kernel %d stride %d", k, stride);
   AQ_LAUNCHED();
   return AQ_OK;
@@ -450,10 +414,11 @@ int aq_effnetb1_fwd(const float* x, const float* packed, float* logits, unsigned
       const int ho = (h + 2 * ((sc.k - 1) / 2) - sc.k) / stride + 1;
       const float* dw_in = act[cur];
       if (sc.expand != 1) {
-        PwArgs a{};
-        a.x = act[cur]; a.wt = wk.take((size_t)cin * cexp); a.bias = wk.take(cexp); a.se = nullptr; a.residual = nullptr; a.y = expb;
-        a.M = (long long)B * h * h; a.K = cin; a.N = cexp; a.hw = h * h; a.epi = kEpiSilu;
-        rc = launch_pointwise(a, st);
+        PwTcArgs a{};
+        a.x = act[cur]; a.w_hi = wk.take((size_t)cin * cexp); a.w_lo = wk.take((size_t)cin * cexp); a.bias = wk.take(cexp);
+        a.se = nullptr; a.residual = nullptr; a.y = expb;
+        a.M = (long long)B * h * h; a.K = cin; a.N = cexp; a.hw = h * h; a.epi = kPwSilu;
+        rc = launch_pointwise_tc(a, st);
         if (rc) return rc;
         dw_in = expb;
       }
@@ -470,16 +435,17 @@ int aq_effnetb1_fwd(const float* x, const float* packed, float* logits, unsigned
         const float* b1 = wk.take(sq);
         const float* w2 = wk.take((size_t)cexp * sq);
         const float* b2 = wk.take(cexp);
-        se_kernel<<<B, 256, (cexp + sq) * sizeof(float), st>>>(pl, w1, b1, w2, b2, scale, cexp, sq, 1.f / (float)(ho * ho));
+        se_kernel<<<dim3(B, (cexp + 255) / 256), 256, (cexp + sq) * sizeof(float), st>>>(pl, w1, b1, w2, b2, scale, cexp, sq, 1.f / (float)(ho * ho));
         AQ_LAUNCHED();
       }
       {
-        PwArgs a{};
-        a.x = dwo; a.wt = wk.take((size_t)cexp * sc.cout); a.bias = wk.take(sc.cout); a.se = scale;
+        PwTcArgs a{};
+        a.x = dwo; a.w_hi = wk.take((size_t)cexp * sc.cout); a.w_lo = wk.take((size_t)cexp * sc.cout); a.bias = wk.take(sc.cout);
+        a.se = scale;
         const bool res = stride == 1 && cin == sc.cout;
         a.residual = res ? act[cur] : nullptr; a.y = act[cur ^ 1];
-        a.M = (long long)B * ho * ho; a.K = cexp; a.N = sc.cout; a.hw = ho * ho; a.epi = res ? kEpiResidual : kEpiNone;
-        rc = launch_pointwise(a, st);
+        a.M = (long long)B * ho * ho; a.K = cexp; a.N = sc.cout; a.hw = ho * ho; a.epi = res ? kPwResidual : kPwNone;
+        rc = launch_pointwise_tc(a, st);
         if (rc) return rc;
       }
       cur ^= 1;
@@ -488,11 +454,11 @@ int aq_effnetb1_fwd(const float* x, const float* packed, float* logits, unsigned
   }
   float* head_pool = pooled + (size_t)B * pooled_off;
   {
-    PwArgs a{};
-    a.x = act[cur]; a.wt = wk.take((size_t)kLastC * kHeadC); a.bias = wk.take(kHeadC); a.se = nullptr; a.residual = nullptr; a.y = head_pool;
-    a.M = (long long)B * h * h; a.K = kLastC; a.N = kHeadC; a.hw = h * h; a.epi = kEpiSiluPool;
-    AQ_REQUIRE((h * h) % kPwBM == 0, AQ_ERR_BAD_SHAPE, "effnetb1_fwd: head map %d x %d is not a multiple of the row tile", h, h);
-    rc = launch_pointwise(a, st);
+    PwTcArgs a{};
+    a.x = act[cur]; a.w_hi = wk.take((size_t)kLastC * kHeadC); a.w_lo = wk.take((size_t)kLastC * kHeadC); a.bias = wk.take(kHeadC);
+    a.se = nullptr; a.residual = nullptr; a.y = head_pool;
+    a.M = (long long)B * h * h; a.K = kLastC; a.N = kHeadC; a.hw = h * h; a.epi = kPwSiluPool;
+    rc = launch_pointwise_tc(a, st);
     if (rc) return rc;
   }
   {
@@ -502,6 +468,28 @@ int aq_effnetb1_fwd(const float* x, const float* packed, float* logits, unsigned
     AQ_LAUNCHED();
   }
   return AQ_OK;
+}
+
+int aq_conv1x1_tf32x3(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* se, const float* residual,
+                      float* y, int64_t M, int K, int N, int hw, int epi, void* stream) {
+  AQ_REQUIRE(x && w_hi && w_lo && bias && y, AQ_ERR_BAD_SHAPE, "conv1x1_tf32x3: NULL operand");
+  AQ_REQUIRE(epi >= 0 && epi <= 3 && (epi != kPwResidual || residual != nullptr), AQ_ERR_BAD_SHAPE, "conv1x1_tf32x3: bad epilogue %d", epi);
+  int rc = check_arch();
+  if (rc) return rc;
+  PwTcArgs a{};
+  a.x = x; a.w_hi = w_hi; a.w_lo = w_lo; a.bias = bias; a.se = se; a.residual = residual; a.y = y;
+  a.M = M; a.K = K; a.N = N; a.hw = hw; a.epi = epi;
+  return launch_pointwise_tc(a, (cudaStream_t)stream);
+}
+
+int aq_depthwise_silu(const float* x, const float* w, const float* bias, float* y, float* pooled, int B, int H, int C, int k,
+                      int stride, void* stream) {
+  AQ_REQUIRE(x && w && bias && y && pooled && B > 0 && H > 0, AQ_ERR_BAD_SHAPE, "depthwise_silu: NULL operand or empty batch");
+  AQ_REQUIRE(C % 4 == 0, AQ_ERR_BAD_SHAPE, "depthwise_silu: C=%d must be a multiple of 4", C);
+  int rc = check_arch();
+  if (rc) return rc;
+  const int ho = (H + 2 * ((k - 1) / 2) - k) / stride + 1;
+  return launch_depthwise(x, w, bias, y, pooled, B, H, C, k, stride, ho, (cudaStream_t)stream);
 }
 
 }  // extern "C"

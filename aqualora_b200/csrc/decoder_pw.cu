@@ -1,0 +1,411 @@
+// Pointwise (1x1) convolutions of the message decoder on the tcgen05 tensor cores with fp32-faithful arithmetic.
+//
+//   Y[m, n] = epi( sum_k (X[m, k] * se[m / hw, k]) * W[n, k] + b[n] )        X [M, K] NHWC pixels, W [N, K], fp32 in / fp32 out
+//
+// The reference runs these convolutions in fp32 (utils/models.py:84-96 never casts the decoder) and the decoded bits must agree
+// with it, so a plain TF32 / bf16 product is not acceptable (logit margins of a random-init decoder go down to 5e-4).  Every
+// product is therefore evaluated as the 3-term split
+//   a * w  ~=  a_hi * w_hi + a_lo * w_hi + a_hi * w_lo ,   x_hi = x with the low 13 mantissa bits cleared (exactly a TF32 number),
+//                                                            x_lo = x - x_hi (exact in fp32)
+// on kind::tf32 MMAs with fp32 accumulation in TMEM; the dropped a_lo * w_lo term is <= 2^-22 |a w|.  Weights are split once at
+// pack time; activations are split by 4 converter warps inside shared memory (in place for the hi part), which is also where the
+// squeeze-excitation scale of the project convolutions is applied.
+//
+// One CTA per SM, persistent over (128-row tile, N tile <= 224) work items, 704 threads:
+//   warps 0-15   epilogue   TMEM lane quadrant = warp % 4, 16-column pieces pc = warp / 4 (mod 4):
+//                           TMEM -> +bias -> [SiLU] -> SMEM transpose -> coalesced 64 B row segments (+ residual) | SiLU + pooled sums
+//   warps 16-19  converter  raw fp32 A tile (TMA, 128B swizzle) -> x * se -> hi (in place) / lo (second tile)
+//   warp 20      TMA producer (A raw, W_hi, W_lo per 32-wide k chunk)
+//   warp 21      TMEM allocator + MMA issuer (3 MMAs per 8-wide k step)
+// The expand convolutions (128 x 96 ... 240 outputs from a 16 ... 40-deep product) are bound by the epilogue's instruction issue
+// (ncu: ~0.75 instructions per output element, the 8 epilogue warps of the previous version busy 90 % of the time, tensor pipe
+// 4 % active), hence 16 epilogue warps -- 4 per scheduler -- an SFU SiLU and an accumulator ring of up to 8 tiles in TMEM.
+#include <string.h>
+
+#include "aq_ptx.cuh"
+#include "decoder_pw.h"
+
+namespace aq {
+
+constexpr int kPwThreads = 704;
+constexpr int kPwEpiWarps = 16;
+constexpr int kPwConvWarp0 = 16, kPwProducerWarp = 20, kPwMmaWarp = 21;
+constexpr int kPwMaxBN = 224;                  // 2 pipeline stages + 16 epilogue staging buffers must fit in 227 KiB
+constexpr int kPwBM = 128;
+constexpr int kPwKC = 32;                      // fp32 elements per k chunk = one 128-byte swizzle row
+constexpr int kPwATile = kPwBM * kPwKC * 4;    // 16 KiB
+constexpr int kPwStgStride = 80;               // 16 fp32 + 16 B pad: odd multiple of 16 B -> conflict-free 16 B accesses
+constexpr int kPwStgWarp = 32 * kPwStgStride;
+constexpr int kPwSmemBudget = 232448 - 1024;
+
+struct PwTcParams {
+  CUtensorMap tmap_x;     // X    [M, K] fp32   box {32, 128}  swizzle 128B
+  CUtensorMap tmap_whi;   // W_hi [N, K] fp32   box {32, BN}   swizzle 128B
+  CUtensorMap tmap_wlo;   // W_lo [N, K]
+  const float* bias;      // [N]
+  const float* se;        // [M / hw, K] or null
+  const float* residual;  // [M, N] or null
+  float* y;               // [M, N]   (pool epilogue: [M / hw, N] sums, accumulated)
+  long long M;
+  int N, K, hw, epi;
+  int BN, num_n_tiles, num_m_tiles, num_kc, stages;
+  int w_resident;   // 1: all W chunks (hi + lo) stay in SMEM for the whole kernel (single N tile, small K): only A streams
+};
+
+// SiLU with the SFU exponential and reciprocal (relative error ~1e-6, far inside the decoder's 1e-4 logit tolerance)
+__device__ __forceinline__ float pw_silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+
+__global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __grid_constant__ PwTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+
+  const int BN = p.BN;
+  const int stages = p.stages;
+  const uint32_t w_bytes = (uint32_t)BN * 128u;                  // one W tile (hi or lo): BN rows x 128 B
+  const bool wres = p.w_resident != 0;
+  const uint32_t stage_bytes = 2u * kPwATile + (wres ? 0u : 2u * w_bytes);
+  // layout: [resident W: num_kc x (hi | lo)] [stages x (A hi | A lo | W hi | W lo)] [epilogue staging, 16 warps] [barriers]
+  const uint32_t wres_bytes = wres ? (uint32_t)p.num_kc * 2u * w_bytes : 0u;
+  const uint32_t ring_off = wres_bytes;
+  const uint32_t stg_off = ring_off + (uint32_t)stages * stage_bytes;
+  const uint32_t bar_off = stg_off + (uint32_t)kPwEpiWarps * kPwStgWarp;
+  const uint32_t bar_base = smem_base + bar_off;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // TMA bytes landed
+  auto conv_bar = [&](int s) { return bar_base + 8u * (8 + s); };           // A split into hi / lo (4 converter warps)
+  auto empty_bar = [&](int s) { return bar_base + 8u * (16 + s); };         // MMAs that read the stage completed
+  auto acc_full_bar = [&](int b) { return bar_base + 8u * (24 + b); };
+  auto acc_empty_bar = [&](int b) { return bar_base + 8u * (32 + b); };
+  const uint32_t w_full_bar = bar_base + 8u * 40;                           // resident W landed (once)
+  const uint32_t tmem_slot = bar_base + 8u * 41;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * 41);
+  // accumulator ring in TMEM: narrow layers (BN = 16 ... 64) keep up to 8 tiles in flight between the MMA thread and the epilogue
+  const uint32_t nacc = min(8u, 512u / (uint32_t)BN);
+
+  auto a_hi = [&](int s) { return smem_base + ring_off + (uint32_t)s * stage_bytes; };
+  auto a_lo = [&](int s) { return smem_base + ring_off + (uint32_t)s * stage_bytes + kPwATile; };
+  // W of k chunk kc in ring stage s, or in the resident region
+  auto w_hi = [&](int s, int kc) { return wres ? smem_base + (uint32_t)kc * 2u * w_bytes : smem_base + ring_off + (uint32_t)s * stage_bytes + 2u * kPwATile; };
+  auto w_lo = [&](int s, int kc) { return w_hi(s, kc) + w_bytes; };
+
+  if (warp == kPwProducerWarp && lane == 0) {
+    tma_prefetch_desc(&p.tmap_x);
+    tma_prefetch_desc(&p.tmap_whi);
+    tma_prefetch_desc(&p.tmap_wlo);
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(conv_bar(s), 4);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 8; ++b) {
+      mbar_init(acc_full_bar(b), 1);
+      mbar_init(acc_empty_bar(b), kPwEpiWarps);
+    }
+    mbar_init(w_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == kPwMmaWarp) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int total_items = p.num_m_tiles * p.num_n_tiles;
+  const int num_kc = p.num_kc;
+
+  if (warp == kPwProducerWarp) {
+    // =========================== TMA producer ===========================
+    int stage = 0;
+    uint32_t phase = 0;
+    if (wres) {
+      // the whole (tiny) weight matrix once: re-fetching it per tile cost 60 % of the TMA traffic of the expand layers and
+      // made every CTA hammer the same few L2 lines
+      if (elect_one()) {
+        mbar_arrive_expect_tx(w_full_bar, (uint32_t)num_kc * 2u * w_bytes);
+        for (int kc = 0; kc < num_kc; ++kc) {
+          tma_load_2d(w_hi(0, kc), &p.tmap_whi, w_full_bar, kc * kPwKC, 0);
+          tma_load_2d(w_lo(0, kc), &p.tmap_wlo, w_full_bar, kc * kPwKC, 0);
+        }
+      }
+      __syncwarp();
+    }
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int m0 = (item / p.num_n_tiles) * kPwBM;
+      const int n0 = (item % p.num_n_tiles) * BN;
+      for (int kc = 0; kc < num_kc; ++kc) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(stage), kPwATile + (wres ? 0u : 2u * w_bytes));
+          tma_load_2d(a_hi(stage), &p.tmap_x, full_bar(stage), kc * kPwKC, m0);
+          if (!wres) {
+            tma_load_2d(w_hi(stage, kc), &p.tmap_whi, full_bar(stage), kc * kPwKC, n0);
+            tma_load_2d(w_lo(stage, kc), &p.tmap_wlo, full_bar(stage), kc * kPwKC, n0);
+          }
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == kPwMmaWarp) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = make_idesc_tf32(kPwBM, (uint32_t)BN);
+    constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    auto desc = [&](uint32_t addr) { return kDescHi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
+    int stage = 0;
+    uint32_t phase = 0, acc_iter = 0;
+    if (wres) {
+      mbar_wait(w_full_bar, 0);
+      tc_fence_after();
+    }
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++acc_iter) {
+      const uint32_t buf = acc_iter % nacc;
+      const uint32_t tmem_acc = tmem_base + buf * (uint32_t)BN;
+      mbar_wait(acc_empty_bar(buf), ((acc_iter / nacc) & 1u) ^ 1u);
+      tc_fence_after();
+      for (int kc = 0; kc < num_kc; ++kc) {
+        mbar_wait(full_bar(stage), phase);   // W tiles (async proxy) ...
+        mbar_wait(conv_bar(stage), phase);   // ... and the hi / lo split of A (generic proxy + fence.proxy.async)
+        tc_fence_after();
+        if (elect_one()) {
+          const int ksteps = min(kPwKC, p.K - kc * kPwKC) >> 3;   // 8 tf32 per MMA; the zero-filled tail is skipped
+          const uint64_t ah = desc(a_hi(stage)), al = desc(a_lo(stage)), wh = desc(w_hi(stage, kc)), wl = desc(w_lo(stage, kc));
+          for (int k = 0; k < ksteps; ++k) {
+            // small terms first, the dominant hi * hi product last
+            umma_tf32(tmem_acc, al + 2 * k, wh + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+            umma_tf32(tmem_acc, ah + 2 * k, wl + 2 * k, idesc, 1u);
+            umma_tf32(tmem_acc, ah + 2 * k, wh + 2 * k, idesc, 1u);
+          }
+          umma_commit(empty_bar(stage));
+          if (kc == num_kc - 1) umma_commit(acc_full_bar(buf));
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= kPwConvWarp0) {
+    // =========================== converter warps: A -> (A * se) hi / lo ===========================
+    const int t = threadIdx.x - kPwConvWarp0 * 32;   // 0..127
+    const int cphys = t & 7;                  // 16-byte chunk inside the 128-byte row (physical, swizzled)
+    const int rlow = (t >> 3) & 7;            // row & 7 of every row this thread touches (rows t/8 + 16 j)
+    const int clog = cphys ^ rlow;            // logical chunk = k offset / 4 inside the chunk
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const long long m0 = (long long)(item / p.num_n_tiles) * kPwBM;
+      const float* se_row = p.se != nullptr ? p.se + (m0 / p.hw) * p.K : nullptr;   // a 128-row tile lies inside one image
+      for (int kc = 0; kc < num_kc; ++kc) {
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+        const int k = kc * kPwKC + clog * 4;
+        if (se_row != nullptr && k < p.K) sc = __ldg(reinterpret_cast<const float4*>(se_row + k));
+        mbar_wait(full_bar(stage), phase);
+        uint8_t* hi = smem_gen + (a_hi(stage) - smem_base);
+        uint8_t* lo = smem_gen + (a_lo(stage) - smem_base);
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(hi + (t + 128 * j) * 16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float x[4] = {v[j].x * sc.x, v[j].y * sc.y, v[j].z * sc.z, v[j].w * sc.w};
+          float h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            h[e] = __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u);
+            l[e] = x[e] - h[e];
+          }
+          *reinterpret_cast<float4*>(hi + (t + 128 * j) * 16) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(lo + (t + 128 * j) * 16) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(conv_bar(stage));
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int q = warp & 3;        // TMEM lane quadrant
+    const int res = warp >> 2;     // this warp takes the 16-column pieces pc = res, res + 4, ...
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint8_t* stg = smem_gen + stg_off + warp * kPwStgWarp;
+    // read-back mapping of a 32 x 16 piece: instruction i covers rows 8 i ... 8 i + 7, 4 x 16 B per row
+    const int rb_row = lane >> 2, rb_col = (lane & 3) * 4;
+    uint32_t acc_iter = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++acc_iter) {
+      const long long m0 = (long long)(item / p.num_n_tiles) * kPwBM;
+      const int n0 = (item % p.num_n_tiles) * BN;
+      const uint32_t buf = acc_iter % nacc;
+      const long long row_base = m0 + q * 32;
+      const int pieces = min(BN, p.N - n0 + 15) >> 4;                  // 16-column pieces that hold at least one valid column
+      const int nmine = pieces > res ? (pieces - res + 3) >> 2 : 0;    // this warp's pieces
+      const bool col_ok = n0 + res * 16 + rb_col < p.N;                // (re-evaluated per piece below)
+      float4 rs[4];
+      if (p.epi == kPwResidual && nmine > 0) {
+        // residual of the first piece: requested before the accumulator wait so its DRAM latency hides behind the MMAs
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long row = row_base + 8 * i + rb_row;
+          rs[i] = (row < p.M && col_ok) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.N + n0 + res * 16 + rb_col))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      mbar_wait(acc_full_bar(buf), (acc_iter / nacc) & 1u);
+      tc_fence_after();
+      if (nmine == 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty_bar(buf));
+        continue;
+      }
+      for (int g = 0; g < nmine; ++g) {
+        const int pc = res + 4 * g;
+        const int c0 = n0 + pc * 16;
+        uint32_t tr[16];
+        tmem_ld_32x16(tmem_base + lane_base + buf * (uint32_t)BN + pc * 16, tr);
+        float4 b4[4];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4)
+          b4[i4] = c0 + i4 * 4 < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.epi == kPwResidual && g > 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const long long row = row_base + 8 * i + rb_row;
+            rs[i] = (row < p.M && c0 + rb_col < p.N) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.N + c0 + rb_col))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        tmem_wait_ld();
+        if (g == nmine - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty_bar(buf));   // this warp has read everything it needs from the accumulator
+        }
+        float f[16];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          f[i4 * 4 + 0] = __uint_as_float(tr[i4 * 4 + 0]) + b4[i4].x;
+          f[i4 * 4 + 1] = __uint_as_float(tr[i4 * 4 + 1]) + b4[i4].y;
+          f[i4 * 4 + 2] = __uint_as_float(tr[i4 * 4 + 2]) + b4[i4].z;
+          f[i4 * 4 + 3] = __uint_as_float(tr[i4 * 4 + 3]) + b4[i4].w;
+        }
+        if (p.epi == kPwSilu || p.epi == kPwSiluPool) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = pw_silu(f[i]);
+        }
+        if (p.epi == kPwSiluPool) {
+          // column sums over this warp's 32 rows (all inside one image: hw % 128 == 0), one atomic per column
+#pragma unroll
+          for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+            const bool up = (lane & bit) != 0;
+#pragma unroll
+            for (int i = 0; i < w; ++i) {
+              const float send = up ? f[i] : f[i + w];
+              const float keep = up ? f[i + w] : f[i];
+              f[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+            }
+          }
+          f[0] += __shfl_xor_sync(0xffffffffu, f[0], 1);   // lanes 2c and 2c+1 hold the two halves of column c
+          const int col = c0 + (lane >> 1);
+          if ((lane & 1) == 0 && col < p.N && row_base < p.M) atomicAdd(p.y + (row_base / p.hw) * p.N + col, f[0]);
+          continue;
+        }
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4)
+          *reinterpret_cast<float4*>(stg + lane * kPwStgStride + i4 * 16) = make_float4(f[i4 * 4], f[i4 * 4 + 1], f[i4 * 4 + 2], f[i4 * 4 + 3]);
+        __syncwarp();
+        // read back row-contiguous: 4 x 16 B per row -> 8 rows per instruction, 64 B runs in global memory
+        float4 o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = *reinterpret_cast<const float4*>(stg + (8 * i + rb_row) * kPwStgStride + rb_col * 4);
+        float* yrow = p.y + (size_t)(row_base + rb_row) * p.N + c0 + rb_col;
+        const size_t ystep = (size_t)8 * p.N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (row_base + 8 * i + rb_row < p.M && c0 + rb_col < p.N) {
+            if (p.epi == kPwResidual) {
+              o[i].x += rs[i].x; o[i].y += rs[i].y; o[i].z += rs[i].z; o[i].w += rs[i].w;
+            }
+            *reinterpret_cast<float4*>(yrow + i * ystep) = o[i];
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kPwMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+static int pick_pw_bn(int N) {
+  const int n16 = (N + 15) / 16 * 16;
+  if (n16 <= kPwMaxBN) return n16;
+  // split into the fewest equal tiles of <= kPwMaxBN columns (multiples of 16)
+  for (int parts = 2; parts <= 32; ++parts) {
+    const int bn = ((N + parts - 1) / parts + 15) / 16 * 16;
+    if (bn <= kPwMaxBN) return bn;
+  }
+  return kPwMaxBN;
+}
+
+int launch_pointwise_tc(const PwTcArgs& a, cudaStream_t st) {
+  AQ_REQUIRE(a.M > 0 && a.K > 0 && a.N > 0, AQ_ERR_BAD_SHAPE, "pointwise: empty problem");
+  AQ_REQUIRE(a.K % 8 == 0 && a.N % 4 == 0, AQ_ERR_BAD_SHAPE, "pointwise: K=%d must be a multiple of 8 and N=%d of 4", a.K, a.N);
+  AQ_REQUIRE((a.se == nullptr && a.epi != kPwSiluPool) || a.hw % kPwBM == 0, AQ_ERR_BAD_SHAPE,
+             "pointwise: %d pixels per image is not a multiple of the %d-row tile", a.hw, kPwBM);
+  PwTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.BN = pick_pw_bn(a.N);
+  {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+    uint64_t str[1] = {(uint64_t)a.K * 4};
+    uint32_t box[2] = {kPwKC, kPwBM};
+    int rc = make_tmap(&p.tmap_x, a.x, 4, 2, dims, str, box, kSwz128);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+    uint64_t str[1] = {(uint64_t)a.K * 4};
+    uint32_t box[2] = {kPwKC, (uint32_t)p.BN};
+    int rc = make_tmap(&p.tmap_whi, a.w_hi, 4, 2, dims, str, box, kSwz128);
+    if (rc) return rc;
+    rc = make_tmap(&p.tmap_wlo, a.w_lo, 4, 2, dims, str, box, kSwz128);
+    if (rc) return rc;
+  }
+  p.bias = a.bias; p.se = a.se; p.residual = a.residual; p.y = a.y;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.hw = a.hw; p.epi = a.epi;
+  p.num_n_tiles = (a.N + p.BN - 1) / p.BN;
+  p.num_m_tiles = (int)((a.M + kPwBM - 1) / kPwBM);
+  p.num_kc = (a.K + kPwKC - 1) / kPwKC;
+  const int w_tile_bytes = 2 * p.BN * 128;                                   // hi + lo of one k chunk
+  const int fixed = kPwEpiWarps * kPwStgWarp + 512;
+  p.w_resident = (p.num_n_tiles == 1 && p.num_kc * w_tile_bytes <= 96 * 1024) ? 1 : 0;
+  const int wres_bytes = p.w_resident ? p.num_kc * w_tile_bytes : 0;
+  const int stage_bytes = 2 * kPwATile + (p.w_resident ? 0 : w_tile_bytes);
+  int stages = (kPwSmemBudget - fixed - wres_bytes) / stage_bytes;
+  if (stages > 6) stages = 6;
+  AQ_REQUIRE(stages >= 2, AQ_ERR_BAD_SHAPE, "pointwise: column tile %d leaves no room for a pipeline", p.BN);
+  p.stages = stages;
+  const int smem = wres_bytes + stages * stage_bytes + fixed + 1024;
+  const int sms = sm_count();
+  if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
+  const long long items = (long long)p.num_m_tiles * p.num_n_tiles;
+  const int grid = (int)(items < sms ? items : sms);
+  static bool attr_set = false;
+  if (!attr_set) {
+    AQ_CHECK_CUDA(cudaFuncSetAttribute(pointwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  pointwise_tc_kernel<<<grid, kPwThreads, smem, st>>>(p);
+  AQ_LAUNCHED();
+  return AQ_OK;
+}
+
+}  // namespace aq

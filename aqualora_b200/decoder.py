@@ -74,19 +74,32 @@ def _fold(sd, conv_key, bn_key):
     return (w * s.view(-1, 1, 1, 1)).float(), (b - mu * s).float()
 
 
+def _split_tf32(w: torch.Tensor):
+    """w = hi + lo exactly, hi = w with the low 13 mantissa bits cleared (a TF32 number): the operands of the 3-term
+    tensor-core product in csrc/decoder_pw.cu."""
+    w = w.contiguous().float()
+    hi = (w.view(torch.int32) & -8192).view(torch.float32)          # -8192 == 0xFFFFE000
+    return hi, w - hi
+
+
 def pack_state_dict(sd: dict, out_features: int, prefix: str = "model.") -> torch.Tensor:
     """Fold every BatchNorm (eval) into its convolution and lay the fp32 parameters out in execution order, each segment
     padded to a multiple of 4 floats -- the layout csrc/decoder.cu walks:
         stem  w [(ky, kx, ci), 32], b [32]
-        block [expand: Wt [cin, cexp], b] , dw w [k*k, cexp], b , se w1 [sq, cexp], b1, w2 [cexp, sq], b2 , project Wt [cexp, cout], b
-        head  Wt [320, 1280], b ; fc w [out, 1280], b
-    The fold is computed in float64 and rounded once."""
+        block [expand: W_hi [cexp, cin], W_lo [cexp, cin], b] , dw w [k*k, cexp], b , se w1 [sq, cexp], b1, w2^T [sq, cexp], b2 ,
+              project W_hi [cout, cexp], W_lo [cout, cexp], b
+        head  W_hi [1280, 320], W_lo, b ; fc w [out, 1280], b
+    The fold is computed in float64 and rounded once; pointwise weights are stored as an exact hi + lo TF32 split."""
     out = []
 
     def put(t):
         t = t.reshape(-1).float()
         padn = (-t.numel()) % 4
         out.append(torch.cat([t, t.new_zeros(padn)]) if padn else t)
+
+    def put_pointwise(w, b):
+        hi, lo = _split_tf32(w.flatten(1))                              # [cout, cin], K-major like the conv weight itself
+        put(hi); put(lo); put(b)
 
     p = prefix + "features."
     w, b = _fold(sd, p + "0.0", p + "0.1")
@@ -96,19 +109,16 @@ def pack_state_dict(sd: dict, out_features: int, prefix: str = "model.") -> torc
             q = f"{p}{si + 1}.{li}.block."
             i = 0
             if expand != 1:
-                w, b = _fold(sd, f"{q}{i}.0", f"{q}{i}.1")
-                put(w.flatten(1).t()); put(b)
+                put_pointwise(*_fold(sd, f"{q}{i}.0", f"{q}{i}.1"))
                 i += 1
             w, b = _fold(sd, f"{q}{i}.0", f"{q}{i}.1")
             put(w.flatten(1).t()); put(b)                     # [cexp, 1, k, k] -> [k*k, cexp]
             i += 1
             put(sd[f"{q}{i}.fc1.weight"].flatten(1)); put(sd[f"{q}{i}.fc1.bias"])
-            put(sd[f"{q}{i}.fc2.weight"].flatten(1)); put(sd[f"{q}{i}.fc2.bias"])
+            put(sd[f"{q}{i}.fc2.weight"].flatten(1).t()); put(sd[f"{q}{i}.fc2.bias"])       # [cexp, sq] -> [sq, cexp]
             i += 1
-            w, b = _fold(sd, f"{q}{i}.0", f"{q}{i}.1")
-            put(w.flatten(1).t()); put(b)
-    w, b = _fold(sd, p + "8.0", p + "8.1")
-    put(w.flatten(1).t()); put(b)
+            put_pointwise(*_fold(sd, f"{q}{i}.0", f"{q}{i}.1"))
+    put_pointwise(*_fold(sd, p + "8.0", p + "8.1"))
     put(sd[prefix + "classifier.1.weight"]); put(sd[prefix + "classifier.1.bias"])
     return torch.cat(out).contiguous()
 

@@ -291,3 +291,34 @@ def effnetb1_fwd(x: torch.Tensor, packed: torch.Tensor, out_features: int, want_
     _lib.call("aq_effnetb1_fwd", x.data_ptr(), packed.data_ptr(), logits.data_ptr(), _ptr(bits), B, out_features, ws.data_ptr(),
               ws.numel(), _stream())
     return logits, bits
+
+
+def conv1x1_tf32x3(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, se: torch.Tensor | None = None,
+                   residual: torch.Tensor | None = None, hw: int = 0, epi: int = 0) -> torch.Tensor:
+    """Pointwise convolution over NHWC pixels on the tensor cores with the fp32-faithful 3-term TF32 split
+    (csrc/decoder_pw.cu).  x [M, K] fp32, w [N, K] fp32 (split here), bias [N]; epi 0 none / 1 SiLU / 2 + residual /
+    3 SiLU + per-image column sums (returns [M // hw, N])."""
+    _need(x, _F32, "x", 2)
+    _need(w, _F32, "w", 2)
+    M, K = x.shape
+    N = w.shape[0]
+    w = w.contiguous()
+    hi = (w.view(torch.int32) & -8192).view(torch.float32)
+    lo = w - hi
+    hw = hw or M
+    y = torch.zeros((M // hw, N), dtype=_F32, device=x.device) if epi == 3 else torch.empty((M, N), dtype=_F32, device=x.device)
+    _lib.call("aq_conv1x1_tf32x3", x.contiguous().data_ptr(), hi.data_ptr(), lo.data_ptr(), bias.contiguous().data_ptr(), _ptr(se),
+              _ptr(residual), y.data_ptr(), M, K, N, hw, epi, _stream())
+    return y
+
+
+def depthwise_silu(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, k: int, stride: int):
+    """SiLU(depthwise k x k conv + bias) over NHWC x [B, H, H, C]; w [k * k, C].  Returns (y [B, Ho, Ho, C], pooled sums [B, C])."""
+    _need(x, _F32, "x", 4)
+    B, H, _, C = x.shape
+    ho = (H + 2 * ((k - 1) // 2) - k) // stride + 1
+    y = torch.empty((B, ho, ho, C), dtype=_F32, device=x.device)
+    pooled = torch.zeros((B, C), dtype=_F32, device=x.device)
+    _lib.call("aq_depthwise_silu", x.contiguous().data_ptr(), w.contiguous().data_ptr(), bias.contiguous().data_ptr(), y.data_ptr(),
+              pooled.data_ptr(), B, H, C, k, stride, _stream())
+    return y, pooled

@@ -151,12 +151,25 @@ int aq_noise_color_jiggle(const float* x, float* y, const float* params, const i
  * x [B, 3, 512, 512] fp32 NCHW in [-1, 1] (resize other sizes first: aq_noise_crop_resize with a full-image crop is
  * the reference's bilinear F.interpolate).  packed: aq_effnetb1_packed_floats(out_features) fp32 values, BatchNorm
  * folded into the preceding conv, in execution order (layout: aqualora_b200/decoder.py:pack_state_dict).
- * logits [B, out_features] fp32; bits [B, out_features / 2] u8 or NULL.  All arithmetic fp32 FFMA (no TF32).
+ * logits [B, out_features] fp32; bits [B, out_features / 2] u8 or NULL.  fp32-faithful arithmetic: pointwise convolutions
+ * as 3-term split-TF32 tensor-core products with fp32 accumulation, everything else fp32 FFMA.
  * ---------------------------------------------------------------------------------------------- */
 size_t aq_effnetb1_packed_floats(int out_features);
 size_t aq_effnetb1_workspace_bytes(int B);
 int aq_effnetb1_fwd(const float* x, const float* packed, float* logits, unsigned char* bits, int B, int out_features,
                     void* ws, size_t ws_bytes, void* stream);
+
+/* The two building blocks of the decoder's MBConv blocks (torchvision MBConv.forward as used by utils/models.py:88-96),
+ * exported for kernel-level parity tests:
+ * aq_conv1x1_tf32x3: y[m, n] = epi(sum_k (x[m, k] * se[m / hw, k]) * (w_hi + w_lo)[n, k] + bias[n]) over NHWC pixels
+ *   x [M, K], y [M, N] fp32; w_hi / w_lo [N, K] = exact TF32 split of the BatchNorm-folded conv weight; se [M / hw, K] or NULL;
+ *   epi: 0 none, 1 SiLU, 2 + residual[M, N], 3 SiLU then per-image column sums into y [M / hw, N] (y must be zeroed).
+ * aq_depthwise_silu: y = SiLU(depthwise_k x k, stride s (x) + bias), NHWC, pad (k - 1) / 2; pooled [B, C] += sum over pixels
+ *   x [B, H, H, C], w [k * k, C], y [B, Ho, Ho, C]. */
+int aq_conv1x1_tf32x3(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* se,
+                      const float* residual, float* y, int64_t M, int K, int N, int hw, int epi, void* stream);
+int aq_depthwise_silu(const float* x, const float* w, const float* bias, float* y, float* pooled, int B, int H, int C, int k,
+                      int stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     torch.manual_seed(0)
-    dec = SecretDecoder(48).to(dev).eval()
+    dec = SecretDecoder(48).eval()      # parameters stay on the host: packing (BN fold) then runs on the CPU, only our kernels hit the GPU
     x = torch.rand(B, 3, 512, 512, device=dev) * 2 - 1
     for _ in range(reps):
         dec.decode_bits(x)
