@@ -345,6 +345,17 @@ def run_cuda(args):
             "cpu_baseline": cpu,
         }
         line.update(extra)
+        if world == 1 and not args.no_secondary:
+            # BASELINE.json configs[3] (decode throughput + bit agreement) rides along as a secondary record; the trainer is
+            # released first so the decoder's workspace and image pool fit beside nothing else
+            del trainer, unet, resident, host
+            torch.cuda.empty_cache()
+            try:
+                d = measure_decode(args.decode_images)
+                line["secondary"] = {k: d[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "config", "gpu_launches",
+                                                       "bit_agreement", "roofline", "cpu_baseline")}
+            except Exception as e:  # the headline line must survive a failure of the secondary workload
+                line["secondary"] = {"metric": "decode_images_per_sec", "error": repr(e)[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -447,7 +458,16 @@ DECODE_BYTES_PER_IMAGE_FP32 = 404.4e6     # 101.09 M activation 
 NOISE_P = [0.4, 0.1, 0.2, 0.05, 0.1, 0.15]
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum over the 93 decoder launches of one 64-image batch (ncu launch list
+# profiles/r01_decoder_launches_v7.txt: 13.59 GB read + 9.91 GB written), per image
+DECODE_DRAM_TRAFFIC_PER_IMAGE = (13.589e9 + 9.913e9) / 64
+
+
 def run_decode(args):
+    print(json.dumps(measure_decode(args.images)), flush=True)
+
+
+def measure_decode(images, cpu_check=True):
     """`--workload decode`: N synthetic 512x512 images in batches of 64; per batch one noise layer drawn with
     p = [.4, .1, .2, .05, .1, .15] (train/latent_wm_pretrain.py:188) from numpy default_rng(7), then the EfficientNet-B1
     decoder; bits checked against the CPU oracle on a bounded sample."""
@@ -466,7 +486,7 @@ def run_decode(args):
     dec.load_state_dict(sd)
     dec = dec.to(dev).eval()
     bs = 64
-    n_batches = max(1, args.images // bs)
+    n_batches = max(1, images // bs)
     names = ["Jpeg", "CropandResize", "GaussianBlur", "GaussianNoise", "ColorJitter"]
     noiser = noise_layers.Noiser(names, NOISE_P, dev, rng=np.random.default_rng(7))
     pool = [noise_layers.unit_noise((bs, 3, 512, 512), seed=7, offset=i * bs * 3 * 512 * 512 // 4, device=dev).clamp_(-3, 3) / 3
@@ -531,11 +551,12 @@ def run_decode(args):
                               "sample": "8 images x 6 noise layers through the CPU oracle with identical layer parameters"},
             "roofline": {"bound": "hbm", "kernel": "decoder chain (csrc/decoder.cu), decoder-only loop", "achieved": round(DECODE_BYTES_PER_IMAGE_FP32 * dec_rate / 1e9, 1),
                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(DECODE_BYTES_PER_IMAGE_FP32 * dec_rate / 1e9 / pk["hbm_gbs"], 4),
-                         "traffic": None, "decoder_images_per_sec": round(dec_rate, 1),
+                         "traffic": round(DECODE_DRAM_TRAFFIC_PER_IMAGE), "traffic_note": "DRAM bytes per image, ncu launch list of one 64-image batch",
+                         "decoder_images_per_sec": round(dec_rate, 1),
                          "algorithmic_bytes_per_image": DECODE_BYTES_PER_IMAGE_FP32},
             "cpu_baseline": {"value": round(48 / t_cpu, 3), "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": f"48 images (8 per noise layer) through oracle noise layer + torch EfficientNet-B1 restatement, {t_cpu:.1f} s"}}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def main():
@@ -551,6 +572,8 @@ def main():
     ap.add_argument("--shapes-out", default=None, help="write the per-shape kernel table (JSON) here")
     ap.add_argument("--workload", default="ppft", choices=["ppft", "decode"], help="ppft = the headline metric; decode = configs[3]")
     ap.add_argument("--images", type=int, default=10_000, help="--workload decode: number of images")
+    ap.add_argument("--decode-images", type=int, default=2048, help="images of the secondary decode record on the ppft line (N = 1)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary decode record")
     args = ap.parse_args()
     if args.workload == "decode":
         run_decode(args)
