@@ -193,7 +193,21 @@ class GemmProbe:
 # --------------------------------------------------------------------------------------------------------------------
 # the CUDA arm
 # --------------------------------------------------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner to fd 1) are re-pointed at stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
 def run_cuda(args):
+    _claim_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -296,9 +310,13 @@ def run_cuda(args):
     # ---- roofline pass (instrumented, after the timed regions) ----------------------------------------------------
     roof = None
     extra = {}
+    probe_steps = 3
+    if rank != 0:
+        # every rank runs the instrumented steps: each step holds the gradient all-reduce, so rank 0 alone would wait forever
+        for i in range(probe_steps):
+            step_from_device(*resident[i % n_pool])
     if rank == 0:
         pk = peaks()
-        probe_steps = 3
         with GemmProbe(ops) as probe:
             for i in range(probe_steps):
                 step_from_device(*resident[i % n_pool])
@@ -356,7 +374,7 @@ def run_cuda(args):
                                                        "bit_agreement", "roofline", "cpu_baseline")}
             except Exception as e:  # the headline line must survive a failure of the secondary workload
                 line["secondary"] = {"metric": "decode_images_per_sec", "error": repr(e)[:300]}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_claim_stdout(), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -464,7 +482,8 @@ DECODE_DRAM_TRAFFIC_PER_IMAGE = (13.589e9 + 9.913e9) / 64
 
 
 def run_decode(args):
-    print(json.dumps(measure_decode(args.images)), flush=True)
+    out = _claim_stdout()
+    print(json.dumps(measure_decode(args.images)), file=out, flush=True)
 
 
 def measure_decode(images, cpu_check=True):
