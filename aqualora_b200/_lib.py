@@ -53,6 +53,8 @@ _SIGNATURES = {
     "aq_effnetb1_fwd": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p], c_int),
     "aq_conv1x1_tf32x3": ([c_void_p] * 7 + [c_int64, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "aq_depthwise_silu": ([c_void_p] * 5 + [c_int] * 5 + [c_void_p], c_int),
+    "aq_lora_fold_down": ([c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_void_p], c_int),
+    "aq_lora_merge": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p], c_int),
     "aq_flat_sumsq": ([c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "aq_flat_clip_adamw": (
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,

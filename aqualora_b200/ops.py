@@ -322,3 +322,29 @@ def depthwise_silu(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, k: int,
     _lib.call("aq_depthwise_silu", x.contiguous().data_ptr(), w.contiguous().data_ptr(), bias.contiguous().data_ptr(), y.data_ptr(),
               pooled.data_ptr(), B, H, C, k, stride, _stream())
     return y, pooled
+
+
+def lora_fold_down(down: torch.Tensor, m: torch.Tensor, scale: float) -> torch.Tensor:
+    """down' = (down * m[:, None...]) * scale for a [r, ...] fp32 LoRA down weight (scripts/create_wm_lora.py:30-37)."""
+    _need(down, _F32, "down")
+    _need(m, _F32, "m", 1)
+    r = down.shape[0]
+    if m.numel() != r:
+        raise _lib.AqualoraError(f"mapper output has {m.numel()} entries, LoRA rank is {r}")
+    d = down.contiguous()
+    out = torch.empty_like(d)
+    _lib.call("aq_lora_fold_down", d.data_ptr(), m.contiguous().data_ptr(), out.data_ptr(), r, d.numel() // r, float(scale), _stream())
+    return out
+
+
+def lora_merge_(w: torch.Tensor, up: torch.Tensor, down: torch.Tensor, coef: float) -> torch.Tensor:
+    """In place: w [dout, din] += coef * (up [dout, r] @ down [r, din]), fp32 (scripts/merge_lora.py:107-120)."""
+    _need(w, _F32, "w")
+    _need(up, _F32, "up")
+    _need(down, _F32, "down")
+    dout, r = up.shape[0], down.shape[0]
+    din = down.numel() // r
+    if not w.is_contiguous() or w.numel() != dout * din or up.numel() != dout * r:
+        raise _lib.AqualoraError(f"merge shapes: w {tuple(w.shape)}, up {tuple(up.shape)}, down {tuple(down.shape)}")
+    _lib.call("aq_lora_merge", w.data_ptr(), up.contiguous().data_ptr(), down.contiguous().data_ptr(), dout, din, r, float(coef), _stream())
+    return w

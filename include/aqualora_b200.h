@@ -171,6 +171,15 @@ int aq_conv1x1_tf32x3(const float* x, const float* w_hi, const float* w_lo, cons
 int aq_depthwise_silu(const float* x, const float* w, const float* bias, float* y, float* pooled, int B, int H, int C, int k,
                       int stride, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Message -> deployable weights (scripts/create_wm_lora.py:23-41, scripts/merge_lora.py:98-120).
+ * aq_lora_fold_down: out[i, :] = (down[i, :] * m[i]) * scale, down / out [r, cols] fp32, m [r] = mapper(msg) (the
+ *   reference's diag_embed(m) @ down * scale for linear targets and down * m[:, None, None, None] * scale for 1x1 convs).
+ * aq_lora_merge: w[dout, din] += coef * (up[dout, r] @ down[r, din]), fp32, coef = ratio * alpha / dim, r <= 64.
+ * ---------------------------------------------------------------------------------------------- */
+int aq_lora_fold_down(const float* down, const float* m, float* out, int r, int64_t cols, float scale, void* stream);
+int aq_lora_merge(float* w, const float* up, const float* down, int dout, int din, int r, float coef, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,3 +141,30 @@ def test_unet_keys_golden(golden_dir):
         with torch.device("meta"):
             unet = UNet2DConditionModel(cfg)
         assert lora_target_keys(unet) == want
+
+
+def test_create_wm_lora_oracle_matches_reference_script(golden_dir):
+    """oracle/deploy_oracle.fold_message == scripts/create_wm_lora.py:create_watermark_lora (run by tools/gen_golden.py), bit for bit."""
+    from oracle import deploy_oracle as DO
+
+    g = _load(golden_dir, "create_wm_lora.pt")
+    out = DO.fold_message(g["lora_sd"], g["emb"], g["hidinfo"], g["scale"])
+    assert set(out) == set(g["out"]) and not any("text_encoder" in k for k in out)
+    for k, v in g["out"].items():
+        assert torch.equal(out[k], v), k
+
+
+def test_merge_delta_oracle_known_answers():
+    """scripts/merge_lora.py:98-120: rank-1 known answer, alpha scaling, 1x1-conv branch == linear branch."""
+    from oracle import deploy_oracle as DO
+
+    w = torch.zeros(3, 2)
+    up = torch.tensor([[1.0], [2.0], [3.0]])
+    down = torch.tensor([[10.0, 100.0]])
+    assert torch.equal(DO.merge_delta(w, up, down, 0.5), torch.tensor([[5.0, 50.0], [10.0, 100.0], [15.0, 150.0]]))
+    assert torch.equal(DO.merge_delta(w, up, down, 1.0, alpha=2.0), 2 * DO.merge_delta(w, up, down, 1.0))
+    g = torch.Generator().manual_seed(0)
+    w, up, down = torch.randn(6, 5, generator=g), torch.randn(6, 4, generator=g), torch.randn(4, 5, generator=g)
+    lin = DO.merge_delta(w, up, down, 0.7)
+    conv = DO.merge_delta(w[:, :, None, None], up[:, :, None, None], down[:, :, None, None], 0.7)
+    assert torch.equal(conv[:, :, 0, 0], lin)

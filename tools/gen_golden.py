@@ -204,7 +204,43 @@ def gen_keys():
     (OUT / "unet_keys.json").write_text(json.dumps(keys, indent=0))
 
 
+def gen_create_wm_lora():
+    """scripts/create_wm_lora.py run unchanged on a synthetic train folder (rank 320 as the reference hard-codes, tiny widths)."""
+    import tempfile
+
+    from safetensors.torch import save_file
+
+    g = torch.Generator().manual_seed(21)
+    r = 320
+    sd = {
+        "unet.down_blocks.0.attentions.0.transformer_blocks.0.attn1.processor.to_q_lora.down.weight": torch.randn(r, 24, generator=g),
+        "unet.down_blocks.0.attentions.0.transformer_blocks.0.attn1.processor.to_q_lora.up.weight": torch.randn(24, r, generator=g),
+        "unet.mid_block.attentions.0.transformer_blocks.0.ff.net.2.lora.down.weight": torch.randn(r, 40, generator=g),
+        "unet.mid_block.attentions.0.transformer_blocks.0.ff.net.2.lora.up.weight": torch.randn(16, r, generator=g),
+        "unet.up_blocks.1.attentions.2.proj_in.lora.down.weight": torch.randn(r, 8, 1, 1, generator=g),
+        "unet.up_blocks.1.attentions.2.proj_in.lora.up.weight": torch.randn(8, r, 1, 1, generator=g),
+        "text_encoder.foo.lora.down.weight": torch.randn(4, 4, generator=g),
+    }
+    emb = torch.randn(48, r, generator=g)
+    hid = "".join(str(int(b)) for b in torch.randint(0, 2, (48,), generator=g))
+    with tempfile.TemporaryDirectory() as td:
+        save_file(sd, f"{td}/pytorch_lora_weights.safetensors")
+        torch.save({"bit_embeddings.weight": emb}, f"{td}/mapper.pt")
+        sys.path.insert(0, str(REF / "scripts"))
+        sys.path.insert(0, str(REF))
+        for m in ("lpips", "timm"):
+            sys.modules.setdefault(m, types.ModuleType(m))
+        cwl = _load("ref_create_wm_lora", REF / "scripts" / "create_wm_lora.py")
+        bits, out = cwl.create_watermark_lora(td, 1.03, 48, hid, save=False)
+    assert bits == hid
+    torch.save({"lora_sd": sd, "emb": emb, "hidinfo": hid, "scale": 1.03, "out": {k: v.detach().clone() for k, v in out.items()}},
+               OUT / "create_wm_lora.pt")
+
+
 def main():
+    if '--create-wm-lora-only' in sys.argv:
+        gen_create_wm_lora()
+        return
     OUT.mkdir(parents=True, exist_ok=True)
     dml = _stub_modules()
     ref_lora = _load("ref_lora_modules", REF / "utils" / "lora_modules.py")
@@ -213,6 +249,7 @@ def main():
     gen_models(ref_models)
     gen_jpeg()
     gen_keys()
+    gen_create_wm_lora()
     for f in sorted(OUT.glob("*")):
         print(f.name, f.stat().st_size)
 
