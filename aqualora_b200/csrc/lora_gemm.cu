@@ -637,7 +637,10 @@ static int launch_bn(const LoraGemmArgs& a, cudaStream_t stream) {
 
 static int pick_bn(int N) {
   if (N <= 64) return 64;
-  // fewest computed columns; ties go to the wider tile (more FLOPs per byte staged through SMEM)
+  // Wide projections (the feed-forward layers, N >= 2560): the 192-column tile moves 28 KiB per 3.1 MFLOP k-block instead of
+  // 26 KiB per 2.6 MFLOP and measured 4 - 12 % faster than 160 despite <= 5 % padded columns (profiles/r01_lora_kernel_check_v2.log).
+  if (N >= 2560) return 192;
+  // otherwise: fewest computed columns; ties go to the wider tile
   int best = 192, best_cols = 1 << 30;
   const int cand[3] = {192, 160, 128};
   for (int i = 0; i < 3; ++i) {
