@@ -11,7 +11,10 @@
 // products with fp32 accumulation (decoder_pw.cu); stem, depthwise, SE and classifier are fp32 FFMA.  HBM-bound by design:
 // activations make one round trip per layer, the elementwise work (bias, SiLU, SE scale, residual, pooling) rides in the
 // producing / consuming kernel.
+#include <string.h>
+
 #include "aq_common.h"
+#include "aq_ptx.cuh"
 #include "decoder_pw.h"
 
 namespace aq {
@@ -28,7 +31,12 @@ static inline size_t pad4(size_t n) { return (n + 3) & ~(size_t)3; }
 
 __device__ __forceinline__ float silu(float v) { return v / (1.f + expf(-v)); }   // exact: SE MLP (tiny tensors)
 // SFU exponential + reciprocal (relative error ~1e-6): the activation maps, where the exact form cost more than the convolution
-__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+__device__ __forceinline__ float silu_fast(float v) {
+  float e, r;   // ex2.approx.ftz saturates cleanly at both ends; see decoder_pw.cu:pw_silu
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return v * r;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // stem: [B, 3, 512, 512] NCHW -> [B, 256, 256, 32] NHWC.  w [27][32] ((ky, kx, ci) major), b [32]
@@ -206,6 +214,225 @@ __global__ void __launch_bounds__(kDwThreads, 3) depthwise_kernel(const float* _
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// depthwise k x k STRIDE 1 with TMA-staged input tiles (the 19 stride-1 launches carry 80 % of the depthwise bytes).
+// The register-window kernel above keeps only ~24 KiB of loads in flight per SM (12 warps x a handful of LDGs) and sat at
+// 1 - 2.6 TB/s; here a producer warp streams (8 + k - 1) x (TW + k - 1) x 32-channel input boxes through a 3 - 4 stage mbarrier
+// ring with cp.async.bulk.tensor.4d (zero-filled halo = the convolution's padding, no bounds checks in the math), so 100+ KiB
+// are in flight per SM and the 8 consumer warps run the same sliding window out of shared memory.
+//   x as a 4-D tensor {C, W, H, B}; box {32, TW + k - 1, 8 + k - 1, 1}; work item = (channel block, image, tile y, tile x)
+//   consumer thread = (V channels, worker); worker = 2 output rows x TW / WCOLS output columns
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kDtConsumers = 256, kDtThreads = 288, kDtTH = 8, kDtCB = 32;
+
+struct DwTmaParams {
+  CUtensorMap tmap_x;
+  const float* w; const float* b; float* y; float* pooled;
+  int B, H, W, C, tiles_x, tiles_y, cblocks, total_items, stages;
+};
+
+template <int KS, int TW>
+__global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __grid_constant__ DwTmaParams p) {
+  constexpr int P = (KS - 1) / 2, THin = kDtTH + KS - 1, TWin = TW + KS - 1;
+  constexpr int V = KS == 3 ? 4 : 2;
+  constexpr int CV = kDtCB / V;                  // channel vectors per block
+  constexpr int WORKERS = kDtConsumers / CV;     // 32 (k = 3) or 16 (k = 5)
+  constexpr int WROWS = kDtTH / 2;               // 4 row pairs
+  constexpr int WCOLS = WORKERS / WROWS;         // 8 or 4
+  constexpr int CPW = TW / WCOLS;                // output columns per worker
+  constexpr int R = 2, NR = R + KS - 1;
+  constexpr uint32_t kTileBytes = THin * TWin * kDtCB * 4;
+  constexpr uint32_t kTileStride = (kTileBytes + 127u) & ~127u;
+  static_assert(CPW >= 1 && TW % WCOLS == 0, "tile width must split evenly over the workers");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int stages = p.stages;
+  const uint32_t pool_off = (uint32_t)stages * kTileStride;            // float pool_s[2][8 warps][32]: per-warp partial squeeze sums
+  const uint32_t bar_off = pool_off + 2 * 8 * kDtCB * 4;
+  auto full_bar = [&](int s) { return smem_base + bar_off + 8u * s; };
+  auto empty_bar = [&](int s) { return smem_base + bar_off + 8u * (8 + s); };
+  float* pool_s = reinterpret_cast<float*>(smem_gen + pool_off);
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), kDtConsumers / 32);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == kDtConsumers / 32) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) tma_prefetch_desc(&p.tmap_x);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      // channel block fastest: the blocks of one spatial tile are fetched by neighbouring CTAs at the same time (a pixel's
+      // channels share 128 B lines / 256 B L2 promotions when C * 4 is not a multiple of 128)
+      const int cb = item % p.cblocks;
+      const int rem = item / p.cblocks;
+      const int n = rem / tiles_per_img, t2 = rem % tiles_per_img;
+      const int ty = t2 / p.tiles_x, tx = t2 % p.tiles_x;
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(full_bar(stage), kTileBytes);
+        tma_load_4d(smem_base + (uint32_t)stage * kTileStride, &p.tmap_x, full_bar(stage), cb * kDtCB, tx * TW - P, ty * kDtTH - P, n);
+      }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // =========================== consumers ===========================
+    const int t = threadIdx.x;
+    const int cv = t % CV, worker = t / CV;
+    const int wy = worker / WCOLS, wx = worker % WCOLS;
+    const int r0 = 2 * wy, cbeg = wx * CPW;
+    float wr[KS * KS][V], bias[V];
+    int cur_cb = -1;
+    int stage = 0;
+    uint32_t phase = 0, it = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+      const int cb = item % p.cblocks;
+      const int rem = item / p.cblocks;
+      const int n = rem / tiles_per_img, t2 = rem % tiles_per_img;
+      const int ty = t2 / p.tiles_x, tx = t2 % p.tiles_x;
+      const int c0 = cb * kDtCB + cv * V;
+      const bool ch_ok = c0 < p.C;
+      if (cb != cur_cb) {
+        cur_cb = cb;
+#pragma unroll
+        for (int i = 0; i < KS * KS; ++i) {
+          if (ch_ok) ldv<V>(p.w + i * p.C + c0, wr[i]);
+          else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) wr[i][v] = 0.f;
+          }
+        }
+        if (ch_ok) ldv<V>(p.b + c0, bias);
+        else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) bias[v] = 0.f;
+        }
+      }
+      mbar_wait(full_bar(stage), phase);
+      const float* tile = reinterpret_cast<const float*>(smem_gen + (uint32_t)stage * kTileStride) + cv * V;
+      auto lds = [&](int row, int col, float (&d)[V]) {
+        const float* q = tile + (row * TWin + col) * kDtCB;
+        if constexpr (V == 4) {
+          const float4 v4 = *reinterpret_cast<const float4*>(q);
+          d[0] = v4.x; d[1] = v4.y; d[2] = v4.z; d[3] = v4.w;
+        } else {
+          const float2 v2 = *reinterpret_cast<const float2*>(q);
+          d[0] = v2.x; d[1] = v2.y;
+        }
+      };
+      // window slot of logical column kx at unrolled output column c: (kx + c) % KS -- nothing is ever shifted
+      float win[NR][KS][V];
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) lds(r0 + r, cbeg + kx, win[r][kx]);
+      float pool[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) pool[v] = 0.f;
+      const int oy0 = ty * kDtTH + r0, ox0 = tx * TW + cbeg;
+      float* yb = p.y + (((size_t)n * p.H + oy0) * p.W + ox0) * p.C + c0;
+#pragma unroll
+      for (int c = 0; c < CPW; ++c) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float acc[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = bias[v];
+#pragma unroll
+          for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+              for (int v = 0; v < V; ++v) acc[v] = fmaf(win[r + ky][(kx + c) % KS][v], wr[ky * KS + kx][v], acc[v]);
+          if (ch_ok && oy0 + r < p.H && ox0 + c < p.W) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              acc[v] = silu_fast(acc[v]);
+              pool[v] += acc[v];
+            }
+            stv<V>(yb + ((size_t)r * p.W + c) * p.C, acc);
+          }
+        }
+        if (c + 1 < CPW) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) lds(r0 + r, cbeg + c + KS, win[r][c % KS]);
+        }
+      }
+      // this thread is done with the tile: hand the stage back to the producer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(stage));
+      if (++stage == stages) { stage = 0; phase ^= 1u; }
+      // squeeze sums: shuffle-reduce over the workers of this warp (lanes with equal cv), per-warp partials in SMEM (no atomics:
+      // a contended shared fp32 atomicAdd is a CAS loop and cost 4 us per item), one global atomic per channel per item
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+#pragma unroll
+        for (int o = CV; o < 32; o <<= 1) pool[v] += __shfl_xor_sync(0xffffffffu, pool[v], o);
+      }
+      float* part = pool_s + ((it & 1u) * 8 + (t >> 5)) * kDtCB;
+      if (lane < CV) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) part[lane * V + v] = pool[v];
+      }
+      named_bar_sync(1, kDtConsumers);
+      if (t < kDtCB) {
+        const float* base = pool_s + (it & 1u) * 8 * kDtCB + t;
+        float sum = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) sum += base[w8 * kDtCB];
+        if (cb * kDtCB + t < p.C) atomicAdd(p.pooled + (size_t)n * p.C + cb * kDtCB + t, sum);
+      }
+    }
+  }
+}
+
+template <int KS, int TW>
+static int launch_depthwise_tma_t(const float* x, const float* w, const float* b, float* y, float* pooled, int B, int H, int C,
+                                  cudaStream_t st) {
+  constexpr int THin = kDtTH + KS - 1, TWin = TW + KS - 1;
+  constexpr int kTileStride = (THin * TWin * kDtCB * 4 + 127) & ~127;
+  DwTmaParams p;
+  memset(&p, 0, sizeof(p));
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)H, (uint64_t)H, (uint64_t)B};
+  uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)H * C * 4, (uint64_t)H * H * C * 4};
+  uint32_t box[4] = {kDtCB, TWin, THin, 1};
+  int rc = make_tmap(&p.tmap_x, x, 4, 4, dims, str, box, kSwzNone);
+  if (rc) return rc;
+  p.w = w; p.b = b; p.y = y; p.pooled = pooled;
+  p.B = B; p.H = H; p.W = H; p.C = C;
+  p.tiles_x = (H + TW - 1) / TW;
+  p.tiles_y = (H + kDtTH - 1) / kDtTH;
+  p.cblocks = (C + kDtCB - 1) / kDtCB;
+  const long long items = (long long)p.cblocks * B * p.tiles_x * p.tiles_y;
+  AQ_REQUIRE(items < (1ll << 31), AQ_ERR_BAD_SHAPE, "depthwise: too many tiles");
+  p.total_items = (int)items;
+  int stages = (200 * 1024) / kTileStride;
+  if (stages > 6) stages = 6;
+  p.stages = stages;
+  const int smem = stages * kTileStride + 2 * 8 * kDtCB * 4 + 16 * 8 + 128;
+  const int sms = sm_count();
+  if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
+  const int grid = (int)(items < sms ? items : sms);
+  static bool attr_set = false;
+  if (!attr_set) {
+    AQ_CHECK_CUDA(cudaFuncSetAttribute(depthwise_tma_kernel<KS, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  depthwise_tma_kernel<KS, TW><<<grid, kDtThreads, smem, st>>>(p);
+  AQ_LAUNCHED();
+  return AQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // SqueezeExcitation MLP: scale[n, c] = sigmoid(b2[c] + sum_j w2t[j, c] * silu(b1[j] + sum_c' w1[j, c'] * mean[n, c']))
 // grid (B, channel chunks of 256): every block recomputes the tiny squeeze vector s1 [SQ] (warp per row of w1, 4 independent
 // accumulators), then one thread per output channel walks w2t [SQ, C] (transposed at pack time -> coalesced).
@@ -344,6 +571,10 @@ static Buffers buffer_plan() {
 
 static int launch_depthwise(const float* x, const float* w, const float* b, float* y, float* pooled, int B, int H, int C, int k,
                             int stride, int Ho, cudaStream_t st) {
+  if (stride == 1 && C >= kDtCB && C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+    if (k == 3) return Ho >= 32 ? launch_depthwise_tma_t<3, 32>(x, w, b, y, pooled, B, H, C, st) : launch_depthwise_tma_t<3, 16>(x, w, b, y, pooled, B, H, C, st);
+    if (k == 5) return Ho >= 32 ? launch_depthwise_tma_t<5, 32>(x, w, b, y, pooled, B, H, C, st) : launch_depthwise_tma_t<5, 16>(x, w, b, y, pooled, B, H, C, st);
+  }
   const int R = 2;   // output rows per thread
   const int TW = Ho >= 64 ? 32 : 16;
   const int V = k == 3 ? 4 : 2;
