@@ -477,8 +477,8 @@ NOISE_P = [0.4, 0.1, 0.2, 0.05, 0.1, 0.15]
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum over the 93 decoder launches of one 64-image batch (ncu launch list
-# profiles/r01_decoder_launches_v7.txt: 13.59 GB read + 9.91 GB written), per image
-DECODE_DRAM_TRAFFIC_PER_IMAGE = (13.589e9 + 9.913e9) / 64
+# profiles/r01_decoder_launches_v9.txt: 13.51 GB read + 9.74 GB written), per image
+DECODE_DRAM_TRAFFIC_PER_IMAGE = (13.511e9 + 9.737e9) / 64
 
 
 def run_decode(args):
