@@ -449,21 +449,32 @@ __global__ void __launch_bounds__(256) se_kernel(const float* __restrict__ poole
   for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pooled[(size_t)n * C + c] * inv_hw;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < SQ; j += 8) {
-    const float* wr = w1 + (size_t)j * C;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int c = lane;
-    for (; c + 96 < C; c += 128) {
-      a0 = fmaf(__ldg(wr + c), mean[c], a0);
-      a1 = fmaf(__ldg(wr + c + 32), mean[c + 32], a1);
-      a2 = fmaf(__ldg(wr + c + 64), mean[c + 64], a2);
-      a3 = fmaf(__ldg(wr + c + 96), mean[c + 96], a3);
-    }
-    for (; c < C; c += 32) a0 = fmaf(__ldg(wr + c), mean[c], a0);
-    float acc = (a0 + a1) + (a2 + a3);
+  // fc1: each warp owns rows j = warp, warp + 8, ...; FOUR rows are walked at once so 16 independent loads are in flight per lane
+  // (one row at a time left the kernel waiting on L2 latency: 75 us for C = 1920)
+  for (int j0 = warp; j0 < SQ; j0 += 32) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* wr[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) s1[j] = silu(acc + b1[j]);
+    for (int u = 0; u < 4; ++u) wr[u] = w1 + (size_t)min(j0 + 8 * u, SQ - 1) * C;
+    for (int c = lane; c < C; c += 128) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cc = c + 32 * k;
+        if (cc < C) {
+          const float mv = mean[cc];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = fmaf(__ldg(wr[u] + cc), mv, acc[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float a = acc[u];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      const int j = j0 + 8 * u;
+      if (lane == 0 && j < SQ) s1[j] = silu(a + b1[j]);
+    }
   }
   __syncthreads();
   const int c = blockIdx.y * 256 + threadIdx.x;

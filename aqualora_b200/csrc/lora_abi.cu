@@ -61,10 +61,8 @@ int aq_lora_linear_bwd(const void* gy, int64_t ldgy, const void* x, int64_t ldx,
   a.force_bn = g_force_bn; a.force_group = g_force_group;
   int rc = launch_lora_gemm(a, st);
   if (rc) return rc;
-  // 2) dUp[dout, r] += G^T Hs      3) dDn[r, din] += dH^T X
-  rc = launch_wgrad(gy, ldgy, hs, r, g_up, r, M, dout, r, 0, st);
-  if (rc) return rc;
-  return launch_wgrad(x, ldx, dh, r, g_down, din, M, din, r, 1, st);
+  // 2) dUp[dout, r] += G^T Hs  and  dDn[r, din] += dH^T X, one launch (grid.z = 2)
+  return launch_wgrad_pair(gy, ldgy, hs, r, g_up, r, dout, r, 0, x, ldx, dh, r, g_down, din, din, r, 1, M, st);
 }
 
 int aq_wgrad_tn(const void* p, int64_t ldp, const void* q, int64_t ldq, float* c, int64_t ldc, int64_t M, int I, int J,

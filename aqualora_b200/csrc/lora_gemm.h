@@ -26,5 +26,9 @@ struct LoraGemmArgs {
 int launch_lora_gemm(const LoraGemmArgs& a, cudaStream_t stream);
 int launch_wgrad(const void* pm, int64_t ldp, const void* qm, int64_t ldq, float* c, int64_t ldc, int64_t M, int I, int J,
                  int transpose_out, cudaStream_t stream);
+// two contractions over the same M rows in one launch (problem 0 / 1: operands p, q, output c, widths I, J, transpose_out)
+int launch_wgrad_pair(const void* p0, int64_t ldp0, const void* q0, int64_t ldq0, float* c0, int64_t ldc0, int I0, int J0, int t0,
+                      const void* p1, int64_t ldp1, const void* q1, int64_t ldq1, float* c1, int64_t ldc1, int I1, int J1, int t1,
+                      int64_t M, cudaStream_t stream);
 
 }  // namespace aq

@@ -34,9 +34,18 @@ struct WgradParams {
   int M, I, J;
   int kb_per_split;     // k-blocks (of 64 rows) per grid.y slice
   int transpose_out;
+  int i_tiles, splits;  // extent of this problem inside the launch grid
 };
 
-__global__ void __launch_bounds__(kWgThreads) lora_wgrad_kernel(const __grid_constant__ WgradParams p) {
+// Up to two independent contractions per launch (grid.z): the backward of one LoRA layer needs dUp = G^T Hs and dDn = dH^T X,
+// both a few microseconds of work -- one launch instead of two halves the launch-floor cost of the 384 weight-gradient kernels.
+struct WgradLaunch {
+  WgradParams prob[2];
+};
+
+__global__ void __launch_bounds__(kWgThreads) lora_wgrad_kernel(const __grid_constant__ WgradLaunch launch) {
+  const WgradParams& p = launch.prob[blockIdx.z];
+  if ((int)blockIdx.x >= p.i_tiles || (int)blockIdx.y >= p.splits) return;   // whole CTA: this problem is smaller than the grid
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -148,18 +157,15 @@ __global__ void __launch_bounds__(kWgThreads) lora_wgrad_kernel(const __grid_con
   if (warp == 2) tmem_dealloc(tmem_base, 64);
 }
 
-int launch_wgrad(const void* pm, int64_t ldp, const void* qm, int64_t ldq, float* c, int64_t ldc, int64_t M, int I, int J,
-                 int transpose_out, cudaStream_t stream) {
+static int fill_wgrad(WgradParams& p, const void* pm, int64_t ldp, const void* qm, int64_t ldq, float* c, int64_t ldc, int64_t M, int I,
+                      int J, int transpose_out) {
   AQ_REQUIRE(M > 0 && I > 0 && J > 0, AQ_ERR_BAD_SHAPE, "wgrad: empty problem");
   AQ_REQUIRE(M < (1ll << 31), AQ_ERR_BAD_SHAPE, "wgrad: M too large");
   AQ_REQUIRE(J <= kWgJ && J % 8 == 0, AQ_ERR_BAD_SHAPE, "wgrad: J=%d must be a multiple of 8 and <= 64", J);
   AQ_REQUIRE(I % 8 == 0 && ldp % 8 == 0 && ldq % 8 == 0, AQ_ERR_BAD_ALIGN, "wgrad: I, ldp, ldq must be multiples of 8");
   AQ_REQUIRE(transpose_out || ldc % 4 == 0, AQ_ERR_BAD_ALIGN, "wgrad: ldc must be a multiple of 4");
   AQ_REQUIRE((reinterpret_cast<uintptr_t>(c) & 15u) == 0, AQ_ERR_BAD_ALIGN, "wgrad: C must be 16-byte aligned");
-  int rc = check_arch();
-  if (rc) return rc;
-  WgradParams p;
-  memset(&p, 0, sizeof(p));
+  int rc;
   {
     uint64_t dims[2] = {(uint64_t)I, (uint64_t)M};
     uint64_t str[1] = {(uint64_t)ldp * 2};
@@ -175,25 +181,58 @@ int launch_wgrad(const void* pm, int64_t ldp, const void* qm, int64_t ldq, float
     if (rc) return rc;
   }
   p.c = c; p.ldc = ldc; p.M = (int)M; p.I = I; p.J = J; p.transpose_out = transpose_out;
-  const int i_tiles = (I + kWgBlockI - 1) / kWgBlockI;
+  p.i_tiles = (I + kWgBlockI - 1) / kWgBlockI;
   const int num_kb = (int)((M + kWgBlockK - 1) / kWgBlockK);
   const int sms = sm_count();
+  if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
   // enough CTAs to keep HBM busy (2 per SM), but at least 8 k-blocks each so the reduction traffic stays small
-  int splits = (2 * sms + i_tiles - 1) / i_tiles;
+  int splits = (2 * sms + p.i_tiles - 1) / p.i_tiles;
   const int max_splits = (num_kb + 7) / 8;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.kb_per_split = (num_kb + splits - 1) / splits;
-  splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  return AQ_OK;
+}
+
+static int launch_wgrad_n(WgradLaunch& l, int n, cudaStream_t stream) {
+  int rc = check_arch();
+  if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     AQ_CHECK_CUDA(cudaFuncSetAttribute(lora_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     attr_set = true;
   }
-  dim3 grid(i_tiles, splits);
-  lora_wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, stream>>>(p);
+  int gx = 0, gy = 0;
+  for (int i = 0; i < n; ++i) {
+    gx = l.prob[i].i_tiles > gx ? l.prob[i].i_tiles : gx;
+    gy = l.prob[i].splits > gy ? l.prob[i].splits : gy;
+  }
+  dim3 grid(gx, gy, n);
+  lora_wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, stream>>>(l);
   AQ_LAUNCHED();
   return AQ_OK;
+}
+
+int launch_wgrad(const void* pm, int64_t ldp, const void* qm, int64_t ldq, float* c, int64_t ldc, int64_t M, int I, int J,
+                 int transpose_out, cudaStream_t stream) {
+  WgradLaunch l;
+  memset(&l, 0, sizeof(l));
+  int rc = fill_wgrad(l.prob[0], pm, ldp, qm, ldq, c, ldc, M, I, J, transpose_out);
+  if (rc) return rc;
+  return launch_wgrad_n(l, 1, stream);
+}
+
+int launch_wgrad_pair(const void* p0, int64_t ldp0, const void* q0, int64_t ldq0, float* c0, int64_t ldc0, int I0, int J0, int t0,
+                      const void* p1, int64_t ldp1, const void* q1, int64_t ldq1, float* c1, int64_t ldc1, int I1, int J1, int t1,
+                      int64_t M, cudaStream_t stream) {
+  WgradLaunch l;
+  memset(&l, 0, sizeof(l));
+  int rc = fill_wgrad(l.prob[0], p0, ldp0, q0, ldq0, c0, ldc0, M, I0, J0, t0);
+  if (rc) return rc;
+  rc = fill_wgrad(l.prob[1], p1, ldp1, q1, ldq1, c1, ldc1, M, I1, J1, t1);
+  if (rc) return rc;
+  return launch_wgrad_n(l, 2, stream);
 }
 
 }  // namespace aq
