@@ -254,7 +254,7 @@ def run_cuda(args):
 
     def step_from_device(lat, noise, t, ctx, msg):
         # train/ppft_train.py:994-996: secret residual from the encoder (no_grad), scaled like the latents
-        wm = enc.encode(msg) * pcfg.scaling_factor
+        wm = enc(lat, msg)[1] * pcfg.scaling_factor      # sec_encoder(latents, msg)[1]: the residual, resized to the latent grid
         bf = torch.bfloat16
         return trainer.step(lat.to(bf), wm.to(bf), noise.to(bf), t, ctx.to(bf), msg)
 
