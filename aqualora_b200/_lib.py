@@ -30,6 +30,7 @@ _SIGNATURES = {
          c_int, c_int, c_int, c_void_p],
         c_int,
     ),
+    "aq_lora_linear_fwd_grouped": ([c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p], c_int),
     "aq_lora_linear_bwd_workspace_bytes": ([c_int64, c_int], c_size_t),
     "aq_lora_linear_bwd": (
         [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
@@ -62,6 +63,14 @@ _SIGNATURES = {
         c_int,
     ),
 }
+
+
+
+class LoraProjection(ctypes.Structure):
+    """`aq_lora_projection` of include/aqualora_b200.h."""
+    _fields_ = [("w", c_void_p), ("bias", c_void_p), ("down", c_void_p), ("up", c_void_p), ("y", c_void_p), ("ldy", c_int64),
+                ("h_save", c_void_p), ("dout", c_int)]
+
 
 _lib = None
 

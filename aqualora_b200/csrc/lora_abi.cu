@@ -33,6 +33,22 @@ int aq_lora_linear_fwd(const void* x, int64_t ldx, const void* w, const void* bi
   return launch_lora_gemm(a, (cudaStream_t)stream);
 }
 
+int aq_lora_linear_fwd_grouped(const void* x, int64_t ldx, const aq_lora_projection* proj, int nproj, const float* scale, int64_t M,
+                               int64_t tokens_per_sample, int din, int r, void* stream) {
+  AQ_REQUIRE(x && proj && nproj >= 1 && nproj <= 32, AQ_ERR_BAD_SHAPE, "lora_linear_fwd_grouped: x / proj NULL or nproj=%d outside 1 ... 32", nproj);
+  LoraGemmArgs args[32];
+  for (int i = 0; i < nproj; ++i) {
+    AQ_REQUIRE(proj[i].w && proj[i].y, AQ_ERR_BAD_SHAPE, "lora_linear_fwd_grouped: projection %d has a NULL w / y", i);
+    AQ_REQUIRE(tokens_per_sample > 0 || proj[i].down == nullptr, AQ_ERR_BAD_SHAPE, "lora_linear_fwd_grouped: tokens_per_sample must be > 0");
+    LoraGemmArgs& a = args[i];
+    a.a = x; a.lda = ldx; a.w = proj[i].w; a.bias = proj[i].bias; a.dn = proj[i].down; a.up = proj[i].up; a.scale = scale;
+    a.y = proj[i].y; a.ldy = proj[i].ldy; a.aux_out0 = proj[i].h_save; a.aux_out1 = nullptr; a.h_in = nullptr; a.g_scale = nullptr;
+    a.M = M; a.tokens = tokens_per_sample; a.K = din; a.N = proj[i].dout; a.r = r; a.mode = 0; a.has_main = 1;
+    a.force_bn = g_force_bn; a.force_group = g_force_group;
+  }
+  return launch_lora_gemm_grouped(args, nproj, (cudaStream_t)stream);
+}
+
 size_t aq_lora_linear_bwd_workspace_bytes(int64_t M, int r) {
   // dH [M, r] bf16 + Hs [M, r] bf16, each padded to 256 bytes
   const size_t one = ((size_t)M * (size_t)r * 2 + 255) & ~(size_t)255;

@@ -38,27 +38,41 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;          // 16 KiB
 constexpr int kDnHalfBytes = (kRankPad / 2) * kBlockK * 2;  // 4 KiB: this CTA's 32 rows of Dn
 constexpr int kHsBytes = kBlockM * kRankPad * 2;            // 16 KiB
 constexpr uint16_t kBothCtas = 0x3;
+constexpr int kMaxGroup = 32;       // projections per grouped launch (32 cross-attention K / V projections in an SD U-Net)
 
-struct LoraGemmParams {
-  CUtensorMap tmap_a;    // A  [M, K]   box {64, 128}    swizzle 128B
+// One projection sharing the launch's A operand.  A grouped launch (NP > 1) walks the work items of several projections of the
+// SAME input -- the 32 cross-attention K / V projections of a U-Net forward all read the text context, q / k / v of a
+// self-attention read the same normed tokens -- so their launch + prologue floor (14 us against < 3 us of work at M ~ 1 k rows)
+// is paid once.
+struct LoraProblem {
   CUtensorMap tmap_w;    // W  [N, K]   box {64, BN/2}   swizzle 128B
   CUtensorMap tmap_dn;   // Dn [r, K]   box {64, 32}     swizzle 128B
   CUtensorMap tmap_up;   // Up [N, r]   box {64, BN/2}   swizzle 128B
   const __nv_bfloat16* bias;   // [N] or null
-  const float* scale;          // [num_samples, r]
   __nv_bfloat16* y;            // [M, ldy]
   __nv_bfloat16* aux_out0;     // mode 0: H [M, r] (may be null); mode 1: dH [M, r]
+  long long ldy;
+  int N, num_n_tiles, group_size, num_groups;
+  int item_begin;              // first work item of this projection
+  int pad_;
+};
+
+template <int NP>
+struct LoraGemmParams {
+  CUtensorMap tmap_a;    // A  [M, K]   box {64, 128}    swizzle 128B
+  const float* scale;          // [num_samples, r]
   __nv_bfloat16* aux_out1;     // mode 1: Hs [M, r]
   const __nv_bfloat16* h_in;   // mode 1: H [M, r] saved by the forward
   float* g_scale;              // mode 1: [num_samples, r] accumulated (may be null)
   long long tokens;            // rows per sample
-  long long ldy;
   int num_samples;
-  int M, N, K, r;
-  int num_m_pairs, num_n_tiles, group_size, num_groups;
+  int M, K, r;
+  int num_m_pairs;
+  int num_problems, total_items;
   int mode;       // 0 forward, 1 backward (dX)
   int has_lora;   // 0: plain GEMM
   int has_main;   // 0: only the H phase + mid epilogue (backward of layers whose input needs no gradient)
+  LoraProblem prob[NP];
 };
 
 template <int BN>
@@ -106,8 +120,8 @@ __device__ __forceinline__ void warp_colsum(float (&v)[N], int lane) {
   }
 }
 
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_gemm_kernel(const __grid_constant__ LoraGemmParams p) {
+template <int BN, int NP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_gemm_kernel(const __grid_constant__ LoraGemmParams<NP> p) {
   using L = SmemLayout<BN>;
   constexpr int kStages = L::kStages;
   constexpr int NC = L::kNC;
@@ -138,10 +152,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
 
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
-    if (p.has_main) tma_prefetch_desc(&p.tmap_w);
+    if (p.has_main) tma_prefetch_desc(&p.prob[0].tmap_w);
     if (p.has_lora) {
-      tma_prefetch_desc(&p.tmap_dn);
-      if (p.has_main) tma_prefetch_desc(&p.tmap_up);
+      tma_prefetch_desc(&p.prob[0].tmap_dn);
+      if (p.has_main) tma_prefetch_desc(&p.prob[0].tmap_up);
     }
   }
   if (warp == 0 && lane == 0) {
@@ -168,7 +182,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
   const uint32_t tmem_base = *tmem_slot_gen;
 
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
-  const int total_items = p.num_m_pairs * p.num_groups;
+  const int total_items = p.total_items;
+  // work item -> (projection, row pair, column-tile group); items of one CTA pair ascend, so the projection index only moves forward
+  auto locate = [&](int item, int& pi) -> const LoraProblem& {
+    while (pi + 1 < p.num_problems && item >= p.prob[pi + 1].item_begin) ++pi;
+    return p.prob[pi];
+  };
   const int item0 = blockIdx.x >> 1, item_step = gridDim.x >> 1;
 
   if (warp == kProducerWarp) {
@@ -177,7 +196,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
     uint32_t phase = 0;
     const int w_row_off = (int)cta_rank * (BN / 2);
     const int dn_row_off = (int)cta_rank * (kRankPad / 2);
-    auto k_loads = [&](int m0, int n0, bool first) {
+    auto k_loads = [&](const LoraProblem& q, int m0, int n0, bool first) {
       const uint32_t bytes = 2u * (kATileBytes + (p.has_main ? L::kWHalfBytes : 0) + (first ? kDnHalfBytes : 0));
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -185,46 +204,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
           const uint32_t fb = mapa_shared(full_bar(stage), 0);
           if (leader) mbar_arrive_expect_tx(full_bar(stage), bytes);
           tma_load_2d_pair(a_tile(stage), &p.tmap_a, fb, kb * kBlockK, m0);
-          if (p.has_main) tma_load_2d_pair(w_tile(stage), &p.tmap_w, fb, kb * kBlockK, n0 + w_row_off);
-          if (first) tma_load_2d_pair(dn_tile(stage), &p.tmap_dn, fb, kb * kBlockK, dn_row_off);
+          if (p.has_main) tma_load_2d_pair(w_tile(stage), &q.tmap_w, fb, kb * kBlockK, n0 + w_row_off);
+          if (first) tma_load_2d_pair(dn_tile(stage), &q.tmap_dn, fb, kb * kBlockK, dn_row_off);
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     };
-    auto up_load = [&](int n0) {
+    auto up_load = [&](const LoraProblem& q, int n0) {
       // the rank-r extra k-block: only the Up tile travels; its A operand (Hs) is produced on chip
       mbar_wait(empty_bar(stage), phase ^ 1u);
       if (elect_one()) {
         const uint32_t fb = mapa_shared(full_bar(stage), 0);
         if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * L::kWHalfBytes);
-        tma_load_2d_pair(w_tile(stage), &p.tmap_up, fb, 0, n0 + w_row_off);
+        tma_load_2d_pair(w_tile(stage), &q.tmap_up, fb, 0, n0 + w_row_off);
       }
       __syncwarp();
       if (++stage == kStages) { stage = 0; phase ^= 1u; }
     };
+    int pi = 0;
     for (int item = item0; item < total_items; item += item_step) {
-      const int m_pair = item % p.num_m_pairs;
-      const int grp = item / p.num_m_pairs;
+      const LoraProblem& q = locate(item, pi);
+      const int local = item - q.item_begin;
+      const int m_pair = local % p.num_m_pairs;
+      const int grp = local / p.num_m_pairs;
       const int m0 = m_pair * kPairM + (int)cta_rank * kBlockM;
-      const int nt_begin = grp * p.group_size;
-      const int nt_end = min(nt_begin + p.group_size, p.num_n_tiles);
+      const int nt_begin = grp * q.group_size;
+      const int nt_end = min(nt_begin + q.group_size, q.num_n_tiles);
       const bool fused = p.has_lora && p.has_main;
       if (fused && nt_end - nt_begin >= 2) {
         // deferred order: the Hs.Up k-blocks of the first two tiles follow the second tile's main loop
-        k_loads(m0, nt_begin * BN, true);
-        k_loads(m0, (nt_begin + 1) * BN, false);
-        up_load(nt_begin * BN);
-        up_load((nt_begin + 1) * BN);
+        k_loads(q, m0, nt_begin * BN, true);
+        k_loads(q, m0, (nt_begin + 1) * BN, false);
+        up_load(q, nt_begin * BN);
+        up_load(q, (nt_begin + 1) * BN);
         for (int nt = nt_begin + 2; nt < nt_end; ++nt) {
-          k_loads(m0, nt * BN, false);
-          up_load(nt * BN);
+          k_loads(q, m0, nt * BN, false);
+          up_load(q, nt * BN);
         }
       } else {
         for (int nt = nt_begin; nt < nt_end; ++nt) {
           const bool first = (nt == nt_begin) && p.has_lora;
-          if (p.has_main || first) k_loads(m0, nt * BN, first);
-          if (fused) up_load(nt * BN);
+          if (p.has_main || first) k_loads(q, m0, nt * BN, first);
+          if (fused) up_load(q, nt * BN);
         }
       }
     }
@@ -290,10 +312,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       };
+      int pi = 0;
       for (int item = item0; item < total_items; item += item_step, ++item_iter) {
-        const int grp = item / p.num_m_pairs;
-        const int nt_begin = grp * p.group_size;
-        const int nt_end = min(nt_begin + p.group_size, p.num_n_tiles);
+        const LoraProblem& q = locate(item, pi);
+        const int grp = (item - q.item_begin) / p.num_m_pairs;
+        const int nt_begin = grp * q.group_size;
+        const int nt_end = min(nt_begin + q.group_size, q.num_n_tiles);
         const bool fused = p.has_lora && p.has_main;
         if (fused && nt_end - nt_begin >= 2) {
           const uint32_t it0 = acc_iter, it1 = acc_iter + 1;
@@ -350,12 +374,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
     const uint32_t acc_empty_remote[2] = {mapa_shared(acc_empty_bar(0), 0), mapa_shared(acc_empty_bar(1), 0)};
     const uint32_t hs_ready_remote = mapa_shared(hs_ready_bar, 0);
     uint32_t acc_iter = 0, item_iter = 0;
+    int pi = 0;
     for (int item = item0; item < total_items; item += item_step, ++item_iter) {
-      const int m_pair = item % p.num_m_pairs;
-      const int grp = item / p.num_m_pairs;
+      const LoraProblem& q_ = locate(item, pi);
+      const int local = item - q_.item_begin;
+      const int m_pair = local % p.num_m_pairs;
+      const int grp = local / p.num_m_pairs;
       const int m0 = m_pair * kPairM + (int)cta_rank * kBlockM;
-      const int nt_begin = grp * p.group_size;
-      const int nt_end = min(nt_begin + p.group_size, p.num_n_tiles);
+      const int nt_begin = grp * q_.group_size;
+      const int nt_end = min(nt_begin + q_.group_size, q_.num_n_tiles);
       const long long grow = (long long)m0 + row_in_tile;
       const bool row_ok = grow < p.M;
       const bool aux_owner = row_ok && grp == 0;   // side outputs (H / dH / Hs / dscale) are emitted once per row block
@@ -404,13 +431,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
             to_smem.z = pack_bf16x2(hb[4] * s[4], hb[5] * s[5]);
             to_smem.w = pack_bf16x2(hb[6] * s[6], hb[7] * s[7]);
             if (p.mode == 0) {
-              if (aux_owner && p.aux_out0 != nullptr) {
+              if (aux_owner && q_.aux_out0 != nullptr) {
                 uint4 hraw;
                 hraw.x = pack_bf16x2(hb[0], hb[1]);
                 hraw.y = pack_bf16x2(hb[2], hb[3]);
                 hraw.z = pack_bf16x2(hb[4], hb[5]);
                 hraw.w = pack_bf16x2(hb[6], hb[7]);
-                *reinterpret_cast<uint4*>(p.aux_out0 + aux_off + j8 * 8) = hraw;
+                *reinterpret_cast<uint4*>(q_.aux_out0 + aux_off + j8 * 8) = hraw;
               }
             } else {
               // hb = dHs (bf16-rounded like the reference's bf16 matmul output); hin = saved H
@@ -422,7 +449,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
                 hval[2 * i + 1] = bf16_hi(hw[i]);
               }
               if (aux_owner) {
-                *reinterpret_cast<uint4*>(p.aux_out0 + aux_off + j8 * 8) = to_smem;  // dH
+                *reinterpret_cast<uint4*>(q_.aux_out0 + aux_off + j8 * 8) = to_smem;  // dH
                 uint4 hs;
                 hs.x = pack_bf16x2(hval[0] * s[0], hval[1] * s[1]);
                 hs.y = pack_bf16x2(hval[2] * s[2], hval[3] * s[3]);
@@ -466,12 +493,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         // this warp's NC bias values: global loads issued before the accumulator wait, parked in SMEM after the TMEM loads
         // are in flight (a dependent load between tcgen05.ld and the stores was 11-16 % of the epilogue's stall samples)
         uint32_t bias_r[(NC / 2 + 31) / 32] = {};
-        if (p.bias != nullptr) {
-          const uint32_t* bw = reinterpret_cast<const uint32_t*>(p.bias + col0);
+        if (q_.bias != nullptr) {
+          const uint32_t* bw = reinterpret_cast<const uint32_t*>(q_.bias + col0);
 #pragma unroll
           for (int j = 0; j < (NC / 2 + 31) / 32; ++j) {
             const int w = j * 32 + lane;
-            bias_r[j] = (w < NC / 2 && col0 + 2 * w < p.N) ? __ldg(bw + w) : 0u;
+            bias_r[j] = (w < NC / 2 && col0 + 2 * w < q_.N) ? __ldg(bw + w) : 0u;
           }
         }
         mbar_wait(acc_full_bar(buf), (acc_iter >> 1) & 1u);
@@ -479,7 +506,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         uint32_t t[NC];
 #pragma unroll
         for (int c = 0; c < NC / 16; ++c) tmem_ld_32x16(tmem_base + lane_base + buf * BN + half * NC + c * 16, t + c * 16);
-        if (p.bias != nullptr) {
+        if (q_.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < (NC / 2 + 31) / 32; ++j) {
             const int w = j * 32 + lane;
@@ -491,7 +518,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(acc_empty_remote[buf]);   // drained -> the MMA thread may reuse this accumulator
         ++acc_iter;
-        if (col0 >= p.N) continue;   // whole slice past the last column (partial last tile)
+        if (col0 >= q_.N) continue;   // whole slice past the last column (partial last tile)
         constexpr int NCP = L::kNCP;     // columns per pass
         constexpr int kCpr = NCP / 8;    // 16-byte chunks per row and pass
         const long long row_base = (long long)m0 + q * 32;
@@ -503,7 +530,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(t[pass * NCP + c8 * 8 + i]);
-            if (p.bias != nullptr) {
+            if (q_.bias != nullptr) {
               const uint4 bw = *reinterpret_cast<const uint4*>(bias_sm + (pass * NCP + c8 * 8) / 2);
               const uint32_t bb[4] = {bw.x, bw.y, bw.z, bw.w};
 #pragma unroll
@@ -531,8 +558,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
           for (int i = 0; i < kCpr; ++i) {
             const int c = i * 32 + lane;
             const int row = c / kCpr, col = pcol0 + (c % kCpr) * 8;
-            if (row_base + row < p.M && col < p.N)
-              *reinterpret_cast<uint4*>(p.y + (size_t)(row_base + row) * p.ldy + col) = o[i];
+            if (row_base + row < p.M && col < q_.N)
+              *reinterpret_cast<uint4*>(q_.y + (size_t)(row_base + row) * q_.ldy + col) = o[i];
           }
           __syncwarp();
         }
@@ -549,10 +576,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN>
-static int launch_bn(const LoraGemmArgs& a, cudaStream_t stream) {
+// Column tiles per work item: the H phase is paid once per item, wave quantisation once per launch.
+static int pick_group(int num_n_tiles, int num_m_pairs, int K, int BN, bool has_lora, int slots) {
+  int best_g = 1;
+  double best_cost = 1e30;
+  const double kb = (double)((K + kBlockK - 1) / kBlockK);
+  for (int g = 1; g <= num_n_tiles; ++g) {
+    const int groups = (num_n_tiles + g - 1) / g;
+    const long long items = (long long)groups * num_m_pairs;
+    const long long waves = (items + slots - 1) / slots;
+    // per item: g tiles of (kb + 1) k-blocks of width BN, plus the H phase (kb k-blocks of width 64); a single-tile
+    // item cannot hide the H -> Hs round trip behind the next tile's main loop
+    const double bubble = has_lora ? (g == 1 ? 6.0 * BN : 1.0 * BN) : 0.0;
+    const double item_cost = g * (kb + (has_lora ? 1.0 : 0.0)) * BN + (has_lora ? kb * kRankPad : 0.0) + bubble;
+    const double cost = (double)waves * item_cost;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_g = g; }
+  }
+  return best_g;
+}
+
+// `probs` are projections of the same A (same M, K, r, scale, tokens, mode); args[0] carries the shared operands.
+template <int BN, int NP>
+static int launch_bn(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) {
   using L = SmemLayout<BN>;
-  LoraGemmParams p;
+  const LoraGemmArgs& a = probs[0];
+  static thread_local LoraGemmParams<NP> p;   // 14 KiB for NP = 32: kept off the stack
   memset(&p, 0, sizeof(p));
   const int has_lora = a.dn != nullptr;
   {
@@ -562,75 +610,68 @@ static int launch_bn(const LoraGemmArgs& a, cudaStream_t stream) {
     int rc = make_tmap(&p.tmap_a, a.a, 2, 2, dims, str, box, kSwz128);
     if (rc) return rc;
   }
-  if (a.has_main) {
-    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
-    uint64_t str[1] = {(uint64_t)a.K * 2};
-    uint32_t box[2] = {kBlockK, (uint32_t)(BN / 2)};
-    int rc = make_tmap(&p.tmap_w, a.w, 2, 2, dims, str, box, kSwz128);
-    if (rc) return rc;
-  }
-  if (has_lora) {
-    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.r};
-    uint64_t str[1] = {(uint64_t)a.K * 2};
-    uint32_t box[2] = {kBlockK, kRankPad / 2};
-    int rc = make_tmap(&p.tmap_dn, a.dn, 2, 2, dims, str, box, kSwz128);
-    if (rc) return rc;
-    if (a.has_main) {
-      uint64_t udims[2] = {(uint64_t)a.r, (uint64_t)a.N};
-      uint64_t ustr[1] = {(uint64_t)a.r * 2};
-      uint32_t ubox[2] = {kRankPad, (uint32_t)(BN / 2)};
-      rc = make_tmap(&p.tmap_up, a.up, 2, 2, udims, ustr, ubox, kSwz128);
-      if (rc) return rc;
-    }
-  }
-  p.bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
   p.scale = a.scale;
-  p.y = reinterpret_cast<__nv_bfloat16*>(a.y);
-  p.ldy = a.ldy;
-  p.aux_out0 = reinterpret_cast<__nv_bfloat16*>(a.aux_out0);
   p.aux_out1 = reinterpret_cast<__nv_bfloat16*>(a.aux_out1);
   p.h_in = reinterpret_cast<const __nv_bfloat16*>(a.h_in);
   p.g_scale = a.g_scale;
   p.tokens = a.tokens > 0 ? a.tokens : a.M;
   p.num_samples = (int)((a.M + p.tokens - 1) / p.tokens);
-  p.M = (int)a.M; p.N = a.N; p.K = a.K; p.r = a.r;
+  p.M = (int)a.M; p.K = a.K; p.r = a.r;
   p.mode = a.mode; p.has_lora = has_lora; p.has_main = a.has_main;
   p.num_m_pairs = (int)((a.M + kPairM - 1) / kPairM);
-  p.num_n_tiles = a.has_main ? (a.N + BN - 1) / BN : 1;
+  p.num_problems = nprob;
 
   const int sms = sm_count();
   if (sms < 2) return fail(AQ_ERR_LAUNCH, "no CUDA device");
   const int slots = sms / 2;   // CTA pairs resident at once
-  // Column tiles per work item: the H phase is paid once per item, wave quantisation once per launch.
-  int best_g = 1;
-  if (a.force_group > 0) {
-    best_g = a.force_group;
-  } else {
-    double best_cost = 1e30;
-    const double kb = (double)((a.K + kBlockK - 1) / kBlockK);
-    for (int g = 1; g <= p.num_n_tiles; ++g) {
-      const int groups = (p.num_n_tiles + g - 1) / g;
-      const long long items = (long long)groups * p.num_m_pairs;
-      const long long waves = (items + slots - 1) / slots;
-      // per item: g tiles of (kb + 1) k-blocks of width BN, plus the H phase (kb k-blocks of width 64); a single-tile
-      // item cannot hide the H -> Hs round trip behind the next tile's main loop
-      const double bubble = has_lora ? (g == 1 ? 6.0 * BN : 1.0 * BN) : 0.0;
-      const double item_cost = g * (kb + (has_lora ? 1.0 : 0.0)) * BN + (has_lora ? kb * kRankPad : 0.0) + bubble;
-      const double cost = (double)waves * item_cost;
-      if (cost < best_cost - 1e-9) { best_cost = cost; best_g = g; }
+  long long items = 0;
+  for (int i = 0; i < nprob; ++i) {
+    const LoraGemmArgs& b = probs[i];
+    LoraProblem& q = p.prob[i];
+    if (a.has_main) {
+      uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)b.N};
+      uint64_t str[1] = {(uint64_t)a.K * 2};
+      uint32_t box[2] = {kBlockK, (uint32_t)(BN / 2)};
+      int rc = make_tmap(&q.tmap_w, b.w, 2, 2, dims, str, box, kSwz128);
+      if (rc) return rc;
     }
+    if (has_lora) {
+      uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.r};
+      uint64_t str[1] = {(uint64_t)a.K * 2};
+      uint32_t box[2] = {kBlockK, kRankPad / 2};
+      int rc = make_tmap(&q.tmap_dn, b.dn, 2, 2, dims, str, box, kSwz128);
+      if (rc) return rc;
+      if (a.has_main) {
+        uint64_t udims[2] = {(uint64_t)a.r, (uint64_t)b.N};
+        uint64_t ustr[1] = {(uint64_t)a.r * 2};
+        uint32_t ubox[2] = {kRankPad, (uint32_t)(BN / 2)};
+        rc = make_tmap(&q.tmap_up, b.up, 2, 2, udims, ustr, ubox, kSwz128);
+        if (rc) return rc;
+      }
+    }
+    q.bias = reinterpret_cast<const __nv_bfloat16*>(b.bias);
+    q.y = reinterpret_cast<__nv_bfloat16*>(b.y);
+    q.ldy = b.ldy;
+    q.aux_out0 = reinterpret_cast<__nv_bfloat16*>(b.aux_out0);
+    q.N = b.N;
+    q.num_n_tiles = a.has_main ? (b.N + BN - 1) / BN : 1;
+    if (a.force_group > 0) q.group_size = a.force_group;
+    else if (nprob > 1) q.group_size = q.num_n_tiles < 2 ? q.num_n_tiles : 2;   // many projections fill the waves; 2 tiles hide the Hs bubble
+    else q.group_size = pick_group(q.num_n_tiles, p.num_m_pairs, a.K, BN, has_lora != 0, slots);
+    q.num_groups = (q.num_n_tiles + q.group_size - 1) / q.group_size;
+    q.item_begin = (int)items;
+    items += (long long)q.num_groups * p.num_m_pairs;
   }
-  p.group_size = best_g;
-  p.num_groups = (p.num_n_tiles + best_g - 1) / best_g;
-  const long long items = (long long)p.num_groups * p.num_m_pairs;
+  AQ_REQUIRE(items < (1ll << 31), AQ_ERR_BAD_SHAPE, "lora_gemm: too many work items");
+  p.total_items = (int)items;
   const int grid = 2 * (int)(items < slots ? items : slots);
 
   static bool attr_set = false;   // benign race: idempotent
   if (!attr_set) {
-    AQ_CHECK_CUDA(cudaFuncSetAttribute(lora_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    AQ_CHECK_CUDA(cudaFuncSetAttribute(lora_gemm_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
-  lora_gemm_kernel<BN><<<grid, kThreads, L::kTotal, stream>>>(p);
+  lora_gemm_kernel<BN, NP><<<grid, kThreads, L::kTotal, stream>>>(p);
   AQ_LAUNCHED();
   return AQ_OK;
 }
@@ -650,7 +691,7 @@ static int pick_bn(int N) {
   return best;
 }
 
-int launch_lora_gemm(const LoraGemmArgs& a, cudaStream_t stream) {
+static int validate(const LoraGemmArgs& a) {
   AQ_REQUIRE(a.M > 0 && a.K > 0, AQ_ERR_BAD_SHAPE, "lora_gemm: empty problem M=%lld K=%d", (long long)a.M, a.K);
   AQ_REQUIRE(a.M < (1ll << 31) - kPairM, AQ_ERR_BAD_SHAPE, "lora_gemm: M=%lld exceeds 2^31-1 rows", (long long)a.M);
   AQ_REQUIRE(a.K % 8 == 0, AQ_ERR_BAD_SHAPE, "lora_gemm: K=%d must be a multiple of 8", a.K);
@@ -664,16 +705,50 @@ int launch_lora_gemm(const LoraGemmArgs& a, cudaStream_t stream) {
   AQ_REQUIRE(a.has_main || a.dn != nullptr, AQ_ERR_BAD_SHAPE, "lora_gemm: nothing to compute");
   AQ_REQUIRE(a.lda % 8 == 0 && (!a.has_main || a.ldy % 8 == 0), AQ_ERR_BAD_ALIGN, "lora_gemm: leading dimensions must be multiples of 8 elements");
   AQ_REQUIRE(!a.has_main || (reinterpret_cast<uintptr_t>(a.y) & 15u) == 0, AQ_ERR_BAD_ALIGN, "lora_gemm: y must be 16-byte aligned");
-  int rc = check_arch();
+  return AQ_OK;
+}
+
+int launch_lora_gemm(const LoraGemmArgs& a, cudaStream_t stream) {
+  int rc = validate(a);
+  if (rc) return rc;
+  rc = check_arch();
   if (rc) return rc;
   const int bn = a.force_bn > 0 ? a.force_bn : pick_bn(a.has_main ? a.N : 64);
   switch (bn) {
-    case 64: return launch_bn<64>(a, stream);
-    case 128: return launch_bn<128>(a, stream);
-    case 160: return launch_bn<160>(a, stream);
-    case 192: return launch_bn<192>(a, stream);
+    case 64: return launch_bn<64, 1>(&a, 1, stream);
+    case 128: return launch_bn<128, 1>(&a, 1, stream);
+    case 160: return launch_bn<160, 1>(&a, 1, stream);
+    case 192: return launch_bn<192, 1>(&a, 1, stream);
     default: return fail(AQ_ERR_BAD_SHAPE, "lora_gemm: unsupported column tile %d", bn);
   }
+}
+
+// Several forward projections of ONE input in one launch (mode 0).  Every entry repeats the shared operands (a, lda, M, K, r,
+// tokens, scale); w / bias / dn / up / y / ldy / aux_out0 / N differ.  All projections use the column tile of the first.
+int launch_lora_gemm_grouped(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) {
+  AQ_REQUIRE(probs != nullptr && nprob >= 1 && nprob <= kMaxGroup, AQ_ERR_BAD_SHAPE, "lora_gemm_grouped: 1 ... %d projections, got %d", kMaxGroup, nprob);
+  for (int i = 0; i < nprob; ++i) {
+    int rc = validate(probs[i]);
+    if (rc) return rc;
+    AQ_REQUIRE(probs[i].mode == 0 && probs[i].has_main == 1, AQ_ERR_BAD_SHAPE, "lora_gemm_grouped: forward projections only");
+    AQ_REQUIRE(probs[i].a == probs[0].a && probs[i].M == probs[0].M && probs[i].K == probs[0].K && probs[i].r == probs[0].r &&
+                   probs[i].lda == probs[0].lda && probs[i].tokens == probs[0].tokens && probs[i].scale == probs[0].scale &&
+                   (probs[i].dn != nullptr) == (probs[0].dn != nullptr),
+               AQ_ERR_BAD_SHAPE, "lora_gemm_grouped: projection %d does not share the input / rank / scale of projection 0", i);
+  }
+  int rc = check_arch();
+  if (rc) return rc;
+  if (nprob == 1) return launch_lora_gemm(probs[0], stream);
+  // one column tile for the whole group: 160 divides every SD width (320 / 640 / 1280 and their multiples)
+  int bn = probs[0].force_bn > 0 ? probs[0].force_bn : 160;
+  for (int i = 0; i < nprob && probs[0].force_bn <= 0; ++i)
+    if (probs[i].N % 160 != 0) bn = 128;
+  if (nprob <= 4) {
+    if (bn == 160) return launch_bn<160, 4>(probs, nprob, stream);
+    return launch_bn<128, 4>(probs, nprob, stream);
+  }
+  if (bn == 160) return launch_bn<160, kMaxGroup>(probs, nprob, stream);
+  return launch_bn<128, kMaxGroup>(probs, nprob, stream);
 }
 
 }  // namespace aq

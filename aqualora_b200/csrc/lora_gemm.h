@@ -24,6 +24,7 @@ struct LoraGemmArgs {
 };
 
 int launch_lora_gemm(const LoraGemmArgs& a, cudaStream_t stream);
+int launch_lora_gemm_grouped(const LoraGemmArgs* probs, int nprob, cudaStream_t stream);
 int launch_wgrad(const void* pm, int64_t ldp, const void* qm, int64_t ldq, float* c, int64_t ldc, int64_t M, int I, int J,
                  int transpose_out, cudaStream_t stream);
 // two contractions over the same M rows in one launch (problem 0 / 1: operands p, q, output c, widths I, J, transpose_out)

@@ -153,6 +153,72 @@ class _FusedLoraProjection(torch.autograd.Function):
                 None if (g_scale is None or scale_direct) else g_scale, None)
 
 
+class _GroupedLoraProjection(torch.autograd.Function):
+    """n projections of the SAME rows in one launch (aq_lora_linear_fwd_grouped): y_i = x W_i^T + b_i + ((x Dn_i^T) (.) s) Up_i^T.
+    `flat` = (weight, bias, down, up) per projection; down/up are given for all projections or for none.  The backward runs
+    the per-projection kernels (the G_i arrive as separate tensors) and sums the dX contributions."""
+
+    @staticmethod
+    def forward(ctx, x2d, scale_eff, tokens, n, *flat):
+        din = x2d.shape[1]
+        need_grad = any(ctx.needs_input_grad)
+        ws, bs, dns, ups = flat[0::4], flat[1::4], flat[2::4], flat[3::4]
+        has_lora = dns[0] is not None
+        projections = []
+        for w, b, dn, up in zip(ws, bs, dns, ups):
+            dout = w.shape[0]
+            if has_lora:
+                r = dn.shape[0]
+                projections.append((w.reshape(dout, din), b, _packed(dn, r, din)[0], _packed(up, dout, r)[0]))
+            else:
+                projections.append((w.reshape(dout, din), b, None, None))
+        outs = ops.lora_linear_fwd_grouped(x2d, projections, scale_eff.detach() if has_lora else None, tokens,
+                                           save_h=need_grad and has_lora)
+        ctx.tokens, ctx.n, ctx.has_lora = tokens, n, has_lora
+        ctx.grad_targets = tuple((getattr(dn, "_aq_grad", None), getattr(up, "_aq_grad", None)) for dn, up in zip(dns, ups))
+        ctx.scale_target = getattr(scale_eff, "_aq_grad", None)
+        ctx.save_for_backward(x2d, scale_eff, *ws, *dns, *ups, *[h for _, h in outs])
+        return tuple(y for y, _ in outs)
+
+    @staticmethod
+    def backward(ctx, *gys):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        x2d, scale_eff = saved[0], saved[1]
+        ws, dns, ups, hs = (saved[2 + k * n: 2 + (k + 1) * n] for k in range(4))
+        din = x2d.shape[1]
+        need_dx = ctx.needs_input_grad[0]
+        gx_total = None
+        g_scale, scale_direct = None, False
+        if ctx.has_lora and ctx.needs_input_grad[1]:
+            g_scale, scale_direct = _grad_target(ctx.scale_target, tuple(scale_eff.shape), x2d.device)
+        flat_grads = []
+        for i in range(n):
+            gy = gys[i]
+            if gy is None:
+                flat_grads.extend([None, None, None, None])
+                continue
+            gy = gy if gy.stride(1) == 1 and gy.stride(0) % 8 == 0 else gy.contiguous()
+            weight, down, up = ws[i], dns[i], ups[i]
+            dout = weight.shape[0]
+            w_t = _weight_t(weight, dout, din) if need_dx else None
+            if not ctx.has_lora:
+                gx = ops.lora_linear_fwd(gy, w_t, None, None, None, None, ctx.tokens)[0] if need_dx else None
+                flat_grads.extend([None, None, None, None])
+            else:
+                r = down.shape[0]
+                _, dn16_t = _packed(down, r, din)
+                _, up16_t = _packed(up, dout, r)
+                g_down, down_direct = _grad_target(ctx.grad_targets[i][0], (r, din), gy.device)
+                g_up, up_direct = _grad_target(ctx.grad_targets[i][1], (dout, r), gy.device)
+                gx = ops.lora_linear_bwd(gy, x2d, w_t, dn16_t, up16_t, scale_eff.detach(), hs[i], g_down, g_up, g_scale, ctx.tokens)
+                flat_grads.extend([None, None, None if down_direct else g_down.view_as(down).to(down.dtype),
+                                   None if up_direct else g_up.view_as(up).to(up.dtype)])
+            if gx is not None:
+                gx_total = gx if gx_total is None else gx_total.add_(gx)
+        return (gx_total, None if (g_scale is None or scale_direct) else g_scale, None, None, *flat_grads)
+
+
 def _effective_scale(scale, lora_layer, nsamples: int, r: int, device, compute_dtype) -> torch.Tensor:
     """[B, r] fp32 diagonal the kernel applies between down and up (utils/lora_modules.py:15-25): the tensor scale
     (rounded to the compute dtype, as the reference's `.to(weight_dtype)` + autocast matmul do), or the float
@@ -283,6 +349,102 @@ def CustomLoRACompatibleConvforward(self, hidden_states: torch.Tensor, scale: fl
     # [Co, C, 1, 1] / [r, C, 1, 1] / [Co, r, 1, 1] are row-major matrices already: the kernel reads them in place
     y = _project_rows(x2d, self.weight, self.bias, lora.down.weight, lora.up.weight, lora, scale, hidden_states.dtype)
     return y.view(B, H, W, -1).permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# several projections of one input in one launch; the attention processor that uses it
+# ------------------------------------------------------------------------------------------------
+def _alpha_over_rank(lora) -> float:
+    a = getattr(lora, "network_alpha", None)
+    return 1.0 if a is None else float(a) / float(lora.rank)
+
+
+def project_group(modules, hidden_states: torch.Tensor, scale=1.0):
+    """`[m(hidden_states, scale) for m in modules]` for LoRA-compatible linears that read the same input -- q / k / v of a
+    self-attention, k / v of a cross-attention, or the K / V projections of every cross-attention of a U-Net (all read the text
+    context) -- as ONE grouped launch of the fused kernel (aq_lora_linear_fwd_grouped).  Each module keeps the semantics of
+    CustomLoRACompatibleLinearforward (utils/lora_modules.py:56-62).  Modules that cannot share a launch (different input width
+    or rank, LoRA on some but not all, more than 32) go through their own fused launch instead."""
+    modules = list(modules)
+    din = hidden_states.shape[-1]
+    ours = all(isinstance(m, nn.Linear) and getattr(m.forward, "__func__", None) is CustomLoRACompatibleLinearforward for m in modules)
+    loras = [None if _LORA_DISABLED else getattr(m, "lora_layer", None) for m in modules]
+    with_lora = [l is not None for l in loras]
+    groupable = (ours and 1 < len(modules) <= 32 and all(m.weight.shape[1] == din and m.weight.dtype == torch.bfloat16 for m in modules)
+                 and (all(with_lora) or not any(with_lora)))
+    if groupable and all(with_lora):
+        r = loras[0].down.weight.shape[0]
+        a = _alpha_over_rank(loras[0])
+        groupable = all(l.down.weight.shape[0] == r and _alpha_over_rank(l) == a for l in loras)
+    if not groupable:
+        return [m(hidden_states, scale) for m in modules]
+    _check_input(hidden_states, "project_group")
+    x2d = _rows_view(hidden_states, din)
+    M = x2d.shape[0]
+    flat = []
+    if all(with_lora):
+        if isinstance(scale, torch.Tensor):
+            nsamp = scale.shape[0]
+            if M % nsamp != 0:
+                raise AqualoraError(f"{M} rows cannot be split over a scale batch of {nsamp}")
+            tokens = M // nsamp
+        else:
+            nsamp, tokens = 1, M
+        s_eff = _effective_scale(scale, loras[0], nsamp, r, x2d.device, hidden_states.dtype)
+        for m, l in zip(modules, loras):
+            flat.extend([m.weight, m.bias, l.down.weight, l.up.weight])
+    else:
+        tokens = M
+        s_eff = torch.empty(0, device=x2d.device)
+        for m in modules:
+            flat.extend([m.weight, m.bias, None, None])
+    ys = _GroupedLoraProjection.apply(x2d, s_eff, tokens, len(modules), *flat)
+    return [y.view(*hidden_states.shape[:-1], m.weight.shape[0]) for y, m in zip(ys, modules)]
+
+
+def precompute_cross_kv(attentions, encoder_hidden_states: torch.Tensor, scale=1.0) -> None:
+    """Run `to_k` / `to_v` of every cross-attention in `attentions` on the text context in one grouped launch and park the
+    results on the modules (`_aq_kv`) for AquaLoRAAttnProcessor, which consumes them.  diffusers calls these 2 x 16 projections
+    one by one inside each AttnProcessor although all of them read the same `encoder_hidden_states`."""
+    attentions = list(attentions)
+    mods = [m for a in attentions for m in (a.to_k, a.to_v)]
+    for i in range(0, len(mods), 32):
+        outs = project_group(mods[i:i + 32], encoder_hidden_states, scale)
+        for j in range(0, len(outs), 2):
+            attentions[(i + j) // 2]._aq_kv = (outs[j], outs[j + 1])
+
+
+class AquaLoRAAttnProcessor:
+    """diffusers-style attention processor (`__call__(attn, hidden_states, encoder_hidden_states, attention_mask, temb, scale)`,
+    the signature of diffusers 0.24 `AttnProcessor2_0`, which threads `cross_attention_kwargs["scale"]` into `attn.to_q/k/v/
+    to_out[0]` -- train/ppft_train.py:1028,1034).  Same arithmetic as calling the four patched projections one by one, but
+    q / k / v of a self-attention (and k / v of a cross-attention) leave in one grouped launch."""
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0):
+        kv = getattr(attn, "_aq_kv", None)
+        if kv is not None:
+            attn._aq_kv = None
+            q = attn.to_q(hidden_states, scale)
+            k, v = kv
+        elif encoder_hidden_states is None:
+            q, k, v = project_group((attn.to_q, attn.to_k, attn.to_v), hidden_states, scale)
+        else:
+            q = attn.to_q(hidden_states, scale)
+            k, v = project_group((attn.to_k, attn.to_v), encoder_hidden_states.to(hidden_states.dtype), scale)
+        B, N, C = q.shape
+        h = attn.heads
+        q = q.view(B, N, h, C // h).transpose(1, 2)
+        k = k.view(B, k.shape[1], h, C // h).transpose(1, 2)
+        v = v.view(B, v.shape[1], h, C // h).transpose(1, 2)
+        if getattr(attn, "upcast", False) or getattr(attn, "upcast_attention", False):
+            o = F.scaled_dot_product_attention(q.float(), k.float(), v.float(), attn_mask=attention_mask).to(v.dtype)
+        else:
+            o = F.scaled_dot_product_attention(q, k, v, attn_mask=attention_mask)
+        o = o.transpose(1, 2).reshape(B, N, C)
+        o = attn.to_out[0](o, scale)
+        if len(attn.to_out) > 1:
+            o = attn.to_out[1](o)      # diffusers: Dropout(p = 0)
+        return o
 
 
 # ------------------------------------------------------------------------------------------------

@@ -5,6 +5,8 @@ from libaqualora_b200.so and raises if the library or a CUDA device is missing.
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -75,6 +77,50 @@ def lora_linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None,
     _lib.call("aq_lora_linear_fwd", x.data_ptr(), _rows(x, "x"), w.data_ptr(), _ptr(bias), _ptr(down), _ptr(up), _ptr(scale),
               y.data_ptr(), _rows(y, "y"), _ptr(h), M, max(int(tokens_per_sample), 1), din, dout, r, _stream())
     return y, h
+
+
+def lora_linear_fwd_grouped(x: torch.Tensor, projections, scale: torch.Tensor | None, tokens_per_sample: int, save_h: bool = False):
+    """Several projections of the same rows x [M, din] in ONE launch (csrc/lora_gemm.cu, grouped work items).
+    projections: list of (w [dout, din], bias [dout] | None, down [r, din] | None, up [dout, r] | None), all bf16, `down` given for
+    all or none.  Returns [(y, h | None), ...] like lora_linear_fwd."""
+    _need(x, _BF16, "x", 2)
+    M, din = x.shape
+    n = len(projections)
+    if not 1 <= n <= 32:
+        raise _lib.AqualoraError(f"grouped projection: 1 ... 32 projections per launch, got {n}")
+    has_lora = projections[0][2] is not None
+    r = projections[0][2].shape[0] if has_lora else 0
+    if has_lora:
+        _need(scale, _F32, "scale", 2)
+        nsamp = (M + tokens_per_sample - 1) // tokens_per_sample
+        if tuple(scale.shape) != (nsamp, r) or not scale.is_contiguous():
+            raise _lib.AqualoraError(f"scale must be contiguous [{nsamp}, {r}], got {tuple(scale.shape)}")
+    arr = (_lib.LoraProjection * n)()
+    outs = []
+    for i, (w, bias, down, up) in enumerate(projections):
+        _need(w, _BF16, "w", 2)
+        dout = w.shape[0]
+        if w.shape[1] != din or not w.is_contiguous():
+            raise _lib.AqualoraError(f"w must be contiguous [dout, {din}], got {tuple(w.shape)}")
+        if (down is not None) != has_lora:
+            raise _lib.AqualoraError("grouped projection: LoRA operands must be given for all projections or for none")
+        h = None
+        if has_lora:
+            _need(down, _BF16, "down", 2)
+            _need(up, _BF16, "up", 2)
+            if tuple(down.shape) != (r, din) or tuple(up.shape) != (dout, r) or not down.is_contiguous() or not up.is_contiguous():
+                raise _lib.AqualoraError(f"down/up must be contiguous [r, din]/[dout, r], got {tuple(down.shape)}/{tuple(up.shape)}")
+            if save_h:
+                h = torch.empty((M, r), dtype=_BF16, device=x.device)
+        if bias is not None:
+            _need(bias, _BF16, "bias", 1)
+        y = torch.empty((M, dout), dtype=_BF16, device=x.device)
+        arr[i].w, arr[i].bias, arr[i].down, arr[i].up = w.data_ptr(), _ptr(bias), _ptr(down), _ptr(up)
+        arr[i].y, arr[i].ldy, arr[i].h_save, arr[i].dout = y.data_ptr(), y.stride(0), _ptr(h), dout
+        outs.append((y, h))
+    _lib.call("aq_lora_linear_fwd_grouped", x.data_ptr(), _rows(x, "x"), ctypes.addressof(arr), n, _ptr(scale),
+              M, max(int(tokens_per_sample), 1), din, r, _stream())
+    return outs
 
 
 def lora_linear_bwd(gy: torch.Tensor, x: torch.Tensor, w_t: torch.Tensor | None, down_t: torch.Tensor, up_t: torch.Tensor,

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .lora_modules import LoRACompatibleConv, LoRACompatibleLinear
+from .lora_modules import AquaLoRAAttnProcessor, LoRACompatibleConv, LoRACompatibleLinear, precompute_cross_kv
 
 
 @dataclass
@@ -109,23 +109,10 @@ class Attention(nn.Module):
         self.to_k = LoRACompatibleLinear(context_dim, query_dim, bias=False)
         self.to_v = LoRACompatibleLinear(context_dim, query_dim, bias=False)
         self.to_out = nn.ModuleList([LoRACompatibleLinear(query_dim, query_dim)])
+        self.processor = AquaLoRAAttnProcessor()
 
     def forward(self, x, context=None, scale=1.0):
-        ctx = x if context is None else context.to(x.dtype)
-        q = self.to_q(x, scale)
-        k = self.to_k(ctx, scale)
-        v = self.to_v(ctx, scale)
-        B, N, C = q.shape
-        h = self.heads
-        q = q.view(B, N, h, C // h).transpose(1, 2)
-        k = k.view(B, k.shape[1], h, C // h).transpose(1, 2)
-        v = v.view(B, v.shape[1], h, C // h).transpose(1, 2)
-        if self.upcast:
-            o = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).to(v.dtype)
-        else:
-            o = F.scaled_dot_product_attention(q, k, v)
-        o = o.transpose(1, 2).reshape(B, N, C)
-        return self.to_out[0](o, scale)
+        return self.processor(self, x, encoder_hidden_states=context, scale=scale)
 
 
 class GEGLU(nn.Module):
@@ -309,6 +296,7 @@ class UNet2DConditionModel(nn.Module):
             self.up_blocks.append(UpBlock(cfg, cin, cout, cprev, len(ch) - 1 - i, rev_attn[i], add_up=i < len(ch) - 1))
         self.conv_norm_out = nn.GroupNorm(cfg.norm_num_groups, ch[0], eps=cfg.norm_eps)
         self.conv_out = nn.Conv2d(ch[0], cfg.out_channels, 3, padding=1)
+        self._cross_attentions = None
 
     @property
     def dtype(self):
@@ -323,6 +311,11 @@ class UNet2DConditionModel(nn.Module):
         temb = self.time_embedding(timestep_embedding(timestep, self.cfg.block_out_channels[0]).to(self.dtype))
         if sample.is_cuda:
             sample = sample.contiguous(memory_format=torch.channels_last)
+        if sample.is_cuda:
+            # the 2 x 16 cross-attention K / V projections all read the text context: one grouped launch up front
+            if self._cross_attentions is None:
+                self._cross_attentions = [m.attn2 for m in self.modules() if isinstance(m, BasicTransformerBlock)]
+            precompute_cross_kv(self._cross_attentions, encoder_hidden_states.to(self.dtype), scale)
         x = self.conv_in(sample)
         skips = [x]
         for blk in self.down_blocks:

@@ -122,7 +122,7 @@ class GemmProbe:
     def __init__(self, ops):
         self.ops = ops
         self.records = []   # (kind, flops, bytes, ev0, ev1, shape)
-        self._fwd, self._bwd = ops.lora_linear_fwd, ops.lora_linear_bwd
+        self._fwd, self._bwd, self._grp = ops.lora_linear_fwd, ops.lora_linear_bwd, ops.lora_linear_fwd_grouped
 
     def __enter__(self):
         ops = self.ops
@@ -154,11 +154,29 @@ class GemmProbe:
             self.records.append(("bwd_dx_wgrad", flops, byts, e0, e1, (M, K, N, r)))
             return res
 
-        ops.lora_linear_fwd, ops.lora_linear_bwd = fwd, bwd
+        def grouped(x, projections, scale, tokens, save_h=False):
+            # one launch carrying several projections of the same rows: the algorithmic counts are the per-projection sums
+            # (x is counted once per projection, as the reference's separate module calls read it)
+            M, K = x.shape
+            r = 0 if projections[0][2] is None else projections[0][2].shape[0]
+            flops = byts = 0.0
+            for w, _b, _d, _u in projections:
+                N = w.shape[0]
+                flops += 2.0 * M * K * N + 2.0 * M * r * (K + N)
+                byts += 2.0 * M * (K + N) + 2.0 * (K * N + r * (K + N)) + (2.0 * M * r if (save_h and r) else 0.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = self._grp(x, projections, scale, tokens, save_h=save_h)
+            e1.record()
+            self.records.append(("gemm_fwd" if r else "gemm_plain", flops, byts, e0, e1,
+                                 (M, K, sum(w.shape[0] for w, *_ in projections), r)))
+            return res
+
+        ops.lora_linear_fwd, ops.lora_linear_bwd, ops.lora_linear_fwd_grouped = fwd, bwd, grouped
         return self
 
     def __exit__(self, *exc):
-        self.ops.lora_linear_fwd, self.ops.lora_linear_bwd = self._fwd, self._bwd
+        self.ops.lora_linear_fwd, self.ops.lora_linear_bwd, self.ops.lora_linear_fwd_grouped = self._fwd, self._bwd, self._grp
 
     def summary(self, steps: int):
         """Per kind and per shape totals.  Each launch is bracketed by its own pair of CUDA events; a bracket also contains

@@ -73,6 +73,24 @@ int aq_lora_set_tuning(int block_n, int group_size);
  * gx [M, din] bf16 (ldgx) or NULL.  g_down [r, din], g_up [dout, r], g_scale [B, r] are fp32 and are
  * ACCUMULATED into (the caller zeroes the flat gradient buffer once per step); g_scale may be NULL.
  * ws: aq_lora_linear_bwd_workspace_bytes(M, r) bytes of scratch. */
+/* Several projections of the SAME input in one launch: the 32 cross-attention to_k / to_v projections of a U-Net forward all
+ * read encoder_hidden_states, to_q / to_k / to_v of a self-attention read the same tokens (what diffusers' AttnProcessor issues
+ * as separate module calls, each the op sequence of utils/lora_modules.py:9-26,56-62).  proj[i]: the per-projection operands of
+ * aq_lora_linear_fwd; x, scale, M, tokens_per_sample, din, r are shared.  down == NULL in every entry runs plain base
+ * projections.  1 <= nproj <= 32. */
+typedef struct aq_lora_projection {
+  const void* w;        /* [dout, din] bf16 */
+  const void* bias;     /* [dout] bf16 or NULL */
+  const void* down;     /* [r, din] bf16 or NULL (all entries alike) */
+  const void* up;       /* [dout, r] bf16 */
+  void* y;              /* [M, dout] bf16, row stride ldy */
+  int64_t ldy;
+  void* h_save;         /* [M, r] bf16 or NULL */
+  int dout;
+} aq_lora_projection;
+int aq_lora_linear_fwd_grouped(const void* x, int64_t ldx, const aq_lora_projection* proj, int nproj, const float* scale,
+                               int64_t M, int64_t tokens_per_sample, int din, int r, void* stream);
+
 size_t aq_lora_linear_bwd_workspace_bytes(int64_t M, int r);
 int aq_lora_linear_bwd(const void* gy, int64_t ldgy, const void* x, int64_t ldx, const void* w_t,
                        const void* down_t, const void* up_t, const float* scale, const void* h_save, void* gx,

@@ -375,3 +375,104 @@ def test_state_dict_keys_follow_reference(cuda_device):
     assert "down_blocks.0.attentions.0.transformer_blocks.0.attn1.processor.to_q_lora.down.weight" in sd
     assert "down_blocks.0.attentions.0.proj_in.lora.up.weight" in sd
     assert "mid_block.attentions.0.transformer_blocks.0.ff.net.0.proj.lora.down.weight" in sd
+
+
+def _projection_family(lm, dev, din, douts, r, seed, bias=False, with_lora=True):
+    g = torch.Generator().manual_seed(seed)
+    mods = []
+    for dout in douts:
+        lin = lm.LoRACompatibleLinear(din, dout, bias=bias)
+        lin.weight.data.copy_(torch.randn(dout, din, generator=g) * din ** -0.5)
+        if bias:
+            lin.bias.data.copy_(torch.randn(dout, generator=g) * 0.1)
+        lin = lin.to(dev, torch.bfloat16).requires_grad_(False)
+        if with_lora:
+            lora = lm.LoRALinearLayer(din, dout, r)
+            lora.down.weight.data.copy_(torch.randn(r, din, generator=g) * din ** -0.5)
+            lora.up.weight.data.copy_(torch.randn(dout, r, generator=g) * 0.1)
+            lin.set_lora_layer(lora.to(dev))
+        mods.append(lin)
+    return mods
+
+
+@pytest.mark.parametrize("B,tok,din,douts,r,bias,need_dx", [
+    (2, 300, 320, (320, 320, 320), 64, False, True),          # q / k / v of a self-attention, ragged last row block
+    (2, 77, 768, (320, 320, 640, 640, 1280, 1280), 64, False, False),   # hoisted cross-attention K / V on the text context
+    (3, 128, 64, (64, 200), 16, True, True),                  # small rank, bias, partial column tile
+])
+def test_grouped_projections_equal_separate_launches(lm, cuda_device, B, tok, din, douts, r, bias, need_dx):
+    """project_group == the same modules called one by one (each utils/lora_modules.py:56-62): forward bit-for-bit (the
+    accumulation order over k-blocks does not depend on the column tile), gradients to bf16 accumulation-order noise, and
+    both within the bf16 bound of the fp32 closed form."""
+    from oracle import lora_oracle as O
+
+    dev = cuda_device
+    mods = _projection_family(lm, dev, din, douts, r, seed=21, bias=bias)
+    g = torch.Generator().manual_seed(22)
+    x0 = torch.randn(B, tok, din, generator=g).bfloat16()
+    s0 = (1 + 0.7 * torch.randn(B, r, generator=g)).bfloat16().float()   # fp32 leaf holding bf16 values: its gradient stays fp32
+    gys = [(torch.randn(B, tok, d, generator=g) * 0.05).bfloat16().to(dev) for d in douts]
+
+    def run(grouped):
+        x = x0.to(dev).requires_grad_(need_dx)
+        s = s0.to(dev).requires_grad_(True)
+        for m in mods:
+            m.lora_layer.zero_grad(set_to_none=True)
+        ys = lm.project_group(mods, x, s) if grouped else [m(x, s) for m in mods]
+        torch.autograd.backward(ys, gys)
+        grads = [p.grad.clone() for m in mods for p in (m.lora_layer.down.weight, m.lora_layer.up.weight)]
+        return [y.detach() for y in ys], (x.grad.clone() if need_dx else None), s.grad.clone(), grads
+
+    run(False)                                               # fills the operand caches (bf16 copies, W^T): not counted below
+    n0 = _launches()
+    ys_g, gx_g, gs_g, gr_g = run(True)
+    n_grouped = _launches() - n0
+    n0 = _launches()
+    ys_s, gx_s, gs_s, gr_s = run(False)
+    n_separate = _launches() - n0
+    assert n_separate - n_grouped == len(douts) - 1          # one forward launch instead of len(douts)
+    for yg, ys, m in zip(ys_g, ys_s, mods):
+        assert torch.equal(yg, ys)
+        want = O.closed_form_linear(x0.float(), m.weight.float().cpu(), None if m.bias is None else m.bias.float().cpu(),
+                                    m.lora_layer.down.weight.detach().bfloat16().float().cpu(),
+                                    m.lora_layer.up.weight.detach().bfloat16().float().cpu(), s0.float())
+        assert _max_rel(yg, want) < BF16_TOL
+    if need_dx:
+        assert _max_rel(gx_g, gx_s) < BF16_TOL
+    assert _fro_rel(gs_g, gs_s) < 2e-3                       # same bf16 operands; fp32 atomics land in a different order
+    for a, b in zip(gr_g, gr_s):
+        assert _fro_rel(a, b) < 2e-3
+
+
+def _launches():
+    from aqualora_b200 import _lib
+
+    return _lib.load().aq_launch_count()
+
+
+def test_grouped_plain_and_fallback(lm, cuda_device):
+    """lora_disabled() groups the plain base projections; a family that cannot share a launch (LoRA on some members only)
+    falls back to one fused launch per module with identical results."""
+    dev = cuda_device
+    mods = _projection_family(lm, dev, 128, (128, 256), 16, seed=5, bias=True)
+    x = torch.randn(2, 50, 128, generator=torch.Generator().manual_seed(6)).bfloat16().to(dev)
+    s = torch.ones(2, 16, device=dev)
+    with torch.no_grad():
+        [m(x, s) for m in mods]                              # operand caches
+    with lm.lora_disabled(), torch.no_grad():
+        n0 = _launches()
+        got = lm.project_group(mods, x, s)
+        assert _launches() - n0 == 1
+        want = [m(x, s) for m in mods]
+    for a, b, m in zip(got, want, mods):
+        assert torch.equal(a, b)
+        ref = torch.nn.functional.linear(x.float(), m.weight.float(), m.bias.float())
+        assert _max_rel(a, ref) < BF16_TOL
+    mods[1].set_lora_layer(None)
+    with torch.no_grad():
+        n0 = _launches()
+        got = lm.project_group(mods, x, s)
+        assert _launches() - n0 == 2
+        want = [m(x, s) for m in mods]
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
