@@ -56,6 +56,11 @@ _SIGNATURES = {
     "aq_depthwise_silu": ([c_void_p] * 5 + [c_int] * 5 + [c_void_p], c_int),
     "aq_lora_fold_down": ([c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_void_p], c_int),
     "aq_lora_merge": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p], c_int),
+    "aq_group_norm_workspace_bytes": ([c_int, c_int], c_size_t),
+    "aq_group_norm_nhwc_fwd": ([c_void_p] * 6 + [c_int] * 4 + [c_float, c_int, c_void_p, c_size_t, c_void_p], c_int),
+    "aq_group_norm_nhwc_bwd": ([c_void_p] * 7 + [c_int] * 4 + [c_float, c_int, c_void_p, c_size_t, c_void_p], c_int),
+    "aq_geglu_fwd": ([c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p], c_int),
+    "aq_geglu_bwd": ([c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p], c_int),
     "aq_flat_sumsq": ([c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "aq_flat_clip_adamw": (
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,

@@ -1,0 +1,491 @@
+// HBM-bound glue of the U-Net around the LoRA projections: GroupNorm (+ broadcast add, + SiLU) over
+// channels-last bf16 activations, forward and backward, and GEGLU forward and backward.
+//
+// Replaces, in scripts/lib/original_unet.py: ResnetBlock2D's `norm1 -> silu`, `+ temb[:, :, None, None] -> norm2 -> silu`
+// (:440-453), Transformer2DModel.norm (:826), conv_norm_out -> silu (:1416), and GEGLU.forward's chunk / gelu / mul (:708-729).
+// PyTorch's native_group_norm only knows NCHW: on the channels-last tensors the tensor-core convolutions want it copies the
+// input to NCHW, normalises, and the next convolution copies back (17 ms of layout copies per PPFT step at B = 16).  Here
+// the rows stay [B, H*W, C]: a thread owns 8 consecutive channels (one 16-byte load) and walks down the rows.
+//
+// Two passes per direction (statistics, then apply); the second read of the activations comes from the 126 MB L2 at the
+// BASELINE sizes ([16, 64, 64, 320] bf16 = 42 MB).  Statistics leave each CTA as fp32 partials and are combined in fp64.
+#include "aq_common.h"
+#include "aq_ptx.cuh"
+
+namespace aq {
+
+constexpr int kGnMaxGroups = 128;
+constexpr int kGnBatch = 4;   // independent 16-byte loads in flight per thread
+
+struct GnParams {
+  const uint4* x;        // [B, HW, C] bf16
+  const uint4* dy;       // backward: [B, HW, C] bf16
+  uint4* out;            // forward: y, backward: dx
+  const __nv_bfloat16* gamma;   // [C]
+  const __nv_bfloat16* beta;    // [C]
+  const __nv_bfloat16* add_bc;  // [B, C] or null: x' = x + add_bc[b, c] is what gets normalised
+  double* sums;          // [B, G, 2] zeroed by the caller of the statistics pass
+  float* mean_rstd;      // [B, G, 2] forward: written; backward: read
+  int HW, C, G, cpg, V, R, rows_per_cta;
+  float eps;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = bf16_lo(w[i]);
+    f[2 * i + 1] = bf16_hi(w[i]);
+  }
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&f)[8]) {
+  unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f);
+}
+
+__device__ __forceinline__ float sigmoidf_fast(float u) { return 1.f / (1.f + __expf(-u)); }
+
+// per-thread partials of 8 channels -> per-group partials of the CTA (shared fp32 atomics) -> fp64 global atomics
+__device__ __forceinline__ void gn_reduce_to_groups(const float (&a)[8], const float (&b)[8], int ch0, const GnParams& p, int batch) {
+  __shared__ float sh[2 * kGnMaxGroups];
+  for (int i = threadIdx.x; i < 2 * p.G; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  // 8 consecutive channels touch one group, or two when the run crosses a boundary, or more when cpg < 8
+  float ra = 0.f, rb = 0.f;
+  int g_run = ch0 / p.cpg;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (ch0 + i) / p.cpg;
+    if (g != g_run) {
+      atomicAdd(&sh[2 * g_run], ra);
+      atomicAdd(&sh[2 * g_run + 1], rb);
+      ra = rb = 0.f;
+      g_run = g;
+    }
+    ra += a[i];
+    rb += b[i];
+  }
+  atomicAdd(&sh[2 * g_run], ra);
+  atomicAdd(&sh[2 * g_run + 1], rb);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * p.G; i += blockDim.x) atomicAdd(p.sums + (size_t)batch * 2 * p.G + i, (double)sh[i]);
+}
+
+// ---------------------------------------------------------------- forward
+__global__ void gn_fwd_stats_kernel(const GnParams p) {
+  const int v = threadIdx.x % p.V, rr = threadIdx.x / p.V;
+  const int b = blockIdx.y;
+  const int r_begin = blockIdx.x * p.rows_per_cta;
+  const int r_end = min(r_begin + p.rows_per_cta, p.HW);
+  const uint4* xb = p.x + (size_t)b * p.HW * p.V + v;
+  float add[8] = {};
+  if (p.add_bc != nullptr) load8_bf16(p.add_bc + (size_t)b * p.C + v * 8, add);
+  float s[8] = {}, ss[8] = {};
+  for (int r = r_begin + rr; r < r_end; r += kGnBatch * p.R) {
+    uint4 q[kGnBatch];
+    bool ok[kGnBatch];
+#pragma unroll
+    for (int j = 0; j < kGnBatch; ++j) {
+      const int rj = r + j * p.R;
+      ok[j] = rj < r_end;
+      q[j] = ok[j] ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < kGnBatch; ++j) {
+      if (!ok[j]) continue;
+      float f[8];
+      unpack8(q[j], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = f[i] + add[i];
+        s[i] += t;
+        ss[i] = fmaf(t, t, ss[i]);
+      }
+    }
+  }
+  gn_reduce_to_groups(s, ss, v * 8, p, b);
+}
+
+// per-channel affine of this thread's 8 channels from the fp64 group sums: y = x * a + c
+__device__ __forceinline__ void gn_channel_affine(const GnParams& p, int b, int ch0, float (&a)[8], float (&c)[8], float (&mean)[8],
+                                                  float (&rstd)[8]) {
+  float gam[8], bet[8];
+  load8_bf16(p.gamma + ch0, gam);
+  load8_bf16(p.beta + ch0, bet);
+  const double n = (double)p.cpg * (double)p.HW;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (ch0 + i) / p.cpg;
+    float m, rs;
+    if (p.sums != nullptr) {
+      const double s = p.sums[((size_t)b * p.G + g) * 2], q = p.sums[((size_t)b * p.G + g) * 2 + 1];
+      const double mu = s / n;
+      double var = q / n - mu * mu;
+      var = var < 0.0 ? 0.0 : var;
+      m = (float)mu;
+      rs = (float)(1.0 / sqrt(var + (double)p.eps));
+    } else {
+      m = p.mean_rstd[((size_t)b * p.G + g) * 2];
+      rs = p.mean_rstd[((size_t)b * p.G + g) * 2 + 1];
+    }
+    mean[i] = m;
+    rstd[i] = rs;
+    a[i] = rs * gam[i];
+    c[i] = bet[i] - m * a[i];
+  }
+}
+
+template <bool SILU>
+__global__ void gn_fwd_apply_kernel(const GnParams p) {
+  const int v = threadIdx.x % p.V, rr = threadIdx.x / p.V;
+  const int b = blockIdx.y;
+  const int r_begin = blockIdx.x * p.rows_per_cta;
+  const int r_end = min(r_begin + p.rows_per_cta, p.HW);
+  float a[8], c[8], mean[8], rstd[8];
+  gn_channel_affine(p, b, v * 8, a, c, mean, rstd);
+  if (p.add_bc != nullptr) {
+    float add[8];
+    load8_bf16(p.add_bc + (size_t)b * p.C + v * 8, add);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = fmaf(add[i], a[i], c[i]);
+  }
+  if (blockIdx.x == 0 && rr == 0 && p.mean_rstd != nullptr) {
+    // one writer per group: the thread that owns the group's first channel
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = v * 8 + i;
+      if (ch % p.cpg == 0) {
+        const int g = ch / p.cpg;
+        p.mean_rstd[((size_t)b * p.G + g) * 2] = mean[i];
+        p.mean_rstd[((size_t)b * p.G + g) * 2 + 1] = rstd[i];
+      }
+    }
+  }
+  const uint4* xb = p.x + (size_t)b * p.HW * p.V + v;
+  uint4* yb = p.out + (size_t)b * p.HW * p.V + v;
+  for (int r = r_begin + rr; r < r_end; r += kGnBatch * p.R) {
+    uint4 q[kGnBatch];
+    bool ok[kGnBatch];
+#pragma unroll
+    for (int j = 0; j < kGnBatch; ++j) {
+      const int rj = r + j * p.R;
+      ok[j] = rj < r_end;
+      q[j] = ok[j] ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < kGnBatch; ++j) {
+      if (!ok[j]) continue;
+      float f[8];
+      unpack8(q[j], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float u = fmaf(f[i], a[i], c[i]);
+        f[i] = SILU ? u * sigmoidf_fast(u) : u;
+      }
+      yb[(size_t)(r + j * p.R) * p.V] = pack8(f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- backward (gamma / beta are frozen: only dx)
+// u = xhat * gamma + beta, y = silu(u) or u;  du = dy * silu'(u);  t = gamma * du
+// dx = rstd * (t - mean_g(t) - xhat * mean_g(t * xhat))
+template <bool SILU>
+__device__ __forceinline__ void gn_bwd_terms(const float (&x)[8], const float (&dy)[8], const float (&a)[8], const float (&c)[8],
+                                             const float (&mean)[8], const float (&rstd)[8], const float (&gam)[8], float (&t)[8],
+                                             float (&xhat)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    xhat[i] = (x[i] - mean[i]) * rstd[i];
+    float du = dy[i];
+    if (SILU) {
+      const float u = fmaf(x[i], a[i], c[i]);
+      const float sg = sigmoidf_fast(u);
+      du *= sg * fmaf(u, 1.f - sg, 1.f);
+    }
+    t[i] = gam[i] * du;
+  }
+}
+
+template <bool SILU>
+__global__ void gn_bwd_stats_kernel(const GnParams p) {
+  const int v = threadIdx.x % p.V, rr = threadIdx.x / p.V;
+  const int b = blockIdx.y;
+  const int r_begin = blockIdx.x * p.rows_per_cta;
+  const int r_end = min(r_begin + p.rows_per_cta, p.HW);
+  GnParams ps = p;
+  ps.sums = nullptr;   // statistics of the forward come from mean_rstd
+  float a[8], c[8], mean[8], rstd[8], gam[8];
+  gn_channel_affine(ps, b, v * 8, a, c, mean, rstd);
+  load8_bf16(p.gamma + v * 8, gam);
+  if (p.add_bc != nullptr) {
+    float add[8];
+    load8_bf16(p.add_bc + (size_t)b * p.C + v * 8, add);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      c[i] = fmaf(add[i], a[i], c[i]);
+      mean[i] -= add[i];   // xhat = (x + add - mean) * rstd
+    }
+  }
+  const uint4* xb = p.x + (size_t)b * p.HW * p.V + v;
+  const uint4* gb = p.dy + (size_t)b * p.HW * p.V + v;
+  float s1[8] = {}, s2[8] = {};
+  for (int r = r_begin + rr; r < r_end; r += kGnBatch * p.R) {
+    uint4 q[kGnBatch], d[kGnBatch];
+    bool ok[kGnBatch];
+#pragma unroll
+    for (int j = 0; j < kGnBatch; ++j) {
+      const int rj = r + j * p.R;
+      ok[j] = rj < r_end;
+      q[j] = ok[j] ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
+      d[j] = ok[j] ? __ldg(gb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < kGnBatch; ++j) {
+      if (!ok[j]) continue;
+      float x[8], dy[8], t[8], xhat[8];
+      unpack8(q[j], x);
+      unpack8(d[j], dy);
+      gn_bwd_terms<SILU>(x, dy, a, c, mean, rstd, gam, t, xhat);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += t[i];
+        s2[i] = fmaf(t[i], xhat[i], s2[i]);
+      }
+    }
+  }
+  gn_reduce_to_groups(s1, s2, v * 8, p, b);
+}
+
+template <bool SILU>
+__global__ void gn_bwd_apply_kernel(const GnParams p) {
+  const int v = threadIdx.x % p.V, rr = threadIdx.x / p.V;
+  const int b = blockIdx.y;
+  const int r_begin = blockIdx.x * p.rows_per_cta;
+  const int r_end = min(r_begin + p.rows_per_cta, p.HW);
+  GnParams ps = p;
+  ps.sums = nullptr;
+  float a[8], c[8], mean[8], rstd[8], gam[8], m1[8], m2[8];
+  gn_channel_affine(ps, b, v * 8, a, c, mean, rstd);
+  load8_bf16(p.gamma + v * 8, gam);
+  const double n = (double)p.cpg * (double)p.HW;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (v * 8 + i) / p.cpg;
+    m1[i] = (float)(p.sums[((size_t)b * p.G + g) * 2] / n);
+    m2[i] = (float)(p.sums[((size_t)b * p.G + g) * 2 + 1] / n);
+  }
+  if (p.add_bc != nullptr) {
+    float add[8];
+    load8_bf16(p.add_bc + (size_t)b * p.C + v * 8, add);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      c[i] = fmaf(add[i], a[i], c[i]);
+      mean[i] -= add[i];
+    }
+  }
+  const uint4* xb = p.x + (size_t)b * p.HW * p.V + v;
+  const uint4* gb = p.dy + (size_t)b * p.HW * p.V + v;
+  uint4* ob = p.out + (size_t)b * p.HW * p.V + v;
+  for (int r = r_begin + rr; r < r_end; r += kGnBatch * p.R) {
+    uint4 q[kGnBatch], d[kGnBatch];
+    bool ok[kGnBatch];
+#pragma unroll
+    for (int j = 0; j < kGnBatch; ++j) {
+      const int rj = r + j * p.R;
+      ok[j] = rj < r_end;
+      q[j] = ok[j] ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
+      d[j] = ok[j] ? __ldg(gb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < kGnBatch; ++j) {
+      if (!ok[j]) continue;
+      float x[8], dy[8], t[8], xhat[8];
+      unpack8(q[j], x);
+      unpack8(d[j], dy);
+      gn_bwd_terms<SILU>(x, dy, a, c, mean, rstd, gam, t, xhat);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = rstd[i] * (t[i] - m1[i] - xhat[i] * m2[i]);
+      ob[(size_t)(r + j * p.R) * p.V] = pack8(t);
+    }
+  }
+}
+
+static int gn_setup(GnParams& p, dim3& grid, int& threads, const void* x, const void* gamma, const void* beta, const void* add_bc,
+                    double* sums, float* mean_rstd, int B, int HW, int C, int G, float eps, const char* who) {
+  AQ_REQUIRE(B > 0 && HW > 0 && C > 0 && G > 0, AQ_ERR_BAD_SHAPE, "%s: empty problem B=%d HW=%d C=%d G=%d", who, B, HW, C, G);
+  AQ_REQUIRE(C % 8 == 0 && C % G == 0, AQ_ERR_BAD_SHAPE, "%s: C=%d must be a multiple of 8 and of G=%d", who, C, G);
+  AQ_REQUIRE(G <= kGnMaxGroups, AQ_ERR_BAD_SHAPE, "%s: at most %d groups, got %d", who, kGnMaxGroups, G);
+  AQ_REQUIRE(C / 8 <= 1024, AQ_ERR_BAD_SHAPE, "%s: C=%d exceeds 8192 channels", who, C);
+  AQ_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0 &&
+                 (reinterpret_cast<uintptr_t>(beta) & 15u) == 0 && (reinterpret_cast<uintptr_t>(add_bc) & 15u) == 0,
+             AQ_ERR_BAD_ALIGN, "%s: pointers must be 16-byte aligned", who);
+  AQ_REQUIRE(sums != nullptr && mean_rstd != nullptr, AQ_ERR_WORKSPACE, "%s: workspace / statistics buffer is NULL", who);
+  int rc = check_arch();
+  if (rc) return rc;
+  p.x = reinterpret_cast<const uint4*>(x);
+  p.gamma = reinterpret_cast<const __nv_bfloat16*>(gamma);
+  p.beta = reinterpret_cast<const __nv_bfloat16*>(beta);
+  p.add_bc = reinterpret_cast<const __nv_bfloat16*>(add_bc);
+  p.sums = sums;
+  p.mean_rstd = mean_rstd;
+  p.HW = HW; p.C = C; p.G = G; p.cpg = C / G; p.V = C / 8; p.eps = eps;
+  p.R = p.V >= 256 ? 1 : 256 / p.V;
+  if (p.R > HW) p.R = HW;
+  threads = p.V * p.R;
+  // ~6 CTAs per SM over the whole batch, at least 2 row batches per thread
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  int slabs = (sms * 6 + B - 1) / B;
+  const int max_slabs = (HW + 2 * p.R - 1) / (2 * p.R);
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  p.rows_per_cta = (HW + slabs - 1) / slabs;
+  p.rows_per_cta = (p.rows_per_cta + p.R - 1) / p.R * p.R;
+  slabs = (HW + p.rows_per_cta - 1) / p.rows_per_cta;
+  grid = dim3((unsigned)slabs, (unsigned)B, 1);
+  return AQ_OK;
+}
+
+// ---------------------------------------------------------------- GEGLU (original_unet.py:708-729)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+__global__ void geglu_fwd_kernel(const uint4* __restrict__ p, uint4* __restrict__ out, long long M, int FV, long long ldp_v) {
+  const long long total = M * FV;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / FV;
+    const int fv = (int)(idx - m * FV);
+    const uint4 hq = __ldg(p + m * ldp_v + fv), gq = __ldg(p + m * ldp_v + FV + fv);
+    float h[8], g[8];
+    unpack8(hq, h);
+    unpack8(gq, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] *= gelu_erf(g[i]);
+    out[idx] = pack8(h);
+  }
+}
+
+__global__ void geglu_bwd_kernel(const uint4* __restrict__ p, const uint4* __restrict__ go, uint4* __restrict__ dp, long long M, int FV,
+                                 long long ldp_v) {
+  const long long total = M * FV;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / FV;
+    const int fv = (int)(idx - m * FV);
+    const uint4 hq = __ldg(p + m * ldp_v + fv), gq = __ldg(p + m * ldp_v + FV + fv), oq = __ldg(go + idx);
+    float h[8], g[8], o[8], dh[8], dg[8];
+    unpack8(hq, h);
+    unpack8(gq, g);
+    unpack8(oq, o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float cdf = 0.5f * (1.f + erff(g[i] * 0.70710678118654752f));
+      const float pdf = 0.3989422804014327f * __expf(-0.5f * g[i] * g[i]);
+      dh[i] = o[i] * g[i] * cdf;
+      dg[i] = o[i] * h[i] * fmaf(g[i], pdf, cdf);
+    }
+    dp[m * (2 * (long long)FV) + fv] = pack8(dh);
+    dp[m * (2 * (long long)FV) + FV + fv] = pack8(dg);
+  }
+}
+
+}  // namespace aq
+
+extern "C" {
+
+size_t aq_group_norm_workspace_bytes(int B, int G) { return (size_t)B * (size_t)G * 2 * sizeof(double); }
+
+int aq_group_norm_nhwc_fwd(const void* x, const void* gamma, const void* beta, const void* add_bc, void* y, float* mean_rstd, int B,
+                           int HW, int C, int G, float eps, int silu, void* ws, size_t ws_bytes, void* stream) {
+  using namespace aq;
+  GnParams p{};
+  dim3 grid;
+  int threads = 0;
+  int rc = gn_setup(p, grid, threads, x, gamma, beta, add_bc, reinterpret_cast<double*>(ws), mean_rstd, B, HW, C, G, eps,
+                    "aq_group_norm_nhwc_fwd");
+  if (rc) return rc;
+  AQ_REQUIRE(ws_bytes >= aq_group_norm_workspace_bytes(B, G), AQ_ERR_WORKSPACE, "aq_group_norm_nhwc_fwd: workspace too small");
+  AQ_REQUIRE(y != nullptr && (reinterpret_cast<uintptr_t>(y) & 15u) == 0, AQ_ERR_BAD_ALIGN, "aq_group_norm_nhwc_fwd: y must be 16-byte aligned");
+  p.out = reinterpret_cast<uint4*>(y);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  AQ_CHECK_CUDA(cudaMemsetAsync(ws, 0, aq_group_norm_workspace_bytes(B, G), st));
+  gn_fwd_stats_kernel<<<grid, threads, 0, st>>>(p);
+  AQ_LAUNCHED();
+  if (silu) gn_fwd_apply_kernel<true><<<grid, threads, 0, st>>>(p);
+  else gn_fwd_apply_kernel<false><<<grid, threads, 0, st>>>(p);
+  AQ_LAUNCHED();
+  return AQ_OK;
+}
+
+int aq_group_norm_nhwc_bwd(const void* dy, const void* x, const void* gamma, const void* beta, const void* add_bc,
+                           const float* mean_rstd, void* dx, int B, int HW, int C, int G, float eps, int silu, void* ws, size_t ws_bytes,
+                           void* stream) {
+  using namespace aq;
+  GnParams p{};
+  dim3 grid;
+  int threads = 0;
+  int rc = gn_setup(p, grid, threads, x, gamma, beta, add_bc, reinterpret_cast<double*>(ws), const_cast<float*>(mean_rstd), B, HW, C, G,
+                    eps, "aq_group_norm_nhwc_bwd");
+  if (rc) return rc;
+  AQ_REQUIRE(ws_bytes >= aq_group_norm_workspace_bytes(B, G), AQ_ERR_WORKSPACE, "aq_group_norm_nhwc_bwd: workspace too small");
+  AQ_REQUIRE(dy != nullptr && dx != nullptr && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0,
+             AQ_ERR_BAD_ALIGN, "aq_group_norm_nhwc_bwd: dy / dx must be 16-byte aligned");
+  p.dy = reinterpret_cast<const uint4*>(dy);
+  p.out = reinterpret_cast<uint4*>(dx);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  AQ_CHECK_CUDA(cudaMemsetAsync(ws, 0, aq_group_norm_workspace_bytes(B, G), st));
+  if (silu) gn_bwd_stats_kernel<true><<<grid, threads, 0, st>>>(p);
+  else gn_bwd_stats_kernel<false><<<grid, threads, 0, st>>>(p);
+  AQ_LAUNCHED();
+  if (silu) gn_bwd_apply_kernel<true><<<grid, threads, 0, st>>>(p);
+  else gn_bwd_apply_kernel<false><<<grid, threads, 0, st>>>(p);
+  AQ_LAUNCHED();
+  return AQ_OK;
+}
+
+static int geglu_grid(long long total) {
+  const int sms = aq::sm_count() > 0 ? aq::sm_count() : 148;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sms * 16;
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+int aq_geglu_fwd(const void* proj, int64_t ldp, void* out, int64_t M, int F, void* stream) {
+  using namespace aq;
+  AQ_REQUIRE(M > 0 && F > 0 && F % 8 == 0 && ldp % 8 == 0 && ldp >= 2 * (int64_t)F, AQ_ERR_BAD_SHAPE,
+             "aq_geglu_fwd: need M > 0, F %% 8 == 0, ldp %% 8 == 0, ldp >= 2F (M=%lld F=%d ldp=%lld)", (long long)M, F, (long long)ldp);
+  AQ_REQUIRE(((reinterpret_cast<uintptr_t>(proj) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0 && proj != nullptr && out != nullptr,
+             AQ_ERR_BAD_ALIGN, "aq_geglu_fwd: pointers must be non-NULL and 16-byte aligned");
+  int rc = check_arch();
+  if (rc) return rc;
+  const int FV = F / 8;
+  geglu_fwd_kernel<<<geglu_grid(M * FV), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(proj), reinterpret_cast<uint4*>(out), M, FV, ldp / 8);
+  AQ_LAUNCHED();
+  return AQ_OK;
+}
+
+int aq_geglu_bwd(const void* proj, int64_t ldp, const void* g_out, void* g_proj, int64_t M, int F, void* stream) {
+  using namespace aq;
+  AQ_REQUIRE(M > 0 && F > 0 && F % 8 == 0 && ldp % 8 == 0 && ldp >= 2 * (int64_t)F, AQ_ERR_BAD_SHAPE,
+             "aq_geglu_bwd: need M > 0, F %% 8 == 0, ldp %% 8 == 0, ldp >= 2F (M=%lld F=%d ldp=%lld)", (long long)M, F, (long long)ldp);
+  AQ_REQUIRE(proj != nullptr && g_out != nullptr && g_proj != nullptr &&
+                 ((reinterpret_cast<uintptr_t>(proj) | reinterpret_cast<uintptr_t>(g_out) | reinterpret_cast<uintptr_t>(g_proj)) & 15u) == 0,
+             AQ_ERR_BAD_ALIGN, "aq_geglu_bwd: pointers must be non-NULL and 16-byte aligned");
+  int rc = check_arch();
+  if (rc) return rc;
+  const int FV = F / 8;
+  geglu_bwd_kernel<<<geglu_grid(M * FV), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(proj), reinterpret_cast<const uint4*>(g_out), reinterpret_cast<uint4*>(g_proj), M, FV, ldp / 8);
+  AQ_LAUNCHED();
+  return AQ_OK;
+}
+
+}  // extern "C"

@@ -394,3 +394,77 @@ def lora_merge_(w: torch.Tensor, up: torch.Tensor, down: torch.Tensor, coef: flo
         raise _lib.AqualoraError(f"merge shapes: w {tuple(w.shape)}, up {tuple(up.shape)}, down {tuple(down.shape)}")
     _lib.call("aq_lora_merge", w.data_ptr(), up.contiguous().data_ptr(), down.contiguous().data_ptr(), dout, din, r, float(coef), _stream())
     return w
+
+
+# ------------------------------------------------------------------------------------------------
+# GroupNorm (+ add, + SiLU) on channels-last bf16 rows, GEGLU
+# ------------------------------------------------------------------------------------------------
+def _nhwc_rows(x: torch.Tensor, name: str) -> tuple[int, int, int]:
+    """(B, HW, C) of an NCHW-shaped tensor stored channels_last, or of a [B, HW, C] contiguous tensor."""
+    _need(x, _BF16, name)
+    if x.dim() == 4:
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            raise _lib.AqualoraError(f"{name} must be stored channels_last, got strides {x.stride()}")
+        return x.shape[0], x.shape[2] * x.shape[3], x.shape[1]
+    if x.dim() == 3 and x.is_contiguous():
+        return x.shape[0], x.shape[1], x.shape[2]
+    raise _lib.AqualoraError(f"{name} must be [B, C, H, W] channels_last or contiguous [B, HW, C], got {tuple(x.shape)}")
+
+
+def group_norm_nhwc_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
+                        add_bc: torch.Tensor | None = None):
+    """y = [silu](group_norm(x + add_bc[:, :, None, None])) ; returns (y, mean_rstd [B, G, 2] fp32)."""
+    B, HW, C = _nhwc_rows(x, "x")
+    _need(gamma, _BF16, "gamma", 1)
+    _need(beta, _BF16, "beta", 1)
+    if gamma.shape[0] != C or beta.shape[0] != C:
+        raise _lib.AqualoraError(f"gamma / beta must be [{C}]")
+    if add_bc is not None:
+        _need(add_bc, _BF16, "add_bc", 2)
+        if tuple(add_bc.shape) != (B, C) or not add_bc.is_contiguous():
+            raise _lib.AqualoraError(f"add_bc must be contiguous [{B}, {C}], got {tuple(add_bc.shape)}")
+    y = torch.empty_like(x)
+    stats = torch.empty(B, groups, 2, dtype=_F32, device=x.device)
+    nbytes = _lib.load().aq_group_norm_workspace_bytes(B, groups)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    _lib.call("aq_group_norm_nhwc_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(add_bc), y.data_ptr(), stats.data_ptr(),
+              B, HW, C, groups, float(eps), int(silu), ws.data_ptr(), nbytes, _stream())
+    return y, stats
+
+
+def group_norm_nhwc_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, stats: torch.Tensor,
+                        groups: int, eps: float, silu: bool, add_bc: torch.Tensor | None = None) -> torch.Tensor:
+    B, HW, C = _nhwc_rows(x, "x")
+    if tuple(_nhwc_rows(dy, "dy")) != (B, HW, C) or dy.stride() != x.stride():
+        raise _lib.AqualoraError("dy must have the shape and strides of x")
+    _need(stats, _F32, "mean_rstd", 3)
+    dx = torch.empty_like(x)
+    nbytes = _lib.load().aq_group_norm_workspace_bytes(B, groups)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    _lib.call("aq_group_norm_nhwc_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(add_bc), stats.data_ptr(),
+              dx.data_ptr(), B, HW, C, groups, float(eps), int(silu), ws.data_ptr(), nbytes, _stream())
+    return dx
+
+
+def geglu_fwd(proj: torch.Tensor) -> torch.Tensor:
+    """proj [..., 2F] bf16 -> proj[..., :F] * gelu(proj[..., F:])."""
+    _need(proj, _BF16, "proj")
+    F2 = proj.shape[-1]
+    p2 = proj.reshape(-1, F2)
+    ldp = _rows(p2, "proj")
+    out = torch.empty(*proj.shape[:-1], F2 // 2, dtype=_BF16, device=proj.device)
+    _lib.call("aq_geglu_fwd", p2.data_ptr(), ldp, out.data_ptr(), p2.shape[0], F2 // 2, _stream())
+    return out
+
+
+def geglu_bwd(proj: torch.Tensor, g_out: torch.Tensor) -> torch.Tensor:
+    _need(proj, _BF16, "proj")
+    _need(g_out, _BF16, "g_out")
+    F2 = proj.shape[-1]
+    p2 = proj.reshape(-1, F2)
+    ldp = _rows(p2, "proj")
+    if not g_out.is_contiguous():
+        raise _lib.AqualoraError("g_out must be contiguous")
+    g_proj = torch.empty(proj.shape, dtype=_BF16, device=proj.device)
+    _lib.call("aq_geglu_bwd", p2.data_ptr(), ldp, g_out.data_ptr(), g_proj.data_ptr(), p2.shape[0], F2 // 2, _stream())
+    return g_proj

@@ -4,7 +4,8 @@ The hot path of this repository is the 192 LoRA-target projections (aqualora_b20
 is the CALLER on either side of it: a compact `UNet2DConditionModel` whose module paths and state-dict keys are the
 diffusers ones, so that `utils/unet_keys.json` (train/ppft_train.py:620-689) resolves on it and checkpoints /
 `pytorch_lora_weights.safetensors` keys (train/ppft_train.py:443-471) line up.  Everything that is not a LoRA target
-(3x3 convolutions, GroupNorm, attention core) is a library call and out of scope of the kernels.
+(3x3 convolutions, LayerNorm, attention core) is a library call; GroupNorm(+SiLU) and GEGLU run as channels-last CUDA
+kernels of this repository on the GPU path (aqualora_b200/unet_ops.py).
 
 Topology follows the SD 1.5 / 2.1 configs quoted in scripts/lib/original_unet.py:22-106; the golden test loads the
 same procedurally generated weights into the reference's vendored U-Net and into this one and compares outputs.
@@ -21,6 +22,23 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .lora_modules import AquaLoRAAttnProcessor, LoRACompatibleConv, LoRACompatibleLinear, precompute_cross_kv
+from .unet_ops import geglu, group_norm_nhwc
+
+
+def _fused_glue(x: torch.Tensor, *params: torch.Tensor) -> bool:
+    """The glue kernels (aq_group_norm_nhwc_*, aq_geglu_*) serve the frozen bf16 U-Net on the GPU; the fp32 CPU copy of this
+    module tree that tests / the CPU baseline patch with the oracle keeps the library ops."""
+    return x.is_cuda and x.dtype == torch.bfloat16 and not any(p.requires_grad for p in params)
+
+
+def _norm_act(norm: nn.GroupNorm, x: torch.Tensor, silu: bool, add_bc: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[silu](norm(x + add_bc[:, :, None, None])) -- scripts/lib/original_unet.py:440-453, :826, :1416."""
+    if _fused_glue(x, norm.weight, norm.bias) and (add_bc is None or not add_bc.requires_grad):
+        return group_norm_nhwc(x, norm.weight, norm.bias, norm.num_groups, norm.eps, silu, add_bc)
+    if add_bc is not None:
+        x = x + add_bc[:, :, None, None]
+    y = norm(x)
+    return F.silu(y) if silu else y
 
 
 @dataclass
@@ -89,9 +107,8 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, temb):
-        h = self.conv1(F.silu(self.norm1(x)))
-        h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
-        h = self.conv2(F.silu(self.norm2(h)))
+        h = self.conv1(_norm_act(self.norm1, x, True))
+        h = self.conv2(_norm_act(self.norm2, h, True, add_bc=self.time_emb_proj(F.silu(temb))))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h
@@ -121,7 +138,10 @@ class GEGLU(nn.Module):
         self.proj = LoRACompatibleLinear(dim_in, dim_out * 2)
 
     def forward(self, x, scale=1.0):
-        h, gate = self.proj(x, scale).chunk(2, dim=-1)
+        p = self.proj(x, scale)
+        if _fused_glue(p):
+            return geglu(p)
+        h, gate = p.chunk(2, dim=-1)
         return h * F.gelu(gate)
 
 
@@ -166,7 +186,7 @@ class Transformer2DModel(nn.Module):
     def forward(self, x, context, scale=1.0):
         B, C, H, W = x.shape
         res = x
-        h = self.norm(x)
+        h = _norm_act(self.norm, x, False)
         if self.linear_proj:
             h = self.proj_in(h.permute(0, 2, 3, 1).reshape(B, H * W, C), scale)
         else:
@@ -330,7 +350,7 @@ class UNet2DConditionModel(nn.Module):
             if odd and i < n_up - 1:
                 up_size = skips[-n_res - 1].shape[2:]
             x = blk(x, skips, temb, encoder_hidden_states, scale, up_size)
-        x = self.conv_out(F.silu(self.conv_norm_out(x)))
+        x = self.conv_out(_norm_act(self.conv_norm_out, x, True))
         return UNetOutput(x) if return_dict else (x,)
 
 

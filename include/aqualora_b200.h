@@ -198,6 +198,32 @@ int aq_depthwise_silu(const float* x, const float* w, const float* bias, float* 
 int aq_lora_fold_down(const float* down, const float* m, float* out, int r, int64_t cols, float scale, void* stream);
 int aq_lora_merge(float* w, const float* up, const float* down, int dout, int din, int r, float coef, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * HBM-bound glue of the U-Net around the LoRA projections, on channels-last bf16 rows.
+ *
+ * GroupNorm [+ per-(sample, channel) add before it] [+ SiLU after it]: replaces `norm1 -> silu`,
+ * `+ temb[:, :, None, None] -> norm2 -> silu` of ResnetBlock2D.forward (scripts/lib/original_unet.py:440-453),
+ * Transformer2DModel.norm (:826) and conv_norm_out -> silu (:1416).
+ *   x, y, dy, dx  [B, HW, C] bf16 (the channels_last storage of an NCHW tensor)      gamma, beta [C] bf16
+ *   add_bc        [B, C] bf16 or NULL: x + add_bc[b, c] is what gets normalised (its gradient is not produced: the
+ *                 time embedding is not trainable)
+ *   mean_rstd     [B, G, 2] fp32 (mean, 1/sqrt(var + eps)), written by fwd, read by bwd
+ *   ws            aq_group_norm_workspace_bytes(B, G) bytes.   C % 8 == 0, C % G == 0, G <= 128.
+ * The backward returns dx only (gamma / beta belong to the frozen U-Net).
+ * ---------------------------------------------------------------------------------------------- */
+size_t aq_group_norm_workspace_bytes(int B, int G);
+int aq_group_norm_nhwc_fwd(const void* x, const void* gamma, const void* beta, const void* add_bc, void* y, float* mean_rstd, int B,
+                           int HW, int C, int G, float eps, int silu, void* ws, size_t ws_bytes, void* stream);
+int aq_group_norm_nhwc_bwd(const void* dy, const void* x, const void* gamma, const void* beta, const void* add_bc,
+                           const float* mean_rstd, void* dx, int B, int HW, int C, int G, float eps, int silu, void* ws, size_t ws_bytes,
+                           void* stream);
+
+/* GEGLU.forward (scripts/lib/original_unet.py:708-729): out = proj[:, :F] * gelu(proj[:, F:2F]) (erf gelu), and its
+ * backward g_proj = [g_out * gelu(gate), g_out * h * gelu'(gate)].  proj [M, 2F] bf16 with row stride ldp; out, g_out
+ * [M, F] and g_proj [M, 2F] contiguous bf16; F % 8 == 0. */
+int aq_geglu_fwd(const void* proj, int64_t ldp, void* out, int64_t M, int F, void* stream);
+int aq_geglu_bwd(const void* proj, int64_t ldp, const void* g_out, void* g_proj, int64_t M, int F, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -439,7 +439,9 @@ def test_grouped_projections_equal_separate_launches(lm, cuda_device, B, tok, di
         assert _max_rel(yg, want) < BF16_TOL
     if need_dx:
         assert _max_rel(gx_g, gx_s) < BF16_TOL
-    assert _fro_rel(gs_g, gs_s) < 2e-3                       # same bf16 operands; fp32 atomics land in a different order
+    # d(scale) flows back through the reference's `.to(weight_dtype)` cast (utils/lora_modules.py:15-17): the grouped call rounds
+    # the SUM over its projections to bf16 once, separate calls round each projection's term -> up to one bf16 ulp (2^-8) apart
+    assert _fro_rel(gs_g, gs_s) < 2.0 ** -8
     for a, b in zip(gr_g, gr_s):
         assert _fro_rel(a, b) < 2e-3
 
