@@ -11,7 +11,8 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libaqualora_b200.so"
+# AQUALORA_B200_LIB: developer override (an instrumented build of the same sources, tools/gemm_trace.py)
+LIB_PATH = Path(os.environ.get("AQUALORA_B200_LIB") or (_PKG / "libaqualora_b200.so"))
 
 
 class AqualoraError(RuntimeError):

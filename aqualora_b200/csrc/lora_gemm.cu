@@ -26,6 +26,34 @@
 
 namespace aq {
 
+#ifdef AQ_GEMM_TRACE
+// developer build only (tools/gemm_trace.py): clock64() stamps of CTA 0's roles (32 slots per work item) and per-CTA
+// globaltimer stamps (entry, after the prologue, exit, SM id)
+__device__ unsigned long long g_trace[64 * 32];
+__device__ unsigned long long g_cta_times[256 * 4];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+#define AQ_TRACE(iter, slot)                                                                        \
+  do {                                                                                              \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (iter) < 64u) g_trace[(iter) * 32 + (slot)] = clock64(); \
+  } while (0)
+#define AQ_CTA_STAMP(k)                                                                                \
+  do {                                                                                                 \
+    if (threadIdx.x == 0 && blockIdx.x < 256) g_cta_times[blockIdx.x * 4 + (k)] = globaltimer_ns();    \
+  } while (0)
+#else
+#define AQ_TRACE(iter, slot) do {} while (0)
+#define AQ_CTA_STAMP(k) do {} while (0)
+#endif
+
 constexpr int kBlockM = 128;         // rows per CTA (the pair covers 256)
 constexpr int kPairM = 2 * kBlockM;
 constexpr int kBlockK = 64;          // 64 bf16 = 128 bytes = one 128B swizzle row
@@ -130,6 +158,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
+  AQ_CTA_STAMP(0);
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -180,6 +209,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
   cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  AQ_CTA_STAMP(1);
 
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
   const int total_items = p.total_items;
@@ -223,7 +253,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
       if (++stage == kStages) { stage = 0; phase ^= 1u; }
     };
     int pi = 0;
-    for (int item = item0; item < total_items; item += item_step) {
+    uint32_t trace_iter = 0;
+    for (int item = item0; item < total_items; item += item_step, ++trace_iter) {
       const LoraProblem& q = locate(item, pi);
       const int local = item - q.item_begin;
       const int m_pair = local % p.num_m_pairs;
@@ -232,6 +263,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
       const int nt_begin = grp * q.group_size;
       const int nt_end = min(nt_begin + q.group_size, q.num_n_tiles);
       const bool fused = p.has_lora && p.has_main;
+      AQ_TRACE(trace_iter, 0);
       if (fused && nt_end - nt_begin >= 2) {
         // deferred order: the Hs.Up k-blocks of the first two tiles follow the second tile's main loop
         k_loads(q, m0, nt_begin * BN, true);
@@ -249,6 +281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
           if (fused) up_load(q, nt * BN);
         }
       }
+      AQ_TRACE(trace_iter, 1);
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer (leader CTA; converged warp, one elected lane issues) ===========================
@@ -276,6 +309,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (kFirst && kb == 0) AQ_TRACE(item_iter, 3);
           if (elect_one()) {
             const uint64_t ad = desc(a_tile(stage));
             const uint64_t wd = desc(w_tile(stage));
@@ -323,16 +357,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
           const uint32_t it0 = acc_iter, it1 = acc_iter + 1;
           const uint32_t acc0 = tmem_base + (it0 & 1u) * BN, acc1 = tmem_base + (it1 & 1u) * BN;
           acquire_acc(it0);
+          AQ_TRACE(item_iter, 2);
           k_mmas(acc0, true);
           commit(h_full_bar);                                // H accumulated -> wake the epilogue warps of both CTAs
+          AQ_TRACE(item_iter, 4);
           acquire_acc(it1);
+          AQ_TRACE(item_iter, 5);
           k_mmas(acc1, false);                               // the tensor core stays busy while Hs is being produced
+          AQ_TRACE(item_iter, 6);
           mbar_wait(hs_ready_bar, item_iter & 1u);           // Hs (bf16, swizzled) is in both CTAs' SMEM
           tc_fence_after();
+          AQ_TRACE(item_iter, 7);
           up_mmas(acc0);
           commit(acc_full_bar(it0 & 1u));
+          AQ_TRACE(item_iter, 8);
           up_mmas(acc1);
           commit(acc_full_bar(it1 & 1u));
+          AQ_TRACE(item_iter, 9);
           acc_iter += 2;
           for (int nt = nt_begin + 2; nt < nt_end; ++nt) {
             const uint32_t acc = tmem_base + (acc_iter & 1u) * BN;
@@ -386,6 +427,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
       const long long grow = (long long)m0 + row_in_tile;
       const bool row_ok = grow < p.M;
       const bool aux_owner = row_ok && grp == 0;   // side outputs (H / dH / Hs / dscale) are emitted once per row block
+      if (warp == 0) AQ_TRACE(item_iter, 10);
       if (p.has_lora) {
         // ---------------- mid epilogue: H (TMEM, fp32) -> Hs (SMEM, bf16, 128B-swizzled K-major) ----------------
         // this warp: 32 rows x H columns [32 * half, 32 * half + 32)
@@ -408,6 +450,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
           sc4[j4] = (hc0 + j4 * 4 < p.r) ? __ldg(reinterpret_cast<const float4*>(sp + j4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         mbar_wait(h_full_bar, item_iter & 1u);
         tc_fence_after();
+        if (warp == 0) AQ_TRACE(item_iter, 11);
         float v[32];
         {
           uint32_t t0[32];
@@ -471,6 +514,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         fence_proxy_async_smem();   // generic-proxy SMEM writes -> visible to the tensor-core (async) proxy
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(hs_ready_remote);
+        if (warp == 0) AQ_TRACE(item_iter, 12);
         if (p.mode == 1 && p.g_scale != nullptr && grp == 0) {
           // dscale[b, j] += sum over this tile's rows of dHs * H
           const long long first_row = (long long)m0 + q * 32;
@@ -503,6 +547,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         }
         mbar_wait(acc_full_bar(buf), (acc_iter >> 1) & 1u);
         tc_fence_after();
+        if (warp == 0 && nt - nt_begin < 4) AQ_TRACE(item_iter, 13 + 3 * (nt - nt_begin));
         uint32_t t[NC];
 #pragma unroll
         for (int c = 0; c < NC / 16; ++c) tmem_ld_32x16(tmem_base + lane_base + buf * BN + half * NC + c * 16, t + c * 16);
@@ -517,6 +562,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(acc_empty_remote[buf]);   // drained -> the MMA thread may reuse this accumulator
+        if (warp == 0 && nt - nt_begin < 4) AQ_TRACE(item_iter, 14 + 3 * (nt - nt_begin));
         ++acc_iter;
         if (col0 >= q_.N) continue;   // whole slice past the last column (partial last tile)
         constexpr int NCP = L::kNCP;     // columns per pass
@@ -563,6 +609,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
           }
           __syncwarp();
         }
+        if (warp == 0 && nt - nt_begin < 4) AQ_TRACE(item_iter, 15 + 3 * (nt - nt_begin));
       }
     }
   }
@@ -571,6 +618,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
   __syncthreads();
   cluster_sync_all();   // no CTA leaves while its pair may still read its SMEM / signal its barriers
   if (warp == kMmaWarp) tmem_dealloc_pair(tmem_base, 512);
+  AQ_CTA_STAMP(2);
+#ifdef AQ_GEMM_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 256) g_cta_times[blockIdx.x * 4 + 3] = smid();
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -752,3 +803,20 @@ int launch_lora_gemm_grouped(const LoraGemmArgs* probs, int nprob, cudaStream_t 
 }
 
 }  // namespace aq
+
+#ifdef AQ_GEMM_TRACE
+extern "C" int aq_debug_gemm_cta_times(unsigned long long* host_out, int clear) {
+  cudaDeviceSynchronize();
+  int rc = (int)cudaMemcpyFromSymbol(host_out, aq::g_cta_times, sizeof(unsigned long long) * 256 * 4);
+  if (clear) {
+    static unsigned long long zeros[64 * 32];
+    cudaMemcpyToSymbol(aq::g_cta_times, zeros, sizeof(unsigned long long) * 256 * 4);
+    cudaMemcpyToSymbol(aq::g_trace, zeros, sizeof(unsigned long long) * 64 * 32);
+  }
+  return rc;
+}
+extern "C" int aq_debug_gemm_trace(unsigned long long* host_out, int n) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host_out, aq::g_trace, sizeof(unsigned long long) * (size_t)(n < 64 * 32 ? n : 64 * 32));
+}
+#endif
