@@ -62,6 +62,8 @@ _SIGNATURES = {
     "aq_group_norm_nhwc_bwd": ([c_void_p] * 7 + [c_int] * 4 + [c_float, c_int, c_void_p, c_size_t, c_void_p], c_int),
     "aq_geglu_fwd": ([c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p], c_int),
     "aq_geglu_bwd": ([c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p], c_int),
+    "aq_layer_norm_fwd": ([c_void_p] * 5 + [c_int64, c_int, c_float, c_void_p], c_int),
+    "aq_layer_norm_bwd": ([c_void_p] * 5 + [c_int64, c_int, c_void_p], c_int),
     "aq_flat_sumsq": ([c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "aq_flat_clip_adamw": (
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,

@@ -489,3 +489,195 @@ int aq_geglu_bwd(const void* proj, int64_t ldp, const void* g_out, void* g_proj,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- LayerNorm over bf16 token rows (BasicTransformerBlock.norm1/2/3,
+// scripts/lib/original_unet.py:732-806).  One warp per row, the whole row in registers (C <= 2048): one read + one write, statistics
+// by warp shuffles (two-pass variance).  The affine parameters are frozen: the backward returns dx only.
+namespace aq {
+
+template <int VPL>
+__global__ void __launch_bounds__(256) layer_norm_fwd_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                                                            const __nv_bfloat16* __restrict__ beta, uint4* __restrict__ y,
+                                                            float2* __restrict__ mean_rstd, long long M, int V, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float gam[VPL][8], bet[VPL][8];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int v = lane + 32 * j;
+    if (v < V) {
+      load8_bf16(gamma + v * 8, gam[j]);
+      load8_bf16(beta + v * 8, bet[j]);
+    }
+  }
+  const float inv_c = 1.f / (float)(V * 8);
+  for (long long row = warp0; row < M; row += nwarps) {
+    uint4 q[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int v = lane + 32 * j;
+      q[j] = v < V ? __ldg(x + row * V + v) : make_uint4(0, 0, 0, 0);
+    }
+    float f[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      unpack8(q[j], f[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += f[j][i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_c;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      if (lane + 32 * j < V) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = f[j][i] - mean;
+          ss = fmaf(d, d, ss);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * inv_c + eps);
+    if (lane == 0 && mean_rstd != nullptr) mean_rstd[row] = make_float2(mean, rstd);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int v = lane + 32 * j;
+      if (v < V) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[j][i] = fmaf((f[j][i] - mean) * rstd, gam[j][i], bet[j][i]);
+        y[row * V + v] = pack8(f[j]);
+      }
+    }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+template <int VPL>
+__global__ void __launch_bounds__(256) layer_norm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ gamma, const float2* __restrict__ mean_rstd,
+                                                            uint4* __restrict__ dx, long long M, int V) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float gam[VPL][8];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int v = lane + 32 * j;
+    if (v < V) load8_bf16(gamma + v * 8, gam[j]);
+  }
+  const float inv_c = 1.f / (float)(V * 8);
+  for (long long row = warp0; row < M; row += nwarps) {
+    uint4 q[VPL], d[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int v = lane + 32 * j;
+      q[j] = v < V ? __ldg(x + row * V + v) : make_uint4(0, 0, 0, 0);
+      d[j] = v < V ? __ldg(dy + row * V + v) : make_uint4(0, 0, 0, 0);
+    }
+    const float2 mr = __ldg(mean_rstd + row);
+    float xh[VPL][8], g[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      unpack8(q[j], xh[j]);
+      unpack8(d[j], g[j]);
+      if (lane + 32 * j < V) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[j][i] = (xh[j][i] - mr.x) * mr.y;
+          g[j][i] *= gam[j][i];
+          s1 += g[j][i];
+          s2 = fmaf(g[j][i], xh[j][i], s2);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 * inv_c, m2 = s2 * inv_c;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int v = lane + 32 * j;
+      if (v < V) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[j][i] = mr.y * (g[j][i] - m1 - xh[j][i] * m2);
+        dx[row * V + v] = pack8(g[j]);
+      }
+    }
+  }
+}
+
+static int ln_grid(long long M) {
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  const long long blocks = (M + 7) / 8;          // 8 warps per CTA, one row per warp at a time
+  const long long cap = (long long)sms * 8;
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+static int ln_check(const void* a, const void* b, const void* c, long long M, int C, const char* who) {
+  AQ_REQUIRE(M > 0 && C > 0 && C % 8 == 0 && C <= 2048, AQ_ERR_BAD_SHAPE, "%s: need M > 0, C %% 8 == 0, C <= 2048 (M=%lld C=%d)", who, M, C);
+  AQ_REQUIRE(a != nullptr && b != nullptr && c != nullptr &&
+                 ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15u) == 0,
+             AQ_ERR_BAD_ALIGN, "%s: pointers must be non-NULL and 16-byte aligned", who);
+  return check_arch();
+}
+
+}  // namespace aq
+
+extern "C" {
+
+int aq_layer_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean_rstd, int64_t M, int C, float eps,
+                      void* stream) {
+  using namespace aq;
+  int rc = ln_check(x, gamma, y, M, C, "aq_layer_norm_fwd");
+  if (rc) return rc;
+  AQ_REQUIRE(beta != nullptr && (reinterpret_cast<uintptr_t>(beta) & 15u) == 0, AQ_ERR_BAD_ALIGN, "aq_layer_norm_fwd: beta must be 16-byte aligned");
+  const int V = C / 8, vpl = (V + 31) / 32;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = ln_grid(M);
+#define AQ_LN_FWD(N)                                                                                                       \
+  layer_norm_fwd_kernel<N><<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const __nv_bfloat16*>(gamma), \
+                                                 reinterpret_cast<const __nv_bfloat16*>(beta), reinterpret_cast<uint4*>(y),   \
+                                                 reinterpret_cast<float2*>(mean_rstd), M, V, eps)
+  if (vpl <= 1) AQ_LN_FWD(1);
+  else if (vpl == 2) AQ_LN_FWD(2);
+  else if (vpl == 3) AQ_LN_FWD(3);
+  else if (vpl <= 5) AQ_LN_FWD(5);
+  else AQ_LN_FWD(8);
+#undef AQ_LN_FWD
+  AQ_LAUNCHED();
+  return AQ_OK;
+}
+
+int aq_layer_norm_bwd(const void* dy, const void* x, const void* gamma, const float* mean_rstd, void* dx, int64_t M, int C, void* stream) {
+  using namespace aq;
+  int rc = ln_check(dy, x, dx, M, C, "aq_layer_norm_bwd");
+  if (rc) return rc;
+  AQ_REQUIRE(gamma != nullptr && mean_rstd != nullptr && (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0, AQ_ERR_BAD_ALIGN,
+             "aq_layer_norm_bwd: gamma / mean_rstd must be non-NULL, gamma 16-byte aligned");
+  const int V = C / 8, vpl = (V + 31) / 32;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = ln_grid(M);
+#define AQ_LN_BWD(N)                                                                                                               \
+  layer_norm_bwd_kernel<N><<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x),             \
+                                                 reinterpret_cast<const __nv_bfloat16*>(gamma), reinterpret_cast<const float2*>(mean_rstd), \
+                                                 reinterpret_cast<uint4*>(dx), M, V)
+  if (vpl <= 1) AQ_LN_BWD(1);
+  else if (vpl == 2) AQ_LN_BWD(2);
+  else if (vpl == 3) AQ_LN_BWD(3);
+  else if (vpl <= 5) AQ_LN_BWD(5);
+  else AQ_LN_BWD(8);
+#undef AQ_LN_BWD
+  AQ_LAUNCHED();
+  return AQ_OK;
+}
+
+}  // extern "C"

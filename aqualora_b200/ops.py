@@ -468,3 +468,30 @@ def geglu_bwd(proj: torch.Tensor, g_out: torch.Tensor) -> torch.Tensor:
     g_proj = torch.empty(proj.shape, dtype=_BF16, device=proj.device)
     _lib.call("aq_geglu_bwd", p2.data_ptr(), ldp, g_out.data_ptr(), g_proj.data_ptr(), p2.shape[0], F2 // 2, _stream())
     return g_proj
+
+
+def layer_norm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, save_stats: bool):
+    """LayerNorm over the last dimension of contiguous bf16 rows; returns (y, mean_rstd [M, 2] fp32 or None)."""
+    _need(x, _BF16, "x")
+    _need(gamma, _BF16, "gamma", 1)
+    _need(beta, _BF16, "beta", 1)
+    C = x.shape[-1]
+    if not x.is_contiguous() or gamma.shape[0] != C or beta.shape[0] != C:
+        raise _lib.AqualoraError(f"layer_norm: x must be contiguous [..., {C}] with gamma / beta [{C}]")
+    M = x.numel() // C
+    y = torch.empty_like(x)
+    stats = torch.empty(M, 2, dtype=_F32, device=x.device) if save_stats else None
+    _lib.call("aq_layer_norm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(stats), M, C, float(eps), _stream())
+    return y, stats
+
+
+def layer_norm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, stats: torch.Tensor) -> torch.Tensor:
+    _need(dy, _BF16, "dy")
+    _need(x, _BF16, "x")
+    _need(stats, _F32, "mean_rstd", 2)
+    C = x.shape[-1]
+    if not dy.is_contiguous() or not x.is_contiguous() or dy.shape != x.shape:
+        raise _lib.AqualoraError("layer_norm_bwd: dy and x must be contiguous and of equal shape")
+    dx = torch.empty_like(x)
+    _lib.call("aq_layer_norm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), stats.data_ptr(), dx.data_ptr(), x.numel() // C, C, _stream())
+    return dx

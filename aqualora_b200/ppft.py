@@ -136,6 +136,7 @@ class PPFTTrainer:
         self.global_step = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.g_scale = None
+        self._graph = None
 
     # -- pieces of the step ------------------------------------------------------------------
     def mapper(self, msg: torch.Tensor) -> torch.Tensor:
@@ -199,6 +200,44 @@ class PPFTTrainer:
         loss = self.forward_backward(latents, wm_latent, noise, timesteps, ctx, msg)
         self.optimizer_step()
         return loss
+
+    # -- CUDA-graph replay of the forward + backward ------------------------------------------------------------------
+    def capture(self, fn: Callable, example_inputs, warmup_steps: int = 2) -> int:
+        """Record `fn(*inputs) -> loss` -- everything of a step up to the gradient exchange, ending in `forward_backward` -- into
+        a CUDA graph over static copies of `example_inputs` (fixed shapes and dtypes).  A PPFT step issues ~10 k kernels; replayed
+        as one graph the host stops being the bottleneck once the glue kernels have shortened the device time.  The gradient
+        all-reduce and the clip / AdamW kernels stay outside (their learning rate and bias-correction step are launch arguments).
+        Returns the number of this library's kernel launches inside the graph (bench.py counts them per replay)."""
+        from . import _lib
+
+        stream = torch.cuda.Stream(device=self.device)
+        stream.wait_stream(torch.cuda.current_stream(self.device))
+        self._static_in = [x.clone() for x in example_inputs]
+        with torch.cuda.stream(stream):
+            for _ in range(max(1, warmup_steps)):      # handles, cuDNN plans and workspaces of the capture stream
+                fn(*self._static_in)
+                self.optimizer_step()
+        torch.cuda.current_stream(self.device).wait_stream(stream)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.load().aq_launch_count()
+        with torch.cuda.graph(graph, stream=stream):
+            self._static_loss = fn(*self._static_in)
+        self._graph_launches = int(_lib.load().aq_launch_count() - n0)
+        self._graph = graph
+        lora_modules.invalidate_packed()               # the capture recorded, but did not run, the operand refresh
+        return self._graph_launches
+
+    def step_graphed(self, *inputs, copy_inputs: bool = True):
+        """One PPFT step through the captured graph: inputs -> static buffers, replay, gradient exchange + clip + AdamW."""
+        if self._graph is None:
+            raise RuntimeError("PPFTTrainer.capture() has not been called")
+        if copy_inputs:
+            for dst, src in zip(self._static_in, inputs):
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        self.optimizer_step()
+        return self._static_loss
 
 
 def build_unet(cfg: UNetConfig, device, dtype=torch.bfloat16, seed: int = 0) -> UNet2DConditionModel:

@@ -4,7 +4,7 @@ The hot path of this repository is the 192 LoRA-target projections (aqualora_b20
 is the CALLER on either side of it: a compact `UNet2DConditionModel` whose module paths and state-dict keys are the
 diffusers ones, so that `utils/unet_keys.json` (train/ppft_train.py:620-689) resolves on it and checkpoints /
 `pytorch_lora_weights.safetensors` keys (train/ppft_train.py:443-471) line up.  Everything that is not a LoRA target
-(3x3 convolutions, LayerNorm, attention core) is a library call; GroupNorm(+SiLU) and GEGLU run as channels-last CUDA
+(3x3 convolutions, attention core, residual adds) is a library call; GroupNorm(+SiLU), LayerNorm and GEGLU run as CUDA
 kernels of this repository on the GPU path (aqualora_b200/unet_ops.py).
 
 Topology follows the SD 1.5 / 2.1 configs quoted in scripts/lib/original_unet.py:22-106; the golden test loads the
@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .lora_modules import AquaLoRAAttnProcessor, LoRACompatibleConv, LoRACompatibleLinear, precompute_cross_kv
-from .unet_ops import geglu, group_norm_nhwc
+from .unet_ops import geglu, group_norm_nhwc, layer_norm
 
 
 def _fused_glue(x: torch.Tensor, *params: torch.Tensor) -> bool:
@@ -96,6 +96,13 @@ class TimestepEmbedding(nn.Module):
         return self.linear_2(F.silu(self.linear_1(x)))
 
 
+def _token_norm(norm: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
+    """BasicTransformerBlock.norm1/2/3 (scripts/lib/original_unet.py:732-806)."""
+    if _fused_glue(x, norm.weight, norm.bias):
+        return layer_norm(x, norm.weight, norm.bias, norm.eps)
+    return norm(x)
+
+
 class ResnetBlock2D(nn.Module):
     def __init__(self, cin: int, cout: int, temb_dim: int, groups: int, eps: float):
         super().__init__()
@@ -165,9 +172,9 @@ class BasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim)
 
     def forward(self, x, context, scale=1.0):
-        x = self.attn1(self.norm1(x), None, scale) + x
-        x = self.attn2(self.norm2(x), context, scale) + x
-        return self.ff(self.norm3(x), scale) + x
+        x = self.attn1(_token_norm(self.norm1, x), None, scale) + x
+        x = self.attn2(_token_norm(self.norm2, x), context, scale) + x
+        return self.ff(_token_norm(self.norm3, x), scale) + x
 
 
 class Transformer2DModel(nn.Module):

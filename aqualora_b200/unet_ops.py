@@ -61,3 +61,25 @@ class _Geglu(torch.autograd.Function):
 def geglu(proj: torch.Tensor) -> torch.Tensor:
     """proj[..., :F] * gelu(proj[..., F:]) (erf gelu) in one pass, one pass for the backward."""
     return _Geglu.apply(proj)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise AqualoraError("layer_norm: gamma / beta must be frozen (no gradient is produced for them)")
+        x = x.contiguous()
+        y, stats = ops.layer_norm_fwd(x, gamma, beta, eps, save_stats=ctx.needs_input_grad[0])
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(x, gamma, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, stats = ctx.saved_tensors
+        return ops.layer_norm_bwd(dy.contiguous(), x, gamma, stats), None, None, None
+
+
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> torch.Tensor:
+    """LayerNorm over the last dimension of bf16 token rows (BasicTransformerBlock.norm1/2/3), frozen affine parameters."""
+    return _LayerNorm.apply(x, gamma, beta, float(eps))

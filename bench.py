@@ -270,11 +270,23 @@ def run_cuda(args):
         f = lambda x: x.to(dev, non_blocking=non_blocking)
         return f(lat), f(noise), f(t), f(ctx), f(msg)
 
-    def step_from_device(lat, noise, t, ctx, msg):
+    def fwd_bwd_from_device(lat, noise, t, ctx, msg):
         # train/ppft_train.py:994-996: secret residual from the encoder (no_grad), scaled like the latents
         wm = enc(lat, msg)[1] * pcfg.scaling_factor      # sec_encoder(latents, msg)[1]: the residual, resized to the latent grid
         bf = torch.bfloat16
-        return trainer.step(lat.to(bf), wm.to(bf), noise.to(bf), t, ctx.to(bf), msg)
+        return trainer.forward_backward(lat.to(bf), wm.to(bf), noise.to(bf), t, ctx.to(bf), msg)
+
+    def eager_step(lat, noise, t, ctx, msg):
+        loss = fwd_bwd_from_device(lat, noise, t, ctx, msg)
+        trainer.optimizer_step()
+        return loss
+
+    graph_state = {"on": False, "launches": 0, "why": "disabled by --no-graph"}
+
+    def step_from_device(lat, noise, t, ctx, msg):
+        if graph_state["on"]:
+            return trainer.step_graphed(lat, noise, t, ctx, msg)
+        return eager_step(lat, noise, t, ctx, msg)
 
     n_pool = 4
     host = [tuple(x.pin_memory() for x in synth_batch(B, cfg, 1234 + i + 1000 * rank)) for i in range(n_pool)]
@@ -286,7 +298,18 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up --------------------------------------------------------------------------------------------------
+    # ---- warm-up (eager), then the forward + backward recorded as one CUDA graph; more warm-up through the graph -----
+    for i in range(3):
+        loss = eager_step(*resident[i % n_pool])
+    barrier()
+    if not args.no_graph:
+        try:
+            graph_state["launches"] = trainer.capture(fwd_bwd_from_device, resident[0])
+            graph_state["on"], graph_state["why"] = True, ""
+        except Exception as e:   # a capture failure must not cost the measurement: fall back to eager issue and say so
+            graph_state["why"] = repr(e)[:200]
+            print(f"[bench] CUDA-graph capture failed, running eagerly: {e!r}", file=sys.stderr, flush=True)
+            torch.cuda.synchronize()
     for i in range(max(args.warmup, 3)):
         loss = step_from_device(*resident[i % n_pool])
     barrier()
@@ -303,7 +326,7 @@ def run_cuda(args):
     e1.record()
     barrier()
     t_wall1 = time.time()
-    launches = lib.aq_launch_count() - launches0
+    launches = lib.aq_launch_count() - launches0 + (args.steps * graph_state["launches"] if graph_state["on"] else 0)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -316,8 +339,13 @@ def run_cuda(args):
     barrier()
     e0.record()
     for i in range(args.steps):
-        batch = to_dev(host[i % n_pool], non_blocking=True)
-        loss_host = float(step_from_device(*batch))       # D2H read of the step's result
+        if graph_state["on"]:
+            for dst, src in zip(trainer._static_in, host[i % n_pool]):     # pinned host -> the graph's input buffers
+                dst.copy_(src, non_blocking=True)
+            loss_host = float(trainer.step_graphed(copy_inputs=False))       # D2H read of the step's result
+        else:
+            batch = to_dev(host[i % n_pool], non_blocking=True)
+            loss_host = float(step_from_device(*batch))
     e1.record()
     barrier()
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -332,12 +360,12 @@ def run_cuda(args):
     if rank != 0:
         # every rank runs the instrumented steps: each step holds the gradient all-reduce, so rank 0 alone would wait forever
         for i in range(probe_steps):
-            step_from_device(*resident[i % n_pool])
+            eager_step(*resident[i % n_pool])
     if rank == 0:
         pk = peaks()
         with GemmProbe(ops) as probe:
             for i in range(probe_steps):
-                step_from_device(*resident[i % n_pool])
+                eager_step(*resident[i % n_pool])      # per-launch CUDA events need eager issue
             kinds, shapes = probe.summary(probe_steps)
         dom = kinds.get("gemm_fwd")
         if dom:
@@ -372,6 +400,8 @@ def run_cuda(args):
                                    f"({cfg.sample_size}x{cfg.sample_size} latents), random-init U-Net, VAE/text-encoder excluded",
                        "per_gpu_batch": B, "global_batch": gb, "parallelism": f"dp{world}",
                        "l2": "each step streams > 126 MB (1.7 GB bf16 U-Net weights + activations), inputs rotate over 4 batches",
+                       "cuda_graph": ("forward + backward replayed as one CUDA graph; all-reduce, clip and AdamW issued eagerly"
+                                      if graph_state["on"] else f"off ({graph_state['why']})"),
                        "final_loss": final_loss},
             "e2e": {"value": round(gb / (e2e_ms / args.steps) * 1e3, 3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms / args.steps, 3)},
@@ -605,6 +635,7 @@ def main():
     ap.add_argument("--model", default="sd15", choices=["sd15", "sd21"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly instead of replaying the captured forward + backward")
     ap.add_argument("--budget", type=float, default=240.0, help="--impl reference: stop after this many seconds of timed CPU steps")
     ap.add_argument("--shapes-out", default=None, help="write the per-shape kernel table (JSON) here")
     ap.add_argument("--workload", default="ppft", choices=["ppft", "decode"], help="ppft = the headline metric; decode = configs[3]")

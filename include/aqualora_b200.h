@@ -224,6 +224,13 @@ int aq_group_norm_nhwc_bwd(const void* dy, const void* x, const void* gamma, con
 int aq_geglu_fwd(const void* proj, int64_t ldp, void* out, int64_t M, int F, void* stream);
 int aq_geglu_bwd(const void* proj, int64_t ldp, const void* g_out, void* g_proj, int64_t M, int F, void* stream);
 
+/* LayerNorm over contiguous bf16 token rows [M, C] (BasicTransformerBlock.norm1/2/3, scripts/lib/original_unet.py:732-806), eps
+ * inside the square root, fp32 statistics, one rounding of the output.  mean_rstd [M, 2] fp32 is written by fwd (may be NULL when
+ * no backward follows) and read by bwd; the backward returns dx only (gamma / beta are frozen).  C % 8 == 0, C <= 2048. */
+int aq_layer_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean_rstd, int64_t M, int C, float eps,
+                      void* stream);
+int aq_layer_norm_bwd(const void* dy, const void* x, const void* gamma, const float* mean_rstd, void* dx, int64_t M, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,26 @@ def test_geglu_matches_fp32_reference(cuda_device, lead, F_):
     _close(pd.grad, pr.grad, abs_frac=1e-4)
 
 
+@pytest.mark.parametrize("lead,C,eps", [((2, 77), 320, 1e-5), ((3, 5), 64, 1e-5), ((2, 9), 1280, 1e-6), ((5,), 2048, 1e-5),
+                                        ((7,), 776, 1e-5), ((16, 4096), 320, 1e-5)])
+def test_layer_norm_matches_fp32_reference(cuda_device, lead, C, eps):
+    from aqualora_b200.unet_ops import layer_norm
+
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(*lead, C, generator=g) * 2 + 0.5).bfloat16()
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).bfloat16()
+    beta = (0.1 * torch.randn(C, generator=g)).bfloat16()
+    dy = torch.randn(*lead, C, generator=g).bfloat16()
+    xr = x.float().requires_grad_(True)
+    want = F.layer_norm(xr, (C,), gamma.float(), beta.float(), eps)
+    want.backward(dy.float())
+    xd = x.to(cuda_device).requires_grad_(True)
+    got = layer_norm(xd, gamma.to(cuda_device), beta.to(cuda_device), eps)
+    got.backward(dy.to(cuda_device))
+    _close(got.detach(), want.detach())
+    _close(xd.grad, xr.grad)
+
+
 def test_unet_forward_uses_glue_kernels_and_matches_library_ops(cuda_device):
     """The tiny U-Net with the glue kernels vs the same module tree with the library op sequence (trainable affine parameters
     switch the dispatch off): outputs agree to bf16 noise, and the fused run launches our kernels."""
@@ -109,13 +129,14 @@ def test_unet_forward_uses_glue_kernels_and_matches_library_ops(cuda_device):
         fused = unet(x, t, ctx).sample
     n_fused = _lib.load().aq_launch_count() - n0
     for m in unet.modules():
-        if isinstance(m, torch.nn.GroupNorm):
+        if isinstance(m, (torch.nn.GroupNorm, torch.nn.LayerNorm)):
             m.weight.requires_grad_(True)
     n0 = _lib.load().aq_launch_count()
     with torch.no_grad():
         plain = unet(x, t, ctx).sample
     n_plain = _lib.load().aq_launch_count() - n0
-    n_norms = sum(isinstance(m, torch.nn.GroupNorm) for m in unet.modules())
-    assert n_fused - n_plain == 2 * n_norms
+    n_gn = sum(isinstance(m, torch.nn.GroupNorm) for m in unet.modules())
+    n_ln = sum(isinstance(m, torch.nn.LayerNorm) for m in unet.modules())
+    assert n_fused - n_plain == 2 * n_gn + n_ln
     rel = ((fused.float() - plain.float()).norm() / plain.float().norm()).item()
     assert rel < 2e-2, rel

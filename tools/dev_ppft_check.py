@@ -139,7 +139,7 @@ def time_sd15(B, steps, profile):
         with tprof(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
             tr.step(*batch)
             torch.cuda.synchronize()
-        tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70)
+        tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=100, max_name_column_width=120)
         print(tab)
     return tr, batch
 
