@@ -44,6 +44,7 @@ _SIGNATURES = {
     "aq_mapper_fwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "aq_mapper_bwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     "aq_cast_transpose_bf16": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),
+    "aq_cast_transpose_bf16_batched": ([c_void_p, c_int, c_int64, c_void_p], c_int),
     "aq_transpose_bf16": ([c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),
     "aq_noise_jpeg": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     "aq_noise_crop_resize": ([c_void_p, c_void_p] + [c_int] * 11 + [c_void_p], c_int),

@@ -60,6 +60,44 @@ __global__ void cast_transpose_kernel(const TIn* __restrict__ src, __nv_bfloat16
   }
 }
 
+// All 384 LoRA matrices in one launch (one per matrix cost 384 x 3 us per step): a device table of jobs, one 32x32 tile per
+// block; the block finds its job by bisection over the tile prefix.
+struct CastJob {   // 7 x int64, built by the host as a plain int64 tensor (include/aqualora_b200.h: aq_cast_job)
+  long long src, dst, dst_t, rows, cols, tile_begin, tiles_x;
+};
+
+__global__ void cast_transpose_batched_kernel(const CastJob* __restrict__ jobs, int njobs) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((long long)blockIdx.x >= jobs[mid].tile_begin) lo = mid; else hi = mid - 1;
+  }
+  const CastJob j = jobs[lo];
+  const int t = (int)(blockIdx.x - j.tile_begin);
+  const int c0 = (t % (int)j.tiles_x) * 32, r0 = (t / (int)j.tiles_x) * 32;
+  const int rows = (int)j.rows, cols = (int)j.cols;
+  const float* src = reinterpret_cast<const float*>(j.src);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(j.dst);
+  __nv_bfloat16* dst_t = reinterpret_cast<__nv_bfloat16*>(j.dst_t);
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int rr = r0 + dy, cc = c0 + threadIdx.x;
+    float v = 0.f;
+    if (rr < rows && cc < cols) {
+      v = src[(size_t)rr * cols + cc];
+      if (dst != nullptr) dst[(size_t)rr * cols + cc] = __float2bfloat16_rn(v);
+    }
+    tile[dy][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (dst_t != nullptr) {
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+      const int cc = c0 + dy, rr = r0 + threadIdx.x;
+      if (rr < rows && cc < cols) dst_t[(size_t)cc * rows + rr] = __float2bfloat16_rn(tile[threadIdx.x][dy]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- flat clip + AdamW
 __global__ void flat_sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
   float acc = 0.f;
@@ -167,6 +205,17 @@ int aq_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int rows, i
   if (rc) return rc;
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   cast_transpose_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_t, rows, cols);
+  AQ_LAUNCHED();
+  return AQ_OK;
+}
+
+int aq_cast_transpose_bf16_batched(const aq_cast_job* jobs, int njobs, int64_t total_tiles, void* stream) {
+  static_assert(sizeof(CastJob) == sizeof(aq_cast_job), "job table layout");
+  AQ_REQUIRE(jobs != nullptr && njobs > 0 && total_tiles > 0 && total_tiles < (1ll << 31), AQ_ERR_BAD_SHAPE,
+             "cast_transpose_batched: bad table (njobs=%d, tiles=%lld)", njobs, (long long)total_tiles);
+  int rc = check_arch();
+  if (rc) return rc;
+  cast_transpose_batched_kernel<<<(unsigned)total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(reinterpret_cast<const CastJob*>(jobs), njobs);
   AQ_LAUNCHED();
   return AQ_OK;
 }

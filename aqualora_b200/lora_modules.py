@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import contextlib
 import types
+import weakref
 from typing import Dict, Iterable, Optional
 
 import torch
@@ -59,10 +60,12 @@ def _packed(param: torch.Tensor, rows: int, cols: int):
     key = id(param)
     ver = (param._version, param.data_ptr(), _PACK_EPOCH)
     hit = _PACK_CACHE.get(key)
+    if hit is not None and (hit[3]() is not param or hit[1].shape != (rows, cols)):
+        hit = None                                   # id() of a collected tensor reused by another parameter
     if hit is not None and hit[0] == ver:
         return hit[1], hit[2]
     src = param.detach().reshape(rows, cols)
-    if hit is not None and hit[1].shape == (rows, cols):
+    if hit is not None:
         d, dt = hit[1], hit[2]                       # reuse the buffers (stable addresses, CUDA-graph friendly)
     else:
         d = torch.empty((rows, cols), dtype=torch.bfloat16, device=param.device)
@@ -74,8 +77,45 @@ def _packed(param: torch.Tensor, rows: int, cols: int):
         dt.copy_(ops.transpose_bf16(src))
     else:
         raise AqualoraError(f"LoRA weights must be fp32 or bf16, got {src.dtype}")
-    _PACK_CACHE[key] = (ver, d, dt)
+    _PACK_CACHE[key] = (ver, d, dt, weakref.ref(param))
     return d, dt
+
+
+_BATCH_TABLES: dict = {}
+
+
+def refresh_packed(params) -> None:
+    """Refresh the bf16 (+ transposed) operand copies of many fp32 2-D parameters (the 384 LoRA matrices after an optimizer
+    step) in ONE launch, and mark them fresh.  The first call packs them one by one (that allocates the stable buffers)."""
+    params = list(params)
+    key = tuple(id(p) for p in params)
+    hit = _BATCH_TABLES.get(key)
+    if hit is None or any(_PACK_CACHE.get(id(p)) is None or _PACK_CACHE[id(p)][3]() is not p for p in params):
+        rows_cols = []
+        for p in params:
+            r = p.shape[0]
+            c = p.numel() // r
+            _packed(p, r, c)
+            rows_cols.append((r, c))
+        table, tiles = [], 0
+        for p, (r, c) in zip(params, rows_cols):
+            if p.dtype != torch.float32:
+                raise AqualoraError("refresh_packed: fp32 master parameters expected")
+            _, d, dt, _ = _PACK_CACHE[id(p)]
+            tx = (c + 31) // 32
+            table.append([p.data_ptr(), d.data_ptr(), dt.data_ptr(), r, c, tiles, tx])
+            tiles += tx * ((r + 31) // 32)
+        hit = (torch.tensor(table, dtype=torch.int64, device=params[0].device), tiles, [p.data_ptr() for p in params])
+        _BATCH_TABLES[key] = hit
+        return                                          # _packed() just refreshed every copy
+    jobs, tiles, ptrs = hit
+    if any(p.data_ptr() != q for p, q in zip(params, ptrs)):
+        del _BATCH_TABLES[key]
+        return refresh_packed(params)
+    ops.cast_transpose_bf16_batched(jobs, tiles)
+    for p in params:
+        _, d, dt, ref = _PACK_CACHE[id(p)]
+        _PACK_CACHE[id(p)] = ((p._version, p.data_ptr(), _PACK_EPOCH), d, dt, ref)
 
 
 def _weight_t(weight: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
@@ -83,16 +123,17 @@ def _weight_t(weight: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
     key = id(weight)
     ver = (weight._version, weight.data_ptr())
     hit = _WT_CACHE.get(key)
-    if hit is not None and hit[0] == ver:
+    if hit is not None and hit[0] == ver and hit[2]() is weight and hit[1].shape == (cols, rows):
         return hit[1]
     wt = ops.transpose_bf16(weight.detach().reshape(rows, cols))
-    _WT_CACHE[key] = (ver, wt)
+    _WT_CACHE[key] = (ver, wt, weakref.ref(weight))
     return wt
 
 
 def clear_caches() -> None:
     _PACK_CACHE.clear()
     _WT_CACHE.clear()
+    _BATCH_TABLES.clear()
 
 
 def _grad_target(tgt, shape, device) -> tuple[torch.Tensor, bool]:

@@ -200,6 +200,14 @@ def cast_transpose_bf16(src: torch.Tensor, dst: torch.Tensor | None, dst_t: torc
     _lib.call("aq_cast_transpose_bf16", src.data_ptr(), _ptr(dst), _ptr(dst_t), rows, cols, _stream())
 
 
+def cast_transpose_bf16_batched(jobs: torch.Tensor, total_tiles: int) -> None:
+    """jobs: int64 [n, 7] device table of (src, dst, dst_t, rows, cols, tile_begin, tiles_x) -- `aq_cast_job`."""
+    _need(jobs, torch.int64, "jobs", 2)
+    if jobs.shape[1] != 7 or not jobs.is_contiguous():
+        raise _lib.AqualoraError("jobs must be a contiguous int64 [n, 7] table")
+    _lib.call("aq_cast_transpose_bf16_batched", jobs.data_ptr(), jobs.shape[0], int(total_tiles), _stream())
+
+
 def transpose_bf16(src: torch.Tensor) -> torch.Tensor:
     _need(src, _BF16, "src", 2)
     rows, cols = src.shape

@@ -194,7 +194,14 @@ class PPFTTrainer:
                             st.region(st.exp_avg_sq, "lora"), st.norm_sq, max_norm=c.max_grad_norm, **common)
         ops.flat_clip_adamw(st.region(st.param, "mapper"), st.region(st.grad, "mapper"), st.region(st.exp_avg, "mapper"),
                             st.region(st.exp_avg_sq, "mapper"), st.norm_sq, max_norm=0.0, **common)
-        lora_modules.invalidate_packed()                             # the bf16 operand copies are stale now
+        lora_modules.invalidate_packed()                             # the bf16 operand copies are stale now ...
+        lora_modules.refresh_packed(st.params)                       # ... and rebuilt by one launch over all 384 matrices
+
+    def refresh_operands(self):
+        """Rebuild the bf16 operand copies from the fp32 master parameters.  `optimizer_step` does it; call it after changing
+        `state.param` any other way (checkpoint load) when stepping through the captured graph, which cannot notice the change."""
+        lora_modules.invalidate_packed()
+        lora_modules.refresh_packed(self.state.params)
 
     def step(self, latents, wm_latent, noise, timesteps, ctx, msg):
         loss = self.forward_backward(latents, wm_latent, noise, timesteps, ctx, msg)

@@ -114,6 +114,16 @@ int aq_mapper_bwd(const float* msg, const float* g_scale, float* g_emb, int B, i
 /* fp32 master LoRA parameters -> the bf16 operand copies the kernels consume.  src [rows, cols] fp32;
  * dst [rows, cols] bf16 and (optional) dst_t [cols, rows] bf16. */
 int aq_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int rows, int cols, void* stream);
+/* The same for many matrices in one launch (the 384 LoRA matrices after every optimizer step).  jobs: DEVICE table; entry i
+ * covers 32x32 tiles [tile_begin, tile_begin + tiles_x * ceil(rows / 32)) of the launch, tiles_x = ceil(cols / 32); entries are
+ * sorted by tile_begin, total_tiles = the sum.  dst or dst_t may be 0. */
+typedef struct aq_cast_job {
+  int64_t src;        /* const float* [rows, cols] */
+  int64_t dst;        /* bf16 [rows, cols] or 0 */
+  int64_t dst_t;      /* bf16 [cols, rows] or 0 */
+  int64_t rows, cols, tile_begin, tiles_x;
+} aq_cast_job;
+int aq_cast_transpose_bf16_batched(const aq_cast_job* jobs, int njobs, int64_t total_tiles, void* stream);
 /* bf16 [rows, cols] -> bf16 [cols, rows] (frozen W -> W^T cache for the dX contraction) */
 int aq_transpose_bf16(const void* src, void* dst, int rows, int cols, void* stream);
 

@@ -478,3 +478,19 @@ def test_grouped_plain_and_fallback(lm, cuda_device):
         want = [m(x, s) for m in mods]
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_operand_cache_ignores_recycled_ids(lm, cuda_device):
+    """The bf16 operand cache is keyed by id(parameter); CPython hands the id of a collected tensor to the next one.  An entry
+    left by another tensor (same id, same version / address / shape by coincidence) must not be served."""
+    import weakref
+
+    p = torch.randn(8, 64, device=cuda_device)
+    other = torch.randn(8, 64, device=cuda_device)
+    d, dt = lm._packed(other, 8, 64)
+    lm._PACK_CACHE[id(p)] = ((p._version, p.data_ptr(), lm._PACK_EPOCH), d, dt, weakref.ref(other))
+    d2, dt2 = lm._packed(p, 8, 64)
+    assert torch.equal(d2.float(), p.bfloat16().float()) and torch.equal(dt2, d2.t())
+    w = torch.randn(16, 64, device=cuda_device).bfloat16()
+    lm._WT_CACHE[id(w)] = ((w._version, w.data_ptr()), dt, weakref.ref(other))
+    assert torch.equal(lm._weight_t(w, 16, 64), w.t())

@@ -49,6 +49,7 @@ def test_graphed_step_matches_eager(cuda_device):
     graphed.state.param.copy_(p0)
     graphed.state.exp_avg.zero_(); graphed.state.exp_avg_sq.zero_(); graphed.state.grad.zero_()
     graphed.global_step = 0
+    graphed.refresh_operands()                               # the replay cannot notice that the master parameters were rewound
     losses_g = [graphed.step_graphed(*b).item() for b in batches]
     p_graph = graphed.state.param.clone()
 
