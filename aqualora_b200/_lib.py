@@ -65,6 +65,7 @@ _SIGNATURES = {
     "aq_geglu_bwd": ([c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p], c_int),
     "aq_layer_norm_fwd": ([c_void_p] * 5 + [c_int64, c_int, c_float, c_void_p], c_int),
     "aq_layer_norm_bwd": ([c_void_p] * 5 + [c_int64, c_int, c_void_p], c_int),
+    "aq_add_bias_rows": ([c_void_p] * 4 + [c_int64, c_int, c_void_p], c_int),
     "aq_flat_sumsq": ([c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "aq_flat_clip_adamw": (
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,

@@ -503,3 +503,16 @@ def layer_norm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, stats
     dx = torch.empty_like(x)
     _lib.call("aq_layer_norm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), stats.data_ptr(), dx.data_ptr(), x.numel() // C, C, _stream())
     return dx
+
+
+def add_bias_nhwc(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """a + b + bias[None, :, None, None] for channels_last bf16 [B, C, H, W] tensors of equal shape."""
+    B, HW, C = _nhwc_rows(a, "a")
+    if tuple(_nhwc_rows(b, "b")) != (B, HW, C) or b.stride() != a.stride():
+        raise _lib.AqualoraError("add_bias_nhwc: a and b must have the same shape and strides")
+    _need(bias, _BF16, "bias", 1)
+    if bias.shape[0] != C:
+        raise _lib.AqualoraError(f"bias must be [{C}]")
+    out = torch.empty_like(a)
+    _lib.call("aq_add_bias_rows", a.data_ptr(), b.data_ptr(), bias.data_ptr(), out.data_ptr(), B * HW, C, _stream())
+    return out

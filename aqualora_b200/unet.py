@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .lora_modules import AquaLoRAAttnProcessor, LoRACompatibleConv, LoRACompatibleLinear, precompute_cross_kv
-from .unet_ops import geglu, group_norm_nhwc, layer_norm
+from .unet_ops import geglu, group_norm_nhwc, layer_norm, residual_add_bias
 
 
 def _fused_glue(x: torch.Tensor, *params: torch.Tensor) -> bool:
@@ -114,11 +114,34 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, temb):
+        frozen = [self.conv1.weight, self.conv1.bias, self.conv2.bias, self.norm1.weight, self.norm2.weight]
+        if self.conv_shortcut is not None:
+            frozen.append(self.conv_shortcut.bias)
+        if _fused_glue(x, *frozen):
+            # no broadcast-bias pass after the convolutions: conv1's bias rides on the time embedding that norm2's kernel adds,
+            # conv2's (and the shortcut's) on the closing residual add
+            h = F.conv2d(_norm_act(self.norm1, x, True), self.conv1.weight, None, padding=1)
+            t = self.time_emb_proj(F.silu(temb)) + self.conv1.bias
+            h = F.conv2d(_norm_act(self.norm2, h, True, add_bc=t), self.conv2.weight, None, padding=1)
+            bias = self.conv2.bias
+            if self.conv_shortcut is not None:
+                x = F.conv2d(x, self.conv_shortcut.weight, None)
+                bias = self._folded_bias()
+            return residual_add_bias(x, h, bias)
         h = self.conv1(_norm_act(self.norm1, x, True))
         h = self.conv2(_norm_act(self.norm2, h, True, add_bc=self.time_emb_proj(F.silu(temb))))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h
+
+    def _folded_bias(self):
+        """conv2.bias + conv_shortcut.bias, cached (both frozen)."""
+        key = (self.conv2.bias._version, self.conv_shortcut.bias._version, self.conv2.bias.data_ptr())
+        hit = getattr(self, "_aq_bias_sum", None)
+        if hit is None or hit[0] != key:
+            hit = (key, (self.conv2.bias.float() + self.conv_shortcut.bias.float()).to(self.conv2.bias.dtype))
+            self._aq_bias_sum = hit
+        return hit[1]
 
 
 class Attention(nn.Module):

@@ -83,3 +83,21 @@ class _LayerNorm(torch.autograd.Function):
 def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> torch.Tensor:
     """LayerNorm over the last dimension of bf16 token rows (BasicTransformerBlock.norm1/2/3), frozen affine parameters."""
     return _LayerNorm.apply(x, gamma, beta, float(eps))
+
+
+class _AddBias(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, bias):
+        if ctx.needs_input_grad[2]:
+            raise AqualoraError("residual_add_bias: the bias must be frozen")
+        cl = torch.channels_last
+        return ops.add_bias_nhwc(a.contiguous(memory_format=cl), b.contiguous(memory_format=cl), bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g if ctx.needs_input_grad[0] else None), (g if ctx.needs_input_grad[1] else None), None
+
+
+def residual_add_bias(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """a + b + bias[None, :, None, None] in one pass (ResnetBlock2D's closing add with the convolution biases folded in)."""
+    return _AddBias.apply(a, b, bias)

@@ -234,6 +234,11 @@ int aq_group_norm_nhwc_bwd(const void* dy, const void* x, const void* gamma, con
 int aq_geglu_fwd(const void* proj, int64_t ldp, void* out, int64_t M, int F, void* stream);
 int aq_geglu_bwd(const void* proj, int64_t ldp, const void* g_out, void* g_proj, int64_t M, int F, void* stream);
 
+/* out = a + b + bias[c] over channels-last bf16 rows [rows, C]: the closing `input_tensor + hidden_states` of ResnetBlock2D.forward
+ * (scripts/lib/original_unet.py:455-460) with the biases of conv2 / conv_shortcut folded in (the convolutions then run without
+ * cuDNN's separate broadcast-bias pass).  C % 8 == 0. */
+int aq_add_bias_rows(const void* a, const void* b, const void* bias, void* out, int64_t rows, int C, void* stream);
+
 /* LayerNorm over contiguous bf16 token rows [M, C] (BasicTransformerBlock.norm1/2/3, scripts/lib/original_unet.py:732-806), eps
  * inside the square root, fp32 statistics, one rounding of the output.  mean_rstd [M, 2] fp32 is written by fwd (may be NULL when
  * no backward follows) and read by bwd; the backward returns dx only (gamma / beta are frozen).  C % 8 == 0, C <= 2048. */

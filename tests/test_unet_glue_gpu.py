@@ -112,6 +112,25 @@ def test_layer_norm_matches_fp32_reference(cuda_device, lead, C, eps):
     _close(xd.grad, xr.grad)
 
 
+@pytest.mark.parametrize("B,C,H,W", [(2, 320, 16, 16), (3, 64, 5, 7), (16, 640, 32, 32)])
+def test_residual_add_bias_matches_fp32_reference(cuda_device, B, C, H, W):
+    from aqualora_b200.unet_ops import residual_add_bias
+
+    g = torch.Generator().manual_seed(C + H)
+    a = torch.randn(B, C, H, W, generator=g).bfloat16()
+    b = torch.randn(B, C, H, W, generator=g).bfloat16()
+    bias = torch.randn(C, generator=g).bfloat16()
+    cl = torch.channels_last
+    ad = a.to(cuda_device).contiguous(memory_format=cl).requires_grad_(True)
+    bd = b.to(cuda_device).requires_grad_(True)                      # NCHW strides: converted
+    got = residual_add_bias(ad, bd, bias.to(cuda_device))
+    want = a.float() + b.float() + bias.float()[None, :, None, None]
+    _close(got.detach(), want, abs_frac=1e-6)
+    dy = torch.randn(B, C, H, W, generator=g).bfloat16().to(cuda_device)
+    got.backward(dy)
+    assert torch.equal(ad.grad, dy) and torch.equal(bd.grad, dy)
+
+
 def test_unet_forward_uses_glue_kernels_and_matches_library_ops(cuda_device):
     """The tiny U-Net with the glue kernels vs the same module tree with the library op sequence (trainable affine parameters
     switch the dispatch off): outputs agree to bf16 noise, and the fused run launches our kernels."""
@@ -137,6 +156,8 @@ def test_unet_forward_uses_glue_kernels_and_matches_library_ops(cuda_device):
     n_plain = _lib.load().aq_launch_count() - n0
     n_gn = sum(isinstance(m, torch.nn.GroupNorm) for m in unet.modules())
     n_ln = sum(isinstance(m, torch.nn.LayerNorm) for m in unet.modules())
-    assert n_fused - n_plain == 2 * n_gn + n_ln
+    from aqualora_b200.unet import ResnetBlock2D
+    n_res = sum(isinstance(m, ResnetBlock2D) for m in unet.modules())
+    assert n_fused - n_plain == 2 * n_gn + n_ln + n_res
     rel = ((fused.float() - plain.float()).norm() / plain.float().norm()).item()
     assert rel < 2e-2, rel

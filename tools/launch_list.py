@@ -37,13 +37,14 @@ def main():
 
         rd, wr = mb("dram__bytes_read.sum"), mb("dram__bytes_write.sum")
         tot += t
-        nm = re.sub(r"\(.*", "", d["name"]).replace("void ", "")[:30]
+        nm = re.sub(r"\(.*", "", d["name"]).replace("void ", "")[:(60 if "--aggregate-only" in sys.argv else 30)]
         a = agg.setdefault(nm, [0.0, 0.0, 0.0, 0])
         a[0] += t; a[1] += rd; a[2] += wr; a[3] += 1
-        print(f"{i:5d} {nm:30s} {d['grid']:>16s} {t:9.1f} us  rd {rd:7.0f} wr {wr:7.0f} MB  {(rd + wr) / t * 1e3:7.0f} GB/s")
+        if "--aggregate-only" not in sys.argv:
+            print(f"{i:5d} {nm:30s} {d['grid']:>16s} {t:9.1f} us  rd {rd:7.0f} wr {wr:7.0f} MB  {(rd + wr) / t * 1e3:7.0f} GB/s")
     print(f"total {tot:.1f} us over {len(ids)} launches")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-        print(f"  {k:30s} {v[0]:9.1f} us  {v[0] / tot * 100:5.1f} %  rd {v[1]:7.0f} wr {v[2]:7.0f} MB  x{v[3]}")
+        print(f"  {k:60s} {v[0]:9.1f} us  {v[0] / tot * 100:5.1f} %  rd {v[1]:7.0f} wr {v[2]:7.0f} MB  x{v[3]}")
 
 
 if __name__ == "__main__":
