@@ -15,7 +15,8 @@
 namespace aq {
 
 constexpr int kGnMaxGroups = 128;
-constexpr int kGnBatch = 4;   // independent 16-byte loads in flight per thread
+constexpr int kGnBatch = 4;      // independent 16-byte loads in flight per thread and tensor (backward: two tensors)
+constexpr int kGnBatchFwd = 8;   // forward: one tensor, so twice the rows
 
 struct GnParams {
   const uint4* x;        // [B, HW, C] bf16
@@ -52,7 +53,7 @@ __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&f)[8]
   unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f);
 }
 
-__device__ __forceinline__ float sigmoidf_fast(float u) { return 1.f / (1.f + __expf(-u)); }
+__device__ __forceinline__ float sigmoidf_fast(float u) { return __fdividef(1.f, 1.f + __expf(-u)); }
 
 // per-thread partials of 8 channels -> per-group partials of the CTA (shared fp32 atomics) -> fp64 global atomics
 __device__ __forceinline__ void gn_reduce_to_groups(const float (&a)[8], const float (&b)[8], int ch0, const GnParams& p, int batch) {
@@ -90,17 +91,17 @@ __global__ void gn_fwd_stats_kernel(const GnParams p) {
   float add[8] = {};
   if (p.add_bc != nullptr) load8_bf16(p.add_bc + (size_t)b * p.C + v * 8, add);
   float s[8] = {}, ss[8] = {};
-  for (int r = r_begin + rr; r < r_end; r += kGnBatch * p.R) {
-    uint4 q[kGnBatch];
-    bool ok[kGnBatch];
+  for (int r = r_begin + rr; r < r_end; r += kGnBatchFwd * p.R) {
+    uint4 q[kGnBatchFwd];
+    bool ok[kGnBatchFwd];
 #pragma unroll
-    for (int j = 0; j < kGnBatch; ++j) {
+    for (int j = 0; j < kGnBatchFwd; ++j) {
       const int rj = r + j * p.R;
       ok[j] = rj < r_end;
       q[j] = ok[j] ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int j = 0; j < kGnBatch; ++j) {
+    for (int j = 0; j < kGnBatchFwd; ++j) {
       if (!ok[j]) continue;
       float f[8];
       unpack8(q[j], f);
@@ -115,32 +116,42 @@ __global__ void gn_fwd_stats_kernel(const GnParams p) {
   gn_reduce_to_groups(s, ss, v * 8, p, b);
 }
 
-// per-channel affine of this thread's 8 channels from the fp64 group sums: y = x * a + c
-__device__ __forceinline__ void gn_channel_affine(const GnParams& p, int b, int ch0, float (&a)[8], float (&c)[8], float (&mean)[8],
-                                                  float (&rstd)[8]) {
-  float gam[8], bet[8];
-  load8_bf16(p.gamma + ch0, gam);
-  load8_bf16(p.beta + ch0, bet);
-  const double n = (double)p.cpg * (double)p.HW;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int g = (ch0 + i) / p.cpg;
+// (mean, rstd) of every group of sample b into shared memory, once per CTA.  Forward: from the fp64 sums -- only the cancelling
+// subtraction E[x^2] - mean^2 is done in double (B200 issues fp64 at 1/64 of the fp32 rate: the first version did a double
+// division and square root per channel per thread and spent more time there than on the data).  Backward: from mean_rstd.
+__device__ __forceinline__ void gn_group_stats(const GnParams& p, int b, float* sh_mr) {
+  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
     float m, rs;
     if (p.sums != nullptr) {
-      const double s = p.sums[((size_t)b * p.G + g) * 2], q = p.sums[((size_t)b * p.G + g) * 2 + 1];
-      const double mu = s / n;
-      double var = q / n - mu * mu;
+      const double inv_n = 1.0 / ((double)p.cpg * (double)p.HW);
+      const double mu = p.sums[((size_t)b * p.G + g) * 2] * inv_n;
+      double var = p.sums[((size_t)b * p.G + g) * 2 + 1] * inv_n - mu * mu;
       var = var < 0.0 ? 0.0 : var;
       m = (float)mu;
-      rs = (float)(1.0 / sqrt(var + (double)p.eps));
+      rs = 1.0f / sqrtf((float)var + p.eps);
     } else {
       m = p.mean_rstd[((size_t)b * p.G + g) * 2];
       rs = p.mean_rstd[((size_t)b * p.G + g) * 2 + 1];
     }
-    mean[i] = m;
-    rstd[i] = rs;
-    a[i] = rs * gam[i];
-    c[i] = bet[i] - m * a[i];
+    sh_mr[2 * g] = m;
+    sh_mr[2 * g + 1] = rs;
+  }
+  __syncthreads();
+}
+
+// per-channel affine of this thread's 8 channels: y = x * a + c
+__device__ __forceinline__ void gn_channel_affine(const GnParams& p, const float* sh_mr, int ch0, float (&a)[8], float (&c)[8],
+                                                  float (&mean)[8], float (&rstd)[8]) {
+  float gam[8], bet[8];
+  load8_bf16(p.gamma + ch0, gam);
+  load8_bf16(p.beta + ch0, bet);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (ch0 + i) / p.cpg;
+    mean[i] = sh_mr[2 * g];
+    rstd[i] = sh_mr[2 * g + 1];
+    a[i] = rstd[i] * gam[i];
+    c[i] = bet[i] - mean[i] * a[i];
   }
 }
 
@@ -150,8 +161,10 @@ __global__ void gn_fwd_apply_kernel(const GnParams p) {
   const int b = blockIdx.y;
   const int r_begin = blockIdx.x * p.rows_per_cta;
   const int r_end = min(r_begin + p.rows_per_cta, p.HW);
+  __shared__ float sh_mr[2 * kGnMaxGroups];
+  gn_group_stats(p, b, sh_mr);
   float a[8], c[8], mean[8], rstd[8];
-  gn_channel_affine(p, b, v * 8, a, c, mean, rstd);
+  gn_channel_affine(p, sh_mr, v * 8, a, c, mean, rstd);
   if (p.add_bc != nullptr) {
     float add[8];
     load8_bf16(p.add_bc + (size_t)b * p.C + v * 8, add);
@@ -172,17 +185,17 @@ __global__ void gn_fwd_apply_kernel(const GnParams p) {
   }
   const uint4* xb = p.x + (size_t)b * p.HW * p.V + v;
   uint4* yb = p.out + (size_t)b * p.HW * p.V + v;
-  for (int r = r_begin + rr; r < r_end; r += kGnBatch * p.R) {
-    uint4 q[kGnBatch];
-    bool ok[kGnBatch];
+  for (int r = r_begin + rr; r < r_end; r += kGnBatchFwd * p.R) {
+    uint4 q[kGnBatchFwd];
+    bool ok[kGnBatchFwd];
 #pragma unroll
-    for (int j = 0; j < kGnBatch; ++j) {
+    for (int j = 0; j < kGnBatchFwd; ++j) {
       const int rj = r + j * p.R;
       ok[j] = rj < r_end;
       q[j] = ok[j] ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int j = 0; j < kGnBatch; ++j) {
+    for (int j = 0; j < kGnBatchFwd; ++j) {
       if (!ok[j]) continue;
       float f[8];
       unpack8(q[j], f);
@@ -224,8 +237,10 @@ __global__ void gn_bwd_stats_kernel(const GnParams p) {
   const int r_end = min(r_begin + p.rows_per_cta, p.HW);
   GnParams ps = p;
   ps.sums = nullptr;   // statistics of the forward come from mean_rstd
+  __shared__ float sh_mr[2 * kGnMaxGroups];
+  gn_group_stats(ps, b, sh_mr);
   float a[8], c[8], mean[8], rstd[8], gam[8];
-  gn_channel_affine(ps, b, v * 8, a, c, mean, rstd);
+  gn_channel_affine(ps, sh_mr, v * 8, a, c, mean, rstd);
   load8_bf16(p.gamma + v * 8, gam);
   if (p.add_bc != nullptr) {
     float add[8];
@@ -274,15 +289,21 @@ __global__ void gn_bwd_apply_kernel(const GnParams p) {
   const int r_end = min(r_begin + p.rows_per_cta, p.HW);
   GnParams ps = p;
   ps.sums = nullptr;
+  __shared__ float sh_mr[2 * kGnMaxGroups];
+  __shared__ float sh_m12[2 * kGnMaxGroups];
+  {
+    const float inv_n = 1.f / ((float)p.cpg * (float)p.HW);
+    for (int i = threadIdx.x; i < 2 * p.G; i += blockDim.x) sh_m12[i] = (float)p.sums[(size_t)b * 2 * p.G + i] * inv_n;
+  }
+  gn_group_stats(ps, b, sh_mr);   // (its barrier also publishes sh_m12)
   float a[8], c[8], mean[8], rstd[8], gam[8], m1[8], m2[8];
-  gn_channel_affine(ps, b, v * 8, a, c, mean, rstd);
+  gn_channel_affine(ps, sh_mr, v * 8, a, c, mean, rstd);
   load8_bf16(p.gamma + v * 8, gam);
-  const double n = (double)p.cpg * (double)p.HW;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = (v * 8 + i) / p.cpg;
-    m1[i] = (float)(p.sums[((size_t)b * p.G + g) * 2] / n);
-    m2[i] = (float)(p.sums[((size_t)b * p.G + g) * 2 + 1] / n);
+    m1[i] = sh_m12[2 * g];
+    m2[i] = sh_m12[2 * g + 1];
   }
   if (p.add_bc != nullptr) {
     float add[8];
