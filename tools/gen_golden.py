@@ -237,7 +237,46 @@ def gen_create_wm_lora():
                OUT / "create_wm_lora.pt")
 
 
+def gen_pretrain():
+    """PRVL_loss and gen_combined_latents of train/latent_wm_pretrain.py, executed from the reference's own source text: the
+    script cannot be imported (accelerate, diffusers, lpips, torchsummary are absent), so the two function bodies are cut out by
+    line range, checked by their first lines, and exec'd."""
+    import random
+    import textwrap
+
+    import torch.nn.functional as F
+
+    lines = (REF / "train" / "latent_wm_pretrain.py").read_text().splitlines()
+    prvl_src = "\n".join(lines[38:50])                       # WINDOW_SIZE, KERNEL, def PRVL_loss
+    assert prvl_src.startswith("WINDOW_SIZE = 32") and "def PRVL_loss(img1, img2):" in prvl_src
+    ns = {"torch": torch, "F": F}
+    exec(prvl_src, ns)
+    comb_src = textwrap.dedent("\n".join(lines[132:150]))    # def gen_combined_latents (a closure of main(): uses random, F, torch)
+    assert comb_src.startswith("def gen_combined_latents(latents, wm_latent, scale=1.0):")
+    ns2 = {"torch": torch, "F": F, "random": random}
+    exec(comb_src, ns2)
+    g = torch.Generator().manual_seed(0)
+    out = {"prvl": [], "combined": []}
+    for shape in [(2, 3, 64, 64), (1, 3, 96, 80), (2, 3, 512, 512)]:
+        a = torch.rand(shape, generator=g) * 2 - 1
+        b = a + 0.1 * torch.randn(shape, generator=g)
+        keep = shape[-1] <= 96
+        out["prvl"].append({"shape": shape, "a": a if keep else None, "b": b if keep else None, "seed_note": "512: regenerate from seed",
+                            "value": ns["PRVL_loss"](a, b).clone()})
+    out["prvl_512_inputs_seed"] = 0
+    for seed in range(8):
+        lat = torch.randn(2, 4, 16, 16, generator=g)
+        wm = torch.randn(2, 4, 16, 16, generator=g) * 0.1
+        random.seed(seed)
+        y = ns2["gen_combined_latents"](lat.clone(), wm.clone(), scale=0.03 if seed % 2 else 1.0)
+        out["combined"].append({"seed": seed, "scale": 0.03 if seed % 2 else 1.0, "latents": lat, "wm": wm, "out": y.clone()})
+    torch.save(out, OUT / "pretrain_small.pt")
+
+
 def main():
+    if '--pretrain-only' in sys.argv:
+        gen_pretrain()
+        return
     if '--create-wm-lora-only' in sys.argv:
         gen_create_wm_lora()
         return
@@ -250,6 +289,7 @@ def main():
     gen_jpeg()
     gen_keys()
     gen_create_wm_lora()
+    gen_pretrain()
     for f in sorted(OUT.glob("*")):
         print(f.name, f.stat().st_size)
 
