@@ -494,3 +494,46 @@ def test_operand_cache_ignores_recycled_ids(lm, cuda_device):
     w = torch.randn(16, 64, device=cuda_device).bfloat16()
     lm._WT_CACHE[id(w)] = ((w._version, w.data_ptr()), dt, weakref.ref(other))
     assert torch.equal(lm._weight_t(w, 16, 64), w.t())
+
+
+def test_cfg_doubled_sampling_forward_matches_oracle(cuda_device):
+    """the sampling call of train/rob_enhance_finetune.py:995-1012 -- classifier-free guidance doubles the batch and the
+    message diagonal rides along as `torch.cat([mapper(msg)] * 2) * 1.03`, on a non-square latent grid (the script draws
+    height / width from 512 ... 768) -- through the tiny U-Net under no_grad, vs the reference op sequence on CPU in fp32."""
+    from aqualora_b200 import lora_modules, ppft
+    from aqualora_b200.unet import UNetConfig, lora_target_keys
+    from oracle import lora_oracle as O
+    from oracle.patch import patch_with_oracle
+
+    dev = cuda_device
+    cfg = UNetConfig.tiny(16)
+    rank, bits, B = 8, 48, 2
+    unet = ppft.build_unet(cfg, dev, seed=3)
+    emb = O.mapper_init(bits, rank, generator=torch.Generator().manual_seed(5))
+    tr = ppft.PPFTTrainer(unet, ppft.PPFTConfig(rank=rank, msg_bits=bits), emb, dev, lora_up_std=0.05, seed=1)
+    g = torch.Generator().manual_seed(21)
+    lat = torch.randn(B, 4, 24, 16, generator=g)
+    ctx = torch.randn(2 * B, 77, cfg.cross_attention_dim, generator=g)          # [uncond; cond]
+    msg = torch.randint(0, 2, (B, bits), generator=g).float()
+    t = torch.tensor([481], dtype=torch.long)
+    r16 = lambda x: x.bfloat16().float()
+    s = r16(O.mapper_forward(msg, tr.state.mapper_emb.detach().cpu()))
+    s2 = r16(torch.cat([s] * 2) * 1.03)
+    x2 = torch.cat([lat] * 2)
+    with torch.no_grad():
+        got = unet(x2.to(dev, torch.bfloat16), t.to(dev), ctx.to(dev, torch.bfloat16),
+                   cross_attention_kwargs={"scale": s2.to(dev)}).sample
+    assert got.shape == (2 * B, 4, 24, 16)
+
+    cpu_unet = ppft.build_unet(cfg, "cpu", dtype=torch.float32, seed=3)
+    lora_modules.inject_lora(cpu_unet, lora_target_keys(cpu_unet), rank)
+    cpu_unet.load_state_dict({k: v.detach().float().cpu() for k, v in unet.state_dict().items()})
+    patch_with_oracle(cpu_unet)
+    with torch.no_grad():
+        want = cpu_unet(r16(x2), t, r16(ctx), cross_attention_kwargs={"scale": s2}).sample
+        base = cpu_unet(r16(x2), t, r16(ctx), cross_attention_kwargs={"scale": torch.zeros_like(s2)}).sample
+    rel = ((got.float().cpu() - want).norm() / want.norm()).item()
+    assert rel < 3e-2, rel
+    # the watermark branch is visible above that noise floor, and the two CFG halves (same latents, different context) differ
+    assert ((want - base).norm() / want.norm()).item() > rel
+    assert not torch.equal(got[:B], got[B:])
