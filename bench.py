@@ -224,6 +224,11 @@ def _claim_stdout():
     return _JSON_OUT
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the fused forward kernel, one ncu launch per shape of the SD1.5 B = 16 step
+# (profiles/r01_gemm_dram_traffic_v13.txt), weighted by the shape's launches per step: 7 890 MB over 129 launches
+GEMM_FWD_DRAM_TRAFFIC_PER_LAUNCH = round(7890e6 / 129)
+
+
 def run_cuda(args):
     _claim_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -372,7 +377,11 @@ def run_cuda(args):
             peak = pk["bf16_tflops_sustained"]     # the kernel is timed inside a long step
             roof = {"bound": "tensor", "kernel": "aq::lora_gemm_kernel (fused base GEMM + watermark LoRA, forward launches)",
                     "achieved": round(dom["tflops"], 1), "peak": peak, "unit": "TFLOP/s", "frac": round(dom["tflops"] / peak, 4),
-                    "peak_kind": f"bf16_tflops_sustained of {pk['source']}", "traffic": None,
+                    "peak_kind": f"bf16_tflops_sustained of {pk['source']}",
+                    "traffic": (GEMM_FWD_DRAM_TRAFFIC_PER_LAUNCH if args.model == "sd15" and B == PER_GPU_BATCH else None),
+                    "traffic_note": "DRAM bytes (read + write) per forward launch, averaged over the 129 launches of a step: ncu "
+                                    "dram__bytes_* of every forward shape, cold caches (profiles/r01_gemm_dram_traffic_v13.txt); "
+                                    "algorithmic bytes per launch = bytes_per_step / launches (outputs largely stay in the 126 MB L2)",
                     "launches_per_step": dom["launch_groups_per_step"], "kernel_ms_per_step": round(dom["ms_per_step"], 3),
                     "flops_per_step": dom["flops_per_step"], "frac_of_burst": round(dom["tflops"] / pk["bf16_tflops"], 4),
                     "kernel_ms_per_step_mean": round(dom["ms_per_step_mean"], 3),
