@@ -15,8 +15,11 @@
 namespace aq {
 
 constexpr int kGnMaxGroups = 128;
-constexpr int kGnBatch = 4;      // independent 16-byte loads in flight per thread and tensor (backward: two tensors)
-constexpr int kGnBatchFwd = 8;   // forward: one tensor, so twice the rows
+// Rows per thread and round.  Every loop below is software-pipelined: the loads of round i + 1 are issued before round i is
+// consumed, so a CTA streams continuously instead of alternating between a load burst and arithmetic (first version: all CTAs of
+// a wave in lock-step, 2.2 TB/s; ncu in profiles/r01_glue_launches_v13.txt).
+constexpr int kGnBatch = 2;      // backward: two tensors, 2 x 2 x 2 loads in flight
+constexpr int kGnBatchFwd = 4;   // forward: one tensor, 2 x 4 loads in flight
 
 struct GnParams {
   const uint4* x;        // [B, HW, C] bf16
@@ -53,7 +56,14 @@ __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&f)[8]
   unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f);
 }
 
-__device__ __forceinline__ float sigmoidf_fast(float u) { return __fdividef(1.f, 1.f + __expf(-u)); }
+// sigmoid(u) = 0.5 tanh(0.5 u) + 0.5 with the single-instruction tanh.approx (max rel. error 2^-11, below the bf16 rounding of the
+// outputs): ONE special-function op per element instead of two (ex2 + rcp) -- at 16 MUFU results per clock and SM the exp / rcp
+// pair alone cost 9 of the 21.7 us of gn_fwd_apply on [16, 320, 64, 64] (profiles/r01_ncu_glue_v14_full_summary.txt)
+__device__ __forceinline__ float sigmoidf_fast(float u) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * u));
+  return fmaf(0.5f, t, 0.5f);
+}
 
 // per-thread partials of 8 channels -> per-group partials of the CTA (shared fp32 atomics) -> fp64 global atomics
 __device__ __forceinline__ void gn_reduce_to_groups(const float (&a)[8], const float (&b)[8], int ch0, const GnParams& p, int batch) {
@@ -82,7 +92,7 @@ __device__ __forceinline__ void gn_reduce_to_groups(const float (&a)[8], const f
 }
 
 // ---------------------------------------------------------------- forward
-__global__ void gn_fwd_stats_kernel(const GnParams p) {
+__global__ void __launch_bounds__(1024) gn_fwd_stats_kernel(const GnParams p) {
   const int v = threadIdx.x % p.V, rr = threadIdx.x / p.V;
   const int b = blockIdx.y;
   const int r_begin = blockIdx.x * p.rows_per_cta;
@@ -91,18 +101,20 @@ __global__ void gn_fwd_stats_kernel(const GnParams p) {
   float add[8] = {};
   if (p.add_bc != nullptr) load8_bf16(p.add_bc + (size_t)b * p.C + v * 8, add);
   float s[8] = {}, ss[8] = {};
-  for (int r = r_begin + rr; r < r_end; r += kGnBatchFwd * p.R) {
-    uint4 q[kGnBatchFwd];
-    bool ok[kGnBatchFwd];
+  auto load = [&](uint4 (&q)[kGnBatchFwd], int r) {
 #pragma unroll
     for (int j = 0; j < kGnBatchFwd; ++j) {
       const int rj = r + j * p.R;
-      ok[j] = rj < r_end;
-      q[j] = ok[j] ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
+      q[j] = rj < r_end ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
     }
+  };
+  uint4 q[kGnBatchFwd], nq[kGnBatchFwd];
+  load(q, r_begin + rr);
+  for (int r = r_begin + rr; r < r_end; r += kGnBatchFwd * p.R) {
+    load(nq, r + kGnBatchFwd * p.R);      // rows past r_end come back as zeros without touching memory
 #pragma unroll
     for (int j = 0; j < kGnBatchFwd; ++j) {
-      if (!ok[j]) continue;
+      if (r + j * p.R >= r_end) continue;
       float f[8];
       unpack8(q[j], f);
 #pragma unroll
@@ -112,6 +124,8 @@ __global__ void gn_fwd_stats_kernel(const GnParams p) {
         ss[i] = fmaf(t, t, ss[i]);
       }
     }
+#pragma unroll
+    for (int j = 0; j < kGnBatchFwd; ++j) q[j] = nq[j];
   }
   gn_reduce_to_groups(s, ss, v * 8, p, b);
 }
@@ -156,7 +170,7 @@ __device__ __forceinline__ void gn_channel_affine(const GnParams& p, const float
 }
 
 template <bool SILU>
-__global__ void gn_fwd_apply_kernel(const GnParams p) {
+__global__ void __launch_bounds__(1024) gn_fwd_apply_kernel(const GnParams p) {
   const int v = threadIdx.x % p.V, rr = threadIdx.x / p.V;
   const int b = blockIdx.y;
   const int r_begin = blockIdx.x * p.rows_per_cta;
@@ -185,18 +199,20 @@ __global__ void gn_fwd_apply_kernel(const GnParams p) {
   }
   const uint4* xb = p.x + (size_t)b * p.HW * p.V + v;
   uint4* yb = p.out + (size_t)b * p.HW * p.V + v;
-  for (int r = r_begin + rr; r < r_end; r += kGnBatchFwd * p.R) {
-    uint4 q[kGnBatchFwd];
-    bool ok[kGnBatchFwd];
+  auto load = [&](uint4 (&q)[kGnBatchFwd], int r) {
 #pragma unroll
     for (int j = 0; j < kGnBatchFwd; ++j) {
       const int rj = r + j * p.R;
-      ok[j] = rj < r_end;
-      q[j] = ok[j] ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
+      q[j] = rj < r_end ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
     }
+  };
+  uint4 q[kGnBatchFwd], nq[kGnBatchFwd];
+  load(q, r_begin + rr);
+  for (int r = r_begin + rr; r < r_end; r += kGnBatchFwd * p.R) {
+    load(nq, r + kGnBatchFwd * p.R);
 #pragma unroll
     for (int j = 0; j < kGnBatchFwd; ++j) {
-      if (!ok[j]) continue;
+      if (r + j * p.R >= r_end) continue;
       float f[8];
       unpack8(q[j], f);
 #pragma unroll
@@ -206,6 +222,8 @@ __global__ void gn_fwd_apply_kernel(const GnParams p) {
       }
       yb[(size_t)(r + j * p.R) * p.V] = pack8(f);
     }
+#pragma unroll
+    for (int j = 0; j < kGnBatchFwd; ++j) q[j] = nq[j];
   }
 }
 
@@ -254,19 +272,21 @@ __global__ void gn_bwd_stats_kernel(const GnParams p) {
   const uint4* xb = p.x + (size_t)b * p.HW * p.V + v;
   const uint4* gb = p.dy + (size_t)b * p.HW * p.V + v;
   float s1[8] = {}, s2[8] = {};
-  for (int r = r_begin + rr; r < r_end; r += kGnBatch * p.R) {
-    uint4 q[kGnBatch], d[kGnBatch];
-    bool ok[kGnBatch];
+  auto load = [&](uint4 (&q)[kGnBatch], uint4 (&d)[kGnBatch], int r) {
 #pragma unroll
     for (int j = 0; j < kGnBatch; ++j) {
       const int rj = r + j * p.R;
-      ok[j] = rj < r_end;
-      q[j] = ok[j] ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
-      d[j] = ok[j] ? __ldg(gb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
+      q[j] = rj < r_end ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
+      d[j] = rj < r_end ? __ldg(gb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
     }
+  };
+  uint4 q[kGnBatch], d[kGnBatch], nq[kGnBatch], nd[kGnBatch];
+  load(q, d, r_begin + rr);
+  for (int r = r_begin + rr; r < r_end; r += kGnBatch * p.R) {
+    load(nq, nd, r + kGnBatch * p.R);
 #pragma unroll
     for (int j = 0; j < kGnBatch; ++j) {
-      if (!ok[j]) continue;
+      if (r + j * p.R >= r_end) continue;
       float x[8], dy[8], t[8], xhat[8];
       unpack8(q[j], x);
       unpack8(d[j], dy);
@@ -276,6 +296,11 @@ __global__ void gn_bwd_stats_kernel(const GnParams p) {
         s1[i] += t[i];
         s2[i] = fmaf(t[i], xhat[i], s2[i]);
       }
+    }
+#pragma unroll
+    for (int j = 0; j < kGnBatch; ++j) {
+      q[j] = nq[j];
+      d[j] = nd[j];
     }
   }
   gn_reduce_to_groups(s1, s2, v * 8, p, b);
@@ -317,19 +342,21 @@ __global__ void gn_bwd_apply_kernel(const GnParams p) {
   const uint4* xb = p.x + (size_t)b * p.HW * p.V + v;
   const uint4* gb = p.dy + (size_t)b * p.HW * p.V + v;
   uint4* ob = p.out + (size_t)b * p.HW * p.V + v;
-  for (int r = r_begin + rr; r < r_end; r += kGnBatch * p.R) {
-    uint4 q[kGnBatch], d[kGnBatch];
-    bool ok[kGnBatch];
+  auto load = [&](uint4 (&q)[kGnBatch], uint4 (&d)[kGnBatch], int r) {
 #pragma unroll
     for (int j = 0; j < kGnBatch; ++j) {
       const int rj = r + j * p.R;
-      ok[j] = rj < r_end;
-      q[j] = ok[j] ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
-      d[j] = ok[j] ? __ldg(gb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
+      q[j] = rj < r_end ? __ldg(xb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
+      d[j] = rj < r_end ? __ldg(gb + (size_t)rj * p.V) : make_uint4(0, 0, 0, 0);
     }
+  };
+  uint4 q[kGnBatch], d[kGnBatch], nq[kGnBatch], nd[kGnBatch];
+  load(q, d, r_begin + rr);
+  for (int r = r_begin + rr; r < r_end; r += kGnBatch * p.R) {
+    load(nq, nd, r + kGnBatch * p.R);
 #pragma unroll
     for (int j = 0; j < kGnBatch; ++j) {
-      if (!ok[j]) continue;
+      if (r + j * p.R >= r_end) continue;
       float x[8], dy[8], t[8], xhat[8];
       unpack8(q[j], x);
       unpack8(d[j], dy);
@@ -338,11 +365,27 @@ __global__ void gn_bwd_apply_kernel(const GnParams p) {
       for (int i = 0; i < 8; ++i) t[i] = rstd[i] * (t[i] - m1[i] - xhat[i] * m2[i]);
       ob[(size_t)(r + j * p.R) * p.V] = pack8(t);
     }
+#pragma unroll
+    for (int j = 0; j < kGnBatch; ++j) {
+      q[j] = nq[j];
+      d[j] = nd[j];
+    }
   }
 }
 
+template <typename K1, typename K2>
+static int gn_ctas_per_sm(K1 k1, K2 k2, int threads) {
+  static int cache[1025] = {0};   // per kernel pair (template instance); benign race: idempotent
+  if (threads >= 0 && threads <= 1024 && cache[threads] > 0) return cache[threads];
+  int a = 0, b = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k1, threads, 0) != cudaSuccess || a < 1) a = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k2, threads, 0) != cudaSuccess || b < 1) b = 1;
+  if (threads >= 0 && threads <= 1024) cache[threads] = a < b ? a : b;
+  return a < b ? a : b;
+}
+
 static int gn_setup(GnParams& p, dim3& grid, int& threads, const void* x, const void* gamma, const void* beta, const void* add_bc,
-                    double* sums, float* mean_rstd, int B, int HW, int C, int G, float eps, const char* who) {
+                    double* sums, float* mean_rstd, int B, int HW, int C, int G, float eps, const char* who, int (*occupancy)(int)) {
   AQ_REQUIRE(B > 0 && HW > 0 && C > 0 && G > 0, AQ_ERR_BAD_SHAPE, "%s: empty problem B=%d HW=%d C=%d G=%d", who, B, HW, C, G);
   AQ_REQUIRE(C % 8 == 0 && C % G == 0, AQ_ERR_BAD_SHAPE, "%s: C=%d must be a multiple of 8 and of G=%d", who, C, G);
   AQ_REQUIRE(G <= kGnMaxGroups, AQ_ERR_BAD_SHAPE, "%s: at most %d groups, got %d", who, kGnMaxGroups, G);
@@ -363,9 +406,10 @@ static int gn_setup(GnParams& p, dim3& grid, int& threads, const void* x, const 
   p.R = p.V >= 256 ? 1 : 256 / p.V;
   if (p.R > HW) p.R = HW;
   threads = p.V * p.R;
-  // ~6 CTAs per SM over the whole batch, at least 2 row batches per thread
+  // one wave of the pair of kernels that will run (2 - 3 CTAs per SM by registers): every CTA starts at once and streams its
+  // slab in several pipelined rounds; at least 2 rows per thread
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  int slabs = (sms * 6 + B - 1) / B;
+  int slabs = (sms * occupancy(threads)) / B;
   const int max_slabs = (HW + 2 * p.R - 1) / (2 * p.R);
   if (slabs > max_slabs) slabs = max_slabs;
   if (slabs < 1) slabs = 1;
@@ -429,8 +473,10 @@ int aq_group_norm_nhwc_fwd(const void* x, const void* gamma, const void* beta, c
   GnParams p{};
   dim3 grid;
   int threads = 0;
+  int (*occ)(int) = silu ? +[](int t) { return gn_ctas_per_sm(gn_fwd_stats_kernel, gn_fwd_apply_kernel<true>, t); }
+                          : +[](int t) { return gn_ctas_per_sm(gn_fwd_stats_kernel, gn_fwd_apply_kernel<false>, t); };
   int rc = gn_setup(p, grid, threads, x, gamma, beta, add_bc, reinterpret_cast<double*>(ws), mean_rstd, B, HW, C, G, eps,
-                    "aq_group_norm_nhwc_fwd");
+                    "aq_group_norm_nhwc_fwd", occ);
   if (rc) return rc;
   AQ_REQUIRE(ws_bytes >= aq_group_norm_workspace_bytes(B, G), AQ_ERR_WORKSPACE, "aq_group_norm_nhwc_fwd: workspace too small");
   AQ_REQUIRE(y != nullptr && (reinterpret_cast<uintptr_t>(y) & 15u) == 0, AQ_ERR_BAD_ALIGN, "aq_group_norm_nhwc_fwd: y must be 16-byte aligned");
@@ -452,8 +498,10 @@ int aq_group_norm_nhwc_bwd(const void* dy, const void* x, const void* gamma, con
   GnParams p{};
   dim3 grid;
   int threads = 0;
+  int (*occ)(int) = silu ? +[](int t) { return gn_ctas_per_sm(gn_bwd_stats_kernel<true>, gn_bwd_apply_kernel<true>, t); }
+                          : +[](int t) { return gn_ctas_per_sm(gn_bwd_stats_kernel<false>, gn_bwd_apply_kernel<false>, t); };
   int rc = gn_setup(p, grid, threads, x, gamma, beta, add_bc, reinterpret_cast<double*>(ws), const_cast<float*>(mean_rstd), B, HW, C, G,
-                    eps, "aq_group_norm_nhwc_bwd");
+                    eps, "aq_group_norm_nhwc_bwd", occ);
   if (rc) return rc;
   AQ_REQUIRE(ws_bytes >= aq_group_norm_workspace_bytes(B, G), AQ_ERR_WORKSPACE, "aq_group_norm_nhwc_bwd: workspace too small");
   AQ_REQUIRE(dy != nullptr && dx != nullptr && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0,
@@ -533,13 +581,18 @@ __global__ void __launch_bounds__(256) layer_norm_fwd_kernel(const uint4* __rest
     }
   }
   const float inv_c = 1.f / (float)(V * 8);
-  for (long long row = warp0; row < M; row += nwarps) {
-    uint4 q[VPL];
+  auto load = [&](uint4 (&q)[VPL], long long row) {   // rows past M come back as zeros without touching memory
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       const int v = lane + 32 * j;
-      q[j] = v < V ? __ldg(x + row * V + v) : make_uint4(0, 0, 0, 0);
+      q[j] = (v < V && row < M) ? __ldg(x + row * V + v) : make_uint4(0, 0, 0, 0);
     }
+  };
+  uint4 q[VPL], nq[VPL];
+  load(q, warp0);
+  for (long long row = warp0; row < M; row += nwarps) {
+    load(nq, row + nwarps);   // the next row's loads are in flight while this one is reduced: one row per warp at a time left the
+                              // kernel latency-bound at 1.5 TB/s (24 warps x 640 B in flight per SM)
     float f[VPL][8];
     float s = 0.f;
 #pragma unroll
@@ -575,6 +628,8 @@ __global__ void __launch_bounds__(256) layer_norm_fwd_kernel(const uint4* __rest
         y[row * V + v] = pack8(f[j]);
       }
     }
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) q[j] = nq[j];
   }
 }
 
@@ -593,15 +648,21 @@ __global__ void __launch_bounds__(256) layer_norm_bwd_kernel(const uint4* __rest
     if (v < V) load8_bf16(gamma + v * 8, gam[j]);
   }
   const float inv_c = 1.f / (float)(V * 8);
-  for (long long row = warp0; row < M; row += nwarps) {
-    uint4 q[VPL], d[VPL];
+  auto load = [&](uint4 (&q)[VPL], uint4 (&d)[VPL], float2& mr, long long row) {
+    const bool in = row < M;
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       const int v = lane + 32 * j;
-      q[j] = v < V ? __ldg(x + row * V + v) : make_uint4(0, 0, 0, 0);
-      d[j] = v < V ? __ldg(dy + row * V + v) : make_uint4(0, 0, 0, 0);
+      q[j] = (v < V && in) ? __ldg(x + row * V + v) : make_uint4(0, 0, 0, 0);
+      d[j] = (v < V && in) ? __ldg(dy + row * V + v) : make_uint4(0, 0, 0, 0);
     }
-    const float2 mr = __ldg(mean_rstd + row);
+    mr = in ? __ldg(mean_rstd + row) : make_float2(0.f, 0.f);
+  };
+  uint4 q[VPL], d[VPL], nq[VPL], nd[VPL];
+  float2 mr, nmr;
+  load(q, d, mr, warp0);
+  for (long long row = warp0; row < M; row += nwarps) {
+    load(nq, nd, nmr, row + nwarps);
     float xh[VPL][8], g[VPL][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -633,6 +694,12 @@ __global__ void __launch_bounds__(256) layer_norm_bwd_kernel(const uint4* __rest
         dx[row * V + v] = pack8(g[j]);
       }
     }
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      q[j] = nq[j];
+      d[j] = nd[j];
+    }
+    mr = nmr;
   }
 }
 
