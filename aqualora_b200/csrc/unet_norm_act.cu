@@ -390,6 +390,7 @@ static int gn_setup(GnParams& p, dim3& grid, int& threads, const void* x, const 
   AQ_REQUIRE(C % 8 == 0 && C % G == 0, AQ_ERR_BAD_SHAPE, "%s: C=%d must be a multiple of 8 and of G=%d", who, C, G);
   AQ_REQUIRE(G <= kGnMaxGroups, AQ_ERR_BAD_SHAPE, "%s: at most %d groups, got %d", who, kGnMaxGroups, G);
   AQ_REQUIRE(C / 8 <= 1024, AQ_ERR_BAD_SHAPE, "%s: C=%d exceeds 8192 channels", who, C);
+  AQ_REQUIRE(B <= 65535, AQ_ERR_BAD_SHAPE, "%s: B=%d exceeds 65535 samples per call", who, B);
   AQ_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15u) == 0 &&
                  (reinterpret_cast<uintptr_t>(beta) & 15u) == 0 && (reinterpret_cast<uintptr_t>(add_bc) & 15u) == 0,
              AQ_ERR_BAD_ALIGN, "%s: pointers must be 16-byte aligned", who);

@@ -235,6 +235,14 @@ class PPFTTrainer:
         lora_modules.invalidate_packed()               # the capture recorded, but did not run, the operand refresh
         return self._graph_launches
 
+    @property
+    def static_inputs(self):
+        """The captured graph's input buffers (same order as the `example_inputs` of `capture`): write the next batch here
+        (e.g. `copy_` straight from pinned host memory) and call `step_graphed(copy_inputs=False)`."""
+        if self._graph is None:
+            raise RuntimeError("PPFTTrainer.capture() has not been called")
+        return self._static_in
+
     def step_graphed(self, *inputs, copy_inputs: bool = True):
         """One PPFT step through the captured graph: inputs -> static buffers, replay, gradient exchange + clip + AdamW."""
         if self._graph is None:

@@ -345,7 +345,7 @@ def run_cuda(args):
     e0.record()
     for i in range(args.steps):
         if graph_state["on"]:
-            for dst, src in zip(trainer._static_in, host[i % n_pool]):     # pinned host -> the graph's input buffers
+            for dst, src in zip(trainer.static_inputs, host[i % n_pool]):     # pinned host -> the graph's input buffers
                 dst.copy_(src, non_blocking=True)
             loss_host = float(trainer.step_graphed(copy_inputs=False))       # D2H read of the step's result
         else:
@@ -395,7 +395,7 @@ def run_cuda(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_arm(args.model, steps=1, warmup=0, budget_s=60.0)
+        cpu = cpu_reference_arm(args.model, steps=4, warmup=1, budget_s=45.0)     # ~11-14 s of CPU work beside the GPU number
 
     if rank == 0:
         gb = B * world
