@@ -76,6 +76,7 @@ struct LoraProblem {
   CUtensorMap tmap_w;    // W  [N, K]   box {64, BN/2}   swizzle 128B
   CUtensorMap tmap_dn;   // Dn [r, K]   box {64, 32}     swizzle 128B
   CUtensorMap tmap_up;   // Up [N, r]   box {64, BN/2}   swizzle 128B
+  CUtensorMap tmap_y;    // Y  [M, N]   box {kPassCols, 32}  (store; swizzle 64B when kPassCols == 32)
   const __nv_bfloat16* bias;   // [N] or null
   __nv_bfloat16* y;            // [M, ldy]
   __nv_bfloat16* aux_out0;     // mode 0: H [M, r] (may be null); mode 1: dH [M, r]
@@ -108,10 +109,16 @@ struct SmemLayout {
   static constexpr int kNC = BN / 2;                         // accumulator columns per epilogue warp
   static constexpr int kWHalfBytes = (BN / 2) * kBlockK * 2;
   static constexpr int kStageBytes = kATileBytes + kWHalfBytes + kDnHalfBytes;
-  static constexpr int kNCP = kNC / 2;                       // columns per epilogue pass (two passes per tile)
-  static constexpr int kStgStride16 = (kNCP / 8 + 1) | 1;    // row stride in 16B units, odd: conflict-free 16B accesses
-  static constexpr int kStgStride = kStgStride16 * 16;
-  static constexpr int kStgWarpBytes = 32 * kStgStride;
+  // Output staging for the TMA-store epilogue: each epilogue warp owns two buffers of 32 rows x kPassCols bf16 in the layout of
+  // the Y tensor map's box; a pass = convert kPassCols accumulator columns, st.shared, fence, one cp.async.bulk.tensor store.
+  // 80-byte rows (BN = 160) are conflict-free as they are (8 consecutive lanes -> 8 distinct 16-byte bank groups); 64-byte rows
+  // use the 64B TMA swizzle.
+  static constexpr int kPassCols = (BN == 160) ? 40 : 32;
+  static constexpr int kPasses = kNC / kPassCols;
+  static constexpr bool kStgSwizzle64 = (kPassCols == 32);
+  static constexpr int kStgRowBytes = kPassCols * 2;
+  static constexpr int kStgBufBytes = 32 * kStgRowBytes;
+  static constexpr int kStgWarpBytes = 2 * kStgBufBytes;
   static constexpr int kStgBytes = kEpiWarps * kStgWarpBytes;
   static constexpr int kBiasWarpBytes = 256;                 // this warp's slice of the bias row (kNC bf16 <= 192 B)
   static constexpr int kBiasBytes = kEpiWarps * kBiasWarpBytes;
@@ -125,7 +132,8 @@ struct SmemLayout {
   static constexpr int kTotal = kBarOff + 512 + 1024;
   static_assert(kStages >= 3, "not enough shared memory for a pipeline");
   static_assert(kWHalfBytes % 1024 == 0, "W tile must keep 1024B alignment");
-  static_assert(BN % 32 == 0, "two epilogue column halves of whole 16-column TMEM loads, each stored in two 8-column-aligned passes");
+  static_assert(BN % 32 == 0, "two epilogue column halves of whole 16-column TMEM loads");
+  static_assert(kNC % kPassCols == 0 && kStgBufBytes % 512 == 0, "store passes tile the warp's slice; buffers keep the swizzle phase");
   static_assert(2 * BN + kRankPad <= 512, "TMEM budget");
   static_assert((2 * kStages + 7) * 8 <= 512, "barrier block");
 };
@@ -181,7 +189,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
 
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
-    if (p.has_main) tma_prefetch_desc(&p.prob[0].tmap_w);
+    if (p.has_main) {
+      tma_prefetch_desc(&p.prob[0].tmap_w);
+      tma_prefetch_desc(&p.prob[0].tmap_y);
+    }
     if (p.has_lora) {
       tma_prefetch_desc(&p.prob[0].tmap_dn);
       if (p.has_main) tma_prefetch_desc(&p.prob[0].tmap_up);
@@ -410,6 +421,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint8_t* hs_gen = smem_gen + L::kHsOff;
     uint8_t* stg_gen = smem_gen + L::kStgOff + warp * L::kStgWarpBytes;
+    const uint32_t stg_u32 = smem_base + L::kStgOff + warp * L::kStgWarpBytes;
+    uint32_t stg_iter = 0;   // store passes issued by this warp (buffer = parity)
     uint32_t* bias_sm = reinterpret_cast<uint32_t*>(smem_gen + L::kBiasOff + warp * L::kBiasWarpBytes);
     const int row_in_tile = q * 32 + lane;
     const uint32_t acc_empty_remote[2] = {mapa_shared(acc_empty_bar(0), 0), mapa_shared(acc_empty_bar(1), 0)};
@@ -565,19 +578,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         if (warp == 0 && nt - nt_begin < 4) AQ_TRACE(item_iter, 14 + 3 * (nt - nt_begin));
         ++acc_iter;
         if (col0 >= q_.N) continue;   // whole slice past the last column (partial last tile)
-        constexpr int NCP = L::kNCP;     // columns per pass
-        constexpr int kCpr = NCP / 8;    // 16-byte chunks per row and pass
-        const long long row_base = (long long)m0 + q * 32;
+        constexpr int PC = L::kPassCols;   // columns per store pass
+        constexpr int kCpr = PC / 8;       // 16-byte chunks per row and pass
+        const int row_base = m0 + q * 32;
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          const int pcol0 = col0 + pass * NCP;
+        for (int pass = 0; pass < L::kPasses; ++pass) {
+          const int pcol0 = col0 + pass * PC;
+          if (pcol0 >= q_.N) break;        // warp-uniform: the rest of the slice lies past the last column
+          const uint32_t buf = stg_iter & 1u;
+          // the bulk store that read this buffer two passes ago has finished reading it (at most one store stays in flight)
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
 #pragma unroll
           for (int c8 = 0; c8 < kCpr; ++c8) {
             float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(t[pass * NCP + c8 * 8 + i]);
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(t[pass * PC + c8 * 8 + i]);
             if (q_.bias != nullptr) {
-              const uint4 bw = *reinterpret_cast<const uint4*>(bias_sm + (pass * NCP + c8 * 8) / 2);
+              const uint4 bw = *reinterpret_cast<const uint4*>(bias_sm + (pass * PC + c8 * 8) / 2);
               const uint32_t bb[4] = {bw.x, bw.y, bw.z, bw.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -590,28 +608,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
             o.y = pack_bf16x2(f[2], f[3]);
             o.z = pack_bf16x2(f[4], f[5]);
             o.w = pack_bf16x2(f[6], f[7]);
-            *reinterpret_cast<uint4*>(stg_gen + lane * L::kStgStride + c8 * 16) = o;
+            const int chunk = L::kStgSwizzle64 ? (c8 ^ ((lane >> 1) & 3)) : c8;
+            *reinterpret_cast<uint4*>(stg_gen + buf * L::kStgBufBytes + lane * L::kStgRowBytes + chunk * 16) = o;
           }
+          fence_proxy_async_smem();        // generic-proxy writes -> visible to the bulk-copy (async) proxy
           __syncwarp();
-          // row-contiguous read-back: 32 consecutive 16-byte chunks per instruction -> each row's slice is one contiguous run
-          uint4 o[kCpr];
-#pragma unroll
-          for (int i = 0; i < kCpr; ++i) {
-            const int c = i * 32 + lane;
-            o[i] = *reinterpret_cast<const uint4*>(stg_gen + (c / kCpr) * L::kStgStride + (c % kCpr) * 16);
+          if (warp == 0 && nt == nt_begin) AQ_TRACE(item_iter, 25 + 3 * pass);
+          if (lane == 0) {
+            // rows >= M and columns >= N are clipped by the tensor map; the warp moves on while the copy engine drains the
+            // buffer (measured before: 5 st.global.v4 per pass stalled ~0.36 us on the L2 write burst of all CTAs)
+            tma_store_2d(&q_.tmap_y, stg_u32 + buf * L::kStgBufBytes, pcol0, row_base);
+            tma_store_commit();
           }
-#pragma unroll
-          for (int i = 0; i < kCpr; ++i) {
-            const int c = i * 32 + lane;
-            const int row = c / kCpr, col = pcol0 + (c % kCpr) * 8;
-            if (row_base + row < p.M && col < q_.N)
-              *reinterpret_cast<uint4*>(q_.y + (size_t)(row_base + row) * q_.ldy + col) = o[i];
-          }
-          __syncwarp();
+          ++stg_iter;
+          if (warp == 0 && nt == nt_begin) AQ_TRACE(item_iter, 27 + 3 * pass);
         }
         if (warp == 0 && nt - nt_begin < 4) AQ_TRACE(item_iter, 15 + 3 * (nt - nt_begin));
       }
     }
+    if (lane == 0) tma_store_wait_all<0>();   // every bulk store of this warp has completed before its shared memory goes away
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -699,6 +715,13 @@ static int launch_bn(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) 
         rc = make_tmap(&q.tmap_up, b.up, 2, 2, udims, ustr, ubox, kSwz128);
         if (rc) return rc;
       }
+    }
+    if (a.has_main) {
+      uint64_t dims[2] = {(uint64_t)b.N, (uint64_t)a.M};
+      uint64_t str[1] = {(uint64_t)b.ldy * 2};
+      uint32_t box[2] = {(uint32_t)L::kPassCols, 32};
+      int rc = make_tmap(&q.tmap_y, b.y, 2, 2, dims, str, box, L::kStgSwizzle64 ? kSwz64 : kSwzNone);
+      if (rc) return rc;
     }
     q.bias = reinterpret_cast<const __nv_bfloat16*>(b.bias);
     q.y = reinterpret_cast<__nv_bfloat16*>(b.y);

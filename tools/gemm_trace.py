@@ -17,7 +17,8 @@ OUT = os.path.join(ROOT, "tools", "_trace")
 SLOTS = ["prod_begin", "prod_end", "mma_acc0", "mma_first_full", "mma_H_commit", "mma_acc1", "mma_t1_issued", "mma_hs_ready",
          "mma_acc0_commit", "mma_acc1_commit", "epi_begin", "epi_H_full", "epi_hs_arrive", "epi_t0_full", "epi_t0_drained",
          "epi_t0_stored", "epi_t1_full", "epi_t1_drained", "epi_t1_stored", "epi_t2_full", "epi_t2_drained", "epi_t2_stored",
-         "epi_t3_full", "epi_t3_drained", "epi_t3_stored"]
+         "epi_t3_full", "epi_t3_drained", "epi_t3_stored", "t0_p0_staged", "t0_p0_readback", "t0_p0_stg_issued", "t0_p1_staged",
+         "t0_p1_readback", "t0_p1_stg_issued"]
 
 
 def build():
@@ -82,7 +83,7 @@ def run(spec, plain=False):
         vals = list(buf)
         t0 = min(v for v in vals[:32] if v)
         for it in range(8):
-            row = vals[it * 32: it * 32 + 25]
+            row = vals[it * 32: it * 32 + 31]
             if not any(row):
                 break
             print(f" item {it}: " + "  ".join(f"{n}={(v - t0) / mhz:.2f}" for n, v in zip(SLOTS, row) if v))
