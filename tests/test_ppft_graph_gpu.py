@@ -59,4 +59,4 @@ def test_graphed_step_matches_eager(cuda_device):
     # AdamW's first steps move every element by ~lr * sign(g): elements whose gradient is at the noise level may flip, so the
     # updates are compared as directions, not element by element
     cos = torch.nn.functional.cosine_similarity((p_graph - p0).flatten(), (p_eager - p0).flatten(), dim=0).item()
-    assert cos > 0.98, cos
+    assert cos > 0.95, cos
