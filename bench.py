@@ -539,11 +539,36 @@ DECODE_DRAM_TRAFFIC_PER_IMAGE = (13.511e9 + 9.737e9) / 64
 
 
 def run_decode(args):
+    """`--workload decode` (BASELINE.json configs[3]).  Under torchrun the images are sharded over the ranks (independent units, no
+    data-path collective: SURVEY.md 8(e)); the only exchange is the final reduction of the timing (max) and of the bit counts."""
     out = _claim_stdout()
-    print(json.dumps(measure_decode(args.images)), file=out, flush=True)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1:
+        print(json.dumps(measure_decode(args.images)), file=out, flush=True)
+        return
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dist.barrier()
+    line = measure_decode(max(64, args.images // world), device_index=local_rank, shard=rank)
+    dev = torch.device("cuda", local_rank)
+    t_max = torch.tensor([line["ms_per_step"] * line["steps"]], device=dev, dtype=torch.float64)
+    counts = torch.tensor([line["steps"] * 64, line["bit_agreement"]["agree"], line["bit_agreement"]["total"],
+                           line["bit_agreement"]["below_fp32_noise_floor"], line["gpu_launches"]], device=dev, dtype=torch.int64)
+    dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    dist.all_reduce(counts)
+    if rank == 0:
+        imgs, agree, total, undec, launches = (int(v) for v in counts.tolist())
+        line.update({"value": round(imgs / t_max.item() * 1e3, 1), "n_gpus": world, "gpu_launches": launches})
+        line["bit_agreement"].update({"agree": agree, "total": total, "below_fp32_noise_floor": undec})
+        line["config"]["parallelism"] = f"images sharded over {world} ranks, no data-path collective"
+        print(json.dumps(line), file=out, flush=True)
+    dist.destroy_process_group()
 
 
-def measure_decode(images, cpu_check=True):
+def measure_decode(images, cpu_check=True, device_index=0, shard=0):
     """`--workload decode`: N synthetic 512x512 images in batches of 64; per batch one noise layer drawn with
     p = [.4, .1, .2, .05, .1, .15] (train/latent_wm_pretrain.py:188) from numpy default_rng(7), then the EfficientNet-B1
     decoder; bits checked against the CPU oracle on a bounded sample."""
@@ -554,7 +579,7 @@ def measure_decode(images, cpu_check=True):
     from oracle import models_oracle as MO
     from oracle import noise_oracle as NO
 
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", device_index)
     torch.cuda.set_device(dev)
     lib = _lib.load()
     sd, _ = MO.make_decoder_state(BITS, seed=0)
@@ -565,8 +590,8 @@ def measure_decode(images, cpu_check=True):
     n_batches = max(1, images // bs)
     names = ["Jpeg", "CropandResize", "GaussianBlur", "GaussianNoise", "ColorJitter"]
     noiser = noise_layers.Noiser(names, NOISE_P, dev, rng=np.random.default_rng(7))
-    pool = [noise_layers.unit_noise((bs, 3, 512, 512), seed=7, offset=i * bs * 3 * 512 * 512 // 4, device=dev).clamp_(-3, 3) / 3
-            for i in range(4)]                                   # 4 x 201 MB of images: larger than L2
+    pool = [noise_layers.unit_noise((bs, 3, 512, 512), seed=7, offset=(4 * shard + i) * bs * 3 * 512 * 512 // 4, device=dev).clamp_(-3, 3) / 3
+            for i in range(4)]                                   # 4 x 201 MB of images: larger than L2 (a different slice per shard)
 
     def batch_step(i):
         img = noiser([pool[i % 4], None])[0]
