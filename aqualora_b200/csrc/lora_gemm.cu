@@ -15,7 +15,7 @@
 // Structure: cluster of 2 CTAs = one 256-row block, one CTA pair per SM pair, persistent over work items
 // (row block, group of column tiles); 320 threads per CTA:
 //   warps 0-7  epilogue          TMEM lane quadrant = warp % 4, column half = warp / 4:
-//                                tcgen05.ld -> bias -> bf16 -> padded SMEM transpose -> coalesced 16B global stores
+//                                tcgen05.ld -> bias -> bf16 -> staging tile (box of Y's tensor map) -> cp.async.bulk.tensor store
 //   warp 8     TMA producer      both CTAs: own A rows, own half of W / Dn / Up; bytes signalled on the LEADER's barrier
 //   warp 9     TMEM allocator; in the leader CTA one thread issues every tcgen05.mma of the pair
 #include <stdio.h>
@@ -544,7 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
       }
       if (!p.has_main) continue;
       for (int nt = nt_begin; nt < nt_end; ++nt) {
-        // ---------------- tile epilogue: accumulator -> (+bias) -> bf16 -> SMEM transpose -> coalesced stores ----------------
+        // ---------------- tile epilogue: accumulator -> (+bias) -> bf16 -> staging tile -> bulk-tensor (TMA) stores ----------------
         const int col0 = nt * BN + half * NC;   // first global column of this warp's slice
         const uint32_t buf = acc_iter & 1u;
         // this warp's NC bias values: global loads issued before the accumulator wait, parked in SMEM after the TMEM loads
