@@ -25,10 +25,13 @@ from .lora_modules import AquaLoRAAttnProcessor, LoRACompatibleConv, LoRACompati
 from .unet_ops import geglu, group_norm_nhwc, layer_norm, residual_add_bias
 
 
+LIBRARY_GLUE = False     # bench.py's PyTorch-eager GPU baseline sets this: every norm / activation stays a library op
+
+
 def _fused_glue(x: torch.Tensor, *params: torch.Tensor) -> bool:
     """The glue kernels (aq_group_norm_nhwc_*, aq_geglu_*) serve the frozen bf16 U-Net on the GPU; the fp32 CPU copy of this
     module tree that tests / the CPU baseline patch with the oracle keeps the library ops."""
-    return x.is_cuda and x.dtype == torch.bfloat16 and not any(p.requires_grad for p in params)
+    return not LIBRARY_GLUE and x.is_cuda and x.dtype == torch.bfloat16 and not any(p.requires_grad for p in params)
 
 
 def _norm_act(norm: nn.GroupNorm, x: torch.Tensor, silu: bool, add_bc: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -14,9 +14,11 @@ north-star path and have no weights offline: latents and text context are synthe
 Prints ONE JSON line (rank 0).  `value` = images/s with the batch already resident in HBM; `e2e` = the same step through the
 public API with the batch in pinned host memory (H2D copies and the D2H read of the loss inside the timed region).
 `roofline` describes the dominant kernel (aq::lora_gemm_kernel, the fused base-GEMM + LoRA contraction): algorithmic FLOPs
-per launch / CUDA-event duration per launch, measured live on the launching stream in instrumented steps that follow the
-timed region, against MEASURED_PEAKS.json.  `cpu_baseline` = the oracle's PyTorch-eager restatement of the reference step
-on the host cores (bounded sample: B=1).
+per launch / average launch duration, measured live and device-only -- the forward launches of one recorded step re-issued
+inside a CUDA graph, CUDA events around its replays -- against MEASURED_PEAKS.json, with the same kernels' CUPTI durations inside
+the training step beside it.  `cpu_baseline` = the oracle's PyTorch-eager restatement of the reference step on the host cores
+(bounded sample: B=1); `gpu_eager_baseline` = the reference's unfused op sequence on PyTorch eager (cuBLAS / cuDNN) on the same
+B200 at the same batch.
 """
 from __future__ import annotations
 
@@ -55,6 +57,12 @@ def synth_batch(B, cfg, seed, encoder_state=None):
     ctx = torch.randn(B, 77, cfg.cross_attention_dim, generator=g)
     msg = torch.randint(0, 2, (B, BITS), generator=g).float()
     return lat, noise, t, ctx, msg
+
+
+def workload_name(model: str, sample_size: int) -> str:
+    return (f"{'SD1.5' if model == 'sd15' else 'SD2.1-base'} PPFT step, LoRA rank {RANK_R} on the 192 unet_keys.json targets, "
+            f"{BITS}-bit messages, {sample_size * 8}x{sample_size * 8} ({sample_size}x{sample_size} latents), random-init U-Net, "
+            "VAE/text-encoder excluded")
 
 
 def peaks():
@@ -113,15 +121,27 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------------------------
-# roofline instrumentation: CUDA events around every aq_lora_linear_* launch, on the launching stream
+# roofline instrumentation: device-only.  One eagerly issued step is RECORDED (which launches, with which tensors), then each
+# kind of launch is re-issued back to back inside its own CUDA graph and the replays are timed with CUDA events: nothing but
+# this library's kernels runs between the two events, so a slow host cannot leak into the number (round 1's per-launch event
+# brackets did: 0.45 on the driver's box vs 0.63 on the builder's).  A torch.profiler (CUPTI) pass over graph-replayed steps
+# gives the same kernels' durations INSIDE the step as a cross-check.
 # --------------------------------------------------------------------------------------------------------------------
-class GemmProbe:
-    """Wraps ops.lora_linear_fwd (the fused kernel: forward, plain projection, and the backward's plain dX) and
-    ops.lora_linear_bwd (fused dX + 2 weight-grad launches) with CUDA events + algorithmic FLOP/byte counts."""
+def _fwd_counts(M, K, N, r, save_h):
+    flops = 2.0 * M * K * N + 2.0 * M * r * (K + N)
+    byts = 2.0 * M * (K + N) + 2.0 * (K * N + r * (K + N)) + (2.0 * M * r if (save_h and r) else 0.0)
+    return flops, byts
+
+
+class LaunchTape:
+    """Records ops.lora_linear_fwd / lora_linear_fwd_grouped / lora_linear_bwd calls (inputs are kept alive by reference, outputs
+    are re-allocated inside the graph's private pool at capture time)."""
+
+    KINDS = ("gemm_plain", "gemm_fwd", "bwd_dx_wgrad")
 
     def __init__(self, ops):
         self.ops = ops
-        self.records = []   # (kind, flops, bytes, ev0, ev1, shape)
+        self.records = []   # (kind, fn, args, kwargs, flops, bytes, shape, n_gemm_launches)
         self._fwd, self._bwd, self._grp = ops.lora_linear_fwd, ops.lora_linear_bwd, ops.lora_linear_fwd_grouped
 
     def __enter__(self):
@@ -131,46 +151,34 @@ class GemmProbe:
             M, K = x.shape
             N = w.shape[0]
             r = 0 if down is None else down.shape[0]
-            flops = 2.0 * M * K * N + 2.0 * M * r * (K + N)
-            byts = 2.0 * M * (K + N) + 2.0 * (K * N + r * (K + N)) + (2.0 * M * r if save_h else 0.0)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            res = self._fwd(x, w, bias, down, up, scale, tokens, save_h=save_h, out=out)
-            e1.record()
-            self.records.append(("gemm_fwd" if r else "gemm_plain", flops, byts, e0, e1, (M, K, N, r)))
-            return res
+            fl, by = _fwd_counts(M, K, N, r, save_h)
+            self.records.append(("gemm_fwd" if r else "gemm_plain", self._fwd, (x, w, bias, down, up, scale, tokens), {"save_h": save_h},
+                                 fl, by, (M, K, N, r), 1))
+            return self._fwd(x, w, bias, down, up, scale, tokens, save_h=save_h, out=out)
 
         def bwd(gy, x, w_t, down_t, up_t, scale, h, g_down, g_up, g_scale, tokens):
             M, N = gy.shape      # N = dout
             K = x.shape[1]       # K = din
             r = h.shape[1]
             dx = w_t is not None
-            flops = (2.0 * M * K * N if dx else 0.0) + 2.0 * M * r * N + (2.0 * M * r * K if dx else 0.0) + 2.0 * M * r * (K + N)
-            byts = 2.0 * M * (N + K + r) + (2.0 * M * K if dx else 0.0) + 2.0 * (K * N + r * (K + N)) + 8.0 * r * (K + N)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            res = self._bwd(gy, x, w_t, down_t, up_t, scale, h, g_down, g_up, g_scale, tokens)
-            e1.record()
-            self.records.append(("bwd_dx_wgrad", flops, byts, e0, e1, (M, K, N, r)))
-            return res
+            fl = (2.0 * M * K * N if dx else 0.0) + 2.0 * M * r * N + (2.0 * M * r * K if dx else 0.0) + 2.0 * M * r * (K + N)
+            by = 2.0 * M * (N + K + r) + (2.0 * M * K if dx else 0.0) + 2.0 * (K * N + r * (K + N)) + 8.0 * r * (K + N)
+            self.records.append(("bwd_dx_wgrad", self._bwd, (gy, x, w_t, down_t, up_t, scale, h, g_down, g_up, g_scale, tokens), {},
+                                 fl, by, (M, K, N, r), 1))
+            return self._bwd(gy, x, w_t, down_t, up_t, scale, h, g_down, g_up, g_scale, tokens)
 
         def grouped(x, projections, scale, tokens, save_h=False):
             # one launch carrying several projections of the same rows: the algorithmic counts are the per-projection sums
             # (x is counted once per projection, as the reference's separate module calls read it)
             M, K = x.shape
             r = 0 if projections[0][2] is None else projections[0][2].shape[0]
-            flops = byts = 0.0
+            fl = by = 0.0
             for w, _b, _d, _u in projections:
-                N = w.shape[0]
-                flops += 2.0 * M * K * N + 2.0 * M * r * (K + N)
-                byts += 2.0 * M * (K + N) + 2.0 * (K * N + r * (K + N)) + (2.0 * M * r if (save_h and r) else 0.0)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            res = self._grp(x, projections, scale, tokens, save_h=save_h)
-            e1.record()
-            self.records.append(("gemm_fwd" if r else "gemm_plain", flops, byts, e0, e1,
-                                 (M, K, sum(w.shape[0] for w, *_ in projections), r)))
-            return res
+                f1, b1 = _fwd_counts(M, K, w.shape[0], r, save_h)
+                fl += f1; by += b1
+            self.records.append(("gemm_fwd" if r else "gemm_plain", self._grp, (x, list(projections), scale, tokens), {"save_h": save_h},
+                                 fl, by, (M, K, sum(w.shape[0] for w, *_ in projections), r), 1))
+            return self._grp(x, projections, scale, tokens, save_h=save_h)
 
         ops.lora_linear_fwd, ops.lora_linear_bwd, ops.lora_linear_fwd_grouped = fwd, bwd, grouped
         return self
@@ -178,34 +186,159 @@ class GemmProbe:
     def __exit__(self, *exc):
         self.ops.lora_linear_fwd, self.ops.lora_linear_bwd, self.ops.lora_linear_fwd_grouped = self._fwd, self._bwd, self._grp
 
-    def summary(self, steps: int):
-        """Per kind and per shape totals.  Each launch is bracketed by its own pair of CUDA events; a bracket also contains
-        any time the GPU waited for the host to issue that launch, so one host hiccup (GC, allocator) can add milliseconds
-        to a 15 us kernel.  Per shape we therefore report mean AND median, and the kind totals use median x count
-        (`ms_per_step`), with the raw mean-based total kept beside it (`ms_per_step_mean`)."""
+    def _graph(self, recs):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for rec in recs:                       # warm-up on the capture stream (allocator, attribute opt-ins)
+                rec[1](*rec[2], **rec[3])
+        torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        per_shape = {}
-        for kind, fl, by, e0, e1, shape in self.records:
-            s = per_shape.setdefault((kind,) + shape, {"fl": fl, "by": by, "ms": []})
-            s["ms"].append(e0.elapsed_time(e1))
-        agg = {}
-        shapes = []
-        for k, v in sorted(per_shape.items()):
-            ms = sorted(v["ms"])
-            n = len(ms)
-            med = ms[n // 2] if n % 2 else 0.5 * (ms[n // 2 - 1] + ms[n // 2])
-            mean = sum(ms) / n
-            a = agg.setdefault(k[0], [0.0, 0.0, 0.0, 0.0, 0])
-            a[0] += v["fl"] * n; a[1] += v["by"] * n; a[2] += med * n; a[3] += mean * n; a[4] += n
-            shapes.append({"kind": k[0], "M": k[1], "K": k[2], "N": k[3], "r": k[4], "calls_per_step": n // steps,
-                           "us_per_call": med * 1e3, "us_per_call_mean": mean * 1e3, "us_min": ms[0] * 1e3, "us_max": ms[-1] * 1e3,
-                           "tflops": v["fl"] / med / 1e9})
-        out = {}
-        for kind, (fl, by, ms_med, ms_mean, n) in agg.items():
-            out[kind] = {"launch_groups_per_step": n // steps, "ms_per_step": ms_med / steps, "ms_per_step_mean": ms_mean / steps,
-                         "tflops": fl / ms_med / 1e9 if ms_med else 0.0, "gbs": by / ms_med / 1e6 if ms_med else 0.0,
-                         "flops_per_step": fl / steps, "bytes_per_step": by / steps}
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for rec in recs:
+                rec[1](*rec[2], **rec[3])
+        return g
+
+    @staticmethod
+    def _time(g, min_ms=400.0, max_reps=400):
+        """ms per replay: CUDA events on the launching stream around back-to-back replays (>= 0.4 s: sustained clocks)."""
+        for _ in range(2):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record()
+        torch.cuda.synchronize()
+        reps = int(min(max_reps, max(5, min_ms / max(e0.elapsed_time(e1), 1e-3))))
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, reps
+
+    def summary(self, per_shape: bool = False):
+        """{kind: launches, ms per step, TFLOP/s, GB/s} from graph replays that hold only that kind's launches (each replay streams
+        every launch's real operands: 12 GB per forward replay, far beyond the 126 MB L2).  per_shape: one graph per (kind, shape)
+        over all of its launches of the step -- shapes with a single launch per step then run L2-warm, noted in the table."""
+        out, shapes = {}, []
+        for kind in self.KINDS:
+            recs = [r for r in self.records if r[0] == kind]
+            if not recs:
+                continue
+            g = self._graph(recs)
+            ms, reps = self._time(g)
+            fl, by = sum(r[4] for r in recs), sum(r[5] for r in recs)
+            out[kind] = {"launch_groups_per_step": len(recs), "ms_per_step": ms, "replays_timed": reps, "tflops": fl / ms / 1e9,
+                         "gbs": by / ms / 1e6, "flops_per_step": fl, "bytes_per_step": by}
+            del g
+            if per_shape:
+                by_shape = {}
+                for r in recs:
+                    by_shape.setdefault(r[6], []).append(r)
+                for shape, rs in sorted(by_shape.items()):
+                    g = self._graph(rs)
+                    ms_s, _ = self._time(g, min_ms=60.0)
+                    shapes.append({"kind": kind, "M": shape[0], "K": shape[1], "N": shape[2], "r": shape[3], "calls_per_step": len(rs),
+                                   "us_per_call": ms_s / len(rs) * 1e3, "tflops": sum(r[4] for r in rs) / ms_s / 1e9,
+                                   "l2_warm": sum(r[5] for r in rs) < 2.5e8})
+                    del g
         return out, shapes
+
+
+def cupti_in_step(step_fn, tape_records, steps=2):
+    """Durations of this library's GEMM kernels INSIDE graph-replayed steps, from CUPTI activity records (torch.profiler): the
+    i-th `lora_gemm_kernel` of a step is the i-th taped launch (same issue order), which labels it plain / fused-forward / dX."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(steps):
+                step_fn()
+            torch.cuda.synchronize()
+        evs = [e for e in prof.events() if getattr(e, "device_type", None) is not None and "cuda" in str(e.device_type).lower()]
+        evs.sort(key=lambda e: e.time_range.start)
+        gemm = [e for e in evs if "lora_gemm_kernel" in e.name]
+        wgrad = [e for e in evs if "lora_wgrad_kernel" in e.name]
+        total_us = sum(e.device_time for e in evs if "Memcpy" not in e.name and "Memset" not in e.name)
+        n = len(tape_records)
+        if n == 0 or len(gemm) != n * steps:
+            return {"error": f"{len(gemm)} lora_gemm_kernel records for {n} taped launches x {steps} steps"}
+        agg = {}
+        for i, e in enumerate(gemm):
+            agg[tape_records[i % n][0]] = agg.get(tape_records[i % n][0], 0.0) + e.device_time
+        out = {k: round(v / steps / 1e3, 3) for k, v in agg.items()}          # ms per step
+        out["wgrad_ms"] = round(sum(e.device_time for e in wgrad) / steps / 1e3, 3)
+        out["all_kernels_ms"] = round(total_us / steps / 1e3, 3)
+        return out
+    except Exception as e:  # the cross-check must never cost the measurement
+        return {"error": repr(e)[:200]}
+
+
+def gpu_eager_baseline(model, B, dev, steps=5, warmup=3):
+    """The bar SURVEY.md 0.1 names, on the SAME B200: the reference's UNFUSED op sequence (utils/lora_modules.py:9-62 restated in
+    oracle/: Linear, down, diag_embed + bmm, up, add -- each its own cuBLAS call) on PyTorch-eager with library GroupNorm / LayerNorm /
+    GELU, bf16 autocast over fp32 LoRA master weights as `accelerate --mixed_precision bf16` runs it (train/ppft_train.py:569-581),
+    clip_grad_norm_ + torch.optim.AdamW, same batch size.  None of this repository's kernels is on this path."""
+    from aqualora_b200 import lora_modules, ppft
+    from aqualora_b200 import unet as unet_mod
+    from aqualora_b200.unet import UNetConfig, lora_target_keys
+    from oracle import lora_oracle as O
+    from oracle.patch import patch_with_oracle
+
+    cfg = UNetConfig.sd15(64) if model == "sd15" else UNetConfig.sd21(96)
+    unet_mod.LIBRARY_GLUE = True
+    try:
+        unet = ppft.build_unet(cfg, dev, seed=0)
+        layers = lora_modules.inject_lora(unet, lora_target_keys(unet), RANK_R)
+        g = torch.Generator().manual_seed(1)
+        params = []
+        for _, _, l in layers:
+            l.up.weight.data.copy_(torch.randn(l.up.weight.shape, generator=g) * 0.02)
+            for p in (l.down.weight, l.up.weight):
+                p.requires_grad_(True)
+                params.append(p)
+        patch_with_oracle(unet)
+        emb = O.mapper_init(BITS, RANK_R, generator=torch.Generator().manual_seed(5)).to(dev).requires_grad_(True)
+        opt = torch.optim.AdamW([{"params": params}, {"params": [emb]}], lr=1e-4, weight_decay=1e-2)
+        ac = ppft.scaled_linear_alphas_cumprod().to(dev)
+        v_pred = model != "sd15"
+        batches = [tuple(x.to(dev) for x in synth_batch(B, cfg, 1234 + i)) for i in range(2)]
+        bf = torch.bfloat16
+
+        def step(i):
+            lat, noise, t, ctx, msg = batches[i % 2]
+            with torch.autocast("cuda", dtype=bf):
+                scale = O.mapper_forward(msg, emb).to(bf)
+                wm = (torch.randn_like(lat) * 0.004).to(bf)           # stands in for the (no_grad) encoder residual
+                noisy = ppft.add_noise(ac, lat.to(bf), noise.to(bf), t)
+                noisy_wm = ppft.add_noise(ac, lat.to(bf) + wm, noise.to(bf), t)
+                clean = unet(noisy, t, ctx.to(bf), cross_attention_kwargs={"scale": torch.zeros_like(scale)}).sample.detach()
+                pred = unet(noisy_wm, t, ctx.to(bf), cross_attention_kwargs={"scale": scale}).sample
+                if v_pred:
+                    pred = ppft.velocity_to_epsilon(ac, pred, noisy_wm, t)
+                    clean = ppft.velocity_to_epsilon(ac, clean, noisy, t)
+                loss = torch.nn.functional.mse_loss(pred.float(), clean.float())
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            opt.zero_grad()
+            return loss
+
+        for i in range(warmup):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": round(B / ms * 1e3, 3), "unit": UNIT, "ms_per_step": round(ms, 3), "per_gpu_batch": B, "steps": steps,
+                "what": "reference op sequence (unfused LoRA: Linear + down + diag_embed/bmm + up + add) on PyTorch eager, cuBLAS / cuDNN, "
+                        "bf16 autocast, library norms, torch AdamW; same B200, same batch, no CUDA graph"}
+    finally:
+        unet_mod.LIBRARY_GLUE = False
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -358,39 +491,57 @@ def run_cuda(args):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms = ms2.item()
 
-    # ---- roofline pass (instrumented, after the timed regions) ----------------------------------------------------
+    # ---- roofline pass (after the timed regions; rank 0 only, no collective inside) ---------------------------------
     roof = None
     extra = {}
-    probe_steps = 3
-    if rank != 0:
-        # every rank runs the instrumented steps: each step holds the gradient all-reduce, so rank 0 alone would wait forever
-        for i in range(probe_steps):
-            eager_step(*resident[i % n_pool])
     if rank == 0:
         pk = peaks()
-        with GemmProbe(ops) as probe:
-            for i in range(probe_steps):
-                eager_step(*resident[i % n_pool])      # per-launch CUDA events need eager issue
-            kinds, shapes = probe.summary(probe_steps)
+        with LaunchTape(ops) as tape:
+            fwd_bwd_from_device(*resident[0])          # ONE eagerly issued forward + backward, recorded (no optimizer step)
+        torch.cuda.synchronize()
+        kinds, shapes = tape.summary(per_shape=bool(args.shapes_out))
+        in_step = None
+        if graph_state["on"]:
+            in_step = cupti_in_step(lambda: trainer._graph.replay(), tape.records)
+        trainer.state.grad.zero_()                     # the probes accumulated weight gradients that belong to no step
+        if trainer.g_scale is not None:
+            trainer.g_scale.zero_()
         dom = kinds.get("gemm_fwd")
         if dom:
-            peak = pk["bf16_tflops_sustained"]     # the kernel is timed inside a long step
+            peak = pk["bf16_tflops_sustained"]         # back-to-back replays for >= 0.4 s: the power-capped regime
+            n_l = dom["launch_groups_per_step"]
             roof = {"bound": "tensor", "kernel": "aq::lora_gemm_kernel (fused base GEMM + watermark LoRA, forward launches)",
                     "achieved": round(dom["tflops"], 1), "peak": peak, "unit": "TFLOP/s", "frac": round(dom["tflops"] / peak, 4),
                     "peak_kind": f"bf16_tflops_sustained of {pk['source']}",
                     "traffic": (GEMM_FWD_DRAM_TRAFFIC_PER_LAUNCH if args.model == "sd15" and B == PER_GPU_BATCH else None),
-                    "traffic_note": "DRAM bytes (read + write) per forward launch, averaged over the 129 launches of a step: ncu "
+                    "traffic_note": "DRAM bytes (read + write) per forward launch, averaged over the launches of a step: ncu "
                                     "dram__bytes_* of every forward shape, cold caches (profiles/r01_gemm_dram_traffic_v13.txt); "
                                     "algorithmic bytes per launch = bytes_per_step / launches (outputs largely stay in the 126 MB L2)",
-                    "launches_per_step": dom["launch_groups_per_step"], "kernel_ms_per_step": round(dom["ms_per_step"], 3),
+                    "launches_per_step": n_l, "kernel_ms_per_step": round(dom["ms_per_step"], 3),
+                    "avg_launch_us": round(dom["ms_per_step"] / n_l * 1e3, 2), "flops_per_launch": dom["flops_per_step"] / n_l,
                     "flops_per_step": dom["flops_per_step"], "frac_of_burst": round(dom["tflops"] / pk["bf16_tflops"], 4),
-                    "kernel_ms_per_step_mean": round(dom["ms_per_step_mean"], 3),
-                    "method": "CUDA events around each launch on the launching stream, 3 instrumented steps after the timed region; "
-                              "per shape median x launch count (a bracket also holds host-issue gaps; the mean-based total is kernel_ms_per_step_mean)"}
-        extra = {"kernel_groups": {k: {kk: (round(vv, 3) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kinds.items()}}
+                    "in_step_cupti_ms": None if not in_step else in_step.get("gemm_fwd"),
+                    "frac_in_step_cupti": (round(dom["flops_per_step"] / in_step["gemm_fwd"] / 1e9 / peak, 4)
+                                           if in_step and in_step.get("gemm_fwd") else None),
+                    "method": "device-only: the forward launches of one recorded step (real shapes, operands, pointers) re-issued back to "
+                              f"back in a CUDA graph; CUDA events on the launching stream around {dom['replays_timed']} replays (kernel-to-kernel "
+                              "gaps included, no host in the timed region; every replay streams 12 GB of operands, L2 126 MB); "
+                              "in_step_cupti_ms = the same kernels' summed CUPTI durations inside graph-replayed training steps"}
+        extra = {"kernel_groups": {k: {kk: (round(vv, 3) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kinds.items()},
+                 "in_step_cupti": in_step}
         if args.shapes_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.shapes_out)), exist_ok=True)
-            json.dump({"kinds": kinds, "shapes": shapes}, open(args.shapes_out, "w"), indent=1)
+            json.dump({"kinds": kinds, "shapes": shapes, "in_step_cupti": in_step}, open(args.shapes_out, "w"), indent=1)
+        del tape
+
+    # ---- the same-box GPU baseline: reference op sequence on PyTorch eager (rank 0, N = 1 only) --------------------
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
+        try:
+            eager = gpu_eager_baseline(args.model, B, dev)
+        except Exception as e:  # must not cost the headline
+            eager = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------------
     cpu = None
@@ -404,9 +555,7 @@ def run_cuda(args):
             "metric": METRIC, "value": round(gb / ms_step * 1e3, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{'SD1.5' if args.model == 'sd15' else 'SD2.1-base'} PPFT step, LoRA rank {RANK_R} on the 192 "
-                                   f"unet_keys.json targets, {BITS}-bit messages, {cfg.sample_size * 8}x{cfg.sample_size * 8} "
-                                   f"({cfg.sample_size}x{cfg.sample_size} latents), random-init U-Net, VAE/text-encoder excluded",
+            "config": {"workload": workload_name(args.model, cfg.sample_size),
                        "per_gpu_batch": B, "global_batch": gb, "parallelism": f"dp{world}",
                        "l2": "each step streams > 126 MB (1.7 GB bf16 U-Net weights + activations), inputs rotate over 4 batches",
                        "cuda_graph": ("forward + backward replayed as one CUDA graph; all-reduce, clip and AdamW issued eagerly"
@@ -418,6 +567,7 @@ def run_cuda(args):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager,
         }
         line.update(extra)
         if world == 1 and not args.no_secondary:
@@ -515,11 +665,13 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": res["steps_done"],
             "warmup": args.warmup, "ms_per_step": round(ms_step, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SD1.5 PPFT step, LoRA rank 64 on the 192 unet_keys.json targets, 48-bit messages, 512x512 (64x64 "
-                                   "latents), random-init U-Net, VAE/text-encoder excluded" if args.model == "sd15" else "SD2.1-base PPFT step",
-                       "per_gpu_batch": 1, "global_batch": 1, "parallelism": "cpu",
-                       "note": "reference op sequence (oracle port of utils/lora_modules.py on a PyTorch-eager U-Net) on host cores; "
-                               "bounded sample B=1 per step"},
+            "config": {"workload": workload_name(args.model, 64 if args.model == "sd15" else 96),
+                       "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus, "parallelism": f"dp{args.gpus}",
+                       "reference_sample": "each timed step is a bounded sample of that workload: ONE image (B = 1) through the full-size "
+                                           "step on the host cores, fp32 (the reference's CPU precision); images/s = images done / time",
+                       "note": "reference op sequence = the reference's unfused LoRA forwards (oracle/lora_oracle.py, bit-identical to "
+                               "utils/lora_modules.py on tests/golden) on the U-Net harness that tests/test_unet_golden.py pins to the "
+                               "reference's vendored scripts/lib/original_unet.py; /root/reference itself does not exist on the GPU box"},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": round(time.time() - t0, 1)}
@@ -669,6 +821,7 @@ def main():
     ap.add_argument("--model", default="sd15", choices=["sd15", "sd21"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager (unfused reference op sequence) GPU baseline")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly instead of replaying the captured forward + backward")
     ap.add_argument("--budget", type=float, default=240.0, help="--impl reference: stop after this many seconds of timed CPU steps")
     ap.add_argument("--shapes-out", default=None, help="write the per-shape kernel table (JSON) here")

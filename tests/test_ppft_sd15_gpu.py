@@ -1,0 +1,93 @@
+"""ONE full-width SD1.5 PPFT step body (rank 64) on the B200 against the REFERENCE: tests/golden/unet_lora_step.pt was
+produced by the reference's vendored U-Net + the reference's own utils/lora_modules.py forwards in fp32 (tools/gen_golden.py,
+train/ppft_train.py:1026-1058).  The CUDA path runs the same procedural weights in bf16 (the BASELINE precision).
+
+Tolerances (bf16 activations through ~700 layers vs fp32; stated per quantity, elementwise where the quantity is a tensor):
+  model_pred / clean_pred : |got - want| <= 4e-2 * rms(want) + 4e-2 * |want|   for >= 99.9 % of the elements,
+                            and relative Frobenius error <= 2e-2
+  loss                    : 5 % relative (a difference of two bf16 predictions)
+  d(scale), LoRA grads    : per-tensor relative Frobenius error <= 8e-2 and cosine >= 0.995 on the stored tensors;
+                            every one of the 384 per-tensor gradient norms within 10 %
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _fro(got, want):
+    want = want.float().cpu()
+    return ((got.float().cpu() - want).norm() / (want.norm() + 1e-30)).item()
+
+
+def _cos(got, want):
+    return torch.nn.functional.cosine_similarity(got.float().cpu().reshape(-1), want.float().cpu().reshape(-1), dim=0).item()
+
+
+def _elementwise_ok(got, want, frac=0.999, rel=4e-2):
+    want = want.float().cpu()
+    got = got.float().cpu()
+    rms = want.pow(2).mean().sqrt()
+    ok = (got - want).abs() <= rel * rms + rel * want.abs()
+    return ok.float().mean().item() >= frac, ok.float().mean().item()
+
+
+def test_sd15_ppft_step_matches_reference(cuda_device, golden_dir):
+    from aqualora_b200 import lora_modules, ppft
+    from aqualora_b200.unet import UNet2DConditionModel, UNetConfig
+    from procedural import load_procedural, procedural_tensor
+
+    dev = cuda_device
+    gold = torch.load(os.path.join(golden_dir, "unet_lora_step.pt"), weights_only=False)
+    r = gold["rank"]
+    with torch.device("meta"):
+        unet = UNet2DConditionModel(UNetConfig.sd15(64))
+    load_procedural(unet, seed=gold["unet_seed"])
+    unet = unet.to(dev, torch.bfloat16).to(memory_format=torch.channels_last).eval()
+    unet.requires_grad_(False)
+    emb = torch.zeros(48, r)
+    tr = ppft.PPFTTrainer(unet, ppft.PPFTConfig(rank=r), emb, dev)
+    for key, _, lora in tr.lora_layers:
+        with torch.no_grad():
+            lora.down.weight.copy_(procedural_tensor(key + ".lora_layer.down.weight", tuple(lora.down.weight.shape), gold["lora_seed"]).to(dev))
+            lora.up.weight.copy_((procedural_tensor(key + ".lora_layer.up.weight", tuple(lora.up.weight.shape), gold["lora_seed"]) * gold["up_gain"]).to(dev))
+    tr.refresh_operands()
+
+    bf = lambda x: x.to(dev, torch.bfloat16)
+    scale = gold["scale"].to(dev).to(torch.bfloat16).float()        # `.to(dtype=weight_dtype)`, train/ppft_train.py:990
+    g_scale = torch.zeros_like(scale)
+    scale.requires_grad_(True)
+    scale._aq_grad = g_scale
+    t = gold["t"].to(dev)
+    with torch.no_grad(), lora_modules.lora_disabled():
+        clean = unet(bf(gold["x_clean"]), t, bf(gold["ctx"])).sample
+    pred = unet(bf(gold["x_wm"]), t, bf(gold["ctx"]), cross_attention_kwargs={"scale": scale}).sample
+    loss = torch.nn.functional.mse_loss(pred.float(), clean.float(), reduction="mean")
+    loss.backward()
+    torch.cuda.synchronize()
+
+    report = {"clean_fro": _fro(clean, gold["clean_pred"]), "pred_fro": _fro(pred, gold["model_pred"]),
+              "loss": (float(loss), gold["loss"]), "g_scale_fro": _fro(g_scale, gold["g_scale"]), "g_scale_cos": _cos(g_scale, gold["g_scale"])}
+    ok_c, frac_c = _elementwise_ok(clean, gold["clean_pred"])
+    ok_p, frac_p = _elementwise_ok(pred.detach(), gold["model_pred"])
+    report["elementwise_frac"] = (frac_c, frac_p)
+    by_key = {k: l for k, _, l in tr.lora_layers}
+    worst_norm, worst_fro, worst_cos = 0.0, 0.0, 1.0
+    for name, want in gold["grad_norms"].items():
+        key, which = name.rsplit(".", 1)
+        got = float(getattr(by_key[key], which).weight._aq_grad.norm())
+        worst_norm = max(worst_norm, abs(got / want - 1))
+    for name, want in gold["grads"].items():
+        key, which = name.rsplit(".", 1)
+        got = getattr(by_key[key], which).weight._aq_grad.view(want.shape)
+        worst_fro = max(worst_fro, _fro(got, want))
+        worst_cos = min(worst_cos, _cos(got, want))
+    report.update({"worst_grad_norm_dev": worst_norm, "worst_grad_fro": worst_fro, "worst_grad_cos": worst_cos})
+    print("sd15 step vs reference:", report)
+    assert report["clean_fro"] <= 2e-2 and report["pred_fro"] <= 2e-2, report
+    assert ok_c and ok_p, report
+    assert abs(float(loss) / gold["loss"] - 1) <= 5e-2, report
+    assert report["g_scale_fro"] <= 8e-2 and report["g_scale_cos"] >= 0.995, report
+    assert worst_norm <= 0.10 and worst_fro <= 8e-2 and worst_cos >= 0.995, report

@@ -273,12 +273,132 @@ def gen_pretrain():
     torch.save(out, OUT / "pretrain_small.pt")
 
 
+def _ref_unet_module():
+    return _load("ref_original_unet", REF / "scripts" / "lib" / "original_unet.py")
+
+
+def _unet_cfgs():
+    return {
+        "sd15": dict(sample_size=64, attention_head_dim=8, cross_attention_dim=768),
+        "sd21": dict(sample_size=96, attention_head_dim=[5, 10, 20, 20], cross_attention_dim=1024, use_linear_projection=True,
+                     upcast_attention=True),
+    }
+
+
+def gen_unet():
+    """The reference's vendored U-Net (scripts/lib/original_unet.py:1311-1585, full SD1.5 / SD2.1 widths) on procedurally
+    generated weights (tests/procedural.py: seeded per state-dict key, so the 3.4 GB state dict is never stored) at small latent
+    sizes.  tests/test_unet_golden.py loads the SAME tensors into aqualora_b200.unet and compares outputs."""
+    sys.path.insert(0, str(OUT.parent))
+    from procedural import load_procedural
+
+    m = _ref_unet_module()
+    g = torch.Generator().manual_seed(4242)
+    out = {}
+    for name, kw in _unet_cfgs().items():
+        with torch.device("meta"):
+            unet = m.UNet2DConditionModel(**kw)
+        load_procedural(unet, seed=0)
+        unet.eval()
+        cases = []
+        specs = [(2, 16, 16, [17, 803]), (1, 20, 12, [500])] if name == "sd15" else [(1, 24, 24, [999])]
+        for (B, H, W, ts) in specs:
+            x = torch.randn(B, 4, H, W, generator=g)
+            ctx = torch.randn(B, 77, kw["cross_attention_dim"], generator=g)
+            t = torch.tensor(ts)
+            with torch.no_grad():
+                y = unet(x, t, ctx).sample
+            cases.append({"x": x, "t": t, "ctx": ctx, "y": y.clone()})
+        out[name] = {"kwargs": kw, "seed": 0, "n_params": sum(p.numel() for p in unet.parameters()), "cases": cases}
+        del unet
+    torch.save(out, OUT / "unet_reference.pt")
+
+
+def gen_unet_lora_step(dml, ref_lora):
+    """One PPFT step body (train/ppft_train.py:1026-1058: clean forward with an all-zero scale, watermarked forward with the
+    mapped scale, MSE, backward) on the reference's vendored SD1.5 U-Net whose 192 unet_keys.json targets were swapped for
+    LoRACompatible{Linear,Conv} containers and monkey-patched with the reference's own utils/lora_modules.py forwards
+    (train/ppft_train.py:681-689).  The vendored U-Net calls its projections without `scale`, so the per-call tensor scale that
+    diffusers threads through cross_attention_kwargs is bound into each patched forward instead.  fp32, CPU, rank 64."""
+    import types as _t
+
+    sys.path.insert(0, str(OUT.parent))
+    from procedural import load_procedural, procedural_tensor
+
+    m = _ref_unet_module()
+    kw = _unet_cfgs()["sd15"]
+    with torch.device("meta"):
+        unet = m.UNet2DConditionModel(**kw)
+    load_procedural(unet, seed=0)
+    unet.requires_grad_(False)
+    keys = json.load(open(REF / "utils" / "unet_keys.json"))
+    r, up_gain = 64, 0.2
+    current = {"scale": 1.0}
+    loras = []
+    for key in keys:
+        parts = key.split(".")
+        parent = unet
+        for sub in parts[:-1]:
+            parent = getattr(parent, sub)
+        old = getattr(parent, parts[-1]) if not parts[-1].isdigit() else parent[int(parts[-1])]
+        if isinstance(old, nn.Conv2d):
+            new = dml.LoRACompatibleConv(old.in_channels, old.out_channels, kernel_size=1)
+            lora = dml.LoRAConv2dLayer(old.in_channels, old.out_channels, rank=r)
+            lin_fwd, lora_fwd = ref_lora.CustomLoRACompatibleConvforward, ref_lora.CustomLoRAConv2dLayerforward
+            shp_d, shp_u = (r, old.in_channels, 1, 1), (old.out_channels, r, 1, 1)
+        else:
+            new = dml.LoRACompatibleLinear(old.in_features, old.out_features, bias=old.bias is not None)
+            lora = dml.LoRALinearLayer(old.in_features, old.out_features, rank=r)
+            lin_fwd, lora_fwd = ref_lora.CustomLoRACompatibleLinearforward, ref_lora.CustomLoRALinearLayerforward
+            shp_d, shp_u = (r, old.in_features), (old.out_features, r)
+        new.weight, new.bias = old.weight, old.bias
+        with torch.no_grad():
+            lora.down.weight.copy_(procedural_tensor(key + ".lora_layer.down.weight", shp_d, 1))
+            lora.up.weight.copy_(procedural_tensor(key + ".lora_layer.up.weight", shp_u, 1) * up_gain)
+        new.lora_layer = lora
+        lora.forward = _t.MethodType(lora_fwd, lora)
+        new.forward = (lambda f, mod: (lambda hs: f(mod, hs, current["scale"])))(lin_fwd, new)
+        if parts[-1].isdigit():
+            parent[int(parts[-1])] = new
+        else:
+            setattr(parent, parts[-1], new)
+        loras.append((key, lora))
+    g = torch.Generator().manual_seed(777)
+    B, H, W = 2, 16, 16
+    x_clean = torch.randn(B, 4, H, W, generator=g)
+    x_wm = x_clean + 0.05 * torch.randn(B, 4, H, W, generator=g)
+    ctx = torch.randn(B, 77, 768, generator=g)
+    t = torch.tensor([123, 871])
+    scale = (1 + 0.5 * torch.randn(B, r, generator=g)).requires_grad_(True)
+    current["scale"] = torch.zeros_like(scale)
+    clean = unet(x_clean, t, ctx).sample.detach()
+    current["scale"] = scale
+    pred = unet(x_wm, t, ctx).sample
+    loss = torch.nn.functional.mse_loss(pred.float(), clean.float(), reduction="mean")
+    loss.backward()
+    keep = {keys[0], keys[5], keys[60], keys[96], keys[107], keys[191]}
+    grads, norms = {}, {}
+    for key, lora in loras:
+        for which, p in (("down", lora.down.weight), ("up", lora.up.weight)):
+            norms[f"{key}.{which}"] = float(p.grad.norm())
+            if key in keep:
+                grads[f"{key}.{which}"] = p.grad.clone()
+    torch.save({"rank": r, "up_gain": up_gain, "lora_seed": 1, "unet_seed": 0, "x_clean": x_clean, "x_wm": x_wm, "ctx": ctx, "t": t,
+                "scale": scale.detach().clone(), "clean_pred": clean.clone(), "model_pred": pred.detach().clone(),
+                "loss": float(loss), "g_scale": scale.grad.clone(), "grad_norms": norms, "grads": grads}, OUT / "unet_lora_step.pt")
+
+
 def main():
     if '--pretrain-only' in sys.argv:
         gen_pretrain()
         return
     if '--create-wm-lora-only' in sys.argv:
         gen_create_wm_lora()
+        return
+    if '--unet-only' in sys.argv:
+        dml = _stub_modules()
+        gen_unet()
+        gen_unet_lora_step(dml, _load("ref_lora_modules", REF / "utils" / "lora_modules.py"))
         return
     OUT.mkdir(parents=True, exist_ok=True)
     dml = _stub_modules()
@@ -290,6 +410,8 @@ def main():
     gen_keys()
     gen_create_wm_lora()
     gen_pretrain()
+    gen_unet()
+    gen_unet_lora_step(dml, ref_lora)
     for f in sorted(OUT.glob("*")):
         print(f.name, f.stat().st_size)
 
