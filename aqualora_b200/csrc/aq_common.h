@@ -33,6 +33,20 @@ int fail(int code, const char* fmt, ...);
     if (!(cond)) return ::aq::fail(code, __VA_ARGS__); \
   } while (0)
 
+// Opt a kernel into more than 48 KiB of dynamic shared memory ONCE PER DEVICE (the attribute is per device: a process that
+// touches a second GPU must opt in again there).  `static` inside the macro gives every call site (= every kernel instantiation)
+// its own flag array; the race between threads is benign (the call is idempotent).
+#define AQ_OPT_IN_SMEM(kernel, bytes)                                                                        \
+  do {                                                                                                       \
+    static bool _aq_done[64] = {};                                                                           \
+    int _aq_dev = 0;                                                                                         \
+    AQ_CHECK_CUDA(cudaGetDevice(&_aq_dev));                                                                  \
+    if (_aq_dev < 0 || _aq_dev >= 64 || !_aq_done[_aq_dev]) {                                                \
+      AQ_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      if (_aq_dev >= 0 && _aq_dev < 64) _aq_done[_aq_dev] = true;                                            \
+    }                                                                                                        \
+  } while (0)
+
 enum TmaSwizzle { kSwzNone = 0, kSwz32 = 1, kSwz64 = 2, kSwz128 = 3 };
 
 // Encode a tiled bf16 / fp32 tensor map (rank 2 or 3).  dims/box are innermost-first; strides are in

@@ -422,11 +422,7 @@ static int launch_depthwise_tma_t(const float* x, const float* w, const float* b
   const int sms = sm_count();
   if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
   const int grid = (int)(items < sms ? items : sms);
-  static bool attr_set = false;
-  if (!attr_set) {
-    AQ_CHECK_CUDA(cudaFuncSetAttribute(depthwise_tma_kernel<KS, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  AQ_OPT_IN_SMEM((depthwise_tma_kernel<KS, TW>), 227 * 1024);
   depthwise_tma_kernel<KS, TW><<<grid, kDtThreads, smem, st>>>(p);
   AQ_LAUNCHED();
   return AQ_OK;

@@ -405,11 +405,7 @@ int launch_pointwise_tc(const PwTcArgs& a, cudaStream_t st) {
   if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
   const long long items = (long long)p.num_m_tiles * p.num_n_tiles;
   const int grid = (int)(items < sms ? items : sms);
-  static bool attr_set = false;
-  if (!attr_set) {
-    AQ_CHECK_CUDA(cudaFuncSetAttribute(pointwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
-  }
+  AQ_OPT_IN_SMEM((pointwise_tc_kernel), 232448);
   pointwise_tc_kernel<<<grid, kPwThreads, smem, st>>>(p);
   AQ_LAUNCHED();
   return AQ_OK;

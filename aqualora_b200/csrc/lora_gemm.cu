@@ -740,11 +740,7 @@ static int launch_bn(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) 
   p.total_items = (int)items;
   const int grid = 2 * (int)(items < slots ? items : slots);
 
-  static bool attr_set = false;   // benign race: idempotent
-  if (!attr_set) {
-    AQ_CHECK_CUDA(cudaFuncSetAttribute(lora_gemm_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    attr_set = true;
-  }
+  AQ_OPT_IN_SMEM((lora_gemm_kernel<BN, NP>), L::kTotal);
   lora_gemm_kernel<BN, NP><<<grid, kThreads, L::kTotal, stream>>>(p);
   AQ_LAUNCHED();
   return AQ_OK;

@@ -198,11 +198,7 @@ static int fill_wgrad(WgradParams& p, const void* pm, int64_t ldp, const void* q
 static int launch_wgrad_n(WgradLaunch& l, int n, cudaStream_t stream) {
   int rc = check_arch();
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AQ_CHECK_CUDA(cudaFuncSetAttribute(lora_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
-    attr_set = true;
-  }
+  AQ_OPT_IN_SMEM((lora_wgrad_kernel), kWgSmemBytes);
   int gx = 0, gy = 0;
   for (int i = 0; i < n; ++i) {
     gx = l.prob[i].i_tiles > gx ? l.prob[i].i_tiles : gx;

@@ -466,11 +466,7 @@ int aq_noise_jpeg(const float* x, float* y, int B, int H, int W, void* stream) {
   int rc = check_arch();
   if (rc) return rc;
   const int smem = 3 * 8 * kJpegRowStride * (int)sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    AQ_CHECK_CUDA(cudaFuncSetAttribute(jpeg_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  AQ_OPT_IN_SMEM((jpeg_mask_kernel), smem);
   dim3 grid((W + kJpegCols - 1) / kJpegCols, (H + 7) / 8, B);
   jpeg_mask_kernel<<<grid, kJpegThreads, smem, (cudaStream_t)stream>>>(x, y, H, W);
   AQ_LAUNCHED();

@@ -17,6 +17,7 @@ straight into the flat gradient buffer (`param._aq_grad` views), so the data-par
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Callable, Optional
 
@@ -25,7 +26,7 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import lora_modules, ops
+from . import checkpoint, lora_modules, ops
 from .unet import UNet2DConditionModel, UNetConfig, lora_target_keys
 
 
@@ -208,6 +209,55 @@ class PPFTTrainer:
         self.optimizer_step()
         return loss
 
+    # -- checkpoint artefacts (train/ppft_train.py:699-748, :943-965, :1079-1103, :1203-1229) ---------------------------------
+    def save(self, output_dir: str, msgdecoder: Optional[nn.Module] = None) -> None:
+        """Final artefacts: pytorch_lora_weights.safetensors + mapper.pt (+ msgdecoder.pt) -- what scripts/create_wm_lora.py reads."""
+        checkpoint.save_ppft_artifacts(output_dir, self.unet, self.keys, self.state.mapper_emb, msgdecoder)
+
+    def load(self, input_dir: str, strict: bool = True) -> None:
+        """Load LoRA weights (+ mapper.pt when present) written by `save` or by the reference's training script, in place into the flat
+        parameter buffer, and rebuild the bf16 operand copies."""
+        checkpoint.load_lora_into_unet(input_dir, self.unet, self.keys, strict=strict)
+        mp = os.path.join(input_dir, "mapper.pt")
+        if os.path.isdir(input_dir) and os.path.exists(mp):
+            emb = torch.load(mp, map_location="cpu")["bit_embeddings.weight"]
+            if tuple(emb.shape) != tuple(self.state.mapper_emb.shape):
+                raise ValueError(f"mapper.pt holds {tuple(emb.shape)} embeddings, the trainer {tuple(self.state.mapper_emb.shape)}")
+            with torch.no_grad():
+                self.state.mapper_emb.copy_(emb.to(self.state.mapper_emb.device, torch.float32))
+        if self.device.type == "cuda":
+            self.refresh_operands()
+
+    def save_state(self, output_dir: str, total_limit: Optional[int] = None, msgdecoder: Optional[nn.Module] = None) -> str:
+        """`accelerator.save_state(<output_dir>/checkpoint-<global_step>)` with `--checkpoints_total_limit` rotation: the artefacts
+        of `save` plus the optimizer moments and the step counter needed to resume."""
+        os.makedirs(output_dir, exist_ok=True)
+        checkpoint.rotate_checkpoints(output_dir, total_limit)
+        path = os.path.join(output_dir, f"checkpoint-{self.global_step}")
+        self.save(path, msgdecoder)
+        st = self.state
+        torch.save({"global_step": self.global_step, "n_lora": st.n_lora, "n_mapper": st.n_mapper, "rank": self.cfg.rank,
+                    "exp_avg": st.exp_avg.detach().cpu().clone(), "exp_avg_sq": st.exp_avg_sq.detach().cpu().clone()},
+                   os.path.join(path, "trainer_state.pt"))
+        return path
+
+    def load_state(self, path: str) -> int:
+        """Resume from a `save_state` directory (or `latest` inside an output dir: train/ppft_train.py:943-965).  Returns the step."""
+        if os.path.basename(os.path.normpath(path)) == "latest":
+            found = checkpoint.latest_checkpoint(os.path.dirname(os.path.normpath(path)))
+            if found is None:
+                raise FileNotFoundError(f"no checkpoint-* directory under {os.path.dirname(os.path.normpath(path))}")
+            path = found
+        self.load(path)
+        ts = torch.load(os.path.join(path, "trainer_state.pt"), map_location="cpu")
+        st = self.state
+        if ts["n_lora"] != st.n_lora or ts["n_mapper"] != st.n_mapper:
+            raise ValueError("trainer_state.pt belongs to a different LoRA configuration")
+        st.exp_avg.copy_(ts["exp_avg"].to(st.exp_avg.device))
+        st.exp_avg_sq.copy_(ts["exp_avg_sq"].to(st.exp_avg_sq.device))
+        self.global_step = int(ts["global_step"])
+        return self.global_step
+
     # -- CUDA-graph replay of the forward + backward ------------------------------------------------------------------
     def capture(self, fn: Callable, example_inputs, warmup_steps: int = 2) -> int:
         """Record `fn(*inputs) -> loss` -- everything of a step up to the gradient exchange, ending in `forward_backward` -- into
@@ -221,19 +271,21 @@ class PPFTTrainer:
         stream.wait_stream(torch.cuda.current_stream(self.device))
         self._static_in = [x.clone() for x in example_inputs]
         with torch.cuda.stream(stream):
-            for _ in range(max(1, warmup_steps)):      # handles, cuDNN plans and workspaces of the capture stream
-                fn(*self._static_in)
-                self.optimizer_step()
+            for _ in range(max(1, warmup_steps)):      # handles, cuDNN plans and workspaces of the capture stream:
+                fn(*self._static_in)                   # forward + backward only -- the warm-up must not train on the example
         torch.cuda.current_stream(self.device).wait_stream(stream)
         torch.cuda.synchronize(self.device)
+        self.state.grad.zero_()                        # batch (no optimizer step, no moment / step-counter / schedule change)
+        if self.g_scale is not None:
+            self.g_scale.zero_()
         graph = torch.cuda.CUDAGraph()
         n0 = _lib.load().aq_launch_count()
         with torch.cuda.graph(graph, stream=stream):
             self._static_loss = fn(*self._static_in)
         self._graph_launches = int(_lib.load().aq_launch_count() - n0)
         self._graph = graph
-        lora_modules.invalidate_packed()               # the capture recorded, but did not run, the operand refresh
-        return self._graph_launches
+        self.state.grad.zero_()                        # a capture records kernels without running them, but stay defensive:
+        return self._graph_launches                    # the first replay must start from zero gradients
 
     @property
     def static_inputs(self):
