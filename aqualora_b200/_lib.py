@@ -41,6 +41,16 @@ _SIGNATURES = {
     "aq_wgrad_tn": ([c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p], c_int),
     "aq_secret_encoder_workspace_bytes": ([c_int, c_int], c_size_t),
     "aq_secret_encoder_fwd": ([c_void_p] * 8 + [c_int] * 6 + [c_void_p, c_void_p], c_int),
+    "aq_secret_encoder_bwd_workspace_bytes": ([c_int, c_int, c_int], c_size_t),
+    "aq_secret_encoder_bwd": ([c_void_p] * 9 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p], c_int),
+    "aq_noise_jpeg_bwd": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    "aq_noise_crop_resize_bwd": ([c_void_p, c_void_p] + [c_int] * 11 + [c_void_p], c_int),
+    "aq_noise_gauss_blur_bwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    "aq_noise_color_jiggle_bwd": ([c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_int), c_int, c_int, c_int, c_void_p], c_int),
+    "aq_prvl_workspace_bytes": ([c_int, c_int, c_int], c_size_t),
+    "aq_prvl_loss_fwd": ([c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p], c_int),
+    "aq_prvl_loss_bwd": ([c_void_p] * 6 + [c_int] * 3 + [c_void_p], c_int),
+    "aq_bce_logits": ([c_void_p] * 4 + [c_int64, c_void_p], c_int),
     "aq_mapper_fwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "aq_mapper_bwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     "aq_cast_transpose_bf16": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),

@@ -86,6 +86,150 @@ __global__ void secret_encoder_resize_add_kernel(const float* __restrict__ c_res
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward (train/latent_wm_pretrain.py:174,216: the encoder is trained through the VAE decoder, the noise layer and the
+// message decoder).  g_c = dL/dc at the latent size; outputs accumulate (+=) into the parameter gradients.
+// ------------------------------------------------------------------------------------------------------------------
+// adjoint of the bilinear resize: scatter into the zeroed res x res map
+__global__ void secret_encoder_resize_bwd_kernel(const float* __restrict__ g_c, float* __restrict__ g_cres, int planes, int res, int H,
+                                                 int W) {
+  const long long n = (long long)planes * H * W;
+  const float sy = (float)res / (float)H, sx = (float)res / (float)W;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int xo = (int)(idx % W);
+    const int yo = (int)((idx / W) % H);
+    const long long pl = idx / ((long long)W * H);
+    float fy = sy * (yo + 0.5f) - 0.5f, fx = sx * (xo + 0.5f) - 0.5f;
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < res - 1 ? 1 : 0), x1 = x0 + (x0 < res - 1 ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0;
+    float* dst = g_cres + pl * res * res;
+    const float g = g_c[idx];
+    atomicAdd(dst + y0 * res + x0, g * (1.f - ly) * (1.f - lx));
+    atomicAdd(dst + y0 * res + x1, g * (1.f - ly) * lx);
+    atomicAdd(dst + y1 * res + x0, g * ly * (1.f - lx));
+    atomicAdd(dst + y1 * res + x1, g * ly * lx);
+  }
+}
+
+// one block per sample: conv weight / bias gradients and the gradient of the pre-activation a = W1 m + b1
+__global__ void __launch_bounds__(256) secret_encoder_bwd_kernel(const float* __restrict__ g_cres, const float* __restrict__ msg,
+                                                                 const float* __restrict__ w1, const float* __restrict__ b1,
+                                                                 const float* __restrict__ wc, float* __restrict__ g_a,
+                                                                 float* __restrict__ g_wc, float* __restrict__ g_bc, int bits, int base,
+                                                                 int res) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x;
+  const int up = res / base;
+  const int nb = base * base;
+  float* a_s = sm;         // [base^2] pre-activation
+  float* u_s = sm + nb;    // [base^2] SiLU(a)
+  __shared__ float wsum[4][9];
+  __shared__ float red[40];
+  const float* m = msg + (size_t)b * bits;
+  for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+    float acc = b1[j];
+    const float* wr = w1 + (size_t)j * bits;
+    for (int i = 0; i < bits; ++i) acc = fmaf(wr[i], m[i], acc);
+    a_s[j] = acc;
+    u_s[j] = acc / (1.f + __expf(-acc));
+  }
+  if (threadIdx.x < 36) {
+    const int co = threadIdx.x / 9, t = threadIdx.x % 9;
+    float s = 0.f;
+    for (int ci = 0; ci < 4; ++ci) s += wc[(co * 4 + ci) * 9 + t];
+    wsum[co][t] = s;
+  }
+  if (threadIdx.x < 40) red[threadIdx.x] = 0.f;
+  __syncthreads();
+  const float* gb = g_cres + (size_t)b * 4 * res * res;
+  // (1) dL/dwc[co, ci, t] = sum_{y, x} g[co, y, x] * in[y + dy, x + dx] (identical for the 4 input channels: they are copies)
+  float pw[4][9], pb[4];
+#pragma unroll
+  for (int co = 0; co < 4; ++co) {
+    pb[co] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) pw[co][t] = 0.f;
+  }
+  for (int idx = threadIdx.x; idx < res * res; idx += blockDim.x) {
+    const int y = idx / res, x = idx % res;
+    float v[9];
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = y + dy, xx = x + dx;
+        v[(dy + 1) * 3 + (dx + 1)] = (yy >= 0 && yy < res && xx >= 0 && xx < res) ? u_s[(yy / up) * base + xx / up] : 0.f;
+      }
+#pragma unroll
+    for (int co = 0; co < 4; ++co) {
+      const float g = gb[(size_t)co * res * res + idx];
+      pb[co] += g;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) pw[co][t] = fmaf(g, v[t], pw[co][t]);
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 4; ++co) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float v = pw[co][t];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&red[co * 9 + t], v);
+    }
+    float v = pb[co];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[36 + co], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 36) {
+    const int co = threadIdx.x / 9, t = threadIdx.x % 9;
+    for (int ci = 0; ci < 4; ++ci) atomicAdd(g_wc + (co * 4 + ci) * 9 + t, red[threadIdx.x]);
+  } else if (threadIdx.x < 40) {
+    atomicAdd(g_bc + (threadIdx.x - 36), red[threadIdx.x]);
+  }
+  // (2) gradient of the hidden map: in[yy, xx] feeds out[yy - dy, xx - dx] through tap (dy, dx) of every output channel; the
+  // nearest upsampling and the channel repeat sum their copies
+  for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+    const int by = j / base, bx = j % base;
+    float s = 0.f;
+    for (int fy = 0; fy < up; ++fy)
+      for (int fx = 0; fx < up; ++fx) {
+        const int yy = by * up + fy, xx = bx * up + fx;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int oy = yy - dy, ox = xx - dx;
+            if (oy < 0 || oy >= res || ox < 0 || ox >= res) continue;
+            const int t = (dy + 1) * 3 + (dx + 1);
+#pragma unroll
+            for (int co = 0; co < 4; ++co) s = fmaf(wsum[co][t], gb[((size_t)co * res + oy) * res + ox], s);
+          }
+      }
+    const float a = a_s[j];
+    const float sg = 1.f / (1.f + __expf(-a));
+    g_a[(size_t)b * nb + j] = s * sg * (1.f + a * (1.f - sg));     // d SiLU(a) / da
+  }
+}
+
+// dL/dW1[j, i] += sum_b g_a[b, j] msg[b, i];  dL/db1[j] += sum_b g_a[b, j]   (column i == bits is the bias)
+__global__ void secret_encoder_wgrad_kernel(const float* __restrict__ g_a, const float* __restrict__ msg, float* __restrict__ g_w1,
+                                            float* __restrict__ g_b1, int B, int bits, int nb) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nb * (bits + 1)) return;
+  const int j = idx / (bits + 1), i = idx % (bits + 1);
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s = fmaf(g_a[(size_t)b * nb + j], i < bits ? msg[(size_t)b * bits + i] : 1.f, s);
+  if (i < bits) g_w1[(size_t)j * bits + i] += s;
+  else g_b1[j] += s;
+}
+
 }  // namespace aq
 
 using namespace aq;
@@ -119,6 +263,45 @@ int aq_secret_encoder_fwd(const float* msg, const float* w1, const float* b1, co
     secret_encoder_resize_add_kernel<<<blocks, 256, 0, st>>>(c_res, x, c_out, x_out, B * 4, res, H, W);
     AQ_LAUNCHED();
   }
+  return AQ_OK;
+}
+
+size_t aq_secret_encoder_bwd_workspace_bytes(int B, int base, int res) {
+  return ((size_t)B * 4 * res * res + (size_t)B * base * base) * sizeof(float);
+}
+
+// g_c [B, 4, H, W] -> g_w1 [base^2, bits] +=, g_b1 [base^2] +=, g_wc [4, 4, 3, 3] +=, g_bc [4] +=
+int aq_secret_encoder_bwd(const float* g_c, const float* msg, const float* w1, const float* b1, const float* wc, float* g_w1, float* g_b1,
+                          float* g_wc, float* g_bc, int B, int bits, int base, int res, int H, int W, void* ws, size_t ws_bytes,
+                          void* stream) {
+  AQ_REQUIRE(B > 0 && bits > 0 && base > 0 && res >= base && res % base == 0 && H > 0 && W > 0, AQ_ERR_BAD_SHAPE,
+             "secret_encoder_bwd: bad shape B=%d bits=%d base=%d res=%d H=%d W=%d", B, bits, base, res, H, W);
+  AQ_REQUIRE(g_c && msg && w1 && b1 && wc && g_w1 && g_b1 && g_wc && g_bc, AQ_ERR_BAD_SHAPE, "secret_encoder_bwd: NULL operand");
+  AQ_REQUIRE(ws != nullptr && ws_bytes >= aq_secret_encoder_bwd_workspace_bytes(B, base, res), AQ_ERR_WORKSPACE,
+             "secret_encoder_bwd: workspace too small");
+  int rc = check_arch();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* g_cres_ws = reinterpret_cast<float*>(ws);
+  float* g_a = g_cres_ws + (size_t)B * 4 * res * res;
+  const float* g_cres = g_c;
+  if (!(H == res && W == res)) {
+    AQ_CHECK_CUDA(cudaMemsetAsync(g_cres_ws, 0, (size_t)B * 4 * res * res * sizeof(float), st));
+    const long long n = (long long)B * 4 * H * W;
+    int blocks = (int)((n + 255) / 256);
+    const int cap = (sm_count() > 0 ? sm_count() : 148) * 8;
+    if (blocks > cap) blocks = cap;
+    secret_encoder_resize_bwd_kernel<<<blocks, 256, 0, st>>>(g_c, g_cres_ws, B * 4, res, H, W);
+    AQ_LAUNCHED();
+    g_cres = g_cres_ws;
+  }
+  const size_t smem = (size_t)2 * base * base * sizeof(float);
+  AQ_REQUIRE(smem <= 48 * 1024, AQ_ERR_BAD_SHAPE, "secret_encoder_bwd: base=%d too large", base);
+  secret_encoder_bwd_kernel<<<B, 256, smem, st>>>(g_cres, msg, w1, b1, wc, g_a, g_wc, g_bc, bits, base, res);
+  AQ_LAUNCHED();
+  const int n = base * base * (bits + 1);
+  secret_encoder_wgrad_kernel<<<(n + 255) / 256, 256, 0, st>>>(g_a, msg, g_w1, g_b1, B, bits, base * base);
+  AQ_LAUNCHED();
   return AQ_OK;
 }
 

@@ -129,7 +129,12 @@ __device__ __forceinline__ void jpeg_block(float* __restrict__ plane, int bx) {
   }
 }
 
-// grid: (ceil(Wp / 512), Hp / 8, B); block: 192 threads
+// grid: (ceil(Wp / 512), Hp / 8, B); block: 192 threads.
+// BWD = false: y = T x with T = unpad . C2 . P . C1 . pad (C1 = RGB->YUV, P = per-channel masked block DCT round trip, C2 = YUV->RGB).
+// BWD = true : gx = T^T gy.  P = sum over kept (a, b) of w_a w_b (d_a (x) d_b)(d_a (x) d_b)^T is symmetric (I = D^T diag(1/8, 1/4, ...)),
+// pad^T = unpad and unpad^T = zero-pad, so T^T = unpad . C1^T . P . C2^T . pad: the SAME kernel with the two colour matrices
+// transposed and swapped.
+template <bool BWD>
 __global__ void __launch_bounds__(kJpegThreads) jpeg_mask_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W) {
   extern __shared__ float sm[];   // [3][8][kJpegRowStride]
   const int col0 = blockIdx.x * kJpegCols;
@@ -162,9 +167,15 @@ __global__ void __launch_bounds__(kJpegThreads) jpeg_mask_kernel(const float* __
     float Y[4], U[4], V[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      Y[k] = 0.299f * R[k] + 0.587f * G[k] + 0.114f * Bv[k];
-      U[k] = -0.14713f * R[k] + -0.28886f * G[k] + 0.436f * Bv[k];
-      V[k] = 0.615f * R[k] + -0.51499f * G[k] + -0.10001f * Bv[k];
+      if constexpr (!BWD) {
+        Y[k] = 0.299f * R[k] + 0.587f * G[k] + 0.114f * Bv[k];
+        U[k] = -0.14713f * R[k] + -0.28886f * G[k] + 0.436f * Bv[k];
+        V[k] = 0.615f * R[k] + -0.51499f * G[k] + -0.10001f * Bv[k];
+      } else {   // C2^T (gR, gG, gB)
+        Y[k] = R[k] + G[k] + Bv[k];
+        U[k] = -0.39465f * G[k] + 2.03211f * Bv[k];
+        V[k] = 1.13983f * R[k] + -0.58060f * G[k];
+      }
     }
     float* d = sm + r * kJpegRowStride + c4;
     *reinterpret_cast<float4*>(d) = make_float4(Y[0], Y[1], Y[2], Y[3]);
@@ -195,9 +206,15 @@ __global__ void __launch_bounds__(kJpegThreads) jpeg_mask_kernel(const float* __
     float R[4], G[4], Bv[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      R[k] = yv[k] + 1.13983f * vv[k];
-      G[k] = yv[k] + -0.39465f * uv[k] + -0.58060f * vv[k];
-      Bv[k] = yv[k] + 2.03211f * uv[k];
+      if constexpr (!BWD) {
+        R[k] = yv[k] + 1.13983f * vv[k];
+        G[k] = yv[k] + -0.39465f * uv[k] + -0.58060f * vv[k];
+        Bv[k] = yv[k] + 2.03211f * uv[k];
+      } else {   // C1^T (gY, gU, gV)
+        R[k] = 0.299f * yv[k] + -0.14713f * uv[k] + 0.615f * vv[k];
+        G[k] = 0.587f * yv[k] + -0.28886f * uv[k] + -0.51499f * vv[k];
+        Bv[k] = 0.114f * yv[k] + 0.436f * uv[k] + -0.10001f * vv[k];
+      }
     }
     const size_t off = (size_t)gr * W + gc;
     if (vec_ok && gc + 3 < W) {
@@ -256,6 +273,42 @@ __global__ void crop_resize_kernel(const float* __restrict__ x, float* __restric
     const float p10 = stage1_pixel(src, a, y1, x0), p11 = stage1_pixel(src, a, y1, x1);
     const float hy = 1.f - ly, hx = 1.f - lx;
     y[idx] = hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
+  }
+}
+
+// adjoint of crop_resize_kernel: every output pixel scatters its gradient over the (up to) 16 crop pixels it read.  fp32 atomics:
+// the summation order (not the set of terms) varies between runs.
+__device__ __forceinline__ void stage1_scatter(float* __restrict__ dst, const CropResizeArgs& a, int iy, int ix, float g) {
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilinear_src(a.sy1, iy, a.ch, y0, y1, ly);
+  bilinear_src(a.sx1, ix, a.cw, x0, x1, lx);
+  float* r0 = dst + (size_t)(a.top + y0) * a.W + a.left;
+  float* r1 = dst + (size_t)(a.top + y1) * a.W + a.left;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  atomicAdd(r0 + x0, g * hy * hx);
+  atomicAdd(r0 + x1, g * hy * lx);
+  atomicAdd(r1 + x0, g * ly * hx);
+  atomicAdd(r1 + x1, g * ly * lx);
+}
+
+__global__ void crop_resize_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, CropResizeArgs a, int planes) {
+  const long long n = (long long)planes * a.oh * a.ow;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % a.ow);
+    const int oy = (int)((idx / a.ow) % a.oh);
+    const long long pl = idx / ((long long)a.ow * a.oh);
+    float* dst = gx + pl * (long long)a.H * a.W;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(a.sy2, oy, a.rh, y0, y1, ly);
+    bilinear_src(a.sx2, ox, a.rw, x0, x1, lx);
+    const float g = __ldg(gy + idx);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    stage1_scatter(dst, a, y0, x0, g * hy * hx);
+    stage1_scatter(dst, a, y0, x1, g * hy * lx);
+    stage1_scatter(dst, a, y1, x0, g * ly * hx);
+    stage1_scatter(dst, a, y1, x1, g * ly * lx);
   }
 }
 
@@ -322,6 +375,57 @@ __global__ void __launch_bounds__(256) gauss_blur_kernel(const float* __restrict
   }
 }
 
+// adjoint of gauss_blur_kernel as a gather.  Forward: y[r, c] = sum_ij ty[i] tx[j] x[refl(r + i - ry), refl(c + j - rx)].  Input pixel
+// (p, q) is read through the direct index and, within a radius of the border, through the reflections -p and 2 (n - 1) - p:
+// gx[p, q] = sum_ij ty[i] tx[j] sum over the (<= 3 x 3) index variants (pv, qv) of gy[pv - i + ry, qv - j + rx] inside the image.
+// grid: (ceil(W / 128), ceil(H / 4), B * 3); block 128 x 4
+__global__ void __launch_bounds__(512) gauss_blur_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx,
+                                                              const float* __restrict__ sigmas, int H, int W, int ky, int kx) {
+  __shared__ float taps_x[kBlurMaxK], taps_y[kBlurMaxK];
+  const int ry = ky / 2, rx = kx / 2;
+  const int plane = blockIdx.z;
+  const float sigma = sigmas[plane / 3];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid < 32) {
+    float g1 = 0.f, g2 = 0.f;
+    if (tid < kx) { const float d = (float)(tid - rx); g1 = expf(-(d * d) / (2.f * sigma * sigma)); }
+    if (tid < ky) { const float d = (float)(tid - ry); g2 = expf(-(d * d) / (2.f * sigma * sigma)); }
+    float sx = g1, sy = g2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    }
+    if (tid < kx) taps_x[tid] = g1 / sx;
+    if (tid < ky) taps_y[tid] = g2 / sy;
+  }
+  __syncthreads();
+  const int q = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y * blockDim.y + threadIdx.y;
+  if (p >= H || q >= W) return;
+  const float* src = gy + (size_t)plane * H * W;
+  // index variants through which (p, q) is read: direct, left/top reflection, right/bottom reflection
+  int pv[3], qv[3], np = 1, nq = 1;
+  pv[0] = p; qv[0] = q;
+  if (p >= 1 && p <= ry) pv[np++] = -p;
+  if (p <= H - 2 && p >= H - 1 - ry) pv[np++] = 2 * (H - 1) - p;
+  if (q >= 1 && q <= rx) qv[nq++] = -q;
+  if (q <= W - 2 && q >= W - 1 - rx) qv[nq++] = 2 * (W - 1) - q;
+  float acc = 0.f;
+  for (int a = 0; a < np; ++a)
+    for (int i = 0; i < ky; ++i) {
+      const int r = pv[a] - i + ry;
+      if (r < 0 || r >= H) continue;
+      float row = 0.f;
+      for (int b = 0; b < nq; ++b)
+        for (int j = 0; j < kx; ++j) {
+          const int c = qv[b] - j + rx;
+          if (c >= 0 && c < W) row = fmaf(taps_x[j], __ldg(src + (size_t)r * W + c), row);
+        }
+      acc = fmaf(taps_y[i], row, acc);
+    }
+  gx[(size_t)plane * H * W + (size_t)p * W + q] = acc;
+}
+
 // ================================================================================================================
 // Gaussian noise: Philox4x32-10 counter RNG + Box-Muller
 // ================================================================================================================
@@ -378,27 +482,65 @@ __global__ void gauss_noise_kernel(const float* __restrict__ x, float* __restric
 struct JiggleOrder { int op[4]; };
 constexpr float kTwoPi = 6.283185307179586f;
 
-__device__ __forceinline__ void rgb2hsv(float r, float g, float b, float& h, float& s, float& v) {
-  const float maxc = fmaxf(r, fmaxf(g, b)), minc = fminf(r, fminf(g, b));
+// Forward-mode dual number carrying the three partial derivatives w.r.t. the input (r, g, b): running the SAME per-pixel code on
+// duals yields the exact 3 x 3 Jacobian of the arithmetic the forward executes (clamps, hue wrap, the piecewise HSV maps included),
+// and the backward is gx = J^T gy.  floor / integer selections are piecewise constant: zero derivative.
+struct Dual3 {
+  float v, d0, d1, d2;
+};
+__device__ __forceinline__ Dual3 mk(float v) { return Dual3{v, 0.f, 0.f, 0.f}; }
+__device__ __forceinline__ Dual3 operator+(Dual3 a, Dual3 b) { return Dual3{a.v + b.v, a.d0 + b.d0, a.d1 + b.d1, a.d2 + b.d2}; }
+__device__ __forceinline__ Dual3 operator-(Dual3 a, Dual3 b) { return Dual3{a.v - b.v, a.d0 - b.d0, a.d1 - b.d1, a.d2 - b.d2}; }
+__device__ __forceinline__ Dual3 operator+(Dual3 a, float b) { return Dual3{a.v + b, a.d0, a.d1, a.d2}; }
+__device__ __forceinline__ Dual3 operator-(Dual3 a, float b) { return Dual3{a.v - b, a.d0, a.d1, a.d2}; }
+__device__ __forceinline__ Dual3 operator-(float a, Dual3 b) { return Dual3{a - b.v, -b.d0, -b.d1, -b.d2}; }
+__device__ __forceinline__ Dual3 operator*(Dual3 a, float b) { return Dual3{a.v * b, a.d0 * b, a.d1 * b, a.d2 * b}; }
+__device__ __forceinline__ Dual3 operator*(float a, Dual3 b) { return b * a; }
+__device__ __forceinline__ Dual3 operator/(Dual3 a, float b) { return Dual3{a.v / b, a.d0 / b, a.d1 / b, a.d2 / b}; }
+__device__ __forceinline__ Dual3 operator*(Dual3 a, Dual3 b) {
+  return Dual3{a.v * b.v, a.d0 * b.v + a.v * b.d0, a.d1 * b.v + a.v * b.d1, a.d2 * b.v + a.v * b.d2};
+}
+__device__ __forceinline__ Dual3 operator/(Dual3 a, Dual3 b) {
+  const float q = a.v / b.v, ib = 1.f / b.v;
+  return Dual3{q, (a.d0 - q * b.d0) * ib, (a.d1 - q * b.d1) * ib, (a.d2 - q * b.d2) * ib};
+}
+__device__ __forceinline__ float val(float a) { return a; }
+__device__ __forceinline__ float val(Dual3 a) { return a.v; }
+__device__ __forceinline__ float t_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float t_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ Dual3 t_max(Dual3 a, Dual3 b) { return a.v >= b.v ? a : b; }
+__device__ __forceinline__ Dual3 t_min(Dual3 a, Dual3 b) { return a.v <= b.v ? a : b; }
+__device__ __forceinline__ float t_const(float, float c) { return c; }
+__device__ __forceinline__ Dual3 t_const(Dual3, float c) { return mk(c); }
+// x shifted by a piecewise-constant amount (floor / fmod wrap): same derivative as x
+__device__ __forceinline__ float t_shift(float x, float newv) { return newv; }
+__device__ __forceinline__ Dual3 t_shift(Dual3 x, float newv) { return Dual3{newv, x.d0, x.d1, x.d2}; }
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+__device__ __forceinline__ Dual3 clamp01(Dual3 a) { return (a.v < 0.f) ? mk(0.f) : ((a.v > 1.f) ? mk(1.f) : a); }
+
+template <typename T>
+__device__ __forceinline__ void rgb2hsv(T r, T g, T b, T& h, T& s, T& v) {
+  const T maxc = t_max(r, t_max(g, b)), minc = t_min(r, t_min(g, b));
   v = maxc;
-  const float delta = maxc - minc;
+  const T delta = maxc - minc;
   s = delta / (maxc + 1e-8f);
-  const float dz = delta == 0.f ? 1.f : delta;
-  const float rc = maxc - r, gc = maxc - g, bc = maxc - b;
-  float hh = (maxc == r) ? (bc - gc) : ((maxc == g) ? (2.f * dz + rc - bc) : (4.f * dz + gc - rc));
+  const T dz = val(delta) == 0.f ? t_const(delta, 1.f) : delta;
+  const T rc = maxc - r, gc = maxc - g, bc = maxc - b;
+  T hh = (val(maxc) == val(r)) ? (bc - gc) : ((val(maxc) == val(g)) ? (2.f * dz + rc - bc) : (4.f * dz + gc - rc));
   hh = hh / dz / 6.f;
-  hh = hh - floorf(hh);            // python % 1.0
+  hh = t_shift(hh, val(hh) - floorf(val(hh)));            // python % 1.0
   h = hh * kTwoPi;
 }
 
-__device__ __forceinline__ void hsv2rgb(float h, float s, float v, float& r, float& g, float& b) {
-  const float h1 = h / kTwoPi;
-  const float h6 = h1 * 6.f;
-  float hi = floorf(h6);
+template <typename T>
+__device__ __forceinline__ void hsv2rgb(T h, T s, T v, T& r, T& g, T& b) {
+  const T h1 = h / kTwoPi;
+  const T h6 = h1 * 6.f;
+  float hi = floorf(val(h6));
   hi = hi - 6.f * floorf(hi / 6.f);          // floor(h*6) % 6
-  const float m6 = h6 - 6.f * floorf(h6 / 6.f);   // (h*6) % 6
-  const float f = m6 - hi;
-  const float p = v * (1.f - s), q = v * (1.f - f * s), t = v * (1.f - (1.f - f) * s);
+  const T m6 = t_shift(h6, val(h6) - 6.f * floorf(val(h6) / 6.f));   // (h*6) % 6
+  const T f = m6 - hi;
+  const T p = v * (1.f - s), q = v * (1.f - f * s), t = v * (1.f - (1.f - f) * s);
   const int i = (int)hi;
   switch (i) {
     case 0: r = v; g = t; b = p; break;
@@ -410,7 +552,30 @@ __device__ __forceinline__ void hsv2rgb(float h, float s, float v, float& r, flo
   }
 }
 
-__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+// the four ColorJiggle ops in the sampled order on one pixel in [0, 1]
+template <typename T>
+__device__ __forceinline__ void jiggle_pixel(T& r, T& g, T& bl, float pb, float pc, float ps, float ph, const JiggleOrder& order) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int op = order.op[k];
+    if (op == 0) {
+      const float d = pb - 1.f;
+      r = clamp01(r + d); g = clamp01(g + d); bl = clamp01(bl + d);
+    } else if (op == 1) {
+      r = clamp01(r * pc); g = clamp01(g * pc); bl = clamp01(bl * pc);
+    } else {
+      T h, s, v;
+      rgb2hsv(r, g, bl, h, s, v);
+      if (op == 2) {
+        s = clamp01(s * ps);
+      } else {
+        const float hv = val(h) + ph * kTwoPi;
+        h = t_shift(h, fmodf(hv, kTwoPi));
+      }
+      hsv2rgb(h, s, v, r, g, bl);
+    }
+  }
+}
 
 // params [B, 4] = (brightness, contrast, saturation, hue) per sample
 __global__ void color_jiggle_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ params,
@@ -420,28 +585,27 @@ __global__ void color_jiggle_kernel(const float* __restrict__ x, float* __restri
     const long long b = idx / hw, px = idx % hw;
     const float* src = x + b * 3 * hw + px;
     float r = src[0] / 2.f + 0.5f, g = src[hw] / 2.f + 0.5f, bl = src[2 * hw] / 2.f + 0.5f;   // [-1, 1] -> [0, 1]
-    const float pb = params[b * 4 + 0], pc = params[b * 4 + 1], ps = params[b * 4 + 2], ph = params[b * 4 + 3];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int op = order.op[k];
-      if (op == 0) {
-        const float d = pb - 1.f;
-        r = clamp01(r + d); g = clamp01(g + d); bl = clamp01(bl + d);
-      } else if (op == 1) {
-        r = clamp01(r * pc); g = clamp01(g * pc); bl = clamp01(bl * pc);
-      } else {
-        float h, s, v;
-        rgb2hsv(r, g, bl, h, s, v);
-        if (op == 2) {
-          s = clamp01(s * ps);
-        } else {
-          h = fmodf(h + ph * kTwoPi, kTwoPi);
-        }
-        hsv2rgb(h, s, v, r, g, bl);
-      }
-    }
+    jiggle_pixel<float>(r, g, bl, params[b * 4 + 0], params[b * 4 + 1], params[b * 4 + 2], params[b * 4 + 3], order);
     float* dst = y + b * 3 * hw + px;
     dst[0] = r * 2.f - 1.f; dst[hw] = g * 2.f - 1.f; dst[2 * hw] = bl * 2.f - 1.f;
+  }
+}
+
+// gx = J^T gy per pixel (the [-1, 1] <-> [0, 1] maps contribute 1/2 * 2 = 1)
+__global__ void color_jiggle_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
+                                        const float* __restrict__ params, JiggleOrder order, int B, long long hw) {
+  const long long n = (long long)B * hw;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const long long b = idx / hw, px = idx % hw;
+    const float* src = x + b * 3 * hw + px;
+    Dual3 r{src[0] / 2.f + 0.5f, 1.f, 0.f, 0.f}, g{src[hw] / 2.f + 0.5f, 0.f, 1.f, 0.f}, bl{src[2 * hw] / 2.f + 0.5f, 0.f, 0.f, 1.f};
+    jiggle_pixel<Dual3>(r, g, bl, params[b * 4 + 0], params[b * 4 + 1], params[b * 4 + 2], params[b * 4 + 3], order);
+    const float* gs = gy + b * 3 * hw + px;
+    const float g0 = gs[0], g1 = gs[hw], g2 = gs[2 * hw];
+    float* dst = gx + b * 3 * hw + px;
+    dst[0] = g0 * r.d0 + g1 * g.d0 + g2 * bl.d0;
+    dst[hw] = g0 * r.d1 + g1 * g.d1 + g2 * bl.d1;
+    dst[2 * hw] = g0 * r.d2 + g1 * g.d2 + g2 * bl.d2;
   }
 }
 
@@ -466,9 +630,23 @@ int aq_noise_jpeg(const float* x, float* y, int B, int H, int W, void* stream) {
   int rc = check_arch();
   if (rc) return rc;
   const int smem = 3 * 8 * kJpegRowStride * (int)sizeof(float);
-  AQ_OPT_IN_SMEM((jpeg_mask_kernel), smem);
+  AQ_OPT_IN_SMEM((jpeg_mask_kernel<false>), smem);
   dim3 grid((W + kJpegCols - 1) / kJpegCols, (H + 7) / 8, B);
-  jpeg_mask_kernel<<<grid, kJpegThreads, smem, (cudaStream_t)stream>>>(x, y, H, W);
+  jpeg_mask_kernel<false><<<grid, kJpegThreads, smem, (cudaStream_t)stream>>>(x, y, H, W);
+  AQ_LAUNCHED();
+  return AQ_OK;
+}
+
+int aq_noise_jpeg_bwd(const float* gy, float* gx, int B, int H, int W, void* stream) {
+  AQ_REQUIRE(gy && gx && B > 0 && H > 0 && W > 0, AQ_ERR_BAD_SHAPE, "noise_jpeg_bwd: bad arguments B=%d H=%d W=%d", B, H, W);
+  AQ_REQUIRE(((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(gx)) & 15u) == 0, AQ_ERR_BAD_ALIGN,
+             "noise_jpeg_bwd: pointers must be 16-byte aligned");
+  int rc = check_arch();
+  if (rc) return rc;
+  const int smem = 3 * 8 * kJpegRowStride * (int)sizeof(float);
+  AQ_OPT_IN_SMEM((jpeg_mask_kernel<true>), smem);
+  dim3 grid((W + kJpegCols - 1) / kJpegCols, (H + 7) / 8, B);
+  jpeg_mask_kernel<true><<<grid, kJpegThreads, smem, (cudaStream_t)stream>>>(gy, gx, H, W);
   AQ_LAUNCHED();
   return AQ_OK;
 }
@@ -487,6 +665,38 @@ int aq_noise_crop_resize(const float* x, float* y, int B, int H, int W, int top,
   a.sy2 = (float)resize_h / (float)out_h; a.sx2 = (float)resize_w / (float)out_w;
   const long long n = (long long)B * 3 * out_h * out_w;
   crop_resize_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, a, B * 3);
+  AQ_LAUNCHED();
+  return AQ_OK;
+}
+
+int aq_noise_crop_resize_bwd(const float* gy, float* gx, int B, int H, int W, int top, int left, int crop_h, int crop_w, int resize_h,
+                             int resize_w, int out_h, int out_w, void* stream) {
+  AQ_REQUIRE(gy && gx && B > 0 && H > 0 && W > 0, AQ_ERR_BAD_SHAPE, "noise_crop_resize_bwd: bad arguments");
+  AQ_REQUIRE(top >= 0 && left >= 0 && crop_h > 0 && crop_w > 0 && top + crop_h <= H && left + crop_w <= W, AQ_ERR_BAD_SHAPE,
+             "noise_crop_resize_bwd: crop box (%d, %d, %d, %d) outside %d x %d", top, left, crop_h, crop_w, H, W);
+  AQ_REQUIRE(resize_h > 0 && resize_w > 0 && out_h > 0 && out_w > 0, AQ_ERR_BAD_SHAPE, "noise_crop_resize_bwd: bad sizes");
+  int rc = check_arch();
+  if (rc) return rc;
+  CropResizeArgs a;
+  a.H = H; a.W = W; a.top = top; a.left = left; a.ch = crop_h; a.cw = crop_w; a.rh = resize_h; a.rw = resize_w; a.oh = out_h; a.ow = out_w;
+  a.sy1 = (float)crop_h / (float)resize_h; a.sx1 = (float)crop_w / (float)resize_w;
+  a.sy2 = (float)resize_h / (float)out_h; a.sx2 = (float)resize_w / (float)out_w;
+  AQ_CHECK_CUDA(cudaMemsetAsync(gx, 0, (size_t)B * 3 * H * W * sizeof(float), (cudaStream_t)stream));   // pixels outside the crop: zero
+  const long long n = (long long)B * 3 * out_h * out_w;
+  crop_resize_bwd_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(gy, gx, a, B * 3);
+  AQ_LAUNCHED();
+  return AQ_OK;
+}
+
+int aq_noise_gauss_blur_bwd(const float* gy, float* gx, const float* sigmas, int B, int H, int W, int ky, int kx, void* stream) {
+  AQ_REQUIRE(gy && gx && sigmas && B > 0 && H > 0 && W > 0, AQ_ERR_BAD_SHAPE, "noise_gauss_blur_bwd: bad arguments");
+  AQ_REQUIRE(ky % 2 == 1 && kx % 2 == 1 && ky <= kBlurMaxK && kx <= kBlurMaxK && ky / 2 < H && kx / 2 < W, AQ_ERR_BAD_SHAPE,
+             "noise_gauss_blur_bwd: kernel (%d, %d) must be odd, <= %d and smaller than the image", ky, kx, kBlurMaxK);
+  int rc = check_arch();
+  if (rc) return rc;
+  dim3 block(128, 4);
+  dim3 grid((W + 127) / 128, (H + 3) / 4, B * 3);
+  gauss_blur_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(gy, gx, sigmas, H, W, ky, kx);
   AQ_LAUNCHED();
   return AQ_OK;
 }
@@ -530,6 +740,25 @@ int aq_noise_color_jiggle(const float* x, float* y, const float* params, const i
   if (rc) return rc;
   const long long hw = (long long)H * W;
   color_jiggle_kernel<<<ew_grid((long long)B * hw, 256), 256, 0, (cudaStream_t)stream>>>(x, y, params, o, B, hw);
+  AQ_LAUNCHED();
+  return AQ_OK;
+}
+
+int aq_noise_color_jiggle_bwd(const float* x, const float* gy, float* gx, const float* params, const int* order_host, int B, int H,
+                              int W, void* stream) {
+  AQ_REQUIRE(x && gy && gx && params && order_host && B > 0 && H > 0 && W > 0, AQ_ERR_BAD_SHAPE, "noise_color_jiggle_bwd: bad arguments");
+  JiggleOrder o;
+  int seen = 0;
+  for (int k = 0; k < 4; ++k) {
+    AQ_REQUIRE(order_host[k] >= 0 && order_host[k] < 4, AQ_ERR_BAD_SHAPE, "noise_color_jiggle_bwd: order must be a permutation of 0..3");
+    o.op[k] = order_host[k];
+    seen |= 1 << order_host[k];
+  }
+  AQ_REQUIRE(seen == 15, AQ_ERR_BAD_SHAPE, "noise_color_jiggle_bwd: order must be a permutation of 0..3");
+  int rc = check_arch();
+  if (rc) return rc;
+  const long long hw = (long long)H * W;
+  color_jiggle_bwd_kernel<<<ew_grid((long long)B * hw, 256), 256, 0, (cudaStream_t)stream>>>(x, gy, gx, params, o, B, hw);
   AQ_LAUNCHED();
   return AQ_OK;
 }

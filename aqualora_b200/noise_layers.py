@@ -37,22 +37,82 @@ def random_int(rng, lo, hi):
     return int(rng.integers(lo, hi))                     # noises.py:17-18 (np.random.randint: hi exclusive)
 
 
-# functional forms (explicit parameters) ------------------------------------------------------------------------------
+# functional forms (explicit parameters), differentiable w.r.t. the image --------------------------------------------------
+# train/latent_wm_pretrain.py:186-216 back-propagates through `noiser(...)` into the encoder, so every layer is an
+# autograd.Function whose backward is the matching input-gradient kernel (csrc/noise.cu); parameters get no gradient.
+class _JpegFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.noise_jpeg(x)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return ops.noise_jpeg_bwd(gy.contiguous())
+
+
+class _CropResizeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, top, left, crop_h, crop_w, resize_h, resize_w, out_hw):
+        ctx.box = (int(top), int(left), int(crop_h), int(crop_w), int(resize_h), int(resize_w))
+        ctx.in_hw = tuple(x.shape[2:])
+        return ops.noise_crop_resize(x, top, left, crop_h, crop_w, resize_h, resize_w, out_hw)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return (ops.noise_crop_resize_bwd(gy.contiguous(), ctx.in_hw, *ctx.box),) + (None,) * 7
+
+
+class _BlurFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, sigmas, ksize):
+        ctx.save_for_backward(sigmas)
+        ctx.ksize = ksize
+        return ops.noise_gauss_blur(x, sigmas, ksize)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (sigmas,) = ctx.saved_tensors
+        return ops.noise_gauss_blur_bwd(gy.contiguous(), sigmas, ctx.ksize), None, None
+
+
+class _NoiseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, std, seed, offset):
+        return ops.noise_gauss_noise(x, std, seed, offset)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return gy, None, None, None            # y = x + std * n: identity
+
+
+class _JiggleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, params, order):
+        ctx.save_for_backward(x, params)
+        ctx.order = tuple(order)
+        return ops.noise_color_jiggle(x, params, order)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, params = ctx.saved_tensors
+        return ops.noise_color_jiggle_bwd(x, gy.contiguous(), params, ctx.order), None, None
+
+
 def jpeg_mask(x: torch.Tensor) -> torch.Tensor:
-    return ops.noise_jpeg(x)
+    return _JpegFn.apply(x)
 
 
 def crop_resize(x, top, left, crop_h, crop_w, resize_h, resize_w, out_hw=(512, 512)):
-    return ops.noise_crop_resize(x, top, left, crop_h, crop_w, resize_h, resize_w, out_hw)
+    return _CropResizeFn.apply(x, top, left, crop_h, crop_w, resize_h, resize_w, tuple(out_hw))
 
 
 def gaussian_blur(x, sigmas, ksize=(3, 9)):
     s = torch.as_tensor(sigmas, dtype=torch.float32).to(x.device)
-    return ops.noise_gauss_blur(x, s, ksize)
+    return _BlurFn.apply(x, s, tuple(ksize))
 
 
 def gaussian_noise(x, std, seed, offset=0):
-    return ops.noise_gauss_noise(x, std, seed, offset)
+    return _NoiseFn.apply(x, std, seed, offset)
 
 
 def unit_noise(shape, seed, offset=0, device="cuda"):
@@ -63,7 +123,7 @@ def unit_noise(shape, seed, offset=0, device="cuda"):
 def color_jiggle(x, brightness, contrast, saturation, hue, order):
     p = torch.tensor([list(map(float, brightness)), list(map(float, contrast)), list(map(float, saturation)), list(map(float, hue))],
                      dtype=torch.float32).t().contiguous().to(x.device)
-    return ops.noise_color_jiggle(x, p, order)
+    return _JiggleFn.apply(x, p, tuple(int(o) for o in order))
 
 
 # layer classes ------------------------------------------------------------------------------------------------------

@@ -318,6 +318,99 @@ def noise_color_jiggle(x: torch.Tensor, params: torch.Tensor, order) -> torch.Te
     return y
 
 
+def secret_encoder_bwd(g_c: torch.Tensor, msg: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, wc: torch.Tensor,
+                       g_w1: torch.Tensor, g_b1: torch.Tensor, g_wc: torch.Tensor, g_bc: torch.Tensor, base: int = 32, res: int = 64) -> None:
+    """Accumulate the SecretEncoder parameter gradients for g_c = dL/dc [B, 4, H, W]."""
+    for t, n in ((g_c, "g_c"), (msg, "msg"), (w1, "w1"), (b1, "b1"), (wc, "wc"), (g_w1, "g_w1"), (g_b1, "g_b1"), (g_wc, "g_wc"), (g_bc, "g_bc")):
+        _need(t, _F32, n)
+        if not t.is_contiguous():
+            raise _lib.AqualoraError(f"{n} must be contiguous")
+    B, bits = msg.shape
+    H, W = g_c.shape[2:]
+    nbytes = _lib.load().aq_secret_encoder_bwd_workspace_bytes(B, base, res)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=g_c.device)
+    _lib.call("aq_secret_encoder_bwd", g_c.data_ptr(), msg.data_ptr(), w1.data_ptr(), b1.data_ptr(), wc.data_ptr(), g_w1.data_ptr(),
+              g_b1.data_ptr(), g_wc.data_ptr(), g_bc.data_ptr(), B, bits, base, res, H, W, ws.data_ptr(), nbytes, _stream())
+
+
+def noise_jpeg_bwd(gy: torch.Tensor) -> torch.Tensor:
+    gy = _image(gy, "gy")
+    B, _, H, W = gy.shape
+    gx = torch.empty_like(gy)
+    _lib.call("aq_noise_jpeg_bwd", gy.data_ptr(), gx.data_ptr(), B, H, W, _stream())
+    return gx
+
+
+def noise_crop_resize_bwd(gy: torch.Tensor, in_hw, top: int, left: int, crop_h: int, crop_w: int, resize_h: int, resize_w: int) -> torch.Tensor:
+    gy = _image(gy, "gy")
+    B, _, oh, ow = gy.shape
+    H, W = in_hw
+    gx = torch.empty((B, 3, H, W), dtype=_F32, device=gy.device)
+    _lib.call("aq_noise_crop_resize_bwd", gy.data_ptr(), gx.data_ptr(), B, H, W, int(top), int(left), int(crop_h), int(crop_w),
+              int(resize_h), int(resize_w), int(oh), int(ow), _stream())
+    return gx
+
+
+def noise_gauss_blur_bwd(gy: torch.Tensor, sigmas: torch.Tensor, ksize=(3, 9)) -> torch.Tensor:
+    gy = _image(gy, "gy")
+    _need(sigmas, _F32, "sigmas", 1)
+    B, _, H, W = gy.shape
+    gx = torch.empty_like(gy)
+    _lib.call("aq_noise_gauss_blur_bwd", gy.data_ptr(), gx.data_ptr(), sigmas.contiguous().data_ptr(), B, H, W, int(ksize[0]),
+              int(ksize[1]), _stream())
+    return gx
+
+
+def noise_color_jiggle_bwd(x: torch.Tensor, gy: torch.Tensor, params: torch.Tensor, order) -> torch.Tensor:
+    import ctypes
+
+    x = _image(x)
+    gy = _image(gy, "gy")
+    _need(params, _F32, "params", 2)
+    B, _, H, W = x.shape
+    gx = torch.empty_like(x)
+    arr = (ctypes.c_int * 4)(*[int(o) for o in order])
+    _lib.call("aq_noise_color_jiggle_bwd", x.data_ptr(), gy.data_ptr(), gx.data_ptr(), params.contiguous().data_ptr(), arr, B, H, W, _stream())
+    return gx
+
+
+def prvl_loss_fwd(img1: torch.Tensor, img2: torch.Tensor):
+    """PRVL_loss (train/latent_wm_pretrain.py:42-50): returns (loss [1] fp32, state [1] int64 for the backward)."""
+    img1, img2 = _image(img1, "img1"), _image(img2, "img2")
+    if img1.shape != img2.shape:
+        raise _lib.AqualoraError("prvl_loss: images must have equal shapes")
+    B, _, H, W = img1.shape
+    loss = torch.empty(1, dtype=_F32, device=img1.device)
+    state = torch.empty(1, dtype=torch.int64, device=img1.device)
+    nbytes = _lib.load().aq_prvl_workspace_bytes(B, H, W)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=img1.device)
+    _lib.call("aq_prvl_loss_fwd", img1.data_ptr(), img2.data_ptr(), loss.data_ptr(), state.data_ptr(), B, H, W, ws.data_ptr(), nbytes, _stream())
+    return loss, state
+
+
+def prvl_loss_bwd(img1: torch.Tensor, img2: torch.Tensor, state: torch.Tensor, g_loss: torch.Tensor, want1: bool, want2: bool):
+    img1, img2 = _image(img1, "img1"), _image(img2, "img2")
+    B, _, H, W = img1.shape
+    g1 = torch.empty_like(img1) if want1 else None
+    g2 = torch.empty_like(img2) if want2 else None
+    g = g_loss.reshape(1).to(_F32).contiguous()
+    _lib.call("aq_prvl_loss_bwd", img1.data_ptr(), img2.data_ptr(), state.data_ptr(), g.data_ptr(), _ptr(g1), _ptr(g2), B, H, W, _stream())
+    return g1, g2
+
+
+def bce_logits(logits: torch.Tensor, targets: torch.Tensor, want_grad: bool = True):
+    """binary_cross_entropy_with_logits, mean reduction: (loss [1], d loss / d logits or None)."""
+    _need(logits, _F32, "logits")
+    _need(targets, _F32, "targets")
+    if logits.shape != targets.shape:
+        raise _lib.AqualoraError("bce_logits: logits and targets must have equal shapes")
+    x, y = logits.contiguous(), targets.contiguous()
+    loss = torch.empty(1, dtype=_F32, device=x.device)
+    g = torch.empty_like(x) if want_grad else None
+    _lib.call("aq_bce_logits", x.data_ptr(), y.data_ptr(), loss.data_ptr(), _ptr(g), x.numel(), _stream())
+    return loss, g
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # message decoder (EfficientNet-B1, utils/models.py:84-96)
 # ------------------------------------------------------------------------------------------------------------------

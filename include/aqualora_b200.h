@@ -148,6 +148,14 @@ int aq_secret_encoder_fwd(const float* msg, const float* w1, const float* b1, co
                           const float* x, float* c_out, float* x_out, int B, int bits, int base, int res, int H, int W,
                           void* ws, void* stream);
 
+/* Backward of aq_secret_encoder_fwd (the encoder is trained through the VAE decoder, the noise layer and the message decoder:
+ * train/latent_wm_pretrain.py:174-216).  g_c [B, 4, H, W] = dL/dc (add dL/dx_out to it first: x_out = x + c);
+ * g_w1 [base*base, bits], g_b1 [base*base], g_wc [4, 4, 3, 3], g_bc [4] fp32 are ACCUMULATED into. */
+size_t aq_secret_encoder_bwd_workspace_bytes(int B, int base, int res);
+int aq_secret_encoder_bwd(const float* g_c, const float* msg, const float* w1, const float* b1, const float* wc, float* g_w1,
+                          float* g_b1, float* g_wc, float* g_bc, int B, int bits, int base, int res, int H, int W, void* ws,
+                          size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (ii) noise_layers distortion stack (utils/noise_layers/*).  x, y: [B, 3, H, W] fp32 NCHW in [-1, 1]; y != x.
  * Every quantity the reference layer samples internally is an explicit argument here (Noiser draws them on the
@@ -171,6 +179,33 @@ int aq_noise_gauss_noise(const float* x, float* y, int64_t n, float std, uint64_
  * contrast, saturation, hue) per sample; order_host[4] = permutation of (0 brightness, 1 contrast, 2 saturation, 3 hue). */
 int aq_noise_color_jiggle(const float* x, float* y, const float* params, const int* order_host, int B, int H, int W,
                           void* stream);
+
+/* Input gradients of the noise layers (train/latent_wm_pretrain.py:186-190 back-propagates through `noiser(...)` into the
+ * encoder).  gy: dL/dy of the matching forward call with the SAME parameters; gx: dL/dx, fully written.
+ *   jpeg          linear and self-adjoint up to the colour matrices: the forward kernel with C1^T / C2^T
+ *   crop_resize   adjoint of the fused double bilinear gather (fp32 atomics: run-to-run summation order varies)
+ *   gauss_blur    adjoint of the reflect-border separable filter, as a gather
+ *   gauss_noise   identity (gx = gy): no entry point
+ *   color_jiggle  gx = J^T gy with the per-pixel 3 x 3 Jacobian of the executed arithmetic (forward-mode duals in the kernel) */
+int aq_noise_jpeg_bwd(const float* gy, float* gx, int B, int H, int W, void* stream);
+int aq_noise_crop_resize_bwd(const float* gy, float* gx, int B, int H, int W, int top, int left, int crop_h, int crop_w,
+                             int resize_h, int resize_w, int out_h, int out_w, void* stream);
+int aq_noise_gauss_blur_bwd(const float* gy, float* gx, const float* sigmas, int B, int H, int W, int ky, int kx, void* stream);
+int aq_noise_color_jiggle_bwd(const float* x, const float* gy, float* gx, const float* params, const int* order_host, int B,
+                              int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (ii) losses of the pretraining step (train/latent_wm_pretrain.py).
+ * PRVL_loss (:42-50): max over all positions (batch included) of the 32 x 32 box mean, zero padding 16, of the channel-mean
+ * |img1 - img2|; img [B, 3, H, W] fp32.  loss[0] receives the value; state (8 bytes, 8-byte aligned) keeps the arg-max for the
+ * backward, which sends g_loss[0] / (1024 * 3) * sign(img1 - img2) to the winning window (g_img1 and / or g_img2, fully written).
+ * binary_cross_entropy_with_logits (:200), mean reduction: loss[0] and, when g_logits != NULL, d loss / d logits. */
+size_t aq_prvl_workspace_bytes(int B, int H, int W);
+int aq_prvl_loss_fwd(const float* img1, const float* img2, float* loss, void* state, int B, int H, int W, void* ws, size_t ws_bytes,
+                     void* stream);
+int aq_prvl_loss_bwd(const float* img1, const float* img2, const void* state, const float* g_loss, float* g_img1, float* g_img2,
+                     int B, int H, int W, void* stream);
+int aq_bce_logits(const float* logits, const float* targets, float* loss, float* g_logits, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (ii) message decoder.  SecretDecoder.forward (utils/models.py:91-96 == evaluation/utils_eval.py:149-154):

@@ -1,0 +1,185 @@
+"""Training side of hot path (ii) on the B200 (train/latent_wm_pretrain.py:164-217): gradients of the encoder, the noise layers
+and the losses against autograd through the CPU oracle on identical inputs and parameters.  fp32 everywhere; tolerances are
+elementwise (rtol 1e-4 / atol 1e-5 of the tensor's max unless stated)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, want, rtol=1e-4, atol_rel=1e-5, what=""):
+    want = want.float().cpu()
+    torch.testing.assert_close(got.float().cpu(), want, rtol=rtol, atol=atol_rel * float(want.abs().max()) + 1e-12, msg=lambda m: f"{what}: {m}")
+
+
+def _layer_grads(layer_idx, params, x, gy, noise=None):
+    from oracle import noise_oracle as NO
+
+    xr = x.clone().requires_grad_(True)
+    y = NO.apply_layer(xr, layer_idx, params, noise)
+    y.backward(gy)
+    return y.detach(), xr.grad
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 80), (1, 3, 37, 50)])
+def test_jpeg_backward(cuda_device, shape):
+    from aqualora_b200 import noise_layers as NL
+
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(shape, generator=g) * 2 - 1
+    gy = torch.randn(shape, generator=g)
+    y_ref, gx_ref = _layer_grads(1, {}, x, gy)
+    xc = x.to(cuda_device).requires_grad_(True)
+    y = NL.jpeg_mask(xc)
+    y.backward(gy.to(cuda_device))
+    _close(y.detach(), y_ref, 1e-4, 2e-5, "jpeg y")
+    _close(xc.grad, gx_ref, 1e-4, 2e-5, "jpeg gx")
+
+
+def test_crop_resize_backward(cuda_device):
+    from aqualora_b200 import noise_layers as NL
+
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(2, 3, 96, 112, generator=g) * 2 - 1
+    for p in (dict(top=5, left=9, crop_h=61, crop_w=70, resize_h=53, resize_w=88), dict(top=0, left=0, crop_h=96, crop_w=112, resize_h=120, resize_w=57)):
+        gy = torch.randn(2, 3, 64, 72, generator=g)
+        from oracle import noise_oracle as NO
+
+        xr = x.clone().requires_grad_(True)
+        NO.crop_resize(xr, out_hw=(64, 72), **p).backward(gy)
+        xc = x.to(cuda_device).requires_grad_(True)
+        NL.crop_resize(xc, out_hw=(64, 72), **p).backward(gy.to(cuda_device))
+        _close(xc.grad, xr.grad, 1e-4, 1e-5, "crop_resize gx")           # atomics: order of the fp32 sums varies
+
+
+def test_gauss_blur_backward(cuda_device):
+    from aqualora_b200 import noise_layers as NL
+
+    g = torch.Generator().manual_seed(3)
+    for shape, sig, ks in (((2, 3, 40, 56), [0.7, 4.0], (3, 9)), ((1, 3, 9, 12), [2.5], (3, 5))):
+        x = torch.rand(shape, generator=g) * 2 - 1
+        gy = torch.randn(shape, generator=g)
+        from oracle import noise_oracle as NO
+
+        xr = x.clone().requires_grad_(True)
+        NO.gaussian_blur(xr, sig, ks).backward(gy)
+        xc = x.to(cuda_device).requires_grad_(True)
+        NL.gaussian_blur(xc, sig, ks).backward(gy.to(cuda_device))
+        _close(xc.grad, xr.grad, 1e-4, 1e-5, "blur gx")
+
+
+def test_gauss_noise_backward_is_identity(cuda_device):
+    from aqualora_b200 import noise_layers as NL
+
+    x = torch.rand(2, 3, 16, 16, device=cuda_device).requires_grad_(True)
+    gy = torch.randn(2, 3, 16, 16, device=cuda_device)
+    NL.gaussian_noise(x, 0.1, 1234, 0).backward(gy)
+    assert torch.equal(x.grad, gy)
+
+
+def test_color_jiggle_backward(cuda_device):
+    from aqualora_b200 import noise_layers as NL
+    from oracle import noise_oracle as NO
+
+    g = torch.Generator().manual_seed(4)
+    rng = np.random.default_rng(4)
+    for trial in range(4):
+        x = torch.rand(2, 3, 24, 40, generator=g) * 2 - 1
+        gy = torch.randn(2, 3, 24, 40, generator=g)
+        p = NO.draw_params(rng, 5, 2)
+        xr = x.clone().requires_grad_(True)
+        NO.color_jiggle(xr, **p).backward(gy)
+        xc = x.to(cuda_device).requires_grad_(True)
+        y = NL.color_jiggle(xc, **p)
+        y.backward(gy.to(cuda_device))
+        # piecewise map: a pixel within rounding of a branch boundary (clamp edge, hue sector, channel tie) may take the other branch
+        # in fp32 on the two machines; everywhere else the Jacobians agree to rounding
+        diff = (xc.grad.cpu() - xr.grad).abs()
+        tol = 1e-3 * xr.grad.abs().max() + 1e-3 * xr.grad.abs()
+        assert (diff <= tol).float().mean().item() >= 0.999, (trial, p["order"], (diff > tol).sum().item())
+
+
+@pytest.mark.parametrize("hw", [(64, 64), (96, 96), (40, 56)])
+def test_secret_encoder_backward(cuda_device, hw):
+    from aqualora_b200.models import SecretEncoder
+    from oracle.pretrain_oracle import SecretEncoderRef
+
+    torch.manual_seed(0)
+    ref = SecretEncoderRef(48)
+    with torch.no_grad():
+        ref.secret_scaler[5].weight.normal_(0, 0.05)
+        ref.secret_scaler[5].bias.normal_(0, 0.05)
+    enc = SecretEncoder(48)
+    enc.load_state_dict(ref.state_dict())
+    enc = enc.to(cuda_device)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 4, *hw, generator=g)
+    msg = torch.randint(0, 2, (3, 48), generator=g).float()
+    g1, g2 = torch.randn(3, 4, *hw, generator=g), torch.randn(3, 4, *hw, generator=g)
+    xr = x.clone().requires_grad_(True)
+    xo_r, c_r = ref(xr, msg)
+    (xo_r * g1).sum().add((c_r * g2).sum()).backward()
+    xc = x.to(cuda_device).requires_grad_(True)
+    xo, c = enc(xc, msg.to(cuda_device))
+    ((xo * g1.to(cuda_device)).sum() + (c * g2.to(cuda_device)).sum()).backward()
+    _close(c.detach(), c_r.detach(), 1e-5, 1e-6, "c")
+    _close(xc.grad, xr.grad, 1e-5, 1e-6, "gx")
+    for (n, p), (_, q) in zip(enc.named_parameters(), ref.named_parameters()):
+        _close(p.grad, q.grad, 2e-4, 2e-5, n)
+    # encode(): the map alone
+    enc.zero_grad(); ref.zero_grad()
+    cm = enc.encode(msg.to(cuda_device))
+    cm.pow(2).sum().backward()
+    ref.secret_scaler(msg).pow(2).sum().backward()
+    for (n, p), (_, q) in zip(enc.named_parameters(), ref.named_parameters()):
+        _close(p.grad, q.grad, 2e-4, 2e-5, "encode " + n)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 64), (1, 3, 96, 80), (2, 3, 512, 512)])
+def test_prvl_loss_and_gradient(cuda_device, shape):
+    from aqualora_b200.losses import PRVL_loss
+    from oracle.pretrain_oracle import prvl_loss
+
+    g = torch.Generator().manual_seed(6)
+    a = torch.rand(shape, generator=g) * 2 - 1
+    b = a + 0.1 * torch.randn(shape, generator=g)
+    br = b.clone().requires_grad_(True)
+    want = prvl_loss(a, br)
+    (want * 1.5).backward()
+    bc = b.to(cuda_device).requires_grad_(True)
+    got = PRVL_loss(a.to(cuda_device), bc)
+    (got * 1.5).backward()
+    assert abs(got.item() - want.item()) <= 2e-6 * abs(want.item()) + 1e-9, (got.item(), want.item())
+    _close(bc.grad, br.grad, 1e-5, 1e-6, "prvl grad")
+    assert int((bc.grad != 0).sum()) <= 3 * 32 * 32
+
+
+def test_prvl_golden(cuda_device, golden_dir):
+    """Values produced by the reference's own PRVL_loss source (tools/gen_golden.py)."""
+    import os
+
+    from aqualora_b200.losses import PRVL_loss
+
+    gold = torch.load(os.path.join(golden_dir, "pretrain_small.pt"), weights_only=False)
+    for c in gold["prvl"]:
+        if c["a"] is None:
+            continue
+        got = PRVL_loss(c["a"].to(cuda_device), c["b"].to(cuda_device))
+        assert abs(got.item() - c["value"].item()) <= 2e-6 * abs(c["value"].item()), (c["shape"], got.item(), c["value"].item())
+
+
+def test_bce_with_logits(cuda_device):
+    from aqualora_b200.losses import binary_cross_entropy_with_logits as bce
+
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(4, 48, 2, generator=g) * 3
+    y = torch.nn.functional.one_hot(torch.randint(0, 2, (4, 48), generator=g), 2).float()
+    xr = x.clone().requires_grad_(True)
+    want = torch.nn.functional.binary_cross_entropy_with_logits(xr, y)
+    want.backward()
+    xc = x.to(cuda_device).requires_grad_(True)
+    got = bce(xc, y.to(cuda_device))
+    got.backward()
+    assert abs(got.item() - want.item()) <= 1e-5 * want.item()
+    _close(xc.grad, xr.grad, 1e-4, 1e-6, "bce grad")
