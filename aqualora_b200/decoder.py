@@ -3,14 +3,19 @@
 The reference wraps torchvision's `efficientnet_b1` and replaces its classifier by `Linear(1280, 2 * bits)`; checkpoints
 (`msgdecoder.pt`, the `sec_decoder` entry of the pretrain checkpoint) are that module's state-dict under `model.`.
 This class keeps exactly those parameter / buffer names (so `load_state_dict` of a reference checkpoint works unchanged)
-but owns no torchvision code: the forward is the fp32 NHWC kernel chain in csrc/decoder.cu with every BatchNorm folded
-into its convolution.  Eval-mode only (PPFT and evaluation run the decoder in eval(): train/ppft_train.py:974,
-evaluation/utils_eval.py:168); calling it in train mode or on CPU tensors raises -- there is no PyTorch fallback.
+but owns no torchvision code.  eval(): the fp32 NHWC kernel chain in csrc/decoder.cu with every BatchNorm folded into its
+convolution (PPFT and evaluation run the decoder in eval(): train/ppft_train.py:974, evaluation/utils_eval.py:168).
+train() (train/latent_wm_pretrain.py:160-217, rob_enhance_finetune.py:995-1040): batch-statistics BatchNorm, StochasticDepth("row")
+and Dropout(0.2) as torchvision's `efficientnet_b1` defines them, differentiable w.r.t. the image and every parameter.  The
+train-mode convolutions are LIBRARY calls (cuDNN / ATen on the GPU) for now -- hand-written training kernels for this net are
+the next step; everything around it in the pretraining step (encoder, noise layers, losses) runs on this
+repository's kernels.  CPU tensors raise in both modes: there is no CPU fallback.
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
 from ._lib import AqualoraError
@@ -142,12 +147,60 @@ class SecretDecoder(nn.Module):
             self._packed_key = key
         return self._packed
 
+    # -- train mode: torchvision's EfficientNet-B1 dataflow on the parameter container (SURVEY.md 8(a) "MBConv dataflow") ---------
+    stochastic_depth_prob = 0.2        # torchvision efficientnet_b1 default
+    dropout_p = 0.2                    # classifier[0]
+
+    def _train_forward(self, x):
+        m = self.model
+        total_blocks = float(sum(layers for *_, layers in B1_STAGES))
+
+        def cba(seq, x, act=True):
+            y = seq[1](seq[0](x))                       # conv (no bias) -> BatchNorm2d with batch statistics (updates running stats)
+            return F.silu(y) if act else y
+
+        x = cba(m.features[0], x)
+        block_id = 0
+        for si, (expand, k, stride, cin, cout, layers) in enumerate(B1_STAGES):
+            for li in range(layers):
+                blk = m.features[si + 1][li].block
+                h, i = x, 0
+                if expand != 1:
+                    h = cba(blk[i], h)
+                    i += 1
+                h = cba(blk[i], h)
+                i += 1
+                se = blk[i]
+                scale = torch.sigmoid(se.fc2(F.silu(se.fc1(F.adaptive_avg_pool2d(h, 1)))))
+                h = h * scale
+                i += 1
+                h = cba(blk[i], h, act=False)
+                if (stride if li == 0 else 1) == 1 and (cin if li == 0 else cout) == cout:
+                    p = self.stochastic_depth_prob * block_id / total_blocks     # StochasticDepth(p, "row")
+                    if p > 0.0:
+                        keep = torch.empty(h.shape[0], 1, 1, 1, dtype=h.dtype, device=h.device).bernoulli_(1.0 - p) / (1.0 - p)
+                        h = h * keep
+                    h = h + x
+                x = h
+                block_id += 1
+        x = cba(m.features[8], x)
+        x = F.adaptive_avg_pool2d(x, 1).flatten(1)
+        x = F.dropout(x, self.dropout_p, training=True)
+        return m.classifier[1](x)
+
     def _run(self, x, want_bits):
-        if self.training:
-            raise AqualoraError("SecretDecoder: only eval() is implemented on the CUDA path (BatchNorm folded; PPFT / evaluation "
-                                "run the decoder in eval mode)")
         if not x.is_cuda:
             raise AqualoraError("SecretDecoder: CPU tensor passed; aqualora_b200 has no CPU fallback")
+        if self.training:
+            x = x.float()
+            if tuple(x.shape[-2:]) != (512, 512):
+                from .noise_layers import crop_resize
+
+                H, W = x.shape[-2:]
+                x = crop_resize(x, 0, 0, H, W, 512, 512, (512, 512))         # F.interpolate(x, (512, 512), 'bilinear'), differentiable
+            logits = self._train_forward(x.contiguous(memory_format=torch.channels_last))
+            bits = logits.view(-1, self.output_size, 2).argmax(-1).to(torch.uint8) if want_bits else None
+            return logits.view(-1, self.output_size, 2), bits
         x = x.float()
         if tuple(x.shape[-2:]) != (512, 512):
             H, W = x.shape[-2:]

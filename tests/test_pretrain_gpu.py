@@ -183,3 +183,96 @@ def test_bce_with_logits(cuda_device):
     got.backward()
     assert abs(got.item() - want.item()) <= 1e-5 * want.item()
     _close(xc.grad, xr.grad, 1e-4, 1e-6, "bce grad")
+
+
+def test_decoder_train_mode_matches_torchvision(cuda_device):
+    """SecretDecoder.train(): batch-statistics BatchNorm forward + backward vs torchvision's efficientnet_b1 in train mode on the
+    CPU (stochastic depth and dropout off on both sides: their masks come from different RNG streams)."""
+    from aqualora_b200.decoder import SecretDecoder
+    from oracle.pretrain_oracle import SecretDecoderRef
+
+    torch.manual_seed(0)
+    ref = SecretDecoderRef(48).train()
+    for mod in ref.modules():
+        if mod.__class__.__name__ == "StochasticDepth":
+            mod.p = 0.0
+    ref.model.classifier[0].p = 0.0
+    dec = SecretDecoder(48)
+    dec.load_state_dict(ref.state_dict())
+    dec = dec.to(cuda_device).train()
+    dec.stochastic_depth_prob, dec.dropout_p = 0.0, 0.0
+    g = torch.Generator().manual_seed(8)
+    x = torch.rand(2, 3, 512, 512, generator=g) * 2 - 1
+    gy = torch.randn(2, 48, 2, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(gy)
+    xc = x.to(cuda_device).requires_grad_(True)
+    yc = dec(xc)
+    yc.backward(gy.to(cuda_device))
+    _close(yc.detach(), yr.detach(), 2e-3, 2e-3, "train logits")
+    _close(xc.grad, xr.grad, 2e-2, 2e-2, "train gx")
+    sd_r, sd_c = ref.state_dict(), dec.state_dict()
+    for k in ("model.features.0.1.running_mean", "model.features.0.1.running_var", "model.features.8.1.running_var",
+              "model.features.4.2.block.1.1.running_mean"):
+        _close(sd_c[k], sd_r[k], 1e-3, 1e-3, k)
+    gr = dict(ref.named_parameters())
+    worst = 0.0
+    for n, p in dec.named_parameters():
+        q = gr[n].grad
+        rel = ((p.grad.cpu() - q).norm() / (q.norm() + 1e-12)).item()
+        worst = max(worst, rel)
+    assert worst < 5e-2, worst          # deep fp32 net, TF32-free library convolutions on both sides; per-tensor relative error
+
+
+def test_pretrain_step_matches_oracle(cuda_device):
+    """configs[0] promoted to the GPU: one train/latent_wm_pretrain.py:164-217 iteration (B = 2, 48 bits, 64 x 64 latents) with the
+    stub VAE / LPIPS of the oracle on both sides, every loss-schedule stage and three noise layers."""
+    import random
+
+    from aqualora_b200 import noise_layers as NL
+    from aqualora_b200 import pretrain
+    from aqualora_b200.decoder import SecretDecoder
+    from aqualora_b200.models import SecretEncoder
+    from oracle import pretrain_oracle as PO
+
+    torch.manual_seed(1)
+    enc_r = PO.SecretEncoderRef(48)
+    with torch.no_grad():
+        enc_r.secret_scaler[5].weight.normal_(0, 0.05)
+    dec_r = PO.SecretDecoderRef(48).train()
+    for mod in dec_r.modules():
+        if mod.__class__.__name__ == "StochasticDepth":
+            mod.p = 0.0
+    dec_r.model.classifier[0].p = 0.0
+    vae = PO.StubVAE(0)
+    vae_c = PO.StubVAE(0).to(cuda_device)        # frozen third-party stand-in: plain torch on both sides
+    g = torch.Generator().manual_seed(9)
+    image = torch.rand(2, 3, 512, 512, generator=g) * 2 - 1
+    msg = torch.randint(0, 2, (2, 48), generator=g)
+    cases = [(0, {}, True, 0), (1, {}, False, 2), (3, {"sigmas": [1.5, 3.0]}, False, 1)]
+    for layer, params, warmup, stage in cases:
+        enc_c = SecretEncoder(48); enc_c.load_state_dict(enc_r.state_dict()); enc_c = enc_c.to(cuda_device).train()
+        dec_c = SecretDecoder(48); dec_c.load_state_dict(dec_r.state_dict()); dec_c = dec_c.to(cuda_device).train()
+        dec_c.stochastic_depth_prob, dec_c.dropout_p = 0.0, 0.0
+        enc_r.zero_grad(); dec_r.zero_grad()
+        out_r = PO.pretrain_step(enc_r, dec_r, vae, image, msg, layer, params, random.Random(3), warmup, stage)
+        if layer == 0:
+            override = lambda im: im
+        elif layer == 1:
+            override = NL.jpeg_mask
+        else:
+            override = lambda im: NL.gaussian_blur(im, params["sigmas"])
+        out_c = pretrain.pretrain_step(enc_c, dec_c, vae_c.encode, vae_c.decode, PO.lpips_stub, None, image.to(cuda_device),
+                                       msg.to(cuda_device), random.Random(3), None, warmup, stage, layer_override=override)
+        for k in ("loss", "msgloss", "lpips", "prvl"):
+            assert abs(out_c[k].item() - out_r[k].item()) <= 2e-3 * abs(out_r[k].item()) + 1e-7, (layer, k, out_c[k].item(), out_r[k].item())
+        _close(out_c["wm_image"], out_r["wm_image"], 1e-4, 1e-5, "wm_image")
+        for (n, p), (_, q) in zip(enc_c.named_parameters(), enc_r.named_parameters()):
+            rel = ((p.grad.cpu() - q.grad).norm() / (q.grad.norm() + 1e-20)).item()
+            assert rel < 5e-2, (layer, n, rel)
+        rel = max(((p.grad.cpu() - dict(dec_r.named_parameters())[n].grad).norm() /
+                   (dict(dec_r.named_parameters())[n].grad.norm() + 1e-12)).item() for n, p in dec_c.named_parameters())
+        assert rel < 5e-2, (layer, "decoder", rel)
+        ck = pretrain.checkpoint_dict(enc_c, dec_c)
+        assert set(ck) == {"sec_decoder", "sec_encoder"} and set(ck["sec_decoder"]) == set(dec_r.state_dict())
