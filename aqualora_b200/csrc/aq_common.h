@@ -54,6 +54,23 @@ enum TmaSwizzle { kSwzNone = 0, kSwz32 = 1, kSwz64 = 2, kSwz128 = 3 };
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, TmaSwizzle swz);
 
+// Launch configuration with the programmatic-dependent-launch attribute (AQ_PDL=0 in the environment disables it): the kernel's
+// prologue (barrier init, TMEM allocation, descriptor prefetch) and its launch latency overlap the tail of the previous kernel in
+// the stream; every kernel launched through this calls griddep_wait() before touching global memory.
+bool pdl_enabled();
+struct PdlLaunch {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  }
+};
+
 void count_launch();
 int sm_count();  // SMs of the current device (cached)
 int check_arch();  // AQ_OK iff the current device is sm_100

@@ -183,6 +183,13 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
 }
 
 // One elected lane of a fully converged warp gets true (deterministic for a fixed member mask).
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may start while its
+// predecessor in the stream is still running; `griddep_wait` blocks until the predecessor grid has completed and its memory is
+// visible (a no-op for a normal launch), `griddep_launch_dependents` lets the NEXT kernel's CTAs be scheduled as soon as every CTA
+// of this grid has issued it (they still pass their own griddep_wait only after this grid is done).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

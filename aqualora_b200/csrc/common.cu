@@ -1,5 +1,6 @@
 // Error reporting, device queries and the TMA descriptor factory shared by all kernels.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -75,6 +76,15 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
     return fail(AQ_ERR_LAUNCH, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu x %llu box %u x %u)", (int)r, rank,
                 (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 1), box[0], rank > 1 ? box[1] : 1u);
   return AQ_OK;
+}
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("AQ_PDL");
+    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
 }
 
 static std::atomic<long long> g_launches{0};

@@ -167,6 +167,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   AQ_CTA_STAMP(0);
+  griddep_launch_dependents();   // PDL: the next kernel's CTAs may queue behind ours now (they wait for this grid before any global access)
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -220,6 +221,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
   cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  griddep_wait();                // PDL: everything above overlapped the previous kernel's tail; from here on we read / write global memory
   AQ_CTA_STAMP(1);
 
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
@@ -741,7 +743,8 @@ static int launch_bn(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) 
   const int grid = 2 * (int)(items < slots ? items : slots);
 
   AQ_OPT_IN_SMEM((lora_gemm_kernel<BN, NP>), L::kTotal);
-  lora_gemm_kernel<BN, NP><<<grid, kThreads, L::kTotal, stream>>>(p);
+  PdlLaunch launch(dim3(grid), dim3(kThreads), L::kTotal, stream);
+  AQ_CHECK_CUDA(cudaLaunchKernelEx(&launch.cfg, lora_gemm_kernel<BN, NP>, p));
   AQ_LAUNCHED();
   return AQ_OK;
 }

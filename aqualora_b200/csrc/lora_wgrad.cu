@@ -44,6 +44,7 @@ struct WgradLaunch {
 };
 
 __global__ void __launch_bounds__(kWgThreads) lora_wgrad_kernel(const __grid_constant__ WgradLaunch launch) {
+  griddep_launch_dependents();   // PDL (see aq_ptx.cuh)
   const WgradParams& p = launch.prob[blockIdx.z];
   if ((int)blockIdx.x >= p.i_tiles || (int)blockIdx.y >= p.splits) return;   // whole CTA: this problem is smaller than the grid
   extern __shared__ uint8_t smem_raw[];
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(kWgThreads) lora_wgrad_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  griddep_wait();                // PDL: the prologue above overlapped the previous kernel (the dX kernel that writes dH / Hs)
 
   if (kb_begin < kb_end) {
     if (warp == 0) {
@@ -204,8 +206,8 @@ static int launch_wgrad_n(WgradLaunch& l, int n, cudaStream_t stream) {
     gx = l.prob[i].i_tiles > gx ? l.prob[i].i_tiles : gx;
     gy = l.prob[i].splits > gy ? l.prob[i].splits : gy;
   }
-  dim3 grid(gx, gy, n);
-  lora_wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, stream>>>(l);
+  PdlLaunch launch(dim3(gx, gy, n), dim3(kWgThreads), kWgSmemBytes, stream);
+  AQ_CHECK_CUDA(cudaLaunchKernelEx(&launch.cfg, lora_wgrad_kernel, l));
   AQ_LAUNCHED();
   return AQ_OK;
 }
