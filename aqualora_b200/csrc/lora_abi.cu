@@ -5,6 +5,10 @@ namespace aq {
 
 static thread_local int g_force_bn = 0;
 static thread_local int g_force_group = 0;
+constexpr int kRankChunk = 64;   // rank slice one launch of the fused kernel covers (TMEM: 2 accumulators + one 64-column H tile)
+
+static inline const void* bf16_at(const void* base, int64_t elems) { return reinterpret_cast<const uint16_t*>(base) + elems; }
+static inline void* bf16_at(void* base, int64_t elems) { return reinterpret_cast<uint16_t*>(base) + elems; }
 
 }  // namespace aq
 
@@ -25,17 +29,31 @@ int aq_lora_linear_fwd(const void* x, int64_t ldx, const void* w, const void* bi
                        int dout, int r, void* stream) {
   AQ_REQUIRE(x && w && y, AQ_ERR_BAD_SHAPE, "lora_linear_fwd: x, w and y must be non-NULL");
   AQ_REQUIRE(tokens_per_sample > 0 || down == nullptr, AQ_ERR_BAD_SHAPE, "lora_linear_fwd: tokens_per_sample must be > 0");
-  LoraGemmArgs a;
-  a.a = x; a.lda = ldx; a.w = w; a.bias = bias; a.dn = down; a.up = up; a.scale = scale; a.y = y; a.ldy = ldy;
-  a.aux_out0 = h_save; a.aux_out1 = nullptr; a.h_in = nullptr; a.g_scale = nullptr;
-  a.M = M; a.tokens = tokens_per_sample; a.K = din; a.N = dout; a.r = r; a.mode = 0; a.has_main = 1;
-  a.force_bn = g_force_bn; a.force_group = g_force_group;
-  return launch_lora_gemm(a, (cudaStream_t)stream);
+  AQ_REQUIRE(down == nullptr || (r >= 8 && r % 8 == 0), AQ_ERR_BAD_SHAPE,
+             "lora_linear_fwd: rank r=%d must be a multiple of 8, >= 8 (pad smaller / odd ranks with zero rows)", r);
+  // Ranks above 64 (the reference's released recipe is rank 320: train/README.md:34-48) run as ceil(r / 64) launches over 64-wide
+  // slices of the LoRA operands: the first is the fused kernel as usual, each further one adds its slice's Hs Up^T to Y in place.
+  const int chunks = down == nullptr ? 1 : (r + kRankChunk - 1) / kRankChunk;
+  for (int c = 0; c < chunks; ++c) {
+    const int r0 = c * kRankChunk, rc_ = down == nullptr ? 0 : (r - r0 < kRankChunk ? r - r0 : kRankChunk);
+    LoraGemmArgs a;
+    a.a = x; a.lda = ldx; a.w = w; a.bias = c == 0 ? bias : nullptr; a.scale = scale ? scale + r0 : nullptr; a.y = y; a.ldy = ldy;
+    a.dn = down ? bf16_at(down, (int64_t)r0 * din) : nullptr;        // rows r0 ... of down [r, din]
+    a.up = up ? bf16_at(up, r0) : nullptr;                            // columns r0 ... of up [dout, r]
+    a.aux_out0 = h_save ? bf16_at(h_save, r0) : nullptr; a.aux_out1 = nullptr; a.h_in = nullptr; a.g_scale = nullptr;
+    a.M = M; a.tokens = tokens_per_sample; a.K = din; a.N = dout; a.r = rc_; a.mode = 0; a.has_main = 1;
+    a.ld_r = r; a.skip_base = c > 0; a.accum_y = c > 0;
+    a.force_bn = g_force_bn; a.force_group = g_force_group;
+    int rc = launch_lora_gemm(a, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return AQ_OK;
 }
 
 int aq_lora_linear_fwd_grouped(const void* x, int64_t ldx, const aq_lora_projection* proj, int nproj, const float* scale, int64_t M,
                                int64_t tokens_per_sample, int din, int r, void* stream) {
   AQ_REQUIRE(x && proj && nproj >= 1 && nproj <= 32, AQ_ERR_BAD_SHAPE, "lora_linear_fwd_grouped: x / proj NULL or nproj=%d outside 1 ... 32", nproj);
+  AQ_REQUIRE(r <= kRankChunk, AQ_ERR_BAD_SHAPE, "lora_linear_fwd_grouped: rank %d > %d runs through aq_lora_linear_fwd per projection", r, kRankChunk);
   LoraGemmArgs args[32];
   for (int i = 0; i < nproj; ++i) {
     AQ_REQUIRE(proj[i].w && proj[i].y, AQ_ERR_BAD_SHAPE, "lora_linear_fwd_grouped: projection %d has a NULL w / y", i);
@@ -66,19 +84,30 @@ int aq_lora_linear_bwd(const void* gy, int64_t ldgy, const void* x, int64_t ldx,
   const size_t need = aq_lora_linear_bwd_workspace_bytes(M, r);
   AQ_REQUIRE(ws != nullptr && ws_bytes >= need, AQ_ERR_WORKSPACE, "lora_linear_bwd: workspace %zu bytes < required %zu", ws_bytes, need);
   AQ_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, AQ_ERR_BAD_ALIGN, "lora_linear_bwd: workspace must be 256-byte aligned");
+  AQ_REQUIRE(r >= 8 && r % 8 == 0, AQ_ERR_BAD_SHAPE, "lora_linear_bwd: rank r=%d must be a multiple of 8, >= 8", r);
   uint8_t* dh = reinterpret_cast<uint8_t*>(ws);
   uint8_t* hs = dh + need / 2;
   cudaStream_t st = (cudaStream_t)stream;
-  // 1) dX = G W + ((G Up) (.) s) Dn, with dH / Hs / dscale produced by the mid-epilogue of the same kernel
-  LoraGemmArgs a;
-  a.a = gy; a.lda = ldgy; a.w = w_t; a.bias = nullptr; a.dn = up_t; a.up = down_t; a.scale = scale; a.y = gx; a.ldy = ldgx;
-  a.aux_out0 = dh; a.aux_out1 = hs; a.h_in = h_save; a.g_scale = g_scale;
-  a.M = M; a.tokens = tokens_per_sample; a.K = dout; a.N = din; a.r = r; a.mode = 1; a.has_main = (gx != nullptr);
-  a.force_bn = g_force_bn; a.force_group = g_force_group;
-  int rc = launch_lora_gemm(a, st);
-  if (rc) return rc;
-  // 2) dUp[dout, r] += G^T Hs  and  dDn[r, din] += dH^T X, one launch (grid.z = 2)
-  return launch_wgrad_pair(gy, ldgy, hs, r, g_up, r, dout, r, 0, x, ldx, dh, r, g_down, din, din, r, 1, M, st);
+  const int chunks = (r + kRankChunk - 1) / kRankChunk;
+  for (int c = 0; c < chunks; ++c) {
+    const int r0 = c * kRankChunk, rc_ = r - r0 < kRankChunk ? r - r0 : kRankChunk;
+    // 1) dX (+)= G W + ((G Up_c) (.) s_c) Dn_c, with dH_c / Hs_c / dscale_c produced by the mid-epilogue of the same kernel
+    LoraGemmArgs a;
+    a.a = gy; a.lda = ldgy; a.w = w_t; a.bias = nullptr; a.scale = scale + r0; a.y = gx; a.ldy = ldgx;
+    a.dn = bf16_at(up_t, (int64_t)r0 * dout);          // rows r0 ... of Up^T [r, dout]
+    a.up = bf16_at(down_t, r0);                        // columns r0 ... of Dn^T [din, r]
+    a.aux_out0 = bf16_at(dh, r0); a.aux_out1 = bf16_at(hs, r0); a.h_in = bf16_at(h_save, r0); a.g_scale = g_scale ? g_scale + r0 : nullptr;
+    a.M = M; a.tokens = tokens_per_sample; a.K = dout; a.N = din; a.r = rc_; a.mode = 1; a.has_main = (gx != nullptr);
+    a.ld_r = r; a.skip_base = (gx != nullptr && c > 0); a.accum_y = a.skip_base;
+    a.force_bn = g_force_bn; a.force_group = g_force_group;
+    int rc = launch_lora_gemm(a, st);
+    if (rc) return rc;
+    // 2) dUp[:, r0:] += G^T Hs_c  and  dDn[r0:, :] += dH_c^T X, one launch (grid.z = 2)
+    rc = launch_wgrad_pair(gy, ldgy, bf16_at(hs, r0), r, g_up + r0, r, dout, rc_, 0, x, ldx, bf16_at(dh, r0), r, g_down + (int64_t)r0 * din,
+                           din, din, rc_, 1, M, st);
+    if (rc) return rc;
+  }
+  return AQ_OK;
 }
 
 int aq_wgrad_tn(const void* p, int64_t ldp, const void* q, int64_t ldq, float* c, int64_t ldc, int64_t M, int I, int J,

@@ -23,23 +23,29 @@ __global__ void __launch_bounds__(256) merge_kernel(float* __restrict__ w, const
   __shared__ float us[kMergeTile][kMergeRank + 1];
   __shared__ float ds[kMergeRank][kMergeTile + 4];
   const int o0 = blockIdx.y * kMergeTile, i0 = blockIdx.x * kMergeTile;
-  for (int t = threadIdx.x; t < kMergeTile * kMergeRank; t += 256) {
-    const int a = t / kMergeRank, j = t % kMergeRank;
-    us[a][j] = (o0 + a < dout && j < r) ? up[(size_t)(o0 + a) * r + j] : 0.f;
-    const int jj = t / kMergeTile, b = t % kMergeTile;
-    ds[jj][b] = (jj < r && i0 + b < din) ? down[(size_t)jj * din + i0 + b] : 0.f;
-  }
-  __syncthreads();
   const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
   float acc[4][4] = {};
-  for (int j = 0; j < r; ++j) {
-    const float4 d4 = *reinterpret_cast<const float4*>(&ds[j][tx * 4]);
-    const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+  // the rank is walked in tiles of 64 (the reference's released LoRAs are rank 320: scripts/create_wm_lora.py:19); the fp32 sum runs
+  // over j in ascending order whatever the tiling
+  for (int j0 = 0; j0 < r; j0 += kMergeRank) {
+    if (j0 > 0) __syncthreads();
+    for (int t = threadIdx.x; t < kMergeTile * kMergeRank; t += 256) {
+      const int a = t / kMergeRank, j = t % kMergeRank;
+      us[a][j] = (o0 + a < dout && j0 + j < r) ? up[(size_t)(o0 + a) * r + j0 + j] : 0.f;
+      const int jj = t / kMergeTile, b = t % kMergeTile;
+      ds[jj][b] = (j0 + jj < r && i0 + b < din) ? down[(size_t)(j0 + jj) * din + i0 + b] : 0.f;
+    }
+    __syncthreads();
+    const int jn = min(kMergeRank, r - j0);
+    for (int j = 0; j < jn; ++j) {
+      const float4 d4 = *reinterpret_cast<const float4*>(&ds[j][tx * 4]);
+      const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const float u = us[ty * 4 + a][j];
+      for (int a = 0; a < 4; ++a) {
+        const float u = us[ty * 4 + a][j];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(u, dv[b], acc[a][b]);
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(u, dv[b], acc[a][b]);
+      }
     }
   }
 #pragma unroll
@@ -72,7 +78,7 @@ int aq_lora_fold_down(const float* down, const float* m, float* out, int r, int6
 
 int aq_lora_merge(float* w, const float* up, const float* down, int dout, int din, int r, float coef, void* stream) {
   AQ_REQUIRE(w && up && down && dout > 0 && din > 0, AQ_ERR_BAD_SHAPE, "lora_merge: NULL operand or empty matrix");
-  AQ_REQUIRE(r > 0 && r <= kMergeRank, AQ_ERR_BAD_SHAPE, "lora_merge: rank %d unsupported (1 ... %d)", r, kMergeRank);
+  AQ_REQUIRE(r > 0, AQ_ERR_BAD_SHAPE, "lora_merge: rank %d must be positive", r);
   int rc = check_arch();
   if (rc) return rc;
   dim3 grid((din + kMergeTile - 1) / kMergeTile, (dout + kMergeTile - 1) / kMergeTile);

@@ -101,6 +101,9 @@ struct LoraGemmParams {
   int mode;       // 0 forward, 1 backward (dX)
   int has_lora;   // 0: plain GEMM
   int has_main;   // 0: only the H phase + mid epilogue (backward of layers whose input needs no gradient)
+  int skip_base;  // 1: a later rank chunk -- no A W^T term, tiles start from Hs Up^T alone
+  int accum_y;    // 1: the tile epilogue adds the Y already in memory
+  long long ld_r; // row stride of scale / H / dH / Hs (>= r: the rank chunk is a column slice of [*, r_total] tensors)
   LoraProblem prob[NP];
 };
 
@@ -191,7 +194,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
     if (p.has_main) {
-      tma_prefetch_desc(&p.prob[0].tmap_w);
+      if (!p.skip_base) tma_prefetch_desc(&p.prob[0].tmap_w);
       tma_prefetch_desc(&p.prob[0].tmap_y);
     }
     if (p.has_lora) {
@@ -239,15 +242,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
     uint32_t phase = 0;
     const int w_row_off = (int)cta_rank * (BN / 2);
     const int dn_row_off = (int)cta_rank * (kRankPad / 2);
+    const bool load_w = p.has_main && !p.skip_base;
     auto k_loads = [&](const LoraProblem& q, int m0, int n0, bool first) {
-      const uint32_t bytes = 2u * (kATileBytes + (p.has_main ? L::kWHalfBytes : 0) + (first ? kDnHalfBytes : 0));
+      const uint32_t bytes = 2u * (kATileBytes + (load_w ? L::kWHalfBytes : 0) + (first ? kDnHalfBytes : 0));
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         if (elect_one()) {
           const uint32_t fb = mapa_shared(full_bar(stage), 0);
           if (leader) mbar_arrive_expect_tx(full_bar(stage), bytes);
           tma_load_2d_pair(a_tile(stage), &p.tmap_a, fb, kb * kBlockK, m0);
-          if (p.has_main) tma_load_2d_pair(w_tile(stage), &q.tmap_w, fb, kb * kBlockK, n0 + w_row_off);
+          if (load_w) tma_load_2d_pair(w_tile(stage), &q.tmap_w, fb, kb * kBlockK, n0 + w_row_off);
           if (first) tma_load_2d_pair(dn_tile(stage), &q.tmap_dn, fb, kb * kBlockK, dn_row_off);
         }
         __syncwarp();
@@ -277,7 +281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
       const int nt_end = min(nt_begin + q.group_size, q.num_n_tiles);
       const bool fused = p.has_lora && p.has_main;
       AQ_TRACE(trace_iter, 0);
-      if (fused && nt_end - nt_begin >= 2) {
+      if (fused && nt_end - nt_begin >= 2 && !p.skip_base) {
         // deferred order: the Hs.Up k-blocks of the first two tiles follow the second tile's main loop
         k_loads(q, m0, nt_begin * BN, true);
         k_loads(q, m0, (nt_begin + 1) * BN, false);
@@ -290,7 +294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
       } else {
         for (int nt = nt_begin; nt < nt_end; ++nt) {
           const bool first = (nt == nt_begin) && p.has_lora;
-          if (p.has_main || first) k_loads(q, m0, nt * BN, first);
+          if (load_w || first) k_loads(q, m0, nt * BN, first);
           if (fused) up_load(q, nt * BN);
         }
       }
@@ -341,8 +345,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
       };
       using TrueC = BoolC<true>;
       using FalseC = BoolC<false>;
+      const bool load_w = p.has_main && !p.skip_base;
       auto k_mmas = [&](uint32_t tmem_acc, bool first) {
-        if (!p.has_main) k_mmas_t(tmem_acc, FalseC{}, TrueC{});
+        if (!load_w) k_mmas_t(tmem_acc, FalseC{}, TrueC{});
         else if (first) k_mmas_t(tmem_acc, TrueC{}, TrueC{});
         else k_mmas_t(tmem_acc, TrueC{}, FalseC{});
       };
@@ -352,8 +357,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         if (elect_one()) {
           const uint64_t ad = desc(hs_tile);
           const uint64_t wd = desc(w_tile(stage));
+          const uint32_t keep = p.skip_base ? 0u : 1u;   // a later rank chunk has no base product underneath: overwrite
 #pragma unroll
-          for (int k = 0; k < kRankPad / 16; ++k) umma_f16_pair(tmem_acc, ad + 2 * k, wd + 2 * k, idesc_main, 1u);
+          for (int k = 0; k < kRankPad / 16; ++k) umma_f16_pair(tmem_acc, ad + 2 * k, wd + 2 * k, idesc_main, k == 0 ? keep : 1u);
           umma_commit_pair(empty_bar(stage), kBothCtas);
         }
         __syncwarp();
@@ -366,7 +372,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         const int nt_begin = grp * q.group_size;
         const int nt_end = min(nt_begin + q.group_size, q.num_n_tiles);
         const bool fused = p.has_lora && p.has_main;
-        if (fused && nt_end - nt_begin >= 2) {
+        if (fused && nt_end - nt_begin >= 2 && !p.skip_base) {
           const uint32_t it0 = acc_iter, it1 = acc_iter + 1;
           const uint32_t acc0 = tmem_base + (it0 & 1u) * BN, acc1 = tmem_base + (it1 & 1u) * BN;
           acquire_acc(it0);
@@ -401,7 +407,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
             const bool first = (nt == nt_begin) && p.has_lora;
             const uint32_t acc = tmem_base + (acc_iter & 1u) * BN;
             if (p.has_main) acquire_acc(acc_iter);
-            if (p.has_main || first) k_mmas(acc, first);
+            if (load_w || first) k_mmas(acc, first);
             if (first) {
               commit(h_full_bar);
               mbar_wait(hs_ready_bar, item_iter & 1u);
@@ -449,8 +455,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         const int hc0 = 32 * half;
         long long sample = grow / p.tokens;
         if (sample > p.num_samples - 1) sample = p.num_samples - 1;
-        const float* sp = p.scale + sample * p.r + hc0;
-        const size_t aux_off = (size_t)grow * p.r + hc0;
+        const float* sp = p.scale + sample * p.ld_r + hc0;
+        const size_t aux_off = (size_t)grow * p.ld_r + hc0;
         uint4 hin[4];
         if (p.mode == 1) {
 #pragma unroll
@@ -536,11 +542,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
           const bool uniform = (p.tokens % 32 == 0) && (first_row + 32 <= p.M);
           if (uniform) {
             warp_colsum<32>(v, lane);
-            if (hc0 + lane < p.r) atomicAdd(p.g_scale + sample * p.r + hc0 + lane, v[0]);
+            if (hc0 + lane < p.r) atomicAdd(p.g_scale + sample * p.ld_r + hc0 + lane, v[0]);
           } else if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (hc0 + j < p.r) atomicAdd(p.g_scale + sample * p.r + hc0 + j, v[j]);
+              if (hc0 + j < p.r) atomicAdd(p.g_scale + sample * p.ld_r + hc0 + j, v[j]);
           }
         }
       }
@@ -603,6 +609,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
               for (int i = 0; i < 4; ++i) {
                 f[2 * i] += bf16_lo(bb[i]);
                 f[2 * i + 1] += bf16_hi(bb[i]);
+              }
+            }
+            if (p.accum_y) {
+              // rank chunks after the first: Y += this chunk's Hs Up^T (the lane owns row `grow`; 16 bytes = 8 columns of it)
+              const int c = pcol0 + c8 * 8;
+              if (row_ok && c < q_.N) {
+                const uint4 yw = *reinterpret_cast<const uint4*>(q_.y + (size_t)grow * q_.ldy + c);
+                const uint32_t yy[4] = {yw.x, yw.y, yw.z, yw.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  f[2 * i] += bf16_lo(yy[i]);
+                  f[2 * i + 1] += bf16_hi(yy[i]);
+                }
               }
             }
             uint4 o;
@@ -687,6 +706,8 @@ static int launch_bn(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) 
   p.num_samples = (int)((a.M + p.tokens - 1) / p.tokens);
   p.M = (int)a.M; p.K = a.K; p.r = a.r;
   p.mode = a.mode; p.has_lora = has_lora; p.has_main = a.has_main;
+  p.skip_base = a.skip_base; p.accum_y = a.accum_y;
+  p.ld_r = a.ld_r > 0 ? a.ld_r : a.r;
   p.num_m_pairs = (int)((a.M + kPairM - 1) / kPairM);
   p.num_problems = nprob;
 
@@ -697,7 +718,7 @@ static int launch_bn(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) 
   for (int i = 0; i < nprob; ++i) {
     const LoraGemmArgs& b = probs[i];
     LoraProblem& q = p.prob[i];
-    if (a.has_main) {
+    if (a.has_main && !a.skip_base) {
       uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)b.N};
       uint64_t str[1] = {(uint64_t)a.K * 2};
       uint32_t box[2] = {kBlockK, (uint32_t)(BN / 2)};
@@ -712,7 +733,7 @@ static int launch_bn(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) 
       if (rc) return rc;
       if (a.has_main) {
         uint64_t udims[2] = {(uint64_t)a.r, (uint64_t)b.N};
-        uint64_t ustr[1] = {(uint64_t)a.r * 2};
+        uint64_t ustr[1] = {(uint64_t)(a.ld_r > 0 ? a.ld_r : a.r) * 2};
         uint32_t ubox[2] = {kRankPad, (uint32_t)(BN / 2)};
         rc = make_tmap(&q.tmap_up, b.up, 2, 2, udims, ustr, ubox, kSwz128);
         if (rc) return rc;
@@ -771,11 +792,13 @@ static int validate(const LoraGemmArgs& a) {
   AQ_REQUIRE(!a.has_main || (a.N > 0 && a.N % 8 == 0), AQ_ERR_BAD_SHAPE, "lora_gemm: N=%d must be a positive multiple of 8", a.N);
   if (a.dn != nullptr) {
     AQ_REQUIRE(a.r >= 8 && a.r <= kRankPad && a.r % 8 == 0, AQ_ERR_BAD_SHAPE,
-               "lora_gemm: rank r=%d unsupported (need 8 <= r <= 64, r %% 8 == 0)", a.r);
+               "lora_gemm: rank chunk r=%d unsupported (one launch covers 8 <= r <= 64, r %% 8 == 0; larger ranks are chunked by the ABI layer)", a.r);
     AQ_REQUIRE(a.scale != nullptr, AQ_ERR_BAD_SHAPE, "lora_gemm: scale is NULL");
     AQ_REQUIRE(!a.has_main || a.up != nullptr, AQ_ERR_BAD_SHAPE, "lora_gemm: up is NULL");
   }
   AQ_REQUIRE(a.has_main || a.dn != nullptr, AQ_ERR_BAD_SHAPE, "lora_gemm: nothing to compute");
+  AQ_REQUIRE(a.ld_r == 0 || (a.ld_r >= a.r && a.ld_r % 8 == 0), AQ_ERR_BAD_SHAPE, "lora_gemm: ld_r=%lld must be a multiple of 8 >= r", (long long)a.ld_r);
+  AQ_REQUIRE(!a.skip_base || (a.dn != nullptr && a.has_main), AQ_ERR_BAD_SHAPE, "lora_gemm: skip_base needs LoRA operands and an output");
   AQ_REQUIRE(a.lda % 8 == 0 && (!a.has_main || a.ldy % 8 == 0), AQ_ERR_BAD_ALIGN, "lora_gemm: leading dimensions must be multiples of 8 elements");
   AQ_REQUIRE(!a.has_main || (reinterpret_cast<uintptr_t>(a.y) & 15u) == 0, AQ_ERR_BAD_ALIGN, "lora_gemm: y must be 16-byte aligned");
   return AQ_OK;

@@ -21,6 +21,10 @@ struct LoraGemmArgs {
   int mode;                         // 0 forward, 1 backward
   int has_main;                     // 0: H phase + mid epilogue only
   int force_bn, force_group;        // 0 = heuristic
+  // rank chunking (r > 64 runs as ceil(r / 64) launches over 64-wide slices of the LoRA operands, see lora_abi.cu):
+  int64_t ld_r = 0;                 // row stride (elements) of scale / H / dH / Hs and of `up` [N, r]; 0 = r
+  int skip_base = 0;                // 1: no A W^T term (a later rank chunk): the tile starts from the LoRA product alone ...
+  int accum_y = 0;                  // 1: ... and the epilogue adds the Y already in memory (Y += chunk)
 };
 
 int launch_lora_gemm(const LoraGemmArgs& a, cudaStream_t stream);

@@ -77,6 +77,9 @@ def _packed(param: torch.Tensor, rows: int, cols: int):
         dt.copy_(ops.transpose_bf16(src))
     else:
         raise AqualoraError(f"LoRA weights must be fp32 or bf16, got {src.dtype}")
+    if len(_PACK_CACHE) > 4096:                      # temporaries (padded ranks) leave dead entries behind: drop them
+        for k in [k for k, v in _PACK_CACHE.items() if v[3]() is None]:
+            del _PACK_CACHE[k]
     _PACK_CACHE[key] = (ver, d, dt, weakref.ref(param))
     return d, dt
 
@@ -134,6 +137,7 @@ def clear_caches() -> None:
     _PACK_CACHE.clear()
     _WT_CACHE.clear()
     _BATCH_TABLES.clear()
+    _W16_CACHE.clear()
 
 
 def _grad_target(tgt, shape, device) -> tuple[torch.Tensor, bool]:
@@ -277,12 +281,41 @@ def _effective_scale(scale, lora_layer, nsamples: int, r: int, device, compute_d
     return torch.full((1, r), float(scale) * a, dtype=torch.float32, device=device)
 
 
-def _check_input(x: torch.Tensor, what: str) -> None:
+def _check_input(x: torch.Tensor, what: str) -> torch.Tensor:
+    """The kernels compute in bf16 (the BASELINE precision: `accelerate --mixed_precision bf16`, train/ppft_train.py:569-581).  fp16 /
+    fp32 activations -- the reference's README recipe trains in fp16 (train/README.md:34-48) -- are accepted by casting AT THE BOUNDARY:
+    the input (and a frozen fp16 / fp32 base weight, once, cached) is rounded to bf16, the result is cast back to the caller's dtype
+    by the four forwards.  bf16 keeps 8 mantissa bits against fp16's 11: results agree with an fp16 run to bf16 rounding (2e-2 of the
+    tensor's max, tests/test_lora_gpu.py::test_fp16_and_fp32_activations_cast_at_the_boundary), not to fp16 rounding."""
     if not x.is_cuda:
         raise AqualoraError(f"{what}: CPU tensor passed; aqualora_b200 runs on sm_100a only and has no CPU fallback "
                             "(patch oracle.lora_oracle forwards in tests that need a CPU reference)")
-    if x.dtype != torch.bfloat16:
-        raise AqualoraError(f"{what}: activations must be bf16 (the BASELINE precision), got {x.dtype}")
+    if x.dtype == torch.bfloat16:
+        return x
+    if x.dtype in (torch.float16, torch.float32):
+        return x.to(torch.bfloat16)
+    raise AqualoraError(f"{what}: activations must be bf16, fp16 or fp32, got {x.dtype}")
+
+
+_W16_CACHE: Dict[int, tuple] = {}
+
+
+def _bf16_weight(weight: torch.Tensor) -> torch.Tensor:
+    """The frozen base weight as bf16: itself, or a cached rounded copy of an fp16 / fp32 weight."""
+    if weight.dtype == torch.bfloat16:
+        return weight
+    if weight.dtype not in (torch.float16, torch.float32):
+        raise AqualoraError(f"frozen projection weights must be bf16, fp16 or fp32, got {weight.dtype}")
+    if weight.requires_grad:
+        raise AqualoraError("the base projection weight is frozen in PPFT (train/ppft_train.py:562-565); a trainable non-bf16 base weight is not supported")
+    key = id(weight)
+    ver = (weight._version, weight.data_ptr())
+    hit = _W16_CACHE.get(key)
+    if hit is not None and hit[0] == ver and hit[2]() is weight:
+        return hit[1]
+    w16 = weight.detach().to(torch.bfloat16)
+    _W16_CACHE[key] = (ver, w16, weakref.ref(weight))
+    return w16
 
 
 def _rows_view(x: torch.Tensor, din: int) -> torch.Tensor:
@@ -295,11 +328,22 @@ def _rows_view(x: torch.Tensor, din: int) -> torch.Tensor:
 def _project_rows(x2d, weight, bias, down, up, lora_meta, scale, compute_dtype):
     """Shared tail of the four forwards: x2d [M, din] bf16 rows -> [M, dout] through the fused kernel."""
     M = x2d.shape[0]
-    if weight.dtype != torch.bfloat16:
-        raise AqualoraError("frozen projection weights must be bf16 (train/ppft_train.py:569-581 casts them)")
+    weight = _bf16_weight(weight)
+    if bias is not None and bias.dtype != torch.bfloat16:
+        bias = bias.detach().to(torch.bfloat16)
     if down is None:
         return _FusedLoraProjection.apply(x2d, weight, bias, None, None, None, M)
     r = down.shape[0]
+    if r % 8 != 0:
+        # ranks that are not a multiple of 8 (ppft_train.py's default --rank is 4): zero rows / columns pad the LoRA operands and
+        # the diagonal up to the next multiple of 8 -- they contribute exactly 0 and F.pad's backward drops their gradients
+        pad = (-r) % 8
+        din = down.numel() // r
+        down = F.pad(down.reshape(r, din), (0, 0, 0, pad))
+        up = F.pad(up.reshape(up.shape[0], r), (0, pad))
+        if isinstance(scale, torch.Tensor):
+            scale = F.pad(scale, (0, pad))
+        r += pad
     if isinstance(scale, torch.Tensor):
         nsamp = scale.shape[0]
         if M % nsamp != 0:
@@ -307,7 +351,7 @@ def _project_rows(x2d, weight, bias, down, up, lora_meta, scale, compute_dtype):
         tokens = M // nsamp
     else:
         nsamp, tokens = 1, M
-    s_eff = _effective_scale(scale, lora_meta, nsamp, r, x2d.device, compute_dtype)
+    s_eff = _effective_scale(scale, lora_meta, nsamp, r, x2d.device, torch.bfloat16)
     return _FusedLoraProjection.apply(x2d, weight, bias, down, up, s_eff, tokens)
 
 
@@ -328,23 +372,25 @@ def _zero_base(dout: int, din: int, device) -> torch.Tensor:
 def CustomLoRALinearLayerforward(self, hidden_states: torch.Tensor, scale: float = 1.0):
     """up(diag(scale) down(x)) [* alpha/rank] [* float scale]  -- utils/lora_modules.py:9-26.
     Stand-alone call (the compatible-linear forward below fuses this into the base projection instead)."""
-    _check_input(hidden_states, "LoRALinearLayer")
+    orig_dtype = hidden_states.dtype
+    hidden_states = _check_input(hidden_states, "LoRALinearLayer")
     down, up = self.down.weight, self.up.weight
     x2d = _rows_view(hidden_states, hidden_states.shape[-1])
     y = _project_rows(x2d, _zero_base(up.shape[0], down.shape[1], x2d.device), None, down, up, self, scale, hidden_states.dtype)
-    return y.view(*hidden_states.shape[:-1], up.shape[0])
+    return y.view(*hidden_states.shape[:-1], up.shape[0]).to(orig_dtype)
 
 
 def CustomLoRACompatibleLinearforward(self, hidden_states: torch.Tensor, scale: float = 1.0):
     """Linear(x) [+ lora_layer(x, scale)]  -- utils/lora_modules.py:56-62, as one fused kernel."""
-    _check_input(hidden_states, "LoRACompatibleLinear")
+    orig_dtype = hidden_states.dtype
+    hidden_states = _check_input(hidden_states, "LoRACompatibleLinear")
     x2d = _rows_view(hidden_states, hidden_states.shape[-1])
     lora = None if _LORA_DISABLED else self.lora_layer
     if lora is None:
         y = _project_rows(x2d, self.weight, self.bias, None, None, None, scale, hidden_states.dtype)
     else:
         y = _project_rows(x2d, self.weight, self.bias, lora.down.weight, lora.up.weight, lora, scale, hidden_states.dtype)
-    return y.view(*hidden_states.shape[:-1], self.weight.shape[0])
+    return y.view(*hidden_states.shape[:-1], self.weight.shape[0]).to(orig_dtype)
 
 
 def _conv_as_rows(hidden_states: torch.Tensor):
@@ -365,31 +411,33 @@ def CustomLoRAConv2dLayerforward(self, hidden_states: torch.Tensor, scale: float
     A pointwise conv over NCHW is the row projection over the channels_last view [B*H*W, C]."""
     if not _is_pointwise(self.down):
         raise AqualoraError("LoRAConv2dLayer: only 1x1 stride-1 down convolutions are implemented (the unet_keys.json targets)")
-    _check_input(hidden_states, "LoRAConv2dLayer")
+    orig_dtype = hidden_states.dtype
+    hidden_states = _check_input(hidden_states, "LoRAConv2dLayer")
     x2d, (B, H, W) = _conv_as_rows(hidden_states)
     down, up = self.down.weight, self.up.weight
     y = _project_rows(x2d, _zero_base(up.shape[0], down.shape[1], x2d.device), None, down, up, self, scale, hidden_states.dtype)
-    return y.view(B, H, W, -1).permute(0, 3, 1, 2)
+    return y.view(B, H, W, -1).permute(0, 3, 1, 2).to(orig_dtype)
 
 
 def CustomLoRACompatibleConvforward(self, hidden_states: torch.Tensor, scale: float = 1.0):
     """conv2d(x) [+ lora_layer(x, scale)]  -- utils/lora_modules.py:46-54."""
     if self.lora_layer is None or (_LORA_DISABLED and not _is_pointwise(self)):
         return F.conv2d(hidden_states, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+    orig_dtype = hidden_states.dtype
     if _LORA_DISABLED:
-        _check_input(hidden_states, "LoRACompatibleConv")
+        hidden_states = _check_input(hidden_states, "LoRACompatibleConv")
         x2d, (B, H, W) = _conv_as_rows(hidden_states)
         y = _project_rows(x2d, self.weight, self.bias, None, None, None, scale, hidden_states.dtype)
-        return y.view(B, H, W, -1).permute(0, 3, 1, 2)
+        return y.view(B, H, W, -1).permute(0, 3, 1, 2).to(orig_dtype)
     if not (_is_pointwise(self) and _is_pointwise(self.lora_layer.down)):
         raise AqualoraError("LoRACompatibleConv with a LoRA layer: only 1x1 stride-1 convolutions are implemented "
                             "(proj_in / proj_out, the only conv targets in utils/unet_keys.json)")
-    _check_input(hidden_states, "LoRACompatibleConv")
+    hidden_states = _check_input(hidden_states, "LoRACompatibleConv")
     x2d, (B, H, W) = _conv_as_rows(hidden_states)
     lora = self.lora_layer
     # [Co, C, 1, 1] / [r, C, 1, 1] / [Co, r, 1, 1] are row-major matrices already: the kernel reads them in place
     y = _project_rows(x2d, self.weight, self.bias, lora.down.weight, lora.up.weight, lora, scale, hidden_states.dtype)
-    return y.view(B, H, W, -1).permute(0, 3, 1, 2)
+    return y.view(B, H, W, -1).permute(0, 3, 1, 2).to(orig_dtype)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -411,12 +459,14 @@ def project_group(modules, hidden_states: torch.Tensor, scale=1.0):
     ours = all(isinstance(m, nn.Linear) and getattr(m.forward, "__func__", None) is CustomLoRACompatibleLinearforward for m in modules)
     loras = [None if _LORA_DISABLED else getattr(m, "lora_layer", None) for m in modules]
     with_lora = [l is not None for l in loras]
-    groupable = (ours and 1 < len(modules) <= 32 and all(m.weight.shape[1] == din and m.weight.dtype == torch.bfloat16 for m in modules)
+    groupable = (ours and 1 < len(modules) <= 32 and hidden_states.dtype == torch.bfloat16
+                 and all(m.weight.shape[1] == din and m.weight.dtype == torch.bfloat16 for m in modules)
                  and (all(with_lora) or not any(with_lora)))
     if groupable and all(with_lora):
         r = loras[0].down.weight.shape[0]
         a = _alpha_over_rank(loras[0])
-        groupable = all(l.down.weight.shape[0] == r and _alpha_over_rank(l) == a for l in loras)
+        # one grouped launch covers ranks up to 64 that are multiples of 8; other ranks take the per-module path (chunked / padded)
+        groupable = r <= 64 and r % 8 == 0 and all(l.down.weight.shape[0] == r and _alpha_over_rank(l) == a for l in loras)
     if not groupable:
         return [m(hidden_states, scale) for m in modules]
     _check_input(hidden_states, "project_group")

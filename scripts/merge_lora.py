@@ -6,7 +6,10 @@ every Linear / Conv2d under a `Transformer2DModel`.  The rank-r update of every 
 (`aq_lora_merge`, csrc/lora_deploy.cu); linear and 1x1-conv targets are implemented (all 192 `utils/unet_keys.json` targets), 3x3 LoRA
 convolutions and text-encoder LoRA are not part of AquaLoRA's training (`--train_text_encoder` off) and raise.
 Checkpoint I/O (`--sd_model`, `--save_to`, LDM <-> diffusers key conversion) is the reference's `scripts/lib/model_util.py`
-and stays there; `merge(args)` below operates on diffusers-keyed U-Net state-dicts (`.safetensors` / `.pt`).
+and stays there; `merge(args)` below operates on DIFFUSERS-KEYED U-NET STATE DICTS (`.safetensors` / `.pt`), not on full SD
+`.ckpt` files: the output holds the U-Net tensors only (no text encoder / VAE / sai metadata).  To merge into a full checkpoint
+keep the reference's `merge(args)` and swap only its `merge_to_sd_model` for the one below.  Any rank is
+supported (the released LoRAs are rank 320).
 """
 from __future__ import annotations
 
@@ -88,7 +91,11 @@ def setup_parser() -> argparse.ArgumentParser:
     parser = argparse.ArgumentParser()
     parser.add_argument("--v2", action="store_true", help="SD 2.x U-Net topology")
     parser.add_argument("--save_precision", type=str, default=None, choices=[None, "float", "fp16", "bf16"])
-    parser.add_argument("--precision", type=str, default="float", choices=["float"], help="merge precision (fp32 accumulate)")
+    parser.add_argument("--precision", type=str, default="float", choices=["float", "fp16", "bf16"],
+                        help="accepted for CLI compatibility with the reference; the merge always accumulates in fp32 (aq_lora_merge)")
+    parser.add_argument("--no_metadata", action="store_true",
+                        help="accepted for CLI compatibility; this script never writes sai_model_spec metadata (scripts/lib/sai_model_spec.py "
+                             "stays the reference's: checkpoint I/O is out of scope)")
     parser.add_argument("--sd_model", type=str, required=True, help="diffusers-keyed U-Net state dict (.safetensors / .pt)")
     parser.add_argument("--save_to", type=str, required=True)
     parser.add_argument("--models", type=str, nargs="*", help="LoRA files (kohya / A1111 names, see diffusers_lora_to_webui.py)")

@@ -91,7 +91,7 @@ def test_other_message_lengths_and_errors(setup, cuda_device):
         dec(x)                                             # CPU tensor
     dec.train()
     with pytest.raises(AqualoraError):
-        dec(x.to(cuda_device))
+        dec(x)                                             # CPU tensor in train mode: no fallback either
     dec.eval()
 
 

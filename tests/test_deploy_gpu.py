@@ -93,8 +93,9 @@ def test_merge_to_sd_model_matches_oracle(cuda_device):
     targets = {"down_blocks.0.attentions.0.proj_in": None, "down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q": None,
                "mid_block.attentions.0.transformer_blocks.0.ff.net.0.proj": 16.0, "up_blocks.1.attentions.2.transformer_blocks.0.ff.net.2": None}
     lora_sd, want, mags = {}, {}, {}
-    r = 32
-    for path, alpha in targets.items():
+    ranks = {"down_blocks.0.attentions.0.proj_in": 320, "mid_block.attentions.0.transformer_blocks.0.ff.net.0.proj": 100}   # the reference's
+    for path, alpha in targets.items():                                       # released rank (create_wm_lora.py:19) and a ragged one
+        r = ranks.get(path, 32)
         mod = unet
         for part in path.split("."):
             mod = getattr(mod, part)

@@ -109,6 +109,82 @@ def test_conv1x1_golden_forward_backward(lm, cuda_device, golden_dir):
             assert _fro_rel(scale.grad, c["g_scale"]) < BF16_TOL
 
 
+@pytest.mark.parametrize("r,B,N,din,dout,bias", [(320, 2, 300, 320, 320, True), (128, 3, 77, 768, 640, False), (72, 2, 256, 640, 1280, True),
+                                                  (4, 2, 64, 64, 96, True), (12, 1, 40, 128, 64, False)])
+def test_other_ranks_forward_backward(lm, cuda_device, r, B, N, din, dout, bias):
+    """Ranks beyond one 64-wide slice (the reference's released recipe is rank 320, train/README.md:34-48: chunked by the ABI layer),
+    ragged ranks, and ranks that are not a multiple of 8 (ppft_train.py's default --rank 4: zero-padded), against the closed form on
+    the bf16-rounded operands."""
+    from oracle import lora_oracle as O
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(100 + r)
+    r16 = lambda t: t.bfloat16().float()
+    x = r16(torch.randn(B, N, din, generator=g))
+    w = r16(torch.randn(dout, din, generator=g) * din ** -0.5)
+    b = r16(torch.randn(dout, generator=g) * 0.1) if bias else None
+    dn = r16(torch.randn(r, din, generator=g) * din ** -0.5)
+    up = r16(torch.randn(dout, r, generator=g) * r ** -0.5)
+    sc = r16(1 + 0.5 * torch.randn(B, r, generator=g))
+    gy = r16(torch.randn(B, N, dout, generator=g) * 0.1)
+    want = O.closed_form_linear(x, w, b, dn, up, sc)
+    dx, dd, du, ds = O.closed_form_linear_grads(x, w, dn, up, sc, gy)
+    lin = lm.LoRACompatibleLinear(din, dout, bias=bias)
+    lin.weight.data.copy_(w)
+    if bias:
+        lin.bias.data.copy_(b)
+    lin = lin.to(dev, torch.bfloat16)
+    lin.requires_grad_(False)
+    lora = lm.LoRALinearLayer(din, dout, r)
+    lora.down.weight.data.copy_(dn); lora.up.weight.data.copy_(up)
+    lin.set_lora_layer(lora.to(dev))
+    xd = x.to(dev, torch.bfloat16).requires_grad_(True)
+    sd = sc.to(dev).requires_grad_(True)
+    y = lin(xd, sd)
+    y.backward(gy.to(dev, torch.bfloat16))
+    assert _max_rel(y, want) < BF16_TOL
+    assert _max_rel(xd.grad, dx) < BF16_TOL
+    assert _fro_rel(lora.down.weight.grad, dd) < BF16_TOL and _fro_rel(lora.up.weight.grad, du) < BF16_TOL
+    assert _fro_rel(sd.grad, ds) < BF16_TOL
+    assert tuple(lora.down.weight.grad.shape) == (r, din) and tuple(sd.grad.shape) == (B, r)
+    # zero diagonal -> bit-identical to the base op also through the chunked launches
+    y0 = lin(xd.detach(), torch.zeros(B, r, device=dev))
+    lin.set_lora_layer(None)
+    assert torch.equal(y0, lin(xd.detach(), 1.0))
+
+
+def test_fp16_and_fp32_activations_cast_at_the_boundary(lm, cuda_device):
+    """The reference's README recipe runs fp16 (train/README.md:34-48): fp16 / fp32 activations and base weights are rounded to bf16 at
+    the boundary and the result is returned in the caller's dtype; agreement is to bf16 rounding (stated in lora_modules._check_input)."""
+    from oracle import lora_oracle as O
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(7)
+    B, N, din, dout, r = 2, 96, 320, 640, 64
+    x = torch.randn(B, N, din, generator=g)
+    w = torch.randn(dout, din, generator=g) * din ** -0.5
+    b = torch.randn(dout, generator=g) * 0.1
+    dn = torch.randn(r, din, generator=g) * din ** -0.5
+    up = torch.randn(dout, r, generator=g) * 0.1
+    sc = 1 + 0.5 * torch.randn(B, r, generator=g)
+    want = O.closed_form_linear(x, w, b, dn, up, sc)
+    for dt in (torch.float16, torch.float32):
+        lin = lm.LoRACompatibleLinear(din, dout)
+        lin.weight.data.copy_(w); lin.bias.data.copy_(b)
+        lin = lin.to(dev, dt)
+        lin.requires_grad_(False)
+        lora = lm.LoRALinearLayer(din, dout, r)
+        lora.down.weight.data.copy_(dn); lora.up.weight.data.copy_(up)
+        lin.set_lora_layer(lora.to(dev))
+        xd = x.to(dev, dt).requires_grad_(True)
+        y = lin(xd, sc.to(dev))
+        assert y.dtype == dt
+        assert _max_rel(y, want) < BF16_TOL
+        y.float().pow(2).sum().backward()
+        assert xd.grad is not None and xd.grad.dtype == dt and torch.isfinite(xd.grad).all()
+        assert lora.down.weight.grad is not None and torch.isfinite(lora.down.weight.grad).all()
+
+
 def test_standalone_lora_layer_matches_oracle(lm, cuda_device):
     """CustomLoRALinearLayerforward called on its own (utils/lora_modules.py:9-26), float and tensor scale."""
     from oracle import lora_oracle as O
