@@ -56,17 +56,17 @@ def jpeg_mask(x: torch.Tensor, keep=(25, 9, 9)) -> torch.Tensor:
     B, C, H, W = x.shape
     ph, pw = (8 - H % 8) % 8, (8 - W % 8) % 8
     xp = F.pad(x, (0, pw, 0, ph))
-    m = torch.tensor(RGB2YUV, dtype=x.dtype)
+    m = torch.tensor(RGB2YUV, dtype=x.dtype, device=x.device)
     yuv = torch.einsum("oc,bchw->bohw", m, xp)
     Hp, Wp = xp.shape[2:]
     blocks = yuv.view(B, 3, Hp // 8, 8, Wp // 8, 8).permute(0, 1, 2, 4, 3, 5)           # [B, 3, by, bx, y, x]
-    d, i = dct_matrices(x.dtype)
+    d, i = (t.to(x.device) for t in dct_matrices(x.dtype))
     coef = torch.einsum("ky,...yx,lx->...kl", d, blocks, d)                               # [.., ky, kx]
-    masks = torch.stack([zigzag_keep_mask(k) for k in keep]).to(x.dtype)                 # [3, ky, kx]
+    masks = torch.stack([zigzag_keep_mask(k) for k in keep]).to(device=x.device, dtype=x.dtype)   # [3, ky, kx]
     coef = coef * masks[None, :, None, None]
     rec = torch.einsum("yk,...kl,xl->...yx", i, coef, i)
     rec = rec.permute(0, 1, 2, 4, 3, 5).reshape(B, 3, Hp, Wp)
-    rgb = torch.einsum("oc,bchw->bohw", torch.tensor(YUV2RGB, dtype=x.dtype), rec)
+    rgb = torch.einsum("oc,bchw->bohw", torch.tensor(YUV2RGB, dtype=x.dtype, device=x.device), rec)
     return rgb[:, :, :H, :W].clone()
 
 
@@ -97,7 +97,7 @@ def gaussian_blur(x: torch.Tensor, sigmas, ksize=(3, 9)) -> torch.Tensor:
     out = torch.empty_like(x)
     for b in range(x.shape[0]):
         s = float(sigmas[b])
-        ty, tx = gaussian_taps(ky, s), gaussian_taps(kx, s)
+        ty, tx = gaussian_taps(ky, s).to(x.device), gaussian_taps(kx, s).to(x.device)
         xb = F.pad(x[b:b + 1], (kx // 2, kx // 2, ky // 2, ky // 2), mode="reflect")
         C = x.shape[1]
         xb = F.conv2d(xb, tx.view(1, 1, 1, kx).repeat(C, 1, 1, 1), groups=C)
@@ -150,10 +150,10 @@ def color_jiggle(x: torch.Tensor, brightness, contrast, saturation, hue, order) 
     """noises.py:95-104: x in [-1, 1] -> [0, 1], ColorJiggle with per-sample factors and one op order, back to [-1, 1].
     order is a permutation of (0 brightness, 1 contrast, 2 saturation, 3 hue)."""
     img = x / 2 + 0.5
-    b = torch.as_tensor(brightness, dtype=x.dtype).view(-1, 1, 1, 1)
-    c = torch.as_tensor(contrast, dtype=x.dtype).view(-1, 1, 1, 1)
-    s = torch.as_tensor(saturation, dtype=x.dtype).view(-1, 1, 1)
-    h = torch.as_tensor(hue, dtype=x.dtype).view(-1, 1, 1)
+    b = torch.as_tensor(brightness, dtype=x.dtype, device=x.device).view(-1, 1, 1, 1)
+    c = torch.as_tensor(contrast, dtype=x.dtype, device=x.device).view(-1, 1, 1, 1)
+    s = torch.as_tensor(saturation, dtype=x.dtype, device=x.device).view(-1, 1, 1)
+    h = torch.as_tensor(hue, dtype=x.dtype, device=x.device).view(-1, 1, 1)
     for op in order:
         if op == 0:
             img = (img + (b - 1)).clamp(0, 1)

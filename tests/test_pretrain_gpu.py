@@ -185,6 +185,21 @@ def test_bce_with_logits(cuda_device):
     _close(xc.grad, xr.grad, 1e-4, 1e-6, "bce grad")
 
 
+def _assert_param_grads_close(got_mod, ref_mod, tol):
+    """Per-tensor relative Frobenius error of every parameter gradient.  A convolution that feeds a batch-statistics BatchNorm has a
+    gradient that is a difference of large cancelling terms (the loss is invariant to the scale and, per channel, the mean of its
+    output), so tensors whose reference gradient is at the fp32 noise floor of that cancellation are compared absolutely against the
+    typical gradient magnitude of the network instead."""
+    gr = dict(ref_mod.named_parameters())
+    rows = []
+    for n, p in got_mod.named_parameters():
+        q = gr[n].grad
+        rows.append((n, float(q.norm()), float((p.grad.cpu() - q).norm()), q.numel()))
+    typical = sorted(r[1] / r[3] ** 0.5 for r in rows)[len(rows) // 2]          # median per-element gradient magnitude
+    bad = [(n, qn, dn) for n, qn, dn, k in rows if dn > tol * qn + 1e-3 * typical * k ** 0.5]
+    assert not bad, (len(bad), sorted(bad, key=lambda r: -r[2] / (r[1] + 1e-30))[:6], typical)
+
+
 def test_decoder_train_mode_matches_torchvision(cuda_device):
     """SecretDecoder.train(): batch-statistics BatchNorm forward + backward vs torchvision's efficientnet_b1 in train mode on the
     CPU (stochastic depth and dropout off on both sides: their masks come from different RNG streams)."""
@@ -216,13 +231,7 @@ def test_decoder_train_mode_matches_torchvision(cuda_device):
     for k in ("model.features.0.1.running_mean", "model.features.0.1.running_var", "model.features.8.1.running_var",
               "model.features.4.2.block.1.1.running_mean"):
         _close(sd_c[k], sd_r[k], 1e-3, 1e-3, k)
-    gr = dict(ref.named_parameters())
-    worst = 0.0
-    for n, p in dec.named_parameters():
-        q = gr[n].grad
-        rel = ((p.grad.cpu() - q).norm() / (q.norm() + 1e-12)).item()
-        worst = max(worst, rel)
-    assert worst < 5e-2, worst          # deep fp32 net, TF32-free library convolutions on both sides; per-tensor relative error
+    _assert_param_grads_close(dec, ref, 5e-2)
 
 
 def test_pretrain_step_matches_oracle(cuda_device):
@@ -271,8 +280,6 @@ def test_pretrain_step_matches_oracle(cuda_device):
         for (n, p), (_, q) in zip(enc_c.named_parameters(), enc_r.named_parameters()):
             rel = ((p.grad.cpu() - q.grad).norm() / (q.grad.norm() + 1e-20)).item()
             assert rel < 5e-2, (layer, n, rel)
-        rel = max(((p.grad.cpu() - dict(dec_r.named_parameters())[n].grad).norm() /
-                   (dict(dec_r.named_parameters())[n].grad.norm() + 1e-12)).item() for n, p in dec_c.named_parameters())
-        assert rel < 5e-2, (layer, "decoder", rel)
+        _assert_param_grads_close(dec_c, dec_r, 5e-2)
         ck = pretrain.checkpoint_dict(enc_c, dec_c)
         assert set(ck) == {"sec_decoder", "sec_encoder"} and set(ck["sec_decoder"]) == set(dec_r.state_dict())
