@@ -80,3 +80,21 @@ def pretrain_step(sec_encoder, sec_decoder, vae_encode: Callable, vae_decode: Ca
 def checkpoint_dict(sec_encoder, sec_decoder) -> dict:
     """train/latent_wm_pretrain.py:246-249 (read back at train/ppft_train.py:550-554)."""
     return {"sec_decoder": sec_decoder.state_dict(), "sec_encoder": sec_encoder.state_dict()}
+
+
+def decoder_finetune_step(msgdecoder, images01: torch.Tensor, msg: torch.Tensor, distort: Optional[Callable] = None):
+    """Stage-3 robustness fine-tuning of the decoder, loop body of train/rob_enhance_finetune.py:1020-1038 after the (third-party)
+    sampling pipeline produced `images01` [B, 3, H, W] in [0, 1]: distort (utils/noise_layers/noiser.py:46-71 `distorsion_unit`
+    mixture, passed in as a callable on [0, 1] images), map to [-1, 1], detach, decode in train mode, BCE against one_hot(msg),
+    backward.  Returns (loss, validation accuracy) as the reference logs them."""
+    x = images01.float()
+    if distort is not None:
+        x = distort(x)
+    x = (x * 2 - 1).detach()
+    logits = msgdecoder(x)
+    decoded = torch.argmax(logits, dim=-1)
+    acc = ((msg - decoded) == 0).float().mean()
+    labels = F.one_hot(msg.long(), num_classes=2).float()
+    loss = losses.binary_cross_entropy_with_logits(logits.float(), labels)
+    loss.backward()
+    return loss.detach(), acc.detach()

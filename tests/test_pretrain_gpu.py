@@ -283,3 +283,38 @@ def test_pretrain_step_matches_oracle(cuda_device):
         _assert_param_grads_close(dec_c, dec_r, 5e-2)
         ck = pretrain.checkpoint_dict(enc_c, dec_c)
         assert set(ck) == {"sec_decoder", "sec_encoder"} and set(ck["sec_decoder"]) == set(dec_r.state_dict())
+
+
+def test_stage3_decoder_finetune_step(cuda_device):
+    """train/rob_enhance_finetune.py:1020-1038 (decoder only, train mode): distort -> decode -> BCE -> backward, vs the oracle."""
+    import numpy as np
+
+    from aqualora_b200 import noise_layers as NL
+    from aqualora_b200 import pretrain
+    from aqualora_b200.decoder import SecretDecoder
+    from oracle import noise_oracle as NO
+    from oracle.pretrain_oracle import SecretDecoderRef
+
+    torch.manual_seed(2)
+    ref = SecretDecoderRef(48).train()
+    for mod in ref.modules():
+        if mod.__class__.__name__ == "StochasticDepth":
+            mod.p = 0.0
+    ref.model.classifier[0].p = 0.0
+    dec = SecretDecoder(48)
+    dec.load_state_dict(ref.state_dict())
+    dec = dec.to(cuda_device).train()
+    dec.stochastic_depth_prob, dec.dropout_p = 0.0, 0.0
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(2, 3, 512, 512, generator=g)
+    msg = torch.randint(0, 2, (2, 48), generator=g)
+    # `blur` branch of distorsion_unit: sigma 4, kernel (3, 5) on [0, 1] images
+    x_ref = (NO.gaussian_blur(img, [4.0, 4.0], (3, 5)) * 2 - 1).detach()
+    logits = ref(x_ref)
+    loss_ref = torch.nn.functional.binary_cross_entropy_with_logits(logits, torch.nn.functional.one_hot(msg, 2).float())
+    loss_ref.backward()
+    loss, acc = pretrain.decoder_finetune_step(dec, img.to(cuda_device), msg.to(cuda_device),
+                                               lambda t: NL.distorsion_unit(t, "blur", rng=np.random.default_rng(0)))
+    assert abs(loss.item() - loss_ref.item()) <= 2e-3 * loss_ref.item()
+    assert 0.0 <= acc.item() <= 1.0
+    _assert_param_grads_close(dec, ref, 5e-2)
