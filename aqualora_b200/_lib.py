@@ -51,6 +51,9 @@ _SIGNATURES = {
     "aq_prvl_loss_fwd": ([c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p], c_int),
     "aq_prvl_loss_bwd": ([c_void_p] * 6 + [c_int] * 3 + [c_void_p], c_int),
     "aq_bce_logits": ([c_void_p] * 4 + [c_int64, c_void_p], c_int),
+    "aq_bn_train_workspace_bytes": ([c_int], c_size_t),
+    "aq_bn_train_fwd": ([c_void_p] * 7 + [c_int64, c_int, c_float, c_float, c_int, c_void_p, c_size_t, c_void_p], c_int),
+    "aq_bn_train_bwd": ([c_void_p] * 8 + [c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p], c_int),
     "aq_mapper_fwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "aq_mapper_bwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     "aq_cast_transpose_bf16": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),

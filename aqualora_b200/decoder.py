@@ -71,6 +71,25 @@ class _EfficientNetB1Params(nn.Module):
         self.classifier = nn.Sequential(nn.Dropout(0.2), nn.Linear(1280, out_features))
 
 
+class _BnActFn(torch.autograd.Function):
+    """Batch-statistics BatchNorm2d (+ SiLU) on the kernels of csrc/bn_train.cu; saves only the convolution output and (mean, rstd)."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, running_mean, running_var, eps, momentum, act):
+        z = z.contiguous(memory_format=torch.channels_last)
+        y, mean_rstd = ops.bn_train_fwd(z, gamma.detach().contiguous(), beta.detach().contiguous(), running_mean, running_var, eps, momentum, act)
+        ctx.save_for_backward(z, gamma, beta, mean_rstd)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        z, gamma, beta, mean_rstd = ctx.saved_tensors
+        gz, g_gamma, g_beta = ops.bn_train_bwd(gy.contiguous(memory_format=torch.channels_last), z, gamma.detach().contiguous(),
+                                               beta.detach().contiguous(), mean_rstd, ctx.act)
+        return gz, g_gamma, g_beta, None, None, None, None, None
+
+
 def _fold(sd, conv_key, bn_key):
     w = sd[conv_key + ".weight"].double()
     g, b = sd[bn_key + ".weight"].double(), sd[bn_key + ".bias"].double()
@@ -156,8 +175,15 @@ class SecretDecoder(nn.Module):
         total_blocks = float(sum(layers for *_, layers in B1_STAGES))
 
         def cba(seq, x, act=True):
-            y = seq[1](seq[0](x))                       # conv (no bias) -> BatchNorm2d with batch statistics (updates running stats)
-            return F.silu(y) if act else y
+            # conv (no bias, library call) -> BatchNorm2d with batch statistics + SiLU (csrc/bn_train.cu; updates the running statistics)
+            bn = seq[1]
+            z = seq[0](x)
+            if z.shape[1] % 4 != 0 or bn.momentum is None:
+                y = bn(z)
+                return F.silu(y) if act else y
+            y = _BnActFn.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, act)
+            bn.num_batches_tracked += 1
+            return y
 
         x = cba(m.features[0], x)
         block_id = 0

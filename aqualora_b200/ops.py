@@ -440,6 +440,42 @@ def effnetb1_fwd(x: torch.Tensor, packed: torch.Tensor, out_features: int, want_
     return logits, bits
 
 
+def _nhwc_f32(x: torch.Tensor, name: str):
+    """(M, C) of a 4-D fp32 tensor stored channels_last (memory = [B, H, W, C] rows)."""
+    _need(x, _F32, name, 4)
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        raise _lib.AqualoraError(f"{name} must be stored channels_last, got strides {x.stride()}")
+    return x.shape[0] * x.shape[2] * x.shape[3], x.shape[1]
+
+
+def bn_train_fwd(z: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, running_mean: torch.Tensor | None,
+                 running_var: torch.Tensor | None, eps: float, momentum: float, act: bool):
+    """Batch-statistics BatchNorm2d (+ SiLU) over a channels_last fp32 tensor; returns (y, mean_rstd [C, 2]); running stats updated."""
+    M, C = _nhwc_f32(z, "z")
+    y = torch.empty_like(z)
+    mean_rstd = torch.empty(C, 2, dtype=_F32, device=z.device)
+    nbytes = _lib.load().aq_bn_train_workspace_bytes(C)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
+    _lib.call("aq_bn_train_fwd", z.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(running_mean), _ptr(running_var), mean_rstd.data_ptr(),
+              y.data_ptr(), M, C, float(eps), float(momentum), int(act), ws.data_ptr(), nbytes, _stream())
+    return y, mean_rstd
+
+
+def bn_train_bwd(gy: torch.Tensor, z: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, mean_rstd: torch.Tensor, act: bool):
+    """Returns (gz, g_gamma, g_beta)."""
+    M, C = _nhwc_f32(z, "z")
+    if tuple(_nhwc_f32(gy, "gy")) != (M, C):
+        raise _lib.AqualoraError("gy must have the shape and layout of z")
+    gz = torch.empty_like(z)
+    g_gamma = torch.zeros(C, dtype=_F32, device=z.device)
+    g_beta = torch.zeros(C, dtype=_F32, device=z.device)
+    nbytes = _lib.load().aq_bn_train_workspace_bytes(C)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
+    _lib.call("aq_bn_train_bwd", gy.data_ptr(), z.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean_rstd.data_ptr(), gz.data_ptr(),
+              g_gamma.data_ptr(), g_beta.data_ptr(), M, C, int(act), ws.data_ptr(), nbytes, _stream())
+    return gz, g_gamma, g_beta
+
+
 def conv1x1_tf32x3(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, se: torch.Tensor | None = None,
                    residual: torch.Tensor | None = None, hw: int = 0, epi: int = 0) -> torch.Tensor:
     """Pointwise convolution over NHWC pixels on the tensor cores with the fp32-faithful 3-term TF32 split

@@ -208,6 +208,19 @@ int aq_prvl_loss_bwd(const float* img1, const float* img2, const void* state, co
 int aq_bce_logits(const float* logits, const float* targets, float* loss, float* g_logits, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (ii) message decoder, train mode (`sec_decoder.train()`: train/latent_wm_pretrain.py:160, rob_enhance_finetune.py:980): the
+ * batch-statistics BatchNorm2d (+ SiLU) of torchvision's Conv2dNormActivation over NHWC fp32 rows z [M = B*H*W, C].
+ * fwd: mean / biased variance over the M rows; y = act(gamma (z - mean) rstd + beta), act = SiLU when `act` != 0; mean_rstd [C, 2]
+ *      is written for the backward; running_mean / running_var (both or neither) are updated with `momentum` (unbiased variance).
+ * bwd: gz fully written; g_gamma / g_beta (either may be NULL) are ACCUMULATED into.  ws: aq_bn_train_workspace_bytes(C).
+ * C % 4 == 0, C <= 2048. */
+size_t aq_bn_train_workspace_bytes(int C);
+int aq_bn_train_fwd(const float* z, const float* gamma, const float* beta, float* running_mean, float* running_var, float* mean_rstd,
+                    float* y, int64_t M, int C, float eps, float momentum, int act, void* ws, size_t ws_bytes, void* stream);
+int aq_bn_train_bwd(const float* gy, const float* z, const float* gamma, const float* beta, const float* mean_rstd, float* gz,
+                    float* g_gamma, float* g_beta, int64_t M, int C, int act, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (ii) message decoder.  SecretDecoder.forward (utils/models.py:91-96 == evaluation/utils_eval.py:149-154):
  * torchvision EfficientNet-B1 (eval) with a Linear(1280, out_features) head; out_features = 2 * bits, viewed as
  * [B, bits, 2]; bit = argmax over the pair (evaluation/utils_eval.py:194).

@@ -196,7 +196,7 @@ def _assert_param_grads_close(got_mod, ref_mod, tol):
         q = gr[n].grad
         rows.append((n, float(q.norm()), float((p.grad.cpu() - q).norm()), q.numel()))
     typical = sorted(r[1] / r[3] ** 0.5 for r in rows)[len(rows) // 2]          # median per-element gradient magnitude
-    bad = [(n, qn, dn) for n, qn, dn, k in rows if dn > tol * qn + 1e-3 * typical * k ** 0.5]
+    bad = [(n, qn, dn) for n, qn, dn, k in rows if dn > tol * qn + tol * typical * k ** 0.5]
     assert not bad, (len(bad), sorted(bad, key=lambda r: -r[2] / (r[1] + 1e-30))[:6], typical)
 
 
