@@ -54,6 +54,11 @@ _SIGNATURES = {
     "aq_bn_train_workspace_bytes": ([c_int], c_size_t),
     "aq_bn_train_fwd": ([c_void_p] * 7 + [c_int64, c_int, c_float, c_float, c_int, c_void_p, c_size_t, c_void_p], c_int),
     "aq_bn_train_bwd": ([c_void_p] * 8 + [c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p], c_int),
+    "aq_dwconv_fwd": ([c_void_p] * 3 + [c_int] * 6 + [c_void_p], c_int),
+    "aq_dwconv_bwd": ([c_void_p] * 5 + [c_int] * 6 + [c_void_p], c_int),
+    "aq_conv1x1_wgrad": ([c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p], c_int),
+    "aq_stem_conv_fwd": ([c_void_p] * 3 + [c_int] * 3 + [c_void_p], c_int),
+    "aq_stem_conv_bwd": ([c_void_p] * 5 + [c_int] * 3 + [c_void_p], c_int),
     "aq_mapper_fwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "aq_mapper_bwd": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     "aq_cast_transpose_bf16": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),

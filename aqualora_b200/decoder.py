@@ -6,10 +6,11 @@ This class keeps exactly those parameter / buffer names (so `load_state_dict` of
 but owns no torchvision code.  eval(): the fp32 NHWC kernel chain in csrc/decoder.cu with every BatchNorm folded into its
 convolution (PPFT and evaluation run the decoder in eval(): train/ppft_train.py:974, evaluation/utils_eval.py:168).
 train() (train/latent_wm_pretrain.py:160-217, rob_enhance_finetune.py:995-1040): batch-statistics BatchNorm, StochasticDepth("row")
-and Dropout(0.2) as torchvision's `efficientnet_b1` defines them, differentiable w.r.t. the image and every parameter.  The
-train-mode convolutions are LIBRARY calls (cuDNN / ATen on the GPU) for now -- hand-written training kernels for this net are
-the next step; everything around it in the pretraining step (encoder, noise layers, losses) runs on this
-repository's kernels.  CPU tensors raise in both modes: there is no CPU fallback.
+and Dropout(0.2) as torchvision's `efficientnet_b1` defines them, differentiable w.r.t. the image and every parameter, on this
+repository's kernels: stem / depthwise / pointwise convolutions with their input and weight gradients (csrc/decoder_train.cu,
+pointwise forward + input gradient on the tensor cores through csrc/decoder_pw.cu), BatchNorm(+SiLU) forward / backward
+(csrc/bn_train.cu).  What stays PyTorch glue: the squeeze-excitation MLP on [B, C] vectors, the average pools, the row masks of
+StochasticDepth / Dropout and the final Linear (each a few kFLOP per image).  CPU tensors raise in both modes: no CPU fallback.
 """
 from __future__ import annotations
 
@@ -88,6 +89,92 @@ class _BnActFn(torch.autograd.Function):
         gz, g_gamma, g_beta = ops.bn_train_bwd(gy.contiguous(memory_format=torch.channels_last), z, gamma.detach().contiguous(),
                                                beta.detach().contiguous(), mean_rstd, ctx.act)
         return gz, g_gamma, g_beta, None, None, None, None, None
+
+
+class _DwConvFn(torch.autograd.Function):
+    """Depthwise k x k convolution of the train path (csrc/decoder_train.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride):
+        x = x.contiguous(memory_format=torch.channels_last)
+        ctx.save_for_backward(x, w)
+        ctx.stride = stride
+        return ops.dwconv_fwd(x, w, stride)
+
+    @staticmethod
+    def backward(ctx, gz):
+        x, w = ctx.saved_tensors
+        gx, gw = ops.dwconv_bwd(gz.contiguous(memory_format=torch.channels_last), x, w, ctx.stride, ctx.needs_input_grad[0])
+        return gx, gw, None
+
+
+class _PwConvFn(torch.autograd.Function):
+    """Pointwise convolution y = (x (.) se) W^T of the train path: forward and input gradient on the tensor cores (3 x TF32,
+    csrc/decoder_pw.cu), weight gradient on csrc/decoder_train.cu.  `se` [B, K] is the squeeze-excitation gate of the project
+    convolution (torchvision MBConv: block = [..., SE, project]), applied while the A tile is staged."""
+
+    @staticmethod
+    def forward(ctx, x, w, se):
+        x = x.contiguous(memory_format=torch.channels_last)
+        B, K, H, W = x.shape
+        N = w.shape[0]
+        x2d = x.permute(0, 2, 3, 1).reshape(B * H * W, K)
+        w2d = w.reshape(N, K)
+        zero_n = torch.zeros(N, dtype=torch.float32, device=x.device)
+        se2d = None if se is None else se.reshape(B, K).contiguous()
+        y2d = ops.conv1x1_tf32x3(x2d, w2d, zero_n, se=se2d, hw=H * W)
+        ctx.save_for_backward(x, w, se2d)
+        return y2d.view(B, H, W, N).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, se2d = ctx.saved_tensors
+        B, K, H, W = x.shape
+        N = w.shape[0]
+        gy2d = gy.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(B * H * W, N)
+        x2d = x.permute(0, 2, 3, 1).reshape(B * H * W, K)
+        gx = g_se = None
+        if ctx.needs_input_grad[0] or (se2d is not None and ctx.needs_input_grad[2]):
+            wt = w.reshape(N, K).t().contiguous()
+            ge2d = ops.conv1x1_tf32x3(gy2d, wt, torch.zeros(K, dtype=torch.float32, device=x.device), hw=H * W)   # d / d (x (.) se)
+            ge = ge2d.view(B, H * W, K)
+            if se2d is None:
+                gx = ge2d.view(B, H, W, K).permute(0, 3, 1, 2)
+            else:
+                g_se = (ge * x2d.view(B, H * W, K)).sum(dim=1).view(B, K, 1, 1)
+                gx = (ge * se2d.view(B, 1, K)).view(B, H, W, K).permute(0, 3, 1, 2)
+        gw = ops.conv1x1_wgrad(gy2d, x2d, se2d, H * W).view_as(w) if ctx.needs_input_grad[1] else None
+        return gx, gw, g_se
+
+
+class _StemConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        x = x.contiguous()
+        ctx.save_for_backward(x, w)
+        return ops.stem_conv_fwd(x, w)
+
+    @staticmethod
+    def backward(ctx, gz):
+        x, w = ctx.saved_tensors
+        gx, gw = ops.stem_conv_bwd(gz.contiguous(memory_format=torch.channels_last), x, w, ctx.needs_input_grad[0])
+        return gx, gw
+
+
+def _train_conv(conv: nn.Conv2d, x: torch.Tensor, se=None) -> torch.Tensor:
+    """One bias-free convolution of the train path on this repository's kernels; shapes outside what they cover (a 512 x 512 decoder
+    never produces one) fall to the library convolution."""
+    w = conv.weight
+    k = w.shape[-1]
+    if conv.groups == 1 and k == 1 and x.shape[1] % 8 == 0 and w.shape[0] % 4 == 0 and (x.shape[2] * x.shape[3]) % 128 == 0:
+        return _PwConvFn.apply(x, w, se)
+    if se is not None:
+        x = x * se
+    if conv.groups == conv.in_channels and conv.groups > 1 and k in (3, 5) and conv.stride[0] in (1, 2) and x.shape[1] % 4 == 0:
+        return _DwConvFn.apply(x, w, conv.stride[0])
+    if conv.groups == 1 and k == 3 and conv.stride[0] == 2 and tuple(w.shape[:2]) == (32, 3):
+        return _StemConvFn.apply(x, w)
+    return conv(x)
 
 
 def _fold(sd, conv_key, bn_key):
@@ -174,10 +261,10 @@ class SecretDecoder(nn.Module):
         m = self.model
         total_blocks = float(sum(layers for *_, layers in B1_STAGES))
 
-        def cba(seq, x, act=True):
-            # conv (no bias, library call) -> BatchNorm2d with batch statistics + SiLU (csrc/bn_train.cu; updates the running statistics)
+        def cba(seq, x, act=True, se=None):
+            # conv (no bias: csrc/decoder_train.cu / decoder_pw.cu) -> BatchNorm2d with batch statistics + SiLU (csrc/bn_train.cu)
             bn = seq[1]
-            z = seq[0](x)
+            z = _train_conv(seq[0], x, se)
             if z.shape[1] % 4 != 0 or bn.momentum is None:
                 y = bn(z)
                 return F.silu(y) if act else y
@@ -197,10 +284,9 @@ class SecretDecoder(nn.Module):
                 h = cba(blk[i], h)
                 i += 1
                 se = blk[i]
-                scale = torch.sigmoid(se.fc2(F.silu(se.fc1(F.adaptive_avg_pool2d(h, 1)))))
-                h = h * scale
+                scale = torch.sigmoid(se.fc2(F.silu(se.fc1(F.adaptive_avg_pool2d(h, 1)))))      # [B, C, 1, 1]: a few kFLOP per image
                 i += 1
-                h = cba(blk[i], h, act=False)
+                h = cba(blk[i], h, act=False, se=scale)      # the gate rides in the project convolution's A-tile staging
                 if (stride if li == 0 else 1) == 1 and (cin if li == 0 else cout) == cout:
                     p = self.stochastic_depth_prob * block_id / total_blocks     # StochasticDepth(p, "row")
                     if p > 0.0:

@@ -476,6 +476,65 @@ def bn_train_bwd(gy: torch.Tensor, z: torch.Tensor, gamma: torch.Tensor, beta: t
     return gz, g_gamma, g_beta
 
 
+def dwconv_fwd(x: torch.Tensor, w: torch.Tensor, stride: int) -> torch.Tensor:
+    """Depthwise k x k convolution (no bias) of a channels_last fp32 tensor; w [C, 1, k, k].  Returns z channels_last."""
+    _, C = _nhwc_f32(x, "x")
+    _need(w, _F32, "w", 4)
+    B, _, H, W = x.shape
+    k = w.shape[-1]
+    p = (k - 1) // 2
+    Ho, Wo = (H + 2 * p - k) // stride + 1, (W + 2 * p - k) // stride + 1
+    z = torch.empty((B, C, Ho, Wo), dtype=_F32, device=x.device).contiguous(memory_format=torch.channels_last)
+    _lib.call("aq_dwconv_fwd", x.data_ptr(), w.contiguous().data_ptr(), z.data_ptr(), B, H, W, C, k, int(stride), _stream())
+    return z
+
+
+def dwconv_bwd(gz: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, need_gx: bool = True):
+    """Returns (gx or None, gw [C, 1, k, k])."""
+    _, C = _nhwc_f32(x, "x")
+    _nhwc_f32(gz, "gz")
+    B, _, H, W = x.shape
+    k = w.shape[-1]
+    gx = torch.empty_like(x) if need_gx else None
+    gw = torch.zeros_like(w, memory_format=torch.contiguous_format)
+    _lib.call("aq_dwconv_bwd", gz.data_ptr(), x.data_ptr(), w.contiguous().data_ptr(), _ptr(gx), gw.data_ptr(), B, H, W, C, k, int(stride), _stream())
+    return gx, gw
+
+
+def conv1x1_wgrad(gz2d: torch.Tensor, x2d: torch.Tensor, se: torch.Tensor | None, hw: int) -> torch.Tensor:
+    """gw [N, K] = gz2d^T [N, M] @ (x2d * se[row // hw]) [M, K]  (fp32)."""
+    _need(gz2d, _F32, "gz", 2)
+    _need(x2d, _F32, "x", 2)
+    M, N = gz2d.shape
+    K = x2d.shape[1]
+    if not gz2d.is_contiguous() or not x2d.is_contiguous() or x2d.shape[0] != M:
+        raise _lib.AqualoraError("conv1x1_wgrad: gz [M, N] and x [M, K] must be contiguous with equal row counts")
+    gw = torch.zeros((N, K), dtype=_F32, device=x2d.device)
+    _lib.call("aq_conv1x1_wgrad", gz2d.data_ptr(), x2d.data_ptr(), _ptr(se), gw.data_ptr(), M, K, N, int(hw), _stream())
+    return gw
+
+
+def stem_conv_fwd(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """3 x 3 stride-2 stem (3 -> 32, no bias): x [B, 3, H, W] NCHW fp32 -> z [B, 32, Ho, Wo] channels_last."""
+    x = _image(x, "x")
+    _need(w, _F32, "w", 4)
+    B, _, H, W = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    z = torch.empty((B, 32, Ho, Wo), dtype=_F32, device=x.device).contiguous(memory_format=torch.channels_last)
+    _lib.call("aq_stem_conv_fwd", x.data_ptr(), w.contiguous().data_ptr(), z.data_ptr(), B, H, W, _stream())
+    return z
+
+
+def stem_conv_bwd(gz: torch.Tensor, x: torch.Tensor, w: torch.Tensor, need_gx: bool):
+    x = _image(x, "x")
+    _nhwc_f32(gz, "gz")
+    B, _, H, W = x.shape
+    gx = torch.empty_like(x) if need_gx else None
+    gw = torch.zeros_like(w, memory_format=torch.contiguous_format)
+    _lib.call("aq_stem_conv_bwd", gz.data_ptr(), x.data_ptr(), w.contiguous().data_ptr(), _ptr(gx), gw.data_ptr(), B, H, W, _stream())
+    return gx, gw
+
+
 def conv1x1_tf32x3(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, se: torch.Tensor | None = None,
                    residual: torch.Tensor | None = None, hw: int = 0, epi: int = 0) -> torch.Tensor:
     """Pointwise convolution over NHWC pixels on the tensor cores with the fp32-faithful 3-term TF32 split

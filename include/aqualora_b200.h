@@ -220,6 +220,20 @@ int aq_bn_train_fwd(const float* z, const float* gamma, const float* beta, float
 int aq_bn_train_bwd(const float* gy, const float* z, const float* gamma, const float* beta, const float* mean_rstd, float* gz,
                     float* g_gamma, float* g_beta, int64_t M, int C, int act, void* ws, size_t ws_bytes, void* stream);
 
+/* Convolutions of the decoder's train path (csrc/decoder_train.cu): fp32, NHWC activations, weights in PyTorch's layouts.
+ *   aq_dwconv_fwd / _bwd    depthwise k x k (k = 3, 5), stride 1 / 2, padding (k - 1) / 2, no bias: x [B, H, W, C], w [C, 1, k, k],
+ *                           z [B, Ho, Wo, C]; bwd writes gx (may be NULL) and ACCUMULATES gw (may be NULL)
+ *   aq_conv1x1_wgrad        gw [N, K] += gz^T [N, M] (x (.) se) [M, K]; se [M / hw, K] = the SE gate of each image or NULL.  (Forward
+ *                           and input gradient of the pointwise convolutions are aq_conv1x1_tf32x3 with w resp. w^T.)
+ *   aq_stem_conv_fwd / _bwd 3 x 3 stride 2 padding 1, 3 -> 32: x [B, 3, H, W] NCHW, w [32, 3, 3, 3], z [B, Ho, Wo, 32] NHWC;
+ *                           bwd writes gx NCHW (may be NULL) and ACCUMULATES gw (may be NULL) */
+int aq_dwconv_fwd(const float* x, const float* w, float* z, int B, int H, int W, int C, int k, int stride, void* stream);
+int aq_dwconv_bwd(const float* gz, const float* x, const float* w, float* gx, float* gw, int B, int H, int W, int C, int k, int stride,
+                  void* stream);
+int aq_conv1x1_wgrad(const float* gz, const float* x, const float* se, float* gw, int64_t M, int K, int N, int hw, void* stream);
+int aq_stem_conv_fwd(const float* x, const float* w, float* z, int B, int H, int W, void* stream);
+int aq_stem_conv_bwd(const float* gz, const float* x, const float* w, float* gx, float* gw, int B, int H, int W, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (ii) message decoder.  SecretDecoder.forward (utils/models.py:91-96 == evaluation/utils_eval.py:149-154):
  * torchvision EfficientNet-B1 (eval) with a Linear(1280, out_features) head; out_features = 2 * bits, viewed as

@@ -318,3 +318,105 @@ def test_stage3_decoder_finetune_step(cuda_device):
     assert abs(loss.item() - loss_ref.item()) <= 2e-3 * loss_ref.item()
     assert 0.0 <= acc.item() <= 1.0
     _assert_param_grads_close(dec, ref, 5e-2)
+
+
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.mark.parametrize("C,k,s,H,W", [(16, 3, 1, 24, 24), (96, 3, 2, 33, 30), (144, 5, 2, 32, 32), (480, 5, 1, 16, 16), (32, 3, 1, 7, 9)])
+def test_train_depthwise_kernels(cuda_device, C, k, s, H, W):
+    """csrc/decoder_train.cu depthwise forward / input gradient / weight gradient vs the library convolution on the same device."""
+    from aqualora_b200.decoder import _DwConvFn
+
+    _no_tf32()
+    g = torch.Generator(device=cuda_device).manual_seed(C + k)
+    x = torch.randn(2, C, H, W, generator=g, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(C, 1, k, k, generator=g, device=cuda_device) * 0.2
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr, None, s, (k - 1) // 2, 1, C)
+    gy = torch.randn(yr.shape, generator=g, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    yr.backward(gy)
+    xc, wc = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yc = _DwConvFn.apply(xc, wc, s)
+    yc.backward(gy)
+    _close(yc.detach(), yr.detach(), 1e-5, 1e-6, "dw y")
+    _close(xc.grad, xr.grad, 1e-5, 1e-6, "dw gx")
+    _close(wc.grad, wr.grad, 1e-4, 1e-5, "dw gw")
+
+
+@pytest.mark.parametrize("K,N,H,with_se", [(16, 96, 16, False), (96, 24, 16, True), (320, 1280, 16, False), (1152, 192, 16, True), (32, 16, 32, True)])
+def test_train_pointwise_kernels(cuda_device, K, N, H, with_se):
+    from aqualora_b200.decoder import _PwConvFn
+
+    _no_tf32()
+    g = torch.Generator(device=cuda_device).manual_seed(K + N)
+    B = 2
+    x = torch.randn(B, K, H, H, generator=g, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(N, K, 1, 1, generator=g, device=cuda_device) * K ** -0.5
+    se = torch.rand(B, K, 1, 1, generator=g, device=cuda_device) if with_se else None
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    ser = se.clone().requires_grad_(True) if with_se else None
+    yr = torch.nn.functional.conv2d(xr * ser if with_se else xr, wr)
+    gy = torch.randn(yr.shape, generator=g, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    yr.backward(gy)
+    xc, wc = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    sec = se.clone().requires_grad_(True) if with_se else None
+    yc = _PwConvFn.apply(xc, wc, sec)
+    yc.backward(gy)
+    _close(yc.detach(), yr.detach(), 2e-5, 2e-6, "pw y")           # 3 x TF32 == fp32 FFMA accuracy
+    _close(xc.grad, xr.grad, 2e-5, 2e-6, "pw gx")
+    _close(wc.grad, wr.grad, 1e-4, 1e-5, "pw gw")
+    if with_se:
+        _close(sec.grad, ser.grad, 1e-4, 1e-5, "pw g_se")
+
+
+def test_train_stem_kernels(cuda_device):
+    from aqualora_b200.decoder import _StemConvFn
+
+    _no_tf32()
+    g = torch.Generator(device=cuda_device).manual_seed(11)
+    for (H, W) in ((64, 64), (37, 50)):
+        x = torch.randn(2, 3, H, W, generator=g, device=cuda_device)
+        w = torch.randn(32, 3, 3, 3, generator=g, device=cuda_device) * 0.2
+        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        yr = torch.nn.functional.conv2d(xr, wr, None, 2, 1)
+        gy = torch.randn(yr.shape, generator=g, device=cuda_device).contiguous(memory_format=torch.channels_last)
+        yr.backward(gy)
+        xc, wc = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        yc = _StemConvFn.apply(xc, wc)
+        yc.backward(gy)
+        _close(yc.detach(), yr.detach(), 1e-5, 1e-6, "stem y")
+        _close(xc.grad, xr.grad, 1e-5, 1e-6, "stem gx")
+        _close(wc.grad, wr.grad, 1e-4, 1e-5, "stem gw")
+
+
+@pytest.mark.parametrize("C,M_hw,act", [(16, 64 * 64, True), (96, 33 * 31, True), (1920, 16 * 16, False), (1152, 8 * 8, True)])
+def test_train_batchnorm_kernels(cuda_device, C, M_hw, act):
+    """csrc/bn_train.cu vs F.batch_norm(training=True) [+ SiLU] incl. the running-statistics update and all three gradients."""
+    from aqualora_b200.decoder import _BnActFn
+
+    g = torch.Generator(device=cuda_device).manual_seed(C)
+    side = int(M_hw ** 0.5)
+    H, W = side, M_hw // side
+    z = (torch.randn(3, C, H, W, generator=g, device=cuda_device) * 2 + 0.5).contiguous(memory_format=torch.channels_last)
+    gamma = torch.rand(C, generator=g, device=cuda_device) + 0.5
+    beta = torch.randn(C, generator=g, device=cuda_device) * 0.1
+    rm0, rv0 = torch.randn(C, generator=g, device=cuda_device) * 0.1, torch.rand(C, generator=g, device=cuda_device) + 0.5
+    zr, gr, br = z.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_r, rv_r = rm0.clone(), rv0.clone()
+    yr = torch.nn.functional.batch_norm(zr, rm_r, rv_r, gr, br, True, 0.1, 1e-5)
+    yr = torch.nn.functional.silu(yr) if act else yr
+    gy = torch.randn(yr.shape, generator=g, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    yr.backward(gy)
+    zc, gc, bc = z.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_c, rv_c = rm0.clone(), rv0.clone()
+    yc = _BnActFn.apply(zc, gc, bc, rm_c, rv_c, 1e-5, 0.1, act)
+    yc.backward(gy)
+    _close(yc.detach(), yr.detach(), 1e-4, 1e-5, "bn y")
+    _close(rm_c, rm_r, 1e-5, 1e-6, "running_mean")
+    _close(rv_c, rv_r, 1e-5, 1e-6, "running_var")
+    _close(zc.grad, zr.grad, 1e-3, 1e-4, "bn gz")
+    _close(gc.grad, gr.grad, 1e-3, 1e-4, "bn g_gamma")
+    _close(bc.grad, br.grad, 1e-3, 1e-4, "bn g_beta")
