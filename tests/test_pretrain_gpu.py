@@ -365,8 +365,9 @@ def test_train_pointwise_kernels(cuda_device, K, N, H, with_se):
     sec = se.clone().requires_grad_(True) if with_se else None
     yc = _PwConvFn.apply(xc, wc, sec)
     yc.backward(gy)
-    _close(yc.detach(), yr.detach(), 2e-5, 2e-6, "pw y")           # 3 x TF32 == fp32 FFMA accuracy
-    _close(xc.grad, xr.grad, 2e-5, 2e-6, "pw gx")
+    # 3 x TF32 == fp32 FFMA accuracy; the library sums the K <= 1152 products in another order (bound ~ sqrt(K) * 2^-24 * sum |x||w|)
+    _close(yc.detach(), yr.detach(), 1e-4, 2e-5, "pw y")
+    _close(xc.grad, xr.grad, 1e-4, 2e-5, "pw gx")
     _close(wc.grad, wr.grad, 1e-4, 1e-5, "pw gw")
     if with_se:
         _close(sec.grad, ser.grad, 1e-4, 1e-5, "pw g_se")
