@@ -31,6 +31,11 @@ _SIGNATURES = {
          c_int, c_int, c_int, c_void_p],
         c_int,
     ),
+    "aq_lora_linear_fwd_residual": (
+        [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+         c_int64, c_int, c_int, c_int, c_void_p],
+        c_int,
+    ),
     "aq_lora_linear_fwd_grouped": ([c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p], c_int),
     "aq_lora_linear_bwd_workspace_bytes": ([c_int64, c_int], c_size_t),
     "aq_lora_linear_bwd": (

@@ -27,6 +27,12 @@ int aq_lora_set_tuning(int block_n, int group_size) {
 int aq_lora_linear_fwd(const void* x, int64_t ldx, const void* w, const void* bias, const void* down, const void* up,
                        const float* scale, void* y, int64_t ldy, void* h_save, int64_t M, int64_t tokens_per_sample, int din,
                        int dout, int r, void* stream) {
+  return aq_lora_linear_fwd_residual(x, ldx, w, bias, down, up, scale, nullptr, 0, y, ldy, h_save, M, tokens_per_sample, din, dout, r, stream);
+}
+
+int aq_lora_linear_fwd_residual(const void* x, int64_t ldx, const void* w, const void* bias, const void* down, const void* up,
+                                const float* scale, const void* residual, int64_t ldres, void* y, int64_t ldy, void* h_save, int64_t M,
+                                int64_t tokens_per_sample, int din, int dout, int r, void* stream) {
   AQ_REQUIRE(x && w && y, AQ_ERR_BAD_SHAPE, "lora_linear_fwd: x, w and y must be non-NULL");
   AQ_REQUIRE(tokens_per_sample > 0 || down == nullptr, AQ_ERR_BAD_SHAPE, "lora_linear_fwd: tokens_per_sample must be > 0");
   AQ_REQUIRE(down == nullptr || (r >= 8 && r % 8 == 0), AQ_ERR_BAD_SHAPE,
@@ -38,6 +44,7 @@ int aq_lora_linear_fwd(const void* x, int64_t ldx, const void* w, const void* bi
     const int r0 = c * kRankChunk, rc_ = down == nullptr ? 0 : (r - r0 < kRankChunk ? r - r0 : kRankChunk);
     LoraGemmArgs a;
     a.a = x; a.lda = ldx; a.w = w; a.bias = c == 0 ? bias : nullptr; a.scale = scale ? scale + r0 : nullptr; a.y = y; a.ldy = ldy;
+    a.res = c == 0 ? residual : nullptr; a.ldres = ldres;
     a.dn = down ? bf16_at(down, (int64_t)r0 * din) : nullptr;        // rows r0 ... of down [r, din]
     a.up = up ? bf16_at(up, r0) : nullptr;                            // columns r0 ... of up [dout, r]
     a.aux_out0 = h_save ? bf16_at(h_save, r0) : nullptr; a.aux_out1 = nullptr; a.h_in = nullptr; a.g_scale = nullptr;

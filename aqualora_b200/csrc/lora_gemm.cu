@@ -78,6 +78,8 @@ struct LoraProblem {
   CUtensorMap tmap_up;   // Up [N, r]   box {64, BN/2}   swizzle 128B
   CUtensorMap tmap_y;    // Y  [M, N]   box {kPassCols, 32}  (store; swizzle 64B when kPassCols == 32)
   const __nv_bfloat16* bias;   // [N] or null
+  const __nv_bfloat16* res;    // [M, ldres] or null: residual added in the tile epilogue (Y = ... + res)
+  long long ldres;
   __nv_bfloat16* y;            // [M, ldy]
   __nv_bfloat16* aux_out0;     // mode 0: H [M, r] (may be null); mode 1: dH [M, r]
   long long ldy;
@@ -611,11 +613,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
                 f[2 * i + 1] += bf16_hi(bb[i]);
               }
             }
-            if (p.accum_y) {
-              // rank chunks after the first: Y += this chunk's Hs Up^T (the lane owns row `grow`; 16 bytes = 8 columns of it)
+            // addend read from memory: the Y of the previous rank chunk (Y += this chunk's Hs Up^T), or the residual stream the
+            // caller adds to this projection (x + to_out(...), x + ff(...), x + proj_out(...) of a transformer block) -- the lane
+            // owns row `grow`; 16 bytes = 8 columns of it
+            const __nv_bfloat16* addend = p.accum_y ? q_.y : q_.res;
+            if (addend != nullptr) {
+              const long long ld_add = p.accum_y ? q_.ldy : q_.ldres;
               const int c = pcol0 + c8 * 8;
               if (row_ok && c < q_.N) {
-                const uint4 yw = *reinterpret_cast<const uint4*>(q_.y + (size_t)grow * q_.ldy + c);
+                const uint4 yw = __ldg(reinterpret_cast<const uint4*>(addend + (size_t)grow * ld_add + c));
                 const uint32_t yy[4] = {yw.x, yw.y, yw.z, yw.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -647,7 +653,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         if (warp == 0 && nt - nt_begin < 4) AQ_TRACE(item_iter, 15 + 3 * (nt - nt_begin));
       }
     }
-    if (lane == 0) tma_store_wait_all<0>();   // every bulk store of this warp has completed before its shared memory goes away
+    // every bulk store of this warp has READ its staging buffer before the shared memory goes away; the global writes themselves
+    // complete asynchronously and are flushed by the end of the grid (waiting for full completion here cost ~0.5 us per CTA tail)
+    if (lane == 0) tma_store_wait_read<0>();
     __syncwarp();
   }
 
@@ -747,6 +755,8 @@ static int launch_bn(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) 
       if (rc) return rc;
     }
     q.bias = reinterpret_cast<const __nv_bfloat16*>(b.bias);
+    q.res = reinterpret_cast<const __nv_bfloat16*>(b.res);
+    q.ldres = b.ldres;
     q.y = reinterpret_cast<__nv_bfloat16*>(b.y);
     q.ldy = b.ldy;
     q.aux_out0 = reinterpret_cast<__nv_bfloat16*>(b.aux_out0);
@@ -799,6 +809,8 @@ static int validate(const LoraGemmArgs& a) {
   AQ_REQUIRE(a.has_main || a.dn != nullptr, AQ_ERR_BAD_SHAPE, "lora_gemm: nothing to compute");
   AQ_REQUIRE(a.ld_r == 0 || (a.ld_r >= a.r && a.ld_r % 8 == 0), AQ_ERR_BAD_SHAPE, "lora_gemm: ld_r=%lld must be a multiple of 8 >= r", (long long)a.ld_r);
   AQ_REQUIRE(!a.skip_base || (a.dn != nullptr && a.has_main), AQ_ERR_BAD_SHAPE, "lora_gemm: skip_base needs LoRA operands and an output");
+  AQ_REQUIRE(a.res == nullptr || (a.has_main && a.ldres % 8 == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15u) == 0 && !a.accum_y), AQ_ERR_BAD_ALIGN,
+             "lora_gemm: residual needs an output, a 16-byte aligned base and a leading dimension that is a multiple of 8");
   AQ_REQUIRE(a.lda % 8 == 0 && (!a.has_main || a.ldy % 8 == 0), AQ_ERR_BAD_ALIGN, "lora_gemm: leading dimensions must be multiples of 8 elements");
   AQ_REQUIRE(!a.has_main || (reinterpret_cast<uintptr_t>(a.y) & 15u) == 0, AQ_ERR_BAD_ALIGN, "lora_gemm: y must be 16-byte aligned");
   return AQ_OK;

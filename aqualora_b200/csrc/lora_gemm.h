@@ -9,6 +9,8 @@ struct LoraGemmArgs {
   const void* a; int64_t lda;       // [M, K] bf16
   const void* w;                    // [N, K] bf16
   const void* bias;                 // [N] bf16 or null
+  const void* res = nullptr;        // [M, ldres] bf16 or null: residual added in the epilogue
+  int64_t ldres = 0;
   const void* dn;                   // [r, K] bf16 or null (null: plain projection)
   const void* up;                   // [N, r] bf16
   const float* scale;               // [num_samples, r] fp32

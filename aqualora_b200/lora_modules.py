@@ -152,17 +152,18 @@ class _FusedLoraProjection(torch.autograd.Function):
     """y = x W^T + b + ((x Dn^T) (.) s) Up^T  on [M, din] bf16 rows; see include/aqualora_b200.h."""
 
     @staticmethod
-    def forward(ctx, x2d, weight, bias, down, up, scale_eff, tokens):
+    def forward(ctx, x2d, weight, bias, down, up, scale_eff, tokens, residual=None):
         dout, din = weight.shape[0], x2d.shape[1]
         w2d = weight.reshape(dout, din)
-        need_grad = any(ctx.needs_input_grad)     # (grad mode itself is off inside Function.forward)
+        need_grad = any(ctx.needs_input_grad[:6])     # (grad mode itself is off inside Function.forward)
         if down is not None:
             r = down.shape[0]
             dn16, _ = _packed(down, r, din)
             up16, _ = _packed(up, dout, r)
-            y, h = ops.lora_linear_fwd(x2d, w2d, bias, dn16, up16, scale_eff.detach(), tokens, save_h=need_grad)
+            y, h = ops.lora_linear_fwd(x2d, w2d, bias, dn16, up16, scale_eff.detach(), tokens, save_h=need_grad, residual=residual)
         else:
-            y, h = ops.lora_linear_fwd(x2d, w2d, bias, None, None, None, tokens)
+            y, h = ops.lora_linear_fwd(x2d, w2d, bias, None, None, None, tokens, residual=residual)
+        ctx.has_residual = residual is not None
         ctx.tokens = tokens
         ctx.has_lora = down is not None
         # python-side handles: `_aq_grad` (direct accumulation target) lives on the caller's tensor objects
@@ -177,11 +178,12 @@ class _FusedLoraProjection(torch.autograd.Function):
         gy = gy if gy.stride(1) == 1 and gy.stride(0) % 8 == 0 else gy.contiguous()
         need_dx = ctx.needs_input_grad[0]
         w_t = _weight_t(weight, dout, din) if need_dx else None
+        g_res = gy if ctx.has_residual and ctx.needs_input_grad[7] else None      # y = ... + residual: identity
         if not ctx.has_lora:
             gx = None
             if need_dx:
                 gx, _ = ops.lora_linear_fwd(gy, w_t, None, None, None, None, ctx.tokens)
-            return gx, None, None, None, None, None, None
+            return gx, None, None, None, None, None, None, g_res
         r = down.shape[0]
         _, dn16_t = _packed(down, r, din)
         _, up16_t = _packed(up, dout, r)
@@ -195,7 +197,7 @@ class _FusedLoraProjection(torch.autograd.Function):
         return (gx, None, None,
                 None if down_direct else g_down.view_as(down).to(down.dtype),
                 None if up_direct else g_up.view_as(up).to(up.dtype),
-                None if (g_scale is None or scale_direct) else g_scale, None)
+                None if (g_scale is None or scale_direct) else g_scale, None, g_res)
 
 
 class _GroupedLoraProjection(torch.autograd.Function):
@@ -325,14 +327,15 @@ def _rows_view(x: torch.Tensor, din: int) -> torch.Tensor:
     return x2d
 
 
-def _project_rows(x2d, weight, bias, down, up, lora_meta, scale, compute_dtype):
-    """Shared tail of the four forwards: x2d [M, din] bf16 rows -> [M, dout] through the fused kernel."""
+def _project_rows(x2d, weight, bias, down, up, lora_meta, scale, compute_dtype, residual=None):
+    """Shared tail of the four forwards: x2d [M, din] bf16 rows -> [M, dout] through the fused kernel (+ residual [M, dout] rows
+    added in the tile epilogue when given)."""
     M = x2d.shape[0]
     weight = _bf16_weight(weight)
     if bias is not None and bias.dtype != torch.bfloat16:
         bias = bias.detach().to(torch.bfloat16)
     if down is None:
-        return _FusedLoraProjection.apply(x2d, weight, bias, None, None, None, M)
+        return _FusedLoraProjection.apply(x2d, weight, bias, None, None, None, M, residual)
     r = down.shape[0]
     if r % 8 != 0:
         # ranks that are not a multiple of 8 (ppft_train.py's default --rank is 4): zero rows / columns pad the LoRA operands and
@@ -352,7 +355,7 @@ def _project_rows(x2d, weight, bias, down, up, lora_meta, scale, compute_dtype):
     else:
         nsamp, tokens = 1, M
     s_eff = _effective_scale(scale, lora_meta, nsamp, r, x2d.device, torch.bfloat16)
-    return _FusedLoraProjection.apply(x2d, weight, bias, down, up, s_eff, tokens)
+    return _FusedLoraProjection.apply(x2d, weight, bias, down, up, s_eff, tokens, residual)
 
 
 _ZERO_BASE: Dict[tuple, torch.Tensor] = {}
@@ -441,6 +444,55 @@ def CustomLoRACompatibleConvforward(self, hidden_states: torch.Tensor, scale: fl
 
 
 # ------------------------------------------------------------------------------------------------
+# projection + residual add in one kernel (SURVEY.md 8(f2): the adds around the LoRA-target GEMMs of a Transformer2D block)
+# ------------------------------------------------------------------------------------------------
+def _residual_rows(residual: torch.Tensor, M: int, dout: int):
+    """[M, dout] bf16 row view of the residual stream, or None when it cannot ride in the epilogue (then the caller adds it)."""
+    if residual is None or not residual.is_cuda or residual.dtype != torch.bfloat16 or residual.numel() != M * dout:
+        return None
+    r2d = residual.reshape(M, dout)
+    if r2d.stride(1) != 1 or r2d.stride(0) % 8 != 0 or r2d.data_ptr() % 16 != 0:
+        return None
+    return r2d
+
+
+def linear_with_residual(module, hidden_states: torch.Tensor, scale, residual: torch.Tensor):
+    """`module(hidden_states, scale) + residual` for a LoRA-compatible linear patched with this library's forward: the add happens in
+    the GEMM's tile epilogue (aq_lora_linear_fwd_residual) instead of a separate pass over [M, dout].  Any other module, dtype or
+    layout takes the plain two-op form -- same arithmetic up to one bf16 rounding (the sum is rounded once instead of twice)."""
+    ours = isinstance(module, nn.Linear) and getattr(module.forward, "__func__", None) is CustomLoRACompatibleLinearforward
+    if ours and hidden_states.is_cuda and hidden_states.dtype == torch.bfloat16:
+        x2d = _rows_view(hidden_states, hidden_states.shape[-1])
+        r2d = _residual_rows(residual, x2d.shape[0], module.weight.shape[0])
+        if r2d is not None:
+            lora = None if _LORA_DISABLED else module.lora_layer
+            if lora is None:
+                y = _project_rows(x2d, module.weight, module.bias, None, None, None, scale, hidden_states.dtype, r2d)
+            else:
+                y = _project_rows(x2d, module.weight, module.bias, lora.down.weight, lora.up.weight, lora, scale, hidden_states.dtype, r2d)
+            return y.view(*hidden_states.shape[:-1], module.weight.shape[0])
+    return module(hidden_states, scale) + residual
+
+
+def conv1x1_with_residual(module, hidden_states: torch.Tensor, scale, residual: torch.Tensor):
+    """`module(hidden_states, scale) + residual` for the 1x1 proj_out convolution of an SD1.5 Transformer2D block (channels_last rows)."""
+    ours = (isinstance(module, nn.Conv2d) and getattr(module.forward, "__func__", None) is CustomLoRACompatibleConvforward and _is_pointwise(module)
+            and (module.lora_layer is None or _is_pointwise(module.lora_layer.down)))
+    if (ours and hidden_states.is_cuda and hidden_states.dtype == torch.bfloat16 and residual.dtype == torch.bfloat16
+            and residual.shape[1] == module.weight.shape[0] and residual.is_contiguous(memory_format=torch.channels_last)):
+        x2d, (B, H, W) = _conv_as_rows(hidden_states)
+        r2d = _residual_rows(residual.permute(0, 2, 3, 1), x2d.shape[0], module.weight.shape[0])
+        if r2d is not None:
+            lora = None if _LORA_DISABLED else module.lora_layer
+            if lora is None:
+                y = _project_rows(x2d, module.weight, module.bias, None, None, None, scale, hidden_states.dtype, r2d)
+            else:
+                y = _project_rows(x2d, module.weight, module.bias, lora.down.weight, lora.up.weight, lora, scale, hidden_states.dtype, r2d)
+            return y.view(B, H, W, -1).permute(0, 3, 1, 2)
+    return module(hidden_states, scale) + residual
+
+
+# ------------------------------------------------------------------------------------------------
 # several projections of one input in one launch; the attention processor that uses it
 # ------------------------------------------------------------------------------------------------
 def _alpha_over_rank(lora) -> float:
@@ -505,13 +557,25 @@ def precompute_cross_kv(attentions, encoder_hidden_states: torch.Tensor, scale=1
             attentions[(i + j) // 2]._aq_kv = (outs[j], outs[j + 1])
 
 
+def _flash_for_short_kv():
+    try:
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+
+        return lambda: sdpa_kernel([SDPBackend.FLASH_ATTENTION, SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH])
+    except ImportError:      # older torch: keep the default dispatch
+        return None
+
+
+_FLASH_FOR_SHORT_KV = _flash_for_short_kv()
+
+
 class AquaLoRAAttnProcessor:
     """diffusers-style attention processor (`__call__(attn, hidden_states, encoder_hidden_states, attention_mask, temb, scale)`,
     the signature of diffusers 0.24 `AttnProcessor2_0`, which threads `cross_attention_kwargs["scale"]` into `attn.to_q/k/v/
     to_out[0]` -- train/ppft_train.py:1028,1034).  Same arithmetic as calling the four patched projections one by one, but
     q / k / v of a self-attention (and k / v of a cross-attention) leave in one grouped launch."""
 
-    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0):
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0, residual=None):
         kv = getattr(attn, "_aq_kv", None)
         if kv is not None:
             attn._aq_kv = None
@@ -529,10 +593,18 @@ class AquaLoRAAttnProcessor:
         v = v.view(B, v.shape[1], h, C // h).transpose(1, 2)
         if getattr(attn, "upcast", False) or getattr(attn, "upcast_attention", False):
             o = F.scaled_dot_product_attention(q.float(), k.float(), v.float(), attn_mask=attention_mask).to(v.dtype)
+        elif k.shape[2] <= 128 and q.is_cuda and q.dtype == torch.bfloat16 and attention_mask is None and _FLASH_FOR_SHORT_KV is not None:
+            # cross-attention (77 text tokens): the library's flash backend beats its cuDNN default for short K / V on B200
+            # (profiles/r02_sdpa_backend_probe.log: 4096 x 77, d = 40: 406 vs 584 us forward + backward)
+            with _FLASH_FOR_SHORT_KV():
+                o = F.scaled_dot_product_attention(q, k, v)
         else:
             o = F.scaled_dot_product_attention(q, k, v, attn_mask=attention_mask)
         o = o.transpose(1, 2).reshape(B, N, C)
-        o = attn.to_out[0](o, scale)
+        if residual is not None:
+            o = linear_with_residual(attn.to_out[0], o, scale, residual)      # x + to_out(...) in the projection's epilogue
+        else:
+            o = attn.to_out[0](o, scale)
         if len(attn.to_out) > 1:
             o = attn.to_out[1](o)      # diffusers: Dropout(p = 0)
         return o

@@ -45,7 +45,7 @@ def set_tuning(block_n: int = 0, group_size: int = 0) -> None:
 
 def lora_linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, down: torch.Tensor | None,
                     up: torch.Tensor | None, scale: torch.Tensor | None, tokens_per_sample: int, save_h: bool = False,
-                    out: torch.Tensor | None = None):
+                    out: torch.Tensor | None = None, residual: torch.Tensor | None = None):
     """y = x @ w.T + bias + ((x @ down.T) * scale[row // tokens]) @ up.T ; returns (y, h or None).
 
     x [M, din] bf16, w [dout, din] bf16, bias [dout] bf16|None, down [r, din] bf16|None, up [dout, r] bf16,
@@ -74,6 +74,14 @@ def lora_linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None,
     if bias is not None:
         _need(bias, _BF16, "bias", 1)
     y = out if out is not None else torch.empty((M, dout), dtype=_BF16, device=x.device)
+    if residual is not None:
+        _need(residual, _BF16, "residual", 2)
+        if tuple(residual.shape) != (M, dout):
+            raise _lib.AqualoraError(f"residual must be [{M}, {dout}], got {tuple(residual.shape)}")
+        _lib.call("aq_lora_linear_fwd_residual", x.data_ptr(), _rows(x, "x"), w.data_ptr(), _ptr(bias), _ptr(down), _ptr(up), _ptr(scale),
+                  residual.data_ptr(), _rows(residual, "residual"), y.data_ptr(), _rows(y, "y"), _ptr(h), M,
+                  max(int(tokens_per_sample), 1), din, dout, r, _stream())
+        return y, h
     _lib.call("aq_lora_linear_fwd", x.data_ptr(), _rows(x, "x"), w.data_ptr(), _ptr(bias), _ptr(down), _ptr(up), _ptr(scale),
               y.data_ptr(), _rows(y, "y"), _ptr(h), M, max(int(tokens_per_sample), 1), din, dout, r, _stream())
     return y, h

@@ -21,7 +21,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .lora_modules import AquaLoRAAttnProcessor, LoRACompatibleConv, LoRACompatibleLinear, precompute_cross_kv
+from .lora_modules import (AquaLoRAAttnProcessor, LoRACompatibleConv, LoRACompatibleLinear, conv1x1_with_residual, linear_with_residual,
+                           precompute_cross_kv)
 from .unet_ops import geglu, group_norm_nhwc, layer_norm, residual_add_bias
 
 
@@ -161,8 +162,11 @@ class Attention(nn.Module):
         self.to_out = nn.ModuleList([LoRACompatibleLinear(query_dim, query_dim)])
         self.processor = AquaLoRAAttnProcessor()
 
-    def forward(self, x, context=None, scale=1.0):
-        return self.processor(self, x, encoder_hidden_states=context, scale=scale)
+    def forward(self, x, context=None, scale=1.0, residual=None):
+        """`residual`: the stream the caller adds to the attention output (x + attn(norm(x))): folded into to_out's epilogue."""
+        if residual is None:
+            return self.processor(self, x, encoder_hidden_states=context, scale=scale)
+        return self.processor(self, x, encoder_hidden_states=context, scale=scale, residual=residual)
 
 
 class GEGLU(nn.Module):
@@ -183,8 +187,11 @@ class FeedForward(nn.Module):
         super().__init__()
         self.net = nn.ModuleList([GEGLU(dim, dim * 4), nn.Identity(), LoRACompatibleLinear(dim * 4, dim)])
 
-    def forward(self, x, scale=1.0):
-        return self.net[2](self.net[0](x, scale), scale)
+    def forward(self, x, scale=1.0, residual=None):
+        h = self.net[0](x, scale)
+        if residual is None:
+            return self.net[2](h, scale)
+        return linear_with_residual(self.net[2], h, scale, residual)
 
 
 class BasicTransformerBlock(nn.Module):
@@ -198,9 +205,10 @@ class BasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim)
 
     def forward(self, x, context, scale=1.0):
-        x = self.attn1(_token_norm(self.norm1, x), None, scale) + x
-        x = self.attn2(_token_norm(self.norm2, x), context, scale) + x
-        return self.ff(_token_norm(self.norm3, x), scale) + x
+        # the three residual adds ride in the epilogue of to_out / to_out / ff.net.2 (aq_lora_linear_fwd_residual)
+        x = self.attn1(_token_norm(self.norm1, x), None, scale, residual=x)
+        x = self.attn2(_token_norm(self.norm2, x), context, scale, residual=x)
+        return self.ff(_token_norm(self.norm3, x), scale, residual=x)
 
 
 class Transformer2DModel(nn.Module):
@@ -227,10 +235,11 @@ class Transformer2DModel(nn.Module):
         for blk in self.transformer_blocks:
             h = blk(h, context, scale)
         if self.linear_proj:
+            if res.is_cuda and res.is_contiguous(memory_format=torch.channels_last):
+                return linear_with_residual(self.proj_out, h, scale, res.permute(0, 2, 3, 1).reshape(B, H * W, C)).reshape(B, H, W, C).permute(0, 3, 1, 2)
             h = self.proj_out(h, scale).reshape(B, H, W, C).permute(0, 3, 1, 2)
-        else:
-            h = self.proj_out(h.reshape(B, H, W, C).permute(0, 3, 1, 2), scale)
-        return h + res
+            return h + res
+        return conv1x1_with_residual(self.proj_out, h.reshape(B, H, W, C).permute(0, 3, 1, 2), scale, res)
 
 
 class Downsample2D(nn.Module):

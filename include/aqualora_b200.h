@@ -51,13 +51,20 @@ long long aq_launch_count(void);    /* kernels this library has launched in this
  * y      [M, dout]  bf16, row stride ldy          h_save [M, r] bf16 or NULL: H before scaling (kept for
  *        the backward).
  * down == NULL runs the plain base projection (lora_layer is None, lora_modules.py:57-59).
- * Constraints: din % 8 == 0, dout % 8 == 0, r % 8 == 0, 8 <= r <= 64, 16-byte aligned pointers.
+ * Constraints: din % 8 == 0, dout % 8 == 0, r % 8 == 0, r >= 8 (ranks above 64 run as ceil(r / 64) launches over 64-wide slices
+ * of the LoRA operands, the later ones accumulating into Y), 16-byte aligned pointers.
  * One kernel: TMA-staged tiles, tcgen05 MMA with TMEM accumulators; H never leaves the SM on its way
  * into the second contraction.
  * ---------------------------------------------------------------------------------------------- */
 int aq_lora_linear_fwd(const void* x, int64_t ldx, const void* w, const void* bias, const void* down,
                        const void* up, const float* scale, void* y, int64_t ldy, void* h_save, int64_t M,
                        int64_t tokens_per_sample, int din, int dout, int r, void* stream);
+/* The same with a residual stream added in the tile epilogue: Y = X W^T + bias + LoRA + residual (residual [M, dout] bf16, row stride
+ * ldres; NULL = none).  In a Transformer2D block the three `x + to_out(...)`, `x + ff(...)`, `res + proj_out(...)` adds
+ * (scripts/lib/original_unet.py:779-806, :881-891) then cost no extra pass over the activations. */
+int aq_lora_linear_fwd_residual(const void* x, int64_t ldx, const void* w, const void* bias, const void* down, const void* up,
+                                const float* scale, const void* residual, int64_t ldres, void* y, int64_t ldy, void* h_save,
+                                int64_t M, int64_t tokens_per_sample, int din, int dout, int r, void* stream);
 
 /* Test / tuning hook: pin the column-tile width (64, 128, 160 or 192) and the number of column tiles per work
  * item for the calling thread's next aq_lora_linear_* launches; (0, 0) restores the built-in heuristics. */

@@ -153,6 +153,48 @@ def test_other_ranks_forward_backward(lm, cuda_device, r, B, N, din, dout, bias)
     assert torch.equal(y0, lin(xd.detach(), 1.0))
 
 
+@pytest.mark.parametrize("M,K,N,r,tok", [(4096, 320, 320, 64, 1024), (1000, 328, 200, 8, 500), (2048, 1280, 640, 320, 1024)])
+def test_residual_rides_in_the_epilogue(lm, cuda_device, M, K, N, r, tok):
+    """aq_lora_linear_fwd_residual == projection, then `+ residual` (one bf16 rounding of the sum instead of two), and the module-level
+    helper routes the residual's gradient through unchanged."""
+    from aqualora_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(M + N)
+    x = torch.randn(M, K, generator=g, device=dev).bfloat16()
+    w = (torch.randn(N, K, generator=g, device=dev) * K ** -0.5).bfloat16()
+    b = torch.randn(N, generator=g, device=dev).bfloat16()
+    dn = (torch.randn(r, K, generator=g, device=dev) * K ** -0.5).bfloat16()
+    up = (torch.randn(N, r, generator=g, device=dev) * 0.1).bfloat16()
+    sc = torch.randn(M // tok, r, generator=g, device=dev)
+    res = torch.randn(M, N, generator=g, device=dev).bfloat16()
+    y_plain, _ = ops.lora_linear_fwd(x, w, b, dn, up, sc, tok)
+    y_res, _ = ops.lora_linear_fwd(x, w, b, dn, up, sc, tok, residual=res)
+    want = y_plain.float() + res.float()
+    # y_plain carries one extra bf16 rounding: |y_res - want| <= 2^-8 |y_plain| (+ the final rounding of y_res)
+    assert ((y_res.float() - want).abs() <= 2 ** -7 * (y_plain.float().abs() + want.abs()) + 1e-6).all()
+    y0, _ = ops.lora_linear_fwd(x, w, None, None, None, None, tok, residual=res)          # plain projection + residual
+    p0, _ = ops.lora_linear_fwd(x, w, None, None, None, None, tok)
+    assert ((y0.float() - (p0.float() + res.float())).abs() <= 2 ** -7 * (p0.float().abs() + (p0.float() + res.float()).abs()) + 1e-6).all()
+    if r <= 64:
+        lin = lm.LoRACompatibleLinear(K, N).to(dev, torch.bfloat16)
+        lin.weight.data.copy_(w); lin.bias.data.copy_(b)
+        lin.requires_grad_(False)
+        lora = lm.LoRALinearLayer(K, N, r)
+        lora.down.weight.data.copy_(dn.float()); lora.up.weight.data.copy_(up.float())
+        lin.set_lora_layer(lora.to(dev))
+        B = M // tok
+        xin = x.view(B, tok, K).clone().requires_grad_(True)
+        rin = res.view(B, tok, N).clone().requires_grad_(True)
+        y = lm.linear_with_residual(lin, xin, sc, rin)
+        gy = torch.randn(B, tok, N, generator=g, device=dev).bfloat16()
+        y.backward(gy)
+        assert torch.equal(rin.grad, gy)
+        xin2 = x.view(B, tok, K).clone().requires_grad_(True)
+        (lin(xin2, sc) + rin.detach()).backward(gy)
+        assert torch.equal(xin.grad, xin2.grad)
+
+
 def test_fp16_and_fp32_activations_cast_at_the_boundary(lm, cuda_device):
     """The reference's README recipe runs fp16 (train/README.md:34-48): fp16 / fp32 activations and base weights are rounded to bf16 at
     the boundary and the result is returned in the caller's dtype; agreement is to bf16 rounding (stated in lora_modules._check_input)."""
