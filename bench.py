@@ -147,14 +147,16 @@ class LaunchTape:
     def __enter__(self):
         ops = self.ops
 
-        def fwd(x, w, bias, down, up, scale, tokens, save_h=False, out=None):
+        def fwd(x, w, bias, down, up, scale, tokens, save_h=False, out=None, residual=None):
             M, K = x.shape
             N = w.shape[0]
             r = 0 if down is None else down.shape[0]
             fl, by = _fwd_counts(M, K, N, r, save_h)
-            self.records.append(("gemm_fwd" if r else "gemm_plain", self._fwd, (x, w, bias, down, up, scale, tokens), {"save_h": save_h},
-                                 fl, by, (M, K, N, r), 1))
-            return self._fwd(x, w, bias, down, up, scale, tokens, save_h=save_h, out=out)
+            if residual is not None:
+                by += 2.0 * M * N                  # the residual stream read by the epilogue (the add it replaces is not counted as FLOPs)
+            self.records.append(("gemm_fwd" if r else "gemm_plain", self._fwd, (x, w, bias, down, up, scale, tokens),
+                                 {"save_h": save_h, "residual": residual}, fl, by, (M, K, N, r), 1))
+            return self._fwd(x, w, bias, down, up, scale, tokens, save_h=save_h, out=out, residual=residual)
 
         def bwd(gy, x, w_t, down_t, up_t, scale, h, g_down, g_up, g_scale, tokens):
             M, N = gy.shape      # N = dout

@@ -171,8 +171,9 @@ def test_residual_rides_in_the_epilogue(lm, cuda_device, M, K, N, r, tok):
     y_plain, _ = ops.lora_linear_fwd(x, w, b, dn, up, sc, tok)
     y_res, _ = ops.lora_linear_fwd(x, w, b, dn, up, sc, tok, residual=res)
     want = y_plain.float() + res.float()
-    # y_plain carries one extra bf16 rounding: |y_res - want| <= 2^-8 |y_plain| (+ the final rounding of y_res)
-    assert ((y_res.float() - want).abs() <= 2 ** -7 * (y_plain.float().abs() + want.abs()) + 1e-6).all()
+    # bf16 roundings: one per rank chunk on either side (ranks above 64 accumulate Y in place, chunk by chunk) + the unfused add
+    tol = 2 ** -8 * (1 + (r + 63) // 64)
+    assert ((y_res.float() - want).abs() <= tol * (y_plain.float().abs() + want.abs() + res.float().abs()) + 1e-6).all()
     y0, _ = ops.lora_linear_fwd(x, w, None, None, None, None, tok, residual=res)          # plain projection + residual
     p0, _ = ops.lora_linear_fwd(x, w, None, None, None, None, tok)
     assert ((y0.float() - (p0.float() + res.float())).abs() <= 2 ** -7 * (p0.float().abs() + (p0.float() + res.float()).abs()) + 1e-6).all()
