@@ -54,7 +54,7 @@ enum TmaSwizzle { kSwzNone = 0, kSwz32 = 1, kSwz64 = 2, kSwz128 = 3 };
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, TmaSwizzle swz);
 
-// Launch configuration with the programmatic-dependent-launch attribute (AQ_PDL=0 in the environment disables it): the kernel's
+// Launch configuration with the programmatic-dependent-launch attribute (opt-in: AQ_PDL=1 in the environment): the kernel's
 // prologue (barrier init, TMEM allocation, descriptor prefetch) and its launch latency overlap the tail of the previous kernel in
 // the stream; every kernel launched through this calls griddep_wait() before touching global memory.
 bool pdl_enabled();

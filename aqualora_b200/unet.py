@@ -26,7 +26,15 @@ from .lora_modules import (AquaLoRAAttnProcessor, LoRACompatibleConv, LoRACompat
 from .unet_ops import geglu, group_norm_nhwc, layer_norm, residual_add_bias
 
 
+import os
+
 LIBRARY_GLUE = False     # bench.py's PyTorch-eager GPU baseline sets this: every norm / activation stays a library op
+# Fold the three residual adds of a transformer block (and the one after proj_out) into the projection's tile epilogue
+# (aq_lora_linear_fwd_residual).  Measured on B200 (profiles/r02_bench_v3_residual_fused.json): the step gains 1.0 ms (77.3 -> 76.3 ms,
+# 96 elementwise adds fewer per step), but the epilogue's row-strided reads of a residual that sits in HBM cost the fused forward
+# GEMMs 0.9 ms and the plain ones 0.65 ms per step (roofline fraction 0.62 -> 0.54).  Off by default until the residual tile is
+# TMA-prefetched into the staging buffer ahead of the accumulator wait; AQ_FUSE_RESIDUAL=1 turns it on.
+FUSE_RESIDUAL = os.environ.get("AQ_FUSE_RESIDUAL", "0") == "1"
 
 
 def _fused_glue(x: torch.Tensor, *params: torch.Tensor) -> bool:
@@ -205,10 +213,14 @@ class BasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim)
 
     def forward(self, x, context, scale=1.0):
-        # the three residual adds ride in the epilogue of to_out / to_out / ff.net.2 (aq_lora_linear_fwd_residual)
-        x = self.attn1(_token_norm(self.norm1, x), None, scale, residual=x)
-        x = self.attn2(_token_norm(self.norm2, x), context, scale, residual=x)
-        return self.ff(_token_norm(self.norm3, x), scale, residual=x)
+        if FUSE_RESIDUAL and x.is_cuda:
+            # the three residual adds ride in the epilogue of to_out / to_out / ff.net.2 (aq_lora_linear_fwd_residual)
+            x = self.attn1(_token_norm(self.norm1, x), None, scale, residual=x)
+            x = self.attn2(_token_norm(self.norm2, x), context, scale, residual=x)
+            return self.ff(_token_norm(self.norm3, x), scale, residual=x)
+        x = self.attn1(_token_norm(self.norm1, x), None, scale) + x
+        x = self.attn2(_token_norm(self.norm2, x), context, scale) + x
+        return self.ff(_token_norm(self.norm3, x), scale) + x
 
 
 class Transformer2DModel(nn.Module):
@@ -234,6 +246,12 @@ class Transformer2DModel(nn.Module):
             h = self.proj_in(h, scale).permute(0, 2, 3, 1).reshape(B, H * W, C)
         for blk in self.transformer_blocks:
             h = blk(h, context, scale)
+        if not (FUSE_RESIDUAL and x.is_cuda):
+            if self.linear_proj:
+                h = self.proj_out(h, scale).reshape(B, H, W, C).permute(0, 3, 1, 2)
+            else:
+                h = self.proj_out(h.reshape(B, H, W, C).permute(0, 3, 1, 2), scale)
+            return h + res
         if self.linear_proj:
             if res.is_cuda and res.is_contiguous(memory_format=torch.channels_last):
                 return linear_with_residual(self.proj_out, h, scale, res.permute(0, 2, 3, 1).reshape(B, H * W, C)).reshape(B, H, W, C).permute(0, 3, 1, 2)

@@ -172,8 +172,14 @@ def test_residual_rides_in_the_epilogue(lm, cuda_device, M, K, N, r, tok):
     y_res, _ = ops.lora_linear_fwd(x, w, b, dn, up, sc, tok, residual=res)
     want = y_plain.float() + res.float()
     # bf16 roundings: one per rank chunk on either side (ranks above 64 accumulate Y in place, chunk by chunk) + the unfused add
-    tol = 2 ** -8 * (1 + (r + 63) // 64)
-    assert ((y_res.float() - want).abs() <= tol * (y_plain.float().abs() + want.abs() + res.float().abs()) + 1e-6).all()
+    # Ranks above 64 accumulate Y in place chunk by chunk, each pass rounding to bf16: the two sides then differ by a few ulps of the
+    # LARGEST intermediate sum, not of the final value -- compare against the fp32 closed form instead, like the other rank tests.
+    if r > 64:
+        want = (x.float() @ w.float().t() + b.float() + ((x.float() @ dn.float().t()).view(M // tok, tok, r) * sc[:, None, :]).view(M, r) @ up.float().t()
+                + res.float())
+        assert _max_rel(y_res, want) < BF16_TOL
+    else:
+        assert ((y_res.float() - want).abs() <= 2 ** -7 * (y_plain.float().abs() + want.abs()) + 1e-6).all()
     y0, _ = ops.lora_linear_fwd(x, w, None, None, None, None, tok, residual=res)          # plain projection + residual
     p0, _ = ops.lora_linear_fwd(x, w, None, None, None, None, tok)
     assert ((y0.float() - (p0.float() + res.float())).abs() <= 2 ** -7 * (p0.float().abs() + (p0.float() + res.float()).abs()) + 1e-6).all()
