@@ -43,6 +43,12 @@ _SIGNATURES = {
          c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p],
         c_int,
     ),
+    "aq_lora_linear_bwd_dx": (
+        [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int,
+         c_int, c_void_p, c_size_t, c_void_p],
+        c_int,
+    ),
+    "aq_lora_wgrad_batch": ([c_void_p, c_int, c_void_p], c_int),
     "aq_wgrad_tn": ([c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p], c_int),
     "aq_secret_encoder_workspace_bytes": ([c_int, c_int], c_size_t),
     "aq_secret_encoder_fwd": ([c_void_p] * 8 + [c_int] * 6 + [c_void_p, c_void_p], c_int),
@@ -103,6 +109,12 @@ class LoraProjection(ctypes.Structure):
     """`aq_lora_projection` of include/aqualora_b200.h."""
     _fields_ = [("w", c_void_p), ("bias", c_void_p), ("down", c_void_p), ("up", c_void_p), ("y", c_void_p), ("ldy", c_int64),
                 ("h_save", c_void_p), ("dout", c_int)]
+
+
+class WgradJob(ctypes.Structure):
+    """`aq_wgrad_job` of include/aqualora_b200.h."""
+    _fields_ = [("gy", c_void_p), ("ldgy", c_int64), ("x", c_void_p), ("ldx", c_int64), ("ws", c_void_p), ("g_down", c_void_p),
+                ("g_up", c_void_p), ("M", c_int64), ("din", c_int), ("dout", c_int), ("r", c_int)]
 
 
 _lib = None

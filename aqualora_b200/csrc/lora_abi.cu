@@ -80,25 +80,24 @@ size_t aq_lora_linear_bwd_workspace_bytes(int64_t M, int r) {
   return 2 * one;
 }
 
-int aq_lora_linear_bwd(const void* gy, int64_t ldgy, const void* x, int64_t ldx, const void* w_t, const void* down_t,
-                       const void* up_t, const float* scale, const void* h_save, void* gx, int64_t ldgx, float* g_down,
-                       float* g_up, float* g_scale, int64_t M, int64_t tokens_per_sample, int din, int dout, int r, void* ws,
-                       size_t ws_bytes, void* stream) {
-  AQ_REQUIRE(gy && x && down_t && up_t && scale && h_save && g_down && g_up, AQ_ERR_BAD_SHAPE,
-             "lora_linear_bwd: gy, x, down_t, up_t, scale, h_save, g_down, g_up must be non-NULL");
-  AQ_REQUIRE((w_t == nullptr) == (gx == nullptr), AQ_ERR_BAD_SHAPE, "lora_linear_bwd: pass both w_t and gx, or neither");
-  AQ_REQUIRE(tokens_per_sample > 0, AQ_ERR_BAD_SHAPE, "lora_linear_bwd: tokens_per_sample must be > 0");
+// dX (+ dH / Hs / dscale side outputs into the workspace) of one layer: part 1 of the backward.  The workspace must stay alive
+// until the matching aq_lora_wgrad_batch job has been launched.
+int aq_lora_linear_bwd_dx(const void* gy, int64_t ldgy, const void* w_t, const void* down_t, const void* up_t, const float* scale,
+                          const void* h_save, void* gx, int64_t ldgx, float* g_scale, int64_t M, int64_t tokens_per_sample, int din,
+                          int dout, int r, void* ws, size_t ws_bytes, void* stream) {
+  AQ_REQUIRE(gy && down_t && up_t && scale && h_save, AQ_ERR_BAD_SHAPE, "lora_linear_bwd_dx: gy, down_t, up_t, scale, h_save must be non-NULL");
+  AQ_REQUIRE((w_t == nullptr) == (gx == nullptr), AQ_ERR_BAD_SHAPE, "lora_linear_bwd_dx: pass both w_t and gx, or neither");
+  AQ_REQUIRE(tokens_per_sample > 0, AQ_ERR_BAD_SHAPE, "lora_linear_bwd_dx: tokens_per_sample must be > 0");
   const size_t need = aq_lora_linear_bwd_workspace_bytes(M, r);
-  AQ_REQUIRE(ws != nullptr && ws_bytes >= need, AQ_ERR_WORKSPACE, "lora_linear_bwd: workspace %zu bytes < required %zu", ws_bytes, need);
-  AQ_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, AQ_ERR_BAD_ALIGN, "lora_linear_bwd: workspace must be 256-byte aligned");
-  AQ_REQUIRE(r >= 8 && r % 8 == 0, AQ_ERR_BAD_SHAPE, "lora_linear_bwd: rank r=%d must be a multiple of 8, >= 8", r);
+  AQ_REQUIRE(ws != nullptr && ws_bytes >= need, AQ_ERR_WORKSPACE, "lora_linear_bwd_dx: workspace %zu bytes < required %zu", ws_bytes, need);
+  AQ_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, AQ_ERR_BAD_ALIGN, "lora_linear_bwd_dx: workspace must be 256-byte aligned");
+  AQ_REQUIRE(r >= 8 && r % 8 == 0, AQ_ERR_BAD_SHAPE, "lora_linear_bwd_dx: rank r=%d must be a multiple of 8, >= 8", r);
   uint8_t* dh = reinterpret_cast<uint8_t*>(ws);
   uint8_t* hs = dh + need / 2;
-  cudaStream_t st = (cudaStream_t)stream;
   const int chunks = (r + kRankChunk - 1) / kRankChunk;
   for (int c = 0; c < chunks; ++c) {
     const int r0 = c * kRankChunk, rc_ = r - r0 < kRankChunk ? r - r0 : kRankChunk;
-    // 1) dX (+)= G W + ((G Up_c) (.) s_c) Dn_c, with dH_c / Hs_c / dscale_c produced by the mid-epilogue of the same kernel
+    // dX (+)= G W + ((G Up_c) (.) s_c) Dn_c, with dH_c / Hs_c / dscale_c produced by the mid-epilogue of the same kernel
     LoraGemmArgs a;
     a.a = gy; a.lda = ldgy; a.w = w_t; a.bias = nullptr; a.scale = scale + r0; a.y = gx; a.ldy = ldgx;
     a.dn = bf16_at(up_t, (int64_t)r0 * dout);          // rows r0 ... of Up^T [r, dout]
@@ -107,14 +106,49 @@ int aq_lora_linear_bwd(const void* gy, int64_t ldgy, const void* x, int64_t ldx,
     a.M = M; a.tokens = tokens_per_sample; a.K = dout; a.N = din; a.r = rc_; a.mode = 1; a.has_main = (gx != nullptr);
     a.ld_r = r; a.skip_base = (gx != nullptr && c > 0); a.accum_y = a.skip_base;
     a.force_bn = g_force_bn; a.force_group = g_force_group;
-    int rc = launch_lora_gemm(a, st);
-    if (rc) return rc;
-    // 2) dUp[:, r0:] += G^T Hs_c  and  dDn[r0:, :] += dH_c^T X, one launch (grid.z = 2)
-    rc = launch_wgrad_pair(gy, ldgy, bf16_at(hs, r0), r, g_up + r0, r, dout, rc_, 0, x, ldx, bf16_at(dh, r0), r, g_down + (int64_t)r0 * din,
-                           din, din, rc_, 1, M, st);
+    int rc = launch_lora_gemm(a, (cudaStream_t)stream);
     if (rc) return rc;
   }
   return AQ_OK;
+}
+
+// dUp += G^T Hs and dDn += dH^T X for a batch of layers (part 2 of their backward) in as few launches as possible: nothing
+// downstream of a layer's backward depends on these, so callers queue them and flush once per group of layers.
+int aq_lora_wgrad_batch(const aq_wgrad_job* jobs, int njobs, void* stream) {
+  AQ_REQUIRE(jobs != nullptr && njobs >= 1 && njobs <= 64, AQ_ERR_BAD_SHAPE, "lora_wgrad_batch: 1 ... 64 jobs, got %d", njobs);
+  static thread_local WgradJob flat[64 * 8];
+  int n = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const aq_wgrad_job& w = jobs[j];
+    AQ_REQUIRE(w.gy && w.x && w.ws && w.g_down && w.g_up && w.M > 0 && w.r >= 8 && w.r % 8 == 0 && w.r <= 8 * kRankChunk, AQ_ERR_BAD_SHAPE,
+               "lora_wgrad_batch: job %d has a NULL operand or an unsupported rank %d", j, w.r);
+    const size_t half = aq_lora_linear_bwd_workspace_bytes(w.M, w.r) / 2;
+    const uint8_t* dh = reinterpret_cast<const uint8_t*>(w.ws);
+    const uint8_t* hs = dh + half;
+    const int chunks = (w.r + kRankChunk - 1) / kRankChunk;
+    for (int c = 0; c < chunks; ++c) {
+      const int r0 = c * kRankChunk, rc_ = w.r - r0 < kRankChunk ? w.r - r0 : kRankChunk;
+      WgradJob& f = flat[n++];
+      f.p0 = w.gy; f.ldp0 = w.ldgy; f.q0 = bf16_at(hs, r0); f.ldq0 = w.r; f.c0 = w.g_up + r0; f.ldc0 = w.r; f.I0 = w.dout;
+      f.p1 = w.x; f.ldp1 = w.ldx; f.q1 = bf16_at(dh, r0); f.ldq1 = w.r; f.c1 = w.g_down + (int64_t)r0 * w.din; f.ldc1 = w.din; f.I1 = w.din;
+      f.J = rc_; f.M = w.M;
+    }
+  }
+  return launch_wgrad_jobs(flat, n, (cudaStream_t)stream);
+}
+
+int aq_lora_linear_bwd(const void* gy, int64_t ldgy, const void* x, int64_t ldx, const void* w_t, const void* down_t,
+                       const void* up_t, const float* scale, const void* h_save, void* gx, int64_t ldgx, float* g_down,
+                       float* g_up, float* g_scale, int64_t M, int64_t tokens_per_sample, int din, int dout, int r, void* ws,
+                       size_t ws_bytes, void* stream) {
+  AQ_REQUIRE(x && g_down && g_up, AQ_ERR_BAD_SHAPE, "lora_linear_bwd: x, g_down, g_up must be non-NULL");
+  int rc = aq_lora_linear_bwd_dx(gy, ldgy, w_t, down_t, up_t, scale, h_save, gx, ldgx, g_scale, M, tokens_per_sample, din, dout, r, ws,
+                                 ws_bytes, stream);
+  if (rc) return rc;
+  aq_wgrad_job job;
+  job.gy = gy; job.ldgy = ldgy; job.x = x; job.ldx = ldx; job.ws = ws; job.g_down = g_down; job.g_up = g_up; job.M = M;
+  job.din = din; job.dout = dout; job.r = r;
+  return aq_lora_wgrad_batch(&job, 1, stream);
 }
 
 int aq_wgrad_tn(const void* p, int64_t ldp, const void* q, int64_t ldq, float* c, int64_t ldc, int64_t M, int I, int J,

@@ -38,4 +38,13 @@ int launch_wgrad_pair(const void* p0, int64_t ldp0, const void* q0, int64_t ldq0
                       const void* p1, int64_t ldp1, const void* q1, int64_t ldq1, float* c1, int64_t ldc1, int I1, int J1, int t1,
                       int64_t M, cudaStream_t stream);
 
+// one layer's (one rank chunk's) pair of weight-gradient contractions over the same M rows:
+//   c0 [I0, J] += p0^T [I0, M] q0 [M, J]            (dUp = G^T Hs)          c1 [J, I1] += (p1^T [I1, M] q1 [M, J])^T   (dDn = dH^T X)
+struct WgradJob {
+  const void* p0; int64_t ldp0; const void* q0; int64_t ldq0; float* c0; int64_t ldc0; int I0;
+  const void* p1; int64_t ldp1; const void* q1; int64_t ldq1; float* c1; int64_t ldc1; int I1;
+  int J; int64_t M;
+};
+int launch_wgrad_jobs(const WgradJob* jobs, int njobs, cudaStream_t stream);
+
 }  // namespace aq

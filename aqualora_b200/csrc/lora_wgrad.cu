@@ -37,16 +37,24 @@ struct WgradParams {
   int i_tiles, splits;  // extent of this problem inside the launch grid
 };
 
-// Up to two independent contractions per launch (grid.z): the backward of one LoRA layer needs dUp = G^T Hs and dDn = dH^T X,
-// both a few microseconds of work -- one launch instead of two halves the launch-floor cost of the 384 weight-gradient kernels.
+// Many independent contractions per launch: the backward of one LoRA layer needs dUp = G^T Hs and dDn = dH^T X, each a few
+// microseconds of work against a launch floor of 5 - 8 us, and nothing downstream depends on them (they only feed the flat
+// gradient buffer) -- so the weight gradients of several layers are queued and leave in ONE launch.  The grid is one-dimensional:
+// CTA -> (problem, row-tile of the output, slice of the reduction) through the prefix table cta_begin.
+constexpr int kWgMaxProblems = 32;
 struct WgradLaunch {
-  WgradParams prob[2];
+  WgradParams prob[kWgMaxProblems];
+  int cta_begin[kWgMaxProblems + 1];
+  int num_problems;
 };
 
 __global__ void __launch_bounds__(kWgThreads) lora_wgrad_kernel(const __grid_constant__ WgradLaunch launch) {
   griddep_launch_dependents();   // PDL (see aq_ptx.cuh)
-  const WgradParams& p = launch.prob[blockIdx.z];
-  if ((int)blockIdx.x >= p.i_tiles || (int)blockIdx.y >= p.splits) return;   // whole CTA: this problem is smaller than the grid
+  int pi = 0;
+  while (pi + 1 < launch.num_problems && (int)blockIdx.x >= launch.cta_begin[pi + 1]) ++pi;
+  const WgradParams& p = launch.prob[pi];
+  const int local_cta = (int)blockIdx.x - launch.cta_begin[pi];
+  const int cta_i = local_cta % p.i_tiles, cta_split = local_cta / p.i_tiles;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -64,9 +72,9 @@ __global__ void __launch_bounds__(kWgThreads) lora_wgrad_kernel(const __grid_con
   auto q_tile = [&](int s) { return smem_base + s * kWgStageBytes + kWgPBytes; };
 
   const int num_kb_total = (p.M + kWgBlockK - 1) / kWgBlockK;
-  const int kb_begin = blockIdx.y * p.kb_per_split;
+  const int kb_begin = cta_split * p.kb_per_split;
   const int kb_end = min(kb_begin + p.kb_per_split, num_kb_total);
-  const int i0 = blockIdx.x * kWgBlockI;
+  const int i0 = cta_i * kWgBlockI;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_p);
@@ -201,12 +209,14 @@ static int launch_wgrad_n(WgradLaunch& l, int n, cudaStream_t stream) {
   int rc = check_arch();
   if (rc) return rc;
   AQ_OPT_IN_SMEM((lora_wgrad_kernel), kWgSmemBytes);
-  int gx = 0, gy = 0;
+  int total = 0;
   for (int i = 0; i < n; ++i) {
-    gx = l.prob[i].i_tiles > gx ? l.prob[i].i_tiles : gx;
-    gy = l.prob[i].splits > gy ? l.prob[i].splits : gy;
+    l.cta_begin[i] = total;
+    total += l.prob[i].i_tiles * l.prob[i].splits;
   }
-  PdlLaunch launch(dim3(gx, gy, n), dim3(kWgThreads), kWgSmemBytes, stream);
+  l.cta_begin[n] = total;
+  l.num_problems = n;
+  PdlLaunch launch(dim3(total), dim3(kWgThreads), kWgSmemBytes, stream);
   AQ_CHECK_CUDA(cudaLaunchKernelEx(&launch.cfg, lora_wgrad_kernel, l));
   AQ_LAUNCHED();
   return AQ_OK;
@@ -214,7 +224,7 @@ static int launch_wgrad_n(WgradLaunch& l, int n, cudaStream_t stream) {
 
 int launch_wgrad(const void* pm, int64_t ldp, const void* qm, int64_t ldq, float* c, int64_t ldc, int64_t M, int I, int J,
                  int transpose_out, cudaStream_t stream) {
-  WgradLaunch l;
+  static thread_local WgradLaunch l;
   memset(&l, 0, sizeof(l));
   int rc = fill_wgrad(l.prob[0], pm, ldp, qm, ldq, c, ldc, M, I, J, transpose_out);
   if (rc) return rc;
@@ -224,13 +234,35 @@ int launch_wgrad(const void* pm, int64_t ldp, const void* qm, int64_t ldq, float
 int launch_wgrad_pair(const void* p0, int64_t ldp0, const void* q0, int64_t ldq0, float* c0, int64_t ldc0, int I0, int J0, int t0,
                       const void* p1, int64_t ldp1, const void* q1, int64_t ldq1, float* c1, int64_t ldc1, int I1, int J1, int t1,
                       int64_t M, cudaStream_t stream) {
-  WgradLaunch l;
+  static thread_local WgradLaunch l;
   memset(&l, 0, sizeof(l));
   int rc = fill_wgrad(l.prob[0], p0, ldp0, q0, ldq0, c0, ldc0, M, I0, J0, t0);
   if (rc) return rc;
   rc = fill_wgrad(l.prob[1], p1, ldp1, q1, ldq1, c1, ldc1, M, I1, J1, t1);
   if (rc) return rc;
   return launch_wgrad_n(l, 2, stream);
+}
+
+// the weight gradients of several layers in as few launches as kWgMaxProblems allows
+int launch_wgrad_jobs(const WgradJob* jobs, int njobs, cudaStream_t stream) {
+  static thread_local WgradLaunch l;
+  memset(&l, 0, sizeof(l));
+  int n = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const WgradJob& w = jobs[j];
+    if (n + 2 > kWgMaxProblems) {
+      int rc = launch_wgrad_n(l, n, stream);
+      if (rc) return rc;
+      memset(&l, 0, sizeof(l));
+      n = 0;
+    }
+    int rc = fill_wgrad(l.prob[n], w.p0, w.ldp0, w.q0, w.ldq0, w.c0, w.ldc0, w.M, w.I0, w.J, 0);
+    if (rc) return rc;
+    rc = fill_wgrad(l.prob[n + 1], w.p1, w.ldp1, w.q1, w.ldq1, w.c1, w.ldc1, w.M, w.I1, w.J, 1);
+    if (rc) return rc;
+    n += 2;
+  }
+  return n > 0 ? launch_wgrad_n(l, n, stream) : AQ_OK;
 }
 
 }  // namespace aq

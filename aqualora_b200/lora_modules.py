@@ -17,6 +17,7 @@ in-repo U-Net harness (aqualora_b200/unet.py) and for tests.
 from __future__ import annotations
 
 import contextlib
+import os
 import types
 import weakref
 from typing import Dict, Iterable, Optional
@@ -134,10 +135,42 @@ def _weight_t(weight: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
 
 
 def clear_caches() -> None:
+    _WGRAD_QUEUE.clear()
     _PACK_CACHE.clear()
     _WT_CACHE.clear()
     _BATCH_TABLES.clear()
     _W16_CACHE.clear()
+
+
+# ------------------------------------------------------------------------------------------------
+# deferred weight gradients: dUp / dDn of a layer feed nothing downstream of its backward, so layers that accumulate straight into
+# a flat gradient buffer (`_aq_grad`) queue their contraction and several layers leave in ONE launch (aq_lora_wgrad_batch): 192
+# launches of a few microseconds each against a 5 - 8 us launch floor become ~16 per step.
+# ------------------------------------------------------------------------------------------------
+_WGRAD_QUEUE: list = []
+_WGRAD_FLUSH_SCHEDULED = False
+WGRAD_BATCH = max(1, int(os.environ.get("AQ_WGRAD_BATCH", "12")))      # layers per launch group (1 = launch with every layer)
+
+
+def flush_wgrad_queue() -> None:
+    """Launch every queued weight-gradient job.  Runs by itself at the end of each backward pass (autograd engine callback) and when
+    the queue is full; call it by hand only if gradients are read in the middle of a backward pass."""
+    global _WGRAD_FLUSH_SCHEDULED
+    _WGRAD_FLUSH_SCHEDULED = False
+    if _WGRAD_QUEUE:
+        jobs = list(_WGRAD_QUEUE)
+        _WGRAD_QUEUE.clear()
+        ops.lora_wgrad_batch(jobs)
+
+
+def _enqueue_wgrad(job, deferrable: bool) -> None:
+    global _WGRAD_FLUSH_SCHEDULED
+    _WGRAD_QUEUE.append(job)
+    if not deferrable or len(_WGRAD_QUEUE) >= WGRAD_BATCH:
+        flush_wgrad_queue()          # gradients handed back to autograd must be complete in stream order: no deferral for those
+    elif not _WGRAD_FLUSH_SCHEDULED:
+        _WGRAD_FLUSH_SCHEDULED = True
+        torch.autograd.Variable._execution_engine.queue_callback(flush_wgrad_queue)
 
 
 def _grad_target(tgt, shape, device) -> tuple[torch.Tensor, bool]:
@@ -193,7 +226,8 @@ class _FusedLoraProjection(torch.autograd.Function):
         g_scale, scale_direct = None, False
         if ctx.needs_input_grad[5]:
             g_scale, scale_direct = _grad_target(t_scale, tuple(scale_eff.shape), gy.device)
-        gx = ops.lora_linear_bwd(gy, x2d, w_t, dn16_t, up16_t, scale_eff.detach(), h, g_down, g_up, g_scale, ctx.tokens)
+        gx, ws = ops.lora_linear_bwd_dx(gy, w_t, dn16_t, up16_t, scale_eff.detach(), h, g_scale, ctx.tokens)
+        _enqueue_wgrad((gy, x2d, ws, g_down, g_up), deferrable=down_direct and up_direct)
         return (gx, None, None,
                 None if down_direct else g_down.view_as(down).to(down.dtype),
                 None if up_direct else g_up.view_as(up).to(up.dtype),
@@ -258,7 +292,8 @@ class _GroupedLoraProjection(torch.autograd.Function):
                 _, up16_t = _packed(up, dout, r)
                 g_down, down_direct = _grad_target(ctx.grad_targets[i][0], (r, din), gy.device)
                 g_up, up_direct = _grad_target(ctx.grad_targets[i][1], (dout, r), gy.device)
-                gx = ops.lora_linear_bwd(gy, x2d, w_t, dn16_t, up16_t, scale_eff.detach(), hs[i], g_down, g_up, g_scale, ctx.tokens)
+                gx, ws = ops.lora_linear_bwd_dx(gy, w_t, dn16_t, up16_t, scale_eff.detach(), hs[i], g_scale, ctx.tokens)
+                _enqueue_wgrad((gy, x2d, ws, g_down, g_up), deferrable=down_direct and up_direct)
                 flat_grads.extend([None, None, None if down_direct else g_down.view_as(down).to(down.dtype),
                                    None if up_direct else g_up.view_as(up).to(up.dtype)])
             if gx is not None:

@@ -170,6 +170,59 @@ def lora_linear_bwd(gy: torch.Tensor, x: torch.Tensor, w_t: torch.Tensor | None,
     return gx
 
 
+def lora_linear_bwd_dx(gy: torch.Tensor, w_t: torch.Tensor | None, down_t: torch.Tensor, up_t: torch.Tensor, scale: torch.Tensor,
+                       h: torch.Tensor, g_scale: torch.Tensor | None, tokens_per_sample: int):
+    """First half of lora_linear_bwd: returns (gx or None, ws) -- `ws` holds dH / Hs for the weight-gradient job of this layer
+    (`lora_wgrad_batch`) and must stay alive until that job has been launched."""
+    _need(gy, _BF16, "gy", 2)
+    _need(h, _BF16, "h", 2)
+    _need(down_t, _BF16, "down_t", 2)
+    _need(up_t, _BF16, "up_t", 2)
+    _need(scale, _F32, "scale", 2)
+    M, dout = gy.shape
+    din, r = down_t.shape
+    if tuple(up_t.shape) != (r, dout) or tuple(h.shape) != (M, r):
+        raise _lib.AqualoraError(f"up_t / h must be [r, dout] / [M, r], got {tuple(up_t.shape)} / {tuple(h.shape)}")
+    for t, n in ((down_t, "down_t"), (up_t, "up_t"), (h, "h"), (scale, "scale")):
+        if not t.is_contiguous():
+            raise _lib.AqualoraError(f"{n} must be contiguous")
+    gx = None
+    if w_t is not None:
+        _need(w_t, _BF16, "w_t", 2)
+        if tuple(w_t.shape) != (din, dout) or not w_t.is_contiguous():
+            raise _lib.AqualoraError(f"w_t must be contiguous [{din}, {dout}]")
+        gx = torch.empty((M, din), dtype=_BF16, device=gy.device)
+    if g_scale is not None:
+        _need(g_scale, _F32, "g_scale", 2)
+    nbytes = _lib.load().aq_lora_linear_bwd_workspace_bytes(M, r)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=gy.device)
+    _lib.call("aq_lora_linear_bwd_dx", gy.data_ptr(), _rows(gy, "gy"), _ptr(w_t), down_t.data_ptr(), up_t.data_ptr(), scale.data_ptr(),
+              h.data_ptr(), _ptr(gx), din if gx is not None else 0, _ptr(g_scale), M, int(tokens_per_sample), din, dout, r, ws.data_ptr(),
+              nbytes, _stream())
+    return gx, ws
+
+
+def lora_wgrad_batch(jobs) -> None:
+    """jobs: list of (gy [M, dout], x [M, din], ws, g_down [r, din] fp32, g_up [dout, r] fp32): the weight gradients of several layers,
+    accumulated in as few launches as possible (aq_lora_wgrad_batch)."""
+    for i in range(0, len(jobs), 64):
+        part = jobs[i:i + 64]
+        arr = (_lib.WgradJob * len(part))()
+        for k, (gy, x, ws, g_down, g_up) in enumerate(part):
+            _need(gy, _BF16, "gy", 2)
+            _need(x, _BF16, "x", 2)
+            _need(g_down, _F32, "g_down", 2)
+            _need(g_up, _F32, "g_up", 2)
+            r, din = g_down.shape
+            dout = g_up.shape[0]
+            if not g_down.is_contiguous() or not g_up.is_contiguous() or gy.shape[0] != x.shape[0]:
+                raise _lib.AqualoraError("lora_wgrad_batch: contiguous gradient buffers and equal row counts expected")
+            arr[k].gy, arr[k].ldgy, arr[k].x, arr[k].ldx = gy.data_ptr(), _rows(gy, "gy"), x.data_ptr(), _rows(x, "x")
+            arr[k].ws, arr[k].g_down, arr[k].g_up = ws.data_ptr(), g_down.data_ptr(), g_up.data_ptr()
+            arr[k].M, arr[k].din, arr[k].dout, arr[k].r = gy.shape[0], din, dout, r
+        _lib.call("aq_lora_wgrad_batch", ctypes.addressof(arr), len(part), _stream())
+
+
 def wgrad_tn(p: torch.Tensor, q: torch.Tensor, c: torch.Tensor, transpose_out: bool = False) -> None:
     """c[i, j] += sum_m p[m, i] * q[m, j]   (c is [J, I] when transpose_out)."""
     _need(p, _BF16, "p", 2)

@@ -171,6 +171,7 @@ class PPFTTrainer:
             clean_pred = velocity_to_epsilon(self.alphas_cumprod, clean_pred, noisy, timesteps)
         loss = F.mse_loss(model_pred.float(), clean_pred.float(), reduction="mean")
         loss.backward()
+        lora_modules.flush_wgrad_queue()          # (the autograd engine's end-of-backward callback already did; explicit for clarity)
         ops.mapper_bwd(msg, self.g_scale, self.state.mapper_grad)
         return loss.detach()
 

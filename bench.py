@@ -143,6 +143,7 @@ class LaunchTape:
         self.ops = ops
         self.records = []   # (kind, fn, args, kwargs, flops, bytes, shape, n_gemm_launches)
         self._fwd, self._bwd, self._grp = ops.lora_linear_fwd, ops.lora_linear_bwd, ops.lora_linear_fwd_grouped
+        self._bwd_dx, self._wg_batch = ops.lora_linear_bwd_dx, ops.lora_wgrad_batch
 
     def __enter__(self):
         ops = self.ops
@@ -182,11 +183,34 @@ class LaunchTape:
                                  fl, by, (M, K, sum(w.shape[0] for w, *_ in projections), r), 1))
             return self._grp(x, projections, scale, tokens, save_h=save_h)
 
+        def bwd_dx(gy, w_t, down_t, up_t, scale, h, g_scale, tokens):
+            # first half of a layer's backward: dX = G W + ((G Up) (.) s) Dn with dH / Hs / dscale side outputs
+            M, N = gy.shape
+            K, r = down_t.shape
+            dx = w_t is not None
+            fl = (2.0 * M * K * N if dx else 0.0) + 2.0 * M * r * N + (2.0 * M * r * K if dx else 0.0)
+            by = 2.0 * M * (N + r) + (2.0 * M * K if dx else 0.0) + 2.0 * (K * N + r * (K + N)) + 4.0 * M * r
+            self.records.append(("bwd_dx_wgrad", self._bwd_dx, (gy, w_t, down_t, up_t, scale, h, g_scale, tokens), {}, fl, by, (M, K, N, r), 1))
+            return self._bwd_dx(gy, w_t, down_t, up_t, scale, h, g_scale, tokens)
+
+        def wg_batch(jobs):
+            # second half, several layers per launch: dUp += G^T Hs, dDn += dH^T X
+            fl = by = 0.0
+            for gy, x, _ws, g_down, g_up in jobs:
+                M, N = gy.shape
+                r, K = g_down.shape
+                fl += 2.0 * M * r * (K + N)
+                by += 2.0 * M * (N + K + 2 * r) + 8.0 * r * (K + N)
+            self.records.append(("bwd_dx_wgrad", self._wg_batch, (list(jobs),), {}, fl, by, (0, 0, 0, len(jobs)), 0))
+            return self._wg_batch(jobs)
+
         ops.lora_linear_fwd, ops.lora_linear_bwd, ops.lora_linear_fwd_grouped = fwd, bwd, grouped
+        ops.lora_linear_bwd_dx, ops.lora_wgrad_batch = bwd_dx, wg_batch
         return self
 
     def __exit__(self, *exc):
         self.ops.lora_linear_fwd, self.ops.lora_linear_bwd, self.ops.lora_linear_fwd_grouped = self._fwd, self._bwd, self._grp
+        self.ops.lora_linear_bwd_dx, self.ops.lora_wgrad_batch = self._bwd_dx, self._wg_batch
 
     def _graph(self, recs):
         side = torch.cuda.Stream()
@@ -262,6 +286,7 @@ def cupti_in_step(step_fn, tape_records, steps=2):
         gemm = [e for e in evs if "lora_gemm_kernel" in e.name]
         wgrad = [e for e in evs if "lora_wgrad_kernel" in e.name]
         total_us = sum(e.device_time for e in evs if "Memcpy" not in e.name and "Memset" not in e.name)
+        tape_records = [r for r in tape_records if r[7] > 0]          # records that launch the GEMM kernel (not the wgrad batches)
         n = len(tape_records)
         if n == 0 or len(gemm) != n * steps:
             return {"error": f"{len(gemm)} lora_gemm_kernel records for {n} taped launches x {steps} steps"}

@@ -104,6 +104,22 @@ int aq_lora_linear_bwd(const void* gy, int64_t ldgy, const void* x, int64_t ldx,
                        int64_t ldgx, float* g_down, float* g_up, float* g_scale, int64_t M,
                        int64_t tokens_per_sample, int din, int dout, int r, void* ws, size_t ws_bytes,
                        void* stream);
+/* The two halves of aq_lora_linear_bwd separately.  `_bwd_dx` writes gx (and accumulates g_scale) and leaves dH / Hs in `ws`;
+ * `aq_lora_wgrad_batch` then accumulates dUp / dDn of up to 64 layers in as few launches as possible (a layer's weight gradients feed
+ * nothing downstream, so a caller queues the jobs of several layers -- each keeps its gy, x and ws alive -- and flushes once). */
+typedef struct aq_wgrad_job {
+  const void* gy; int64_t ldgy;   /* [M, dout] bf16 */
+  const void* x; int64_t ldx;     /* [M, din] bf16 */
+  const void* ws;                 /* the workspace aq_lora_linear_bwd_dx filled for this layer */
+  float* g_down;                  /* [r, din] fp32, accumulated */
+  float* g_up;                    /* [dout, r] fp32, accumulated */
+  int64_t M;
+  int din, dout, r;
+} aq_wgrad_job;
+int aq_lora_linear_bwd_dx(const void* gy, int64_t ldgy, const void* w_t, const void* down_t, const void* up_t, const float* scale,
+                          const void* h_save, void* gx, int64_t ldgx, float* g_scale, int64_t M, int64_t tokens_per_sample, int din,
+                          int dout, int r, void* ws, size_t ws_bytes, void* stream);
+int aq_lora_wgrad_batch(const aq_wgrad_job* jobs, int njobs, void* stream);
 
 /* Skinny weight-gradient contraction used by the backward:  C[i, j] (+)= sum_m P[m, i] * Q[m, j]
  * P [M, I] bf16 (ldp), Q [M, J] bf16 (ldq, J <= 64), C fp32 [I, J] (transpose_out = 0) or [J, I] (= 1),

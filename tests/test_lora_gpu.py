@@ -662,3 +662,46 @@ def test_cfg_doubled_sampling_forward_matches_oracle(cuda_device):
     # the watermark branch is visible above that noise floor, and the two CFG halves (same latents, different context) differ
     assert ((want - base).norm() / want.norm()).item() > rel
     assert not torch.equal(got[:B], got[B:])
+
+
+def test_deferred_weight_gradients_match_immediate(lm, cuda_device, monkeypatch):
+    """Layers that accumulate into a flat gradient buffer queue their dUp / dDn contractions and flush them in one launch at the end
+    of the backward pass (aq_lora_wgrad_batch); the result equals launching them layer by layer."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+
+    def run(batch):
+        monkeypatch.setattr(lm, "WGRAD_BATCH", batch)
+        torch.manual_seed(0)
+        layers, flats = [], []
+        for (din, dout, r) in ((320, 320, 64), (320, 640, 64), (640, 320, 32), (320, 320, 128)):
+            lin = lm.LoRACompatibleLinear(din, dout).to(dev, torch.bfloat16)
+            lin.requires_grad_(False)
+            lora = lm.LoRALinearLayer(din, dout, r)
+            torch.nn.init.normal_(lora.up.weight, std=0.05)
+            lora = lora.to(dev)
+            for p in (lora.down.weight, lora.up.weight):
+                buf = torch.zeros(p.numel(), device=dev)
+                p._aq_grad = buf                      # direct accumulation target, as PPFTTrainer's flat buffer provides
+                flats.append(buf)
+            lin.set_lora_layer(lora)
+            layers.append(lin)
+        gg = torch.Generator().manual_seed(5)
+        x = torch.randn(2, 512, 320, generator=gg).to(dev, torch.bfloat16).requires_grad_(True)
+        sc = {64: (1 + 0.5 * torch.randn(2, 64, generator=gg)).to(dev), 32: (1 + 0.5 * torch.randn(2, 32, generator=gg)).to(dev),
+              128: (1 + 0.5 * torch.randn(2, 128, generator=gg)).to(dev)}
+        h = layers[0](x, sc[64])
+        h = layers[1](h, sc[64])
+        h = layers[2](h, sc[32])
+        h = layers[3](h, sc[128])
+        h.float().pow(2).mean().backward()
+        torch.cuda.synchronize()
+        assert not lm._WGRAD_QUEUE                      # flushed by the end-of-backward callback
+        return [f.clone() for f in flats], x.grad.clone()
+
+    imm, gx_imm = run(1)
+    deferred, gx_def = run(12)
+    assert torch.equal(gx_imm, gx_def)
+    for a, b in zip(imm, deferred):
+        assert a.abs().sum() > 0
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6 * float(a.abs().max()))       # fp32 atomics: order only
