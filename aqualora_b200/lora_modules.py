@@ -292,8 +292,8 @@ class _GroupedLoraProjection(torch.autograd.Function):
                 _, up16_t = _packed(up, dout, r)
                 g_down, down_direct = _grad_target(ctx.grad_targets[i][0], (r, din), gy.device)
                 g_up, up_direct = _grad_target(ctx.grad_targets[i][1], (dout, r), gy.device)
-                gx, ws = ops.lora_linear_bwd_dx(gy, w_t, dn16_t, up16_t, scale_eff.detach(), hs[i], g_scale, ctx.tokens)
-                _enqueue_wgrad((gy, x2d, ws, g_down, g_up), deferrable=down_direct and up_direct)
+                gx, side = ops.lora_linear_bwd_dx(gy, w_t, dn16_t, up16_t, scale_eff.detach(), hs[i], g_scale, ctx.tokens)
+                _enqueue_wgrad((gy, x2d, side, g_down, g_up), deferrable=down_direct and up_direct)
                 flat_grads.extend([None, None, None if down_direct else g_down.view_as(down).to(down.dtype),
                                    None if up_direct else g_up.view_as(up).to(up.dtype)])
             if gx is not None:
