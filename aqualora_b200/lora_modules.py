@@ -145,11 +145,12 @@ def clear_caches() -> None:
 # ------------------------------------------------------------------------------------------------
 # deferred weight gradients: dUp / dDn of a layer feed nothing downstream of its backward, so layers that accumulate straight into
 # a flat gradient buffer (`_aq_grad`) queue their contraction and several layers leave in ONE launch (aq_lora_wgrad_batch): 192
-# launches of a few microseconds each against a 5 - 8 us launch floor become ~16 per step.
+# launches of a few microseconds each against a 5 - 8 us launch floor become 12 per step (measured: 3.50 -> 2.33 ms of kernel time per
+# step, profiles/r02_bench_wgrad_batch_ab.txt).
 # ------------------------------------------------------------------------------------------------
 _WGRAD_QUEUE: list = []
 _WGRAD_FLUSH_SCHEDULED = False
-WGRAD_BATCH = max(1, int(os.environ.get("AQ_WGRAD_BATCH", "12")))      # layers per launch group (1 = launch with every layer)
+WGRAD_BATCH = max(1, int(os.environ.get("AQ_WGRAD_BATCH", "32")))      # layers per launch group (1 = launch with every layer)
 
 
 def flush_wgrad_queue() -> None:
