@@ -161,7 +161,11 @@ __device__ __forceinline__ void warp_colsum(float (&v)[N], int lane) {
   }
 }
 
-template <int BN, int NP>
+// MODE (0 forward, 1 backward dX) is a template parameter: each kernel carries only its own mid-epilogue (smaller instruction
+// footprint: ncu attributes a visible share of the epilogue warps' compute stalls to instruction fetch), and the projection /
+// launch parameters the epilogue loops need are read into registers once per item (a constant-bank read behind a uniform branch
+// inside an unrolled loop is a dependent LDCU -> compare -> branch chain per 8 columns).
+template <int BN, int NP, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_gemm_kernel(const __grid_constant__ LoraGemmParams<NP> p) {
   using L = SmemLayout<BN>;
   constexpr int kStages = L::kStages;
@@ -459,18 +463,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         if (sample > p.num_samples - 1) sample = p.num_samples - 1;
         const float* sp = p.scale + sample * p.ld_r + hc0;
         const size_t aux_off = (size_t)grow * p.ld_r + hc0;
+        const int rr = p.r;
+        __nv_bfloat16* const aux0 = q_.aux_out0;
+        __nv_bfloat16* const aux1 = p.aux_out1;
+        const bool store_h = aux_owner && aux0 != nullptr;
         uint4 hin[4];
-        if (p.mode == 1) {
+        if (MODE == 1) {
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             hin[j8] = make_uint4(0, 0, 0, 0);
-            if (row_ok && hc0 + j8 * 8 < p.r) hin[j8] = __ldg(reinterpret_cast<const uint4*>(p.h_in + aux_off + j8 * 8));
+            if (row_ok && hc0 + j8 * 8 < rr) hin[j8] = __ldg(reinterpret_cast<const uint4*>(p.h_in + aux_off + j8 * 8));
           }
         }
         float4 sc4[8];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4)
-          sc4[j4] = (hc0 + j4 * 4 < p.r) ? __ldg(reinterpret_cast<const float4*>(sp + j4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          sc4[j4] = (hc0 + j4 * 4 < rr) ? __ldg(reinterpret_cast<const float4*>(sp + j4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         mbar_wait(h_full_bar, item_iter & 1u);
         tc_fence_after();
         if (warp == 0) AQ_TRACE(item_iter, 11);
@@ -486,24 +494,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
           uint4 to_smem = make_uint4(0, 0, 0, 0);
-          if (hc0 + j8 * 8 < p.r) {
+          if (hc0 + j8 * 8 < rr) {
             const float4 s0 = sc4[2 * j8], s1 = sc4[2 * j8 + 1];
             const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            // H rounded to bf16 as packed pairs (one F2FP per two values), unpacked by shift / mask
+            uint32_t hp[4];
             float hb[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) hb[i] = bf16_round(v[j8 * 8 + i]);
+            for (int i = 0; i < 4; ++i) {
+              hp[i] = pack_bf16x2(v[j8 * 8 + 2 * i], v[j8 * 8 + 2 * i + 1]);
+              hb[2 * i] = bf16_lo(hp[i]);
+              hb[2 * i + 1] = bf16_hi(hp[i]);
+            }
             to_smem.x = pack_bf16x2(hb[0] * s[0], hb[1] * s[1]);
             to_smem.y = pack_bf16x2(hb[2] * s[2], hb[3] * s[3]);
             to_smem.z = pack_bf16x2(hb[4] * s[4], hb[5] * s[5]);
             to_smem.w = pack_bf16x2(hb[6] * s[6], hb[7] * s[7]);
-            if (p.mode == 0) {
-              if (aux_owner && q_.aux_out0 != nullptr) {
-                uint4 hraw;
-                hraw.x = pack_bf16x2(hb[0], hb[1]);
-                hraw.y = pack_bf16x2(hb[2], hb[3]);
-                hraw.z = pack_bf16x2(hb[4], hb[5]);
-                hraw.w = pack_bf16x2(hb[6], hb[7]);
-                *reinterpret_cast<uint4*>(q_.aux_out0 + aux_off + j8 * 8) = hraw;
+            if (MODE == 0) {
+              if (store_h) {
+                *reinterpret_cast<uint4*>(aux0 + aux_off + j8 * 8) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
               }
             } else {
               // hb = dHs (bf16-rounded like the reference's bf16 matmul output); hin = saved H
@@ -515,18 +524,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
                 hval[2 * i + 1] = bf16_hi(hw[i]);
               }
               if (aux_owner) {
-                *reinterpret_cast<uint4*>(q_.aux_out0 + aux_off + j8 * 8) = to_smem;  // dH
+                *reinterpret_cast<uint4*>(aux0 + aux_off + j8 * 8) = to_smem;  // dH
                 uint4 hs;
                 hs.x = pack_bf16x2(hval[0] * s[0], hval[1] * s[1]);
                 hs.y = pack_bf16x2(hval[2] * s[2], hval[3] * s[3]);
                 hs.z = pack_bf16x2(hval[4] * s[4], hval[5] * s[5]);
                 hs.w = pack_bf16x2(hval[6] * s[6], hval[7] * s[7]);
-                *reinterpret_cast<uint4*>(p.aux_out1 + aux_off + j8 * 8) = hs;       // Hs
+                *reinterpret_cast<uint4*>(aux1 + aux_off + j8 * 8) = hs;       // Hs
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[j8 * 8 + i] = row_ok ? hb[i] * hval[i] : 0.f;  // dscale integrand
             }
-          } else if (p.mode == 1) {
+          } else if (MODE == 1) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[j8 * 8 + i] = 0.f;
           }
@@ -538,7 +547,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(hs_ready_remote);
         if (warp == 0) AQ_TRACE(item_iter, 12);
-        if (p.mode == 1 && p.g_scale != nullptr && grp == 0) {
+        if (MODE == 1 && p.g_scale != nullptr && grp == 0) {
           // dscale[b, j] += sum over this tile's rows of dHs * H
           const long long first_row = (long long)m0 + q * 32;
           const bool uniform = (p.tokens % 32 == 0) && (first_row + 32 <= p.M);
@@ -553,6 +562,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         }
       }
       if (!p.has_main) continue;
+      const __nv_bfloat16* const bias_p = q_.bias;
+      const int n_cols = q_.N;
+      const __nv_bfloat16* const addend = p.accum_y ? q_.y : q_.res;
+      const long long ld_add = p.accum_y ? q_.ldy : q_.ldres;
+      const CUtensorMap* const tmap_y = &q_.tmap_y;
       for (int nt = nt_begin; nt < nt_end; ++nt) {
         // ---------------- tile epilogue: accumulator -> (+bias) -> bf16 -> staging tile -> bulk-tensor (TMA) stores ----------------
         const int col0 = nt * BN + half * NC;   // first global column of this warp's slice
@@ -560,12 +574,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         // this warp's NC bias values: global loads issued before the accumulator wait, parked in SMEM after the TMEM loads
         // are in flight (a dependent load between tcgen05.ld and the stores was 11-16 % of the epilogue's stall samples)
         uint32_t bias_r[(NC / 2 + 31) / 32] = {};
-        if (q_.bias != nullptr) {
-          const uint32_t* bw = reinterpret_cast<const uint32_t*>(q_.bias + col0);
+        if (bias_p != nullptr) {
+          const uint32_t* bw = reinterpret_cast<const uint32_t*>(bias_p + col0);
 #pragma unroll
           for (int j = 0; j < (NC / 2 + 31) / 32; ++j) {
             const int w = j * 32 + lane;
-            bias_r[j] = (w < NC / 2 && col0 + 2 * w < q_.N) ? __ldg(bw + w) : 0u;
+            bias_r[j] = (w < NC / 2 && col0 + 2 * w < n_cols) ? __ldg(bw + w) : 0u;
           }
         }
         mbar_wait(acc_full_bar(buf), (acc_iter >> 1) & 1u);
@@ -574,7 +588,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         uint32_t t[NC];
 #pragma unroll
         for (int c = 0; c < NC / 16; ++c) tmem_ld_32x16(tmem_base + lane_base + buf * BN + half * NC + c * 16, t + c * 16);
-        if (q_.bias != nullptr) {
+        if (bias_p != nullptr) {
 #pragma unroll
           for (int j = 0; j < (NC / 2 + 31) / 32; ++j) {
             const int w = j * 32 + lane;
@@ -587,14 +601,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         if (lane == 0) mbar_arrive_cluster_relaxed(acc_empty_remote[buf]);   // drained -> the MMA thread may reuse this accumulator
         if (warp == 0 && nt - nt_begin < 4) AQ_TRACE(item_iter, 14 + 3 * (nt - nt_begin));
         ++acc_iter;
-        if (col0 >= q_.N) continue;   // whole slice past the last column (partial last tile)
+        if (col0 >= n_cols) continue;   // whole slice past the last column (partial last tile)
         constexpr int PC = L::kPassCols;   // columns per store pass
         constexpr int kCpr = PC / 8;       // 16-byte chunks per row and pass
         const int row_base = m0 + q * 32;
 #pragma unroll
         for (int pass = 0; pass < L::kPasses; ++pass) {
           const int pcol0 = col0 + pass * PC;
-          if (pcol0 >= q_.N) break;        // warp-uniform: the rest of the slice lies past the last column
+          if (pcol0 >= n_cols) break;        // warp-uniform: the rest of the slice lies past the last column
           const uint32_t buf = stg_iter & 1u;
           // the bulk store that read this buffer two passes ago has finished reading it (at most one store stays in flight)
           if (lane == 0) tma_store_wait_read<1>();
@@ -604,7 +618,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(t[pass * PC + c8 * 8 + i]);
-            if (q_.bias != nullptr) {
+            if (bias_p != nullptr) {
               const uint4 bw = *reinterpret_cast<const uint4*>(bias_sm + (pass * PC + c8 * 8) / 2);
               const uint32_t bb[4] = {bw.x, bw.y, bw.z, bw.w};
 #pragma unroll
@@ -616,11 +630,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
             // addend read from memory: the Y of the previous rank chunk (Y += this chunk's Hs Up^T), or the residual stream the
             // caller adds to this projection (x + to_out(...), x + ff(...), x + proj_out(...) of a transformer block) -- the lane
             // owns row `grow`; 16 bytes = 8 columns of it
-            const __nv_bfloat16* addend = p.accum_y ? q_.y : q_.res;
             if (addend != nullptr) {
-              const long long ld_add = p.accum_y ? q_.ldy : q_.ldres;
               const int c = pcol0 + c8 * 8;
-              if (row_ok && c < q_.N) {
+              if (row_ok && c < n_cols) {
                 const uint4 yw = __ldg(reinterpret_cast<const uint4*>(addend + (size_t)grow * ld_add + c));
                 const uint32_t yy[4] = {yw.x, yw.y, yw.z, yw.w};
 #pragma unroll
@@ -644,7 +656,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
           if (lane == 0) {
             // rows >= M and columns >= N are clipped by the tensor map; the warp moves on while the copy engine drains the
             // buffer (measured before: 5 st.global.v4 per pass stalled ~0.36 us on the L2 write burst of all CTAs)
-            tma_store_2d(&q_.tmap_y, stg_u32 + buf * L::kStgBufBytes, pcol0, row_base);
+            tma_store_2d(tmap_y, stg_u32 + buf * L::kStgBufBytes, pcol0, row_base);
             tma_store_commit();
           }
           ++stg_iter;
@@ -692,7 +704,7 @@ static int pick_group(int num_n_tiles, int num_m_pairs, int K, int BN, bool has_
 }
 
 // `probs` are projections of the same A (same M, K, r, scale, tokens, mode); args[0] carries the shared operands.
-template <int BN, int NP>
+template <int BN, int NP, int MODE>
 static int launch_bn(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) {
   using L = SmemLayout<BN>;
   const LoraGemmArgs& a = probs[0];
@@ -773,9 +785,9 @@ static int launch_bn(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) 
   p.total_items = (int)items;
   const int grid = 2 * (int)(items < slots ? items : slots);
 
-  AQ_OPT_IN_SMEM((lora_gemm_kernel<BN, NP>), L::kTotal);
+  AQ_OPT_IN_SMEM((lora_gemm_kernel<BN, NP, MODE>), L::kTotal);
   PdlLaunch launch(dim3(grid), dim3(kThreads), L::kTotal, stream);
-  AQ_CHECK_CUDA(cudaLaunchKernelEx(&launch.cfg, lora_gemm_kernel<BN, NP>, p));
+  AQ_CHECK_CUDA(cudaLaunchKernelEx(&launch.cfg, lora_gemm_kernel<BN, NP, MODE>, p));
   AQ_LAUNCHED();
   return AQ_OK;
 }
@@ -823,10 +835,10 @@ int launch_lora_gemm(const LoraGemmArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   const int bn = a.force_bn > 0 ? a.force_bn : pick_bn(a.has_main ? a.N : 64);
   switch (bn) {
-    case 64: return launch_bn<64, 1>(&a, 1, stream);
-    case 128: return launch_bn<128, 1>(&a, 1, stream);
-    case 160: return launch_bn<160, 1>(&a, 1, stream);
-    case 192: return launch_bn<192, 1>(&a, 1, stream);
+    case 64: return a.mode ? launch_bn<64, 1, 1>(&a, 1, stream) : launch_bn<64, 1, 0>(&a, 1, stream);
+    case 128: return a.mode ? launch_bn<128, 1, 1>(&a, 1, stream) : launch_bn<128, 1, 0>(&a, 1, stream);
+    case 160: return a.mode ? launch_bn<160, 1, 1>(&a, 1, stream) : launch_bn<160, 1, 0>(&a, 1, stream);
+    case 192: return a.mode ? launch_bn<192, 1, 1>(&a, 1, stream) : launch_bn<192, 1, 0>(&a, 1, stream);
     default: return fail(AQ_ERR_BAD_SHAPE, "lora_gemm: unsupported column tile %d", bn);
   }
 }
@@ -852,11 +864,11 @@ int launch_lora_gemm_grouped(const LoraGemmArgs* probs, int nprob, cudaStream_t 
   for (int i = 0; i < nprob && probs[0].force_bn <= 0; ++i)
     if (probs[i].N % 160 != 0) bn = 128;
   if (nprob <= 4) {
-    if (bn == 160) return launch_bn<160, 4>(probs, nprob, stream);
-    return launch_bn<128, 4>(probs, nprob, stream);
+    if (bn == 160) return launch_bn<160, 4, 0>(probs, nprob, stream);
+    return launch_bn<128, 4, 0>(probs, nprob, stream);
   }
-  if (bn == 160) return launch_bn<160, kMaxGroup>(probs, nprob, stream);
-  return launch_bn<128, kMaxGroup>(probs, nprob, stream);
+  if (bn == 160) return launch_bn<160, kMaxGroup, 0>(probs, nprob, stream);
+  return launch_bn<128, kMaxGroup, 0>(probs, nprob, stream);
 }
 
 }  // namespace aq
