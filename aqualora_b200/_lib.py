@@ -85,6 +85,7 @@ _SIGNATURES = {
     "aq_effnetb1_fwd": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p], c_int),
     "aq_conv1x1_tf32x3": ([c_void_p] * 7 + [c_int64, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "aq_depthwise_silu": ([c_void_p] * 5 + [c_int] * 5 + [c_void_p], c_int),
+    "aq_expand_dw_fused": ([c_void_p] * 8 + [c_int] * 6 + [c_void_p], c_int),
     "aq_lora_fold_down": ([c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_void_p], c_int),
     "aq_lora_merge": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p], c_int),
     "aq_group_norm_workspace_bytes": ([c_int, c_int], c_size_t),

@@ -11,10 +11,12 @@
 // products with fp32 accumulation (decoder_pw.cu); stem, depthwise, SE and classifier are fp32 FFMA.  HBM-bound by design:
 // activations make one round trip per layer, the elementwise work (bias, SiLU, SE scale, residual, pooling) rides in the
 // producing / consuming kernel.
+#include <stdlib.h>
 #include <string.h>
 
 #include "aq_common.h"
 #include "aq_ptx.cuh"
+#include "decoder_fused.h"
 #include "decoder_pw.h"
 
 namespace aq {
@@ -41,47 +43,75 @@ __device__ __forceinline__ float silu_fast(float v) {
 // ---------------------------------------------------------------------------------------------------------------
 // stem: [B, 3, 512, 512] NCHW -> [B, 256, 256, 32] NHWC.  w [27][32] ((ky, kx, ci) major), b [32]
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kStemTile = 128;   // output pixels (one row segment) per block
+// One thread = TWO adjacent output pixels x 32 channels: the 27 x 32 weights come from shared memory once per pixel pair
+// (216 LDS.128 for 1728 FMAs; one pixel per thread was bound by instruction issue and the LSU pipe at 75 % each, ncu
+// profiles/r02_ncu_decoder_kernels_v10.txt), the 3 x 5 input window per channel is one aligned float4 + one scalar per row.
+constexpr int kStemThreads = 128;
+constexpr int kStemTile = 2 * kStemThreads;   // output pixels (one row segment) per block
 
-__global__ void __launch_bounds__(kStemTile) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                           const float* __restrict__ b, float* __restrict__ y, int H, int W,
-                                                           int Ho, int Wo) {
-  __shared__ float ws[27 * 32 + 32];
-  __shared__ float outs[kStemTile][33];
+__global__ void __launch_bounds__(kStemThreads) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ b, float* __restrict__ y, int H, int W,
+                                                              int Ho, int Wo) {
+  __shared__ __align__(16) float ws[27 * 32 + 32];
+  __shared__ __align__(16) float outs[kStemTile][36];   // 144-byte rows: float4-aligned, 8 consecutive lanes cover all 32 banks
   for (int i = threadIdx.x; i < 27 * 32 + 32; i += blockDim.x) ws[i] = i < 27 * 32 ? w[i] : b[i - 27 * 32];
   __syncthreads();
-  const int ox = blockIdx.x * kStemTile + threadIdx.x, oy = blockIdx.y, n = blockIdx.z;
-  float acc[32];
+  const int ox0 = blockIdx.x * kStemTile + 2 * threadIdx.x, oy = blockIdx.y, n = blockIdx.z;
+  float acc[2][32];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) acc[c] = ws[27 * 32 + c];
-  if (ox < Wo) {
+  for (int c = 0; c < 32; ++c) acc[0][c] = acc[1][c] = ws[27 * 32 + c];
+  if (ox0 < Wo) {
     const float* xn = x + (size_t)n * 3 * H * W;
+    const int ix0 = 2 * ox0;   // input columns ix0 - 1 ... ix0 + 3 (ix0 is a multiple of 4: the float4 below is aligned)
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = oy * 2 - 1 + ky;
       if (iy < 0 || iy >= H) continue;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ox * 2 - 1 + kx;
-        if (ix < 0 || ix >= W) continue;
+      for (int ci = 0; ci < 3; ++ci) {
+        const float* row = xn + ((size_t)ci * H + iy) * W;
+        float v[5];
+        v[0] = ix0 > 0 ? __ldg(row + ix0 - 1) : 0.f;
+        if (ix0 + 3 < W) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(row + ix0));
+          v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w;
+        } else {
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-          const float v = __ldg(xn + ((size_t)ci * H + iy) * W + ix);
-          const float* wr = ws + ((ky * 3 + kx) * 3 + ci) * 32;
+          for (int j = 0; j < 4; ++j) v[1 + j] = ix0 + j < W ? __ldg(row + ix0 + j) : 0.f;
+        }
 #pragma unroll
-          for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + ci) * 32);
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 wv = wr[c4];
+            acc[0][4 * c4 + 0] = fmaf(v[kx], wv.x, acc[0][4 * c4 + 0]);
+            acc[0][4 * c4 + 1] = fmaf(v[kx], wv.y, acc[0][4 * c4 + 1]);
+            acc[0][4 * c4 + 2] = fmaf(v[kx], wv.z, acc[0][4 * c4 + 2]);
+            acc[0][4 * c4 + 3] = fmaf(v[kx], wv.w, acc[0][4 * c4 + 3]);
+            acc[1][4 * c4 + 0] = fmaf(v[kx + 2], wv.x, acc[1][4 * c4 + 0]);
+            acc[1][4 * c4 + 1] = fmaf(v[kx + 2], wv.y, acc[1][4 * c4 + 1]);
+            acc[1][4 * c4 + 2] = fmaf(v[kx + 2], wv.z, acc[1][4 * c4 + 2]);
+            acc[1][4 * c4 + 3] = fmaf(v[kx + 2], wv.w, acc[1][4 * c4 + 3]);
+          }
         }
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < 32; ++c) outs[threadIdx.x][c] = silu_fast(acc[c]);
+  for (int c4 = 0; c4 < 8; ++c4) {
+    *reinterpret_cast<float4*>(&outs[2 * threadIdx.x][4 * c4]) =
+        make_float4(silu_fast(acc[0][4 * c4]), silu_fast(acc[0][4 * c4 + 1]), silu_fast(acc[0][4 * c4 + 2]), silu_fast(acc[0][4 * c4 + 3]));
+    *reinterpret_cast<float4*>(&outs[2 * threadIdx.x + 1][4 * c4]) =
+        make_float4(silu_fast(acc[1][4 * c4]), silu_fast(acc[1][4 * c4 + 1]), silu_fast(acc[1][4 * c4 + 2]), silu_fast(acc[1][4 * c4 + 3]));
+  }
   __syncthreads();
-  // coalesced NHWC store: the tile is 128 pixels x 32 channels = 4096 contiguous floats
-  float* dst = y + (((size_t)n * Ho + oy) * Wo + (size_t)blockIdx.x * kStemTile) * 32;
-  const int valid = min(kStemTile, Wo - blockIdx.x * kStemTile) * 32;
-  for (int i = threadIdx.x; i < kStemTile * 32; i += blockDim.x)
-    if (i < valid) dst[i] = outs[i >> 5][i & 31];
+  // coalesced NHWC store: the tile is 256 pixels x 32 channels = 2048 contiguous float4
+  float4* dst = reinterpret_cast<float4*>(y + (((size_t)n * Ho + oy) * Wo + (size_t)blockIdx.x * kStemTile) * 32);
+  const int valid4 = min(kStemTile, Wo - blockIdx.x * kStemTile) * 8;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < kStemTile * 8; i += kStemThreads)
+    if (i < valid4) dst[i] = *reinterpret_cast<const float4*>(&outs[i >> 3][(i & 7) * 4]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -230,17 +260,17 @@ struct DwTmaParams {
   int B, H, W, C, tiles_x, tiles_y, cblocks, total_items, stages;
 };
 
-template <int KS, int TW>
+template <int KS, int TW, int CB>
 __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __grid_constant__ DwTmaParams p) {
   constexpr int P = (KS - 1) / 2, THin = kDtTH + KS - 1, TWin = TW + KS - 1;
   constexpr int V = KS == 3 ? 4 : 2;
-  constexpr int CV = kDtCB / V;                  // channel vectors per block
+  constexpr int CV = CB / V;                  // channel vectors per block
   constexpr int WORKERS = kDtConsumers / CV;     // 32 (k = 3) or 16 (k = 5)
   constexpr int WROWS = kDtTH / 2;               // 4 row pairs
   constexpr int WCOLS = WORKERS / WROWS;         // 8 or 4
   constexpr int CPW = TW / WCOLS;                // output columns per worker
   constexpr int R = 2, NR = R + KS - 1;
-  constexpr uint32_t kTileBytes = THin * TWin * kDtCB * 4;
+  constexpr uint32_t kTileBytes = THin * TWin * CB * 4;
   constexpr uint32_t kTileStride = (kTileBytes + 127u) & ~127u;
   static_assert(CPW >= 1 && TW % WCOLS == 0, "tile width must split evenly over the workers");
   extern __shared__ uint8_t smem_raw[];
@@ -248,7 +278,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stages = p.stages;
   const uint32_t pool_off = (uint32_t)stages * kTileStride;            // float pool_s[2][8 warps][32]: per-warp partial squeeze sums
-  const uint32_t bar_off = pool_off + 2 * 8 * kDtCB * 4;
+  const uint32_t bar_off = pool_off + 2 * 8 * CB * 4;
   auto full_bar = [&](int s) { return smem_base + bar_off + 8u * s; };
   auto empty_bar = [&](int s) { return smem_base + bar_off + 8u * (8 + s); };
   float* pool_s = reinterpret_cast<float*>(smem_gen + pool_off);
@@ -279,7 +309,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
       mbar_wait(empty_bar(stage), phase ^ 1u);
       if (elect_one()) {
         mbar_arrive_expect_tx(full_bar(stage), kTileBytes);
-        tma_load_4d(smem_base + (uint32_t)stage * kTileStride, &p.tmap_x, full_bar(stage), cb * kDtCB, tx * TW - P, ty * kDtTH - P, n);
+        tma_load_4d(smem_base + (uint32_t)stage * kTileStride, &p.tmap_x, full_bar(stage), cb * CB, tx * TW - P, ty * kDtTH - P, n);
       }
       __syncwarp();
       if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -299,7 +329,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
       const int rem = item / p.cblocks;
       const int n = rem / tiles_per_img, t2 = rem % tiles_per_img;
       const int ty = t2 / p.tiles_x, tx = t2 % p.tiles_x;
-      const int c0 = cb * kDtCB + cv * V;
+      const int c0 = cb * CB + cv * V;
       const bool ch_ok = c0 < p.C;
       if (cb != cur_cb) {
         cur_cb = cb;
@@ -320,7 +350,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
       mbar_wait(full_bar(stage), phase);
       const float* tile = reinterpret_cast<const float*>(smem_gen + (uint32_t)stage * kTileStride) + cv * V;
       auto lds = [&](int row, int col, float (&d)[V]) {
-        const float* q = tile + (row * TWin + col) * kDtCB;
+        const float* q = tile + (row * TWin + col) * CB;
         if constexpr (V == 4) {
           const float4 v4 = *reinterpret_cast<const float4*>(q);
           d[0] = v4.x; d[1] = v4.y; d[2] = v4.z; d[3] = v4.w;
@@ -378,110 +408,119 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
 #pragma unroll
         for (int o = CV; o < 32; o <<= 1) pool[v] += __shfl_xor_sync(0xffffffffu, pool[v], o);
       }
-      float* part = pool_s + ((it & 1u) * 8 + (t >> 5)) * kDtCB;
+      float* part = pool_s + ((it & 1u) * 8 + (t >> 5)) * CB;
       if (lane < CV) {
 #pragma unroll
         for (int v = 0; v < V; ++v) part[lane * V + v] = pool[v];
       }
       named_bar_sync(1, kDtConsumers);
-      if (t < kDtCB) {
-        const float* base = pool_s + (it & 1u) * 8 * kDtCB + t;
+      if (t < CB) {
+        const float* base = pool_s + (it & 1u) * 8 * CB + t;
         float sum = 0.f;
 #pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) sum += base[w8 * kDtCB];
-        if (cb * kDtCB + t < p.C) atomicAdd(p.pooled + (size_t)n * p.C + cb * kDtCB + t, sum);
+        for (int w8 = 0; w8 < 8; ++w8) sum += base[w8 * CB];
+        if (cb * CB + t < p.C) atomicAdd(p.pooled + (size_t)n * p.C + cb * CB + t, sum);
       }
     }
   }
 }
 
-template <int KS, int TW>
+template <int KS, int TW, int CB>
 static int launch_depthwise_tma_t(const float* x, const float* w, const float* b, float* y, float* pooled, int B, int H, int C,
                                   cudaStream_t st) {
   constexpr int THin = kDtTH + KS - 1, TWin = TW + KS - 1;
-  constexpr int kTileStride = (THin * TWin * kDtCB * 4 + 127) & ~127;
+  constexpr int kTileStride = (THin * TWin * CB * 4 + 127) & ~127;
   DwTmaParams p;
   memset(&p, 0, sizeof(p));
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)H, (uint64_t)H, (uint64_t)B};
   uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)H * C * 4, (uint64_t)H * H * C * 4};
-  uint32_t box[4] = {kDtCB, TWin, THin, 1};
+  uint32_t box[4] = {CB, TWin, THin, 1};
   int rc = make_tmap(&p.tmap_x, x, 4, 4, dims, str, box, kSwzNone);
   if (rc) return rc;
   p.w = w; p.b = b; p.y = y; p.pooled = pooled;
   p.B = B; p.H = H; p.W = H; p.C = C;
   p.tiles_x = (H + TW - 1) / TW;
   p.tiles_y = (H + kDtTH - 1) / kDtTH;
-  p.cblocks = (C + kDtCB - 1) / kDtCB;
+  p.cblocks = (C + CB - 1) / CB;
   const long long items = (long long)p.cblocks * B * p.tiles_x * p.tiles_y;
   AQ_REQUIRE(items < (1ll << 31), AQ_ERR_BAD_SHAPE, "depthwise: too many tiles");
   p.total_items = (int)items;
   int stages = (200 * 1024) / kTileStride;
   if (stages > 6) stages = 6;
   p.stages = stages;
-  const int smem = stages * kTileStride + 2 * 8 * kDtCB * 4 + 16 * 8 + 128;
+  const int smem = stages * kTileStride + 2 * 8 * CB * 4 + 16 * 8 + 128;
   const int sms = sm_count();
   if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
   const int grid = (int)(items < sms ? items : sms);
-  AQ_OPT_IN_SMEM((depthwise_tma_kernel<KS, TW>), 227 * 1024);
-  depthwise_tma_kernel<KS, TW><<<grid, kDtThreads, smem, st>>>(p);
+  AQ_OPT_IN_SMEM((depthwise_tma_kernel<KS, TW, CB>), 227 * 1024);
+  depthwise_tma_kernel<KS, TW, CB><<<grid, kDtThreads, smem, st>>>(p);
   AQ_LAUNCHED();
   return AQ_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // SqueezeExcitation MLP: scale[n, c] = sigmoid(b2[c] + sum_j w2t[j, c] * silu(b1[j] + sum_c' w1[j, c'] * mean[n, c']))
-// grid (B, channel chunks of 256): every block recomputes the tiny squeeze vector s1 [SQ] (warp per row of w1, 4 independent
-// accumulators), then one thread per output channel walks w2t [SQ, C] (transposed at pack time -> coalesced).
+// One CLUSTER of 4 CTAs per image (grid (4, B), 512 threads): the kernel is a chain of two tiny matrix-vector products whose
+// time is the latency of streaming w1 [SQ, C] and w2t [SQ, C] (up to 2 x 614 KB) through ONE SM, so the rows of w1 and the
+// channels of w2t are split over the cluster: CTA r computes the squeeze entries j = r, r + 4, ... (a warp per row, float4 loads,
+// 4 independent loads in flight per lane), stores them into the s1 array of every CTA of the cluster (st.shared::cluster), and
+// after the cluster barrier produces the channels [r C/4, (r+1) C/4) (8 rows of w2t in flight per thread).  Earlier layouts:
+// a block per 256 channels, each recomputing s1 (31 - 68 us per launch on the 1152 / 1920-channel layers); one block per 1024
+// channels (38 - 63 us: the same latency chain on fewer SMs) -- profiles/r02_decoder_launches_v10/v11.txt.
 // pooled holds SUMS over hw pixels.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) se_kernel(const float* __restrict__ pooled, const float* __restrict__ w1,
-                                                  const float* __restrict__ b1, const float* __restrict__ w2t,
-                                                  const float* __restrict__ b2, float* __restrict__ scale, int C, int SQ,
-                                                  float inv_hw) {
-  extern __shared__ float sm[];   // mean [C], s1 [SQ]
+constexpr int kSeThreads = 512, kSeCluster = 4;
+
+__global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(kSeThreads)
+se_kernel(const float* __restrict__ pooled, const float* __restrict__ w1, const float* __restrict__ b1,
+          const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ scale, int C, int SQ, float inv_hw) {
+  extern __shared__ __align__(16) float sm[];   // mean [C], s1 [SQ]
   float* mean = sm;
   float* s1 = sm + C;
-  const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pooled[(size_t)n * C + c] * inv_hw;
+  const int n = blockIdx.y;
+  const uint32_t rank = cluster_ctarank();
+  for (int c = threadIdx.x; c < C; c += kSeThreads) mean[c] = pooled[(size_t)n * C + c] * inv_hw;
   __syncthreads();
+  cluster_sync_all();   // every CTA of the cluster is running (its shared memory exists) before remote stores target it
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // fc1: each warp owns rows j = warp, warp + 8, ...; FOUR rows are walked at once so 16 independent loads are in flight per lane
-  // (one row at a time left the kernel waiting on L2 latency: 75 us for C = 1920)
-  for (int j0 = warp; j0 < SQ; j0 += 32) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* wr[4];
+  constexpr int kWarps = kSeThreads / 32;
+  const int c4n = C >> 2;   // C % 4 == 0 (expanded widths of the network are multiples of 16)
+  for (int j = (int)rank + kSeCluster * warp; j < SQ; j += kSeCluster * kWarps) {
+    const float4* row = reinterpret_cast<const float4*>(w1 + (size_t)j * C);
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c4 = lane; c4 < c4n; c4 += 128) {
+      float4 u[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) wr[u] = w1 + (size_t)min(j0 + 8 * u, SQ - 1) * C;
-    for (int c = lane; c < C; c += 128) {
+      for (int k = 0; k < 4; ++k) u[k] = c4 + 32 * k < c4n ? __ldg(row + c4 + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int cc = c + 32 * k;
-        if (cc < C) {
-          const float mv = mean[cc];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) acc[u] = fmaf(__ldg(wr[u] + cc), mv, acc[u]);
+        if (c4 + 32 * k < c4n) {
+          const float4 m = *reinterpret_cast<const float4*>(mean + 4 * (c4 + 32 * k));
+          a[k] = fmaf(u[k].x, m.x, fmaf(u[k].y, m.y, fmaf(u[k].z, m.z, fmaf(u[k].w, m.w, a[k]))));
         }
       }
     }
+    float acc = (a[0] + a[1]) + (a[2] + a[3]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float a = acc[u];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      const int j = j0 + 8 * u;
-      if (lane == 0 && j < SQ) s1[j] = silu(a + b1[j]);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane < kSeCluster) {
+      const float v = silu(acc + b1[j]);
+      const uint32_t remote = mapa_shared(smem_u32(s1 + j), (uint32_t)lane);
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
     }
   }
-  __syncthreads();
-  const int c = blockIdx.y * 256 + threadIdx.x;
-  if (c < C) {
+  cluster_sync_all();   // release / acquire at cluster scope: all of s1 is visible in every CTA
+  const int cper = ((C + kSeCluster - 1) / kSeCluster + 3) & ~3;
+  const int c = (int)rank * cper + threadIdx.x;
+  if (threadIdx.x < cper && c < C) {
     float a0 = b2[c], a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int j = 0;
-    for (; j + 3 < SQ; j += 4) {
-      a0 = fmaf(__ldg(w2t + (size_t)j * C + c), s1[j], a0);
-      a1 = fmaf(__ldg(w2t + (size_t)(j + 1) * C + c), s1[j + 1], a1);
-      a2 = fmaf(__ldg(w2t + (size_t)(j + 2) * C + c), s1[j + 2], a2);
-      a3 = fmaf(__ldg(w2t + (size_t)(j + 3) * C + c), s1[j + 3], a3);
+    for (; j + 7 < SQ; j += 8) {
+      float w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w[k] = __ldg(w2t + (size_t)(j + k) * C + c);
+      a0 = fmaf(w[0], s1[j], a0); a1 = fmaf(w[1], s1[j + 1], a1); a2 = fmaf(w[2], s1[j + 2], a2); a3 = fmaf(w[3], s1[j + 3], a3);
+      a0 = fmaf(w[4], s1[j + 4], a0); a1 = fmaf(w[5], s1[j + 5], a1); a2 = fmaf(w[6], s1[j + 6], a2); a3 = fmaf(w[7], s1[j + 7], a3);
     }
     for (; j < SQ; ++j) a0 = fmaf(__ldg(w2t + (size_t)j * C + c), s1[j], a0);
     const float acc = (a0 + a1) + (a2 + a3);
@@ -576,12 +615,32 @@ static Buffers buffer_plan() {
   return bf;
 }
 
+// Which MBConv blocks run expand -> depthwise as one kernel (decoder_fused.cu).  Measured per 64 images (ncu launch list,
+// profiles/r02_decoder_launches_v12_fused_all.txt): 16 -> 96 k3 s2 at 256 x 256: 943 us fused vs 597 + 420 us unfused;
+// 24 -> 144 k3 s1 at 128 x 128: 625 vs 199 + 282 us; 24 -> 144 k5 s2: 846 vs 197 + 293 us -- the fused kernel removes the expanded
+// map's HBM round trip but pays the SiLU epilogue on the halo pixels too (1.2x ... 1.6x) at ~1.2 instructions per clock, so only
+// the first block (the largest map, stride 2: the output is 4x smaller than the expanded input) wins.  AQ_DEC_FUSED=0: never,
+// AQ_DEC_FUSED=2: every supported shape (A/B measurements, kernel tests); default: the winning shape only.
+static int fused_mode() {
+  static const int mode = [] { const char* e = getenv("AQ_DEC_FUSED"); return e == nullptr ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)); }();
+  return mode;
+}
+static bool fused_enabled(int cin, int cexp, int k, int stride) {
+  const int mode = fused_mode();
+  if (mode == 0) return false;
+  if (mode == 2) return true;
+  return cin == 16 && cexp == 96 && k == 3 && stride == 2;
+}
+
 static int launch_depthwise(const float* x, const float* w, const float* b, float* y, float* pooled, int B, int H, int C, int k,
                             int stride, int Ho, cudaStream_t st) {
   if (stride == 1 && C >= kDtCB && C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
-    if (k == 3) return Ho >= 32 ? launch_depthwise_tma_t<3, 32>(x, w, b, y, pooled, B, H, C, st) : launch_depthwise_tma_t<3, 16>(x, w, b, y, pooled, B, H, C, st);
-    if (k == 5) return Ho >= 32 ? launch_depthwise_tma_t<5, 32>(x, w, b, y, pooled, B, H, C, st) : launch_depthwise_tma_t<5, 16>(x, w, b, y, pooled, B, H, C, st);
+    if (k == 3) return Ho >= 32 ? launch_depthwise_tma_t<3, 32, kDtCB>(x, w, b, y, pooled, B, H, C, st) : launch_depthwise_tma_t<3, 16, kDtCB>(x, w, b, y, pooled, B, H, C, st);
+    if (k == 5) return Ho >= 32 ? launch_depthwise_tma_t<5, 32, kDtCB>(x, w, b, y, pooled, B, H, C, st) : launch_depthwise_tma_t<5, 16, kDtCB>(x, w, b, y, pooled, B, H, C, st);
   }
+  // the 16-channel depthwise of the second stage-1 block (256 x 256 maps): same kernel with a 16-channel block
+  if (stride == 1 && C == 16 && k == 3 && Ho >= 32 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0)
+    return launch_depthwise_tma_t<3, 32, 16>(x, w, b, y, pooled, B, H, C, st);
   const int R = 2;   // output rows per thread
   const int TW = Ho >= 64 ? 32 : 16;
   const int V = k == 3 ? 4 : 2;
@@ -639,7 +698,7 @@ int aq_effnetb1_fwd(const float* x, const float* packed, float* logits, unsigned
     const float* w = wk.take(27 * 32);
     const float* b = wk.take(32);
     dim3 grid((h + kStemTile - 1) / kStemTile, h, B);
-    stem_kernel<<<grid, kStemTile, 0, st>>>(x, w, b, act[0], kImg, kImg, h, h);
+    stem_kernel<<<grid, kStemThreads, 0, st>>>(x, w, b, act[0], kImg, kImg, h, h);
     AQ_LAUNCHED();
   }
   int cur = 0;
@@ -651,18 +710,27 @@ int aq_effnetb1_fwd(const float* x, const float* packed, float* logits, unsigned
       const int sq = cin / 4 > 1 ? cin / 4 : 1;
       const int ho = (h + 2 * ((sc.k - 1) / 2) - sc.k) / stride + 1;
       const float* dw_in = act[cur];
-      if (sc.expand != 1) {
-        PwTcArgs a{};
-        a.x = act[cur]; a.w_hi = wk.take((size_t)cin * cexp); a.w_lo = wk.take((size_t)cin * cexp); a.bias = wk.take(cexp);
-        a.se = nullptr; a.residual = nullptr; a.y = expb;
-        a.M = (long long)B * h * h; a.K = cin; a.N = cexp; a.hw = h * h; a.epi = kPwSilu;
-        rc = launch_pointwise_tc(a, st);
-        if (rc) return rc;
-        dw_in = expb;
-      }
       float* pl = pooled + (size_t)B * pooled_off;
       pooled_off += pad4(cexp);
-      {
+      // early blocks: expand 1x1 -> depthwise in ONE kernel, the 6x expanded map never reaches HBM (decoder_fused.cu)
+      const bool fused = sc.expand != 1 && fused_enabled(cin, cexp, sc.k, stride) && fused_expand_dw_supported(cin, cexp, sc.k, stride, h);
+      if (fused) {
+        FusedArgs a{};
+        a.x = act[cur]; a.w_hi = wk.take((size_t)cin * cexp); a.w_lo = wk.take((size_t)cin * cexp); a.b_e = wk.take(cexp);
+        a.w_d = wk.take((size_t)sc.k * sc.k * cexp); a.b_d = wk.take(cexp);
+        a.y = dwo; a.pooled = pl; a.B = B; a.H = h; a.cin = cin; a.cexp = cexp; a.k = sc.k; a.stride = stride;
+        rc = launch_fused_expand_dw(a, st);
+        if (rc) return rc;
+      } else {
+        if (sc.expand != 1) {
+          PwTcArgs a{};
+          a.x = act[cur]; a.w_hi = wk.take((size_t)cin * cexp); a.w_lo = wk.take((size_t)cin * cexp); a.bias = wk.take(cexp);
+          a.se = nullptr; a.residual = nullptr; a.y = expb;
+          a.M = (long long)B * h * h; a.K = cin; a.N = cexp; a.hw = h * h; a.epi = kPwSilu;
+          rc = launch_pointwise_tc(a, st);
+          if (rc) return rc;
+          dw_in = expb;
+        }
         const float* w = wk.take((size_t)sc.k * sc.k * cexp);
         const float* b = wk.take(cexp);
         rc = launch_depthwise(dw_in, w, b, dwo, pl, B, h, cexp, sc.k, stride, ho, st);
@@ -673,7 +741,8 @@ int aq_effnetb1_fwd(const float* x, const float* packed, float* logits, unsigned
         const float* b1 = wk.take(sq);
         const float* w2 = wk.take((size_t)cexp * sq);
         const float* b2 = wk.take(cexp);
-        se_kernel<<<dim3(B, (cexp + 255) / 256), 256, (cexp + sq) * sizeof(float), st>>>(pl, w1, b1, w2, b2, scale, cexp, sq, 1.f / (float)(ho * ho));
+        AQ_REQUIRE(cexp <= kSeCluster * kSeThreads, AQ_ERR_BAD_SHAPE, "se: %d channels exceed %d", cexp, kSeCluster * kSeThreads);
+        se_kernel<<<dim3(kSeCluster, B), kSeThreads, (cexp + sq) * sizeof(float), st>>>(pl, w1, b1, w2, b2, scale, cexp, sq, 1.f / (float)(ho * ho));
         AQ_LAUNCHED();
       }
       {
@@ -706,6 +775,16 @@ int aq_effnetb1_fwd(const float* x, const float* packed, float* logits, unsigned
     AQ_LAUNCHED();
   }
   return AQ_OK;
+}
+
+int aq_expand_dw_fused(const float* x, const float* w_hi, const float* w_lo, const float* b_e, const float* w_d, const float* b_d, float* y,
+                       float* pooled, int B, int H, int cin, int cexp, int k, int stride, void* stream) {
+  int rc = check_arch();
+  if (rc) return rc;
+  FusedArgs a{};
+  a.x = x; a.w_hi = w_hi; a.w_lo = w_lo; a.b_e = b_e; a.w_d = w_d; a.b_d = b_d; a.y = y; a.pooled = pooled;
+  a.B = B; a.H = H; a.cin = cin; a.cexp = cexp; a.k = k; a.stride = stride;
+  return launch_fused_expand_dw(a, (cudaStream_t)stream);
 }
 
 int aq_conv1x1_tf32x3(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* se, const float* residual,

@@ -214,6 +214,9 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
         mbar_wait(full_bar(stage), phase);
         uint8_t* hi = smem_gen + (a_hi(stage) - smem_base);
         uint8_t* lo = smem_gen + (a_lo(stage) - smem_base);
+        // columns at or past K are never read by the MMAs (the k-step count stops at K): for the 16 / 24 / 40-deep expand
+        // layers that is up to half of the chunk's shared-memory traffic (the LSU data pipe was 65 % busy there, ncu)
+        if (k < p.K) {
         float4 v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(hi + (t + 128 * j) * 16);
@@ -228,6 +231,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
           }
           *reinterpret_cast<float4*>(hi + (t + 128 * j) * 16) = make_float4(h[0], h[1], h[2], h[3]);
           *reinterpret_cast<float4*>(lo + (t + 128 * j) * 16) = make_float4(l[0], l[1], l[2], l[3]);
+        }
         }
         fence_proxy_async_smem();
         __syncwarp();

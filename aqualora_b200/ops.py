@@ -627,6 +627,25 @@ def depthwise_silu(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, k: int,
     return y, pooled
 
 
+def expand_dw_fused(x: torch.Tensor, w_e: torch.Tensor, b_e: torch.Tensor, w_d: torch.Tensor, b_d: torch.Tensor, k: int, stride: int):
+    """Front half of an MBConv block in one kernel (csrc/decoder_fused.cu): SiLU(depthwise_k,s(SiLU(x W_e^T + b_e)) + b_d) over NHWC
+    x [B, H, H, cin]; w_e [cexp, cin] (split into TF32 hi / lo here), w_d [k * k, cexp].  Returns (y [B, Ho, Ho, cexp], pooled sums
+    [B, cexp]).  Only the early EfficientNet-B1 shapes have a fused kernel; others raise AqualoraError (BAD_SHAPE)."""
+    _need(x, _F32, "x", 4)
+    _need(w_e, _F32, "w_e", 2)
+    B, H, _, cin = x.shape
+    cexp = w_e.shape[0]
+    ho = (H + 2 * ((k - 1) // 2) - k) // stride + 1
+    w_e = w_e.contiguous()
+    hi = (w_e.view(torch.int32) & -8192).view(torch.float32)
+    lo = w_e - hi
+    y = torch.empty((B, ho, ho, cexp), dtype=_F32, device=x.device)
+    pooled = torch.zeros((B, cexp), dtype=_F32, device=x.device)
+    _lib.call("aq_expand_dw_fused", x.contiguous().data_ptr(), hi.data_ptr(), lo.data_ptr(), b_e.contiguous().data_ptr(),
+              w_d.contiguous().data_ptr(), b_d.contiguous().data_ptr(), y.data_ptr(), pooled.data_ptr(), B, H, cin, cexp, k, stride, _stream())
+    return y, pooled
+
+
 def lora_fold_down(down: torch.Tensor, m: torch.Tensor, scale: float) -> torch.Tensor:
     """down' = (down * m[:, None...]) * scale for a [r, ...] fp32 LoRA down weight (scripts/create_wm_lora.py:30-37)."""
     _need(down, _F32, "down")

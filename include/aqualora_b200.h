@@ -283,6 +283,13 @@ int aq_conv1x1_tf32x3(const float* x, const float* w_hi, const float* w_lo, cons
                       const float* residual, float* y, int64_t M, int K, int N, int hw, int epi, void* stream);
 int aq_depthwise_silu(const float* x, const float* w, const float* bias, float* y, float* pooled, int B, int H, int C, int k,
                       int stride, void* stream);
+/* aq_expand_dw_fused: the two calls above as ONE kernel for the early blocks (expand 1x1 + SiLU -> depthwise + SiLU + squeeze sums;
+ *   the 6x expanded map stays in shared memory): y [B, Ho, Ho, cexp] = SiLU(dw_k,s(SiLU(x W_e^T + b_e)) + b_d), pooled += sum.
+ *   Supported (cin, cexp, k, stride): (16, 96, 3, 2), (24, 144, 3, 1), (24, 144, 5, 2) with Ho a multiple of 8 (16 for the stride-1 shape); other shapes
+ *   return AQ_ERR_BAD_SHAPE (aq_effnetb1_fwd then runs the unfused pair).  Same arithmetic as aq_conv1x1_tf32x3 (3-term TF32
+ *   split, fp32 accumulate) and aq_depthwise_silu (fp32 FMA). */
+int aq_expand_dw_fused(const float* x, const float* w_hi, const float* w_lo, const float* b_e, const float* w_d, const float* b_d,
+                       float* y, float* pooled, int B, int H, int cin, int cexp, int k, int stride, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Message -> deployable weights (scripts/create_wm_lora.py:23-41, scripts/merge_lora.py:98-120).

@@ -86,3 +86,44 @@ def test_depthwise_silu_matches_float64(cuda_device, B, H, C, k, stride):
     assert (y.cpu().double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
     want_pool = ref.sum((1, 2))
     assert (pooled.cpu().double() - want_pool).abs().max().item() <= 1e-4 * want_pool.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("B,H,cin,cexp,k,stride", [(2, 64, 16, 96, 3, 2), (3, 32, 24, 144, 3, 1), (2, 48, 24, 144, 5, 2), (1, 256, 16, 96, 3, 2),
+                                                    (5, 16, 24, 144, 3, 1)])
+def test_expand_dw_fused_matches_float64_and_the_unfused_pair(cuda_device, B, H, cin, cexp, k, stride):
+    """aq_expand_dw_fused (csrc/decoder_fused.cu: expand 1x1 + SiLU -> depthwise + SiLU + squeeze sums, the expanded map stays in
+    shared memory) against float64 PyTorch and against the two stand-alone kernels it replaces.  Tolerances: the expand product is
+    the same 3-term TF32 split (<= 2e-6 of sum |x||w|), SiLU uses the SFU ex2 / rcp (~1e-6 relative), the depthwise stage is an
+    fp32 FMA chain of k*k terms: 3e-5 of the output's largest magnitude element-wise, as for aq_depthwise_silu."""
+    from aqualora_b200 import ops
+
+    g = torch.Generator().manual_seed(B + H + cin + k)
+    x = torch.randn(B, H, H, cin, generator=g) * 2
+    w_e = torch.randn(cexp, cin, generator=g) * cin ** -0.5
+    b_e = torch.randn(cexp, generator=g)
+    w_d = torch.randn(cexp, 1, k, k, generator=g) * 0.3
+    b_d = torch.randn(cexp, generator=g)
+    e = _silu(x.double() @ w_e.double().t() + b_e.double())                       # [B, H, H, cexp]
+    ref = torch.nn.functional.conv2d(e.permute(0, 3, 1, 2), w_d.double(), b_d.double(), stride, (k - 1) // 2, groups=cexp)
+    ref = _silu(ref).permute(0, 2, 3, 1)
+    dev = cuda_device
+    wd_flat = w_d.reshape(cexp, k * k).t().contiguous().to(dev)
+    y, pooled = ops.expand_dw_fused(x.to(dev), w_e.to(dev), b_e.to(dev), wd_flat, b_d.to(dev), k, stride)
+    assert y.shape == ref.shape
+    assert (y.cpu().double() - ref).abs().max().item() <= 3e-5 * ref.abs().max().item()
+    want_pool = ref.sum((1, 2))
+    assert (pooled.cpu().double() - want_pool).abs().max().item() <= 1e-4 * want_pool.abs().max().item() + 1e-3
+    # the pair of kernels it replaces
+    e_dev = ops.conv1x1_tf32x3(x.to(dev).reshape(-1, cin), w_e.to(dev), b_e.to(dev), hw=H * H, epi=1).view(B, H, H, cexp)
+    y2, pooled2 = ops.depthwise_silu(e_dev, wd_flat, b_d.to(dev), k, stride)
+    assert (y - y2).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    assert (pooled - pooled2).abs().max().item() <= 1e-4 * want_pool.abs().max().item() + 1e-3
+
+
+def test_expand_dw_fused_rejects_other_shapes(cuda_device):
+    from aqualora_b200 import _lib, ops
+
+    dev = cuda_device
+    with pytest.raises(_lib.AqualoraError):
+        ops.expand_dw_fused(torch.zeros(1, 32, 32, 40, device=dev), torch.zeros(240, 40, device=dev), torch.zeros(240, device=dev),
+                            torch.zeros(9, 240, device=dev), torch.zeros(240, device=dev), 3, 2)
