@@ -20,6 +20,7 @@
 // The expand convolutions (128 x 96 ... 240 outputs from a 16 ... 40-deep product) are bound by the epilogue's instruction issue
 // (ncu: ~0.75 instructions per output element, the 8 epilogue warps of the previous version busy 90 % of the time, tensor pipe
 // 4 % active), hence 16 epilogue warps -- 4 per scheduler -- an SFU SiLU and an accumulator ring of up to 8 tiles in TMEM.
+#include <stdlib.h>
 #include <string.h>
 
 #include "aq_ptx.cuh"
@@ -355,6 +356,293 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
   if (warp == kPwMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// CTA-pair edition (cluster of 2, tcgen05 cta_group::2) for the layers whose weights do NOT fit in shared memory -- the late,
+// wide MBConv blocks (K = 480 ... 1920) and the head.  There the single-CTA kernel keeps ONE 32-deep k chunk in flight (A hi/lo
+// 32 KB + W hi/lo up to 56 KB per stage = 2 stages) and every CTA streams the whole W (hi + lo) for its 128 rows: ncu
+// (profiles/r02_ncu_decoder_kernels_v10.txt) shows the tensor pipe 39 - 47 % active, 42 warps per issue waiting, 5.6 TB/s of
+// L2 -> SM traffic.  A pair shares W: each CTA loads half of the W tile (the MMA reads both halves), so a stage is 32 KB + <= 28 KB
+// (3 stages), the W traffic per row halves, and M = 256 rows per MMA.
+//   producer (both CTAs)   own 128 rows of A + own half of W_hi / W_lo, bytes on the CTA's OWN full barrier
+//   converters (both CTAs) wait for the own full barrier (A and the W half have landed), split A, then arrive on the LEADER's
+//                          conv barrier (8 arrivals = 4 warps x 2 CTAs): its completion covers both CTAs' operands
+//   MMA (leader CTA)       3 x tcgen05.mma.cta_group::2.kind::tf32 per k-step, commits multicast to both CTAs' empty / acc_full barriers
+//   epilogue (both CTAs)   own 128 TMEM lanes; "accumulator drained" arrives on the leader's barrier (32 arrivals)
+// ------------------------------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwThreads, 1) pointwise_tc_pair_kernel(const __grid_constant__ PwTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  const int BN = p.BN;
+  const int stages = p.stages;
+  const uint32_t w_bytes = (uint32_t)(BN / 2) * 128u;              // this CTA's half of one W tile (hi or lo)
+  const uint32_t stage_bytes = 2u * kPwATile + 2u * w_bytes;
+  const uint32_t stg_off = (uint32_t)stages * stage_bytes;
+  const uint32_t bar_off = stg_off + (uint32_t)kPwEpiWarps * kPwStgWarp;
+  const uint32_t bar_base = smem_base + bar_off;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // own TMA bytes landed (local)
+  auto conv_bar = [&](int s) { return bar_base + 8u * (8 + s); };           // leader: both CTAs' operands ready (8 warp arrivals)
+  auto empty_bar = [&](int s) { return bar_base + 8u * (16 + s); };         // both CTAs (multicast commit)
+  auto acc_full_bar = [&](int b) { return bar_base + 8u * (24 + b); };      // both CTAs (multicast commit)
+  auto acc_empty_bar = [&](int b) { return bar_base + 8u * (32 + b); };     // leader: 32 warp arrivals
+  const uint32_t tmem_slot = bar_base + 8u * 41;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * 41);
+  const uint32_t nacc = min(8u, 512u / (uint32_t)BN);
+
+  auto a_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
+  auto a_lo = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + kPwATile; };
+  auto w_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + 2u * kPwATile; };
+  auto w_lo = [&](int s) { return w_hi(s) + w_bytes; };
+
+  if (warp == kPwProducerWarp && lane == 0) {
+    tma_prefetch_desc(&p.tmap_x);
+    tma_prefetch_desc(&p.tmap_whi);
+    tma_prefetch_desc(&p.tmap_wlo);
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(conv_bar(s), 8);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 8; ++b) {
+      mbar_init(acc_full_bar(b), 1);
+      mbar_init(acc_empty_bar(b), 2 * kPwEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kPwMmaWarp) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int num_m_pairs = (p.num_m_tiles + 1) >> 1;
+  const int total_items = num_m_pairs * p.num_n_tiles;
+  const int num_kc = p.num_kc;
+  const int item0 = blockIdx.x >> 1, item_step = gridDim.x >> 1;
+
+  if (warp == kPwProducerWarp) {
+    // =========================== TMA producer (both CTAs) ===========================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = item0; item < total_items; item += item_step) {
+      const int m0 = ((item / p.num_n_tiles) * 2 + (int)cta_rank) * kPwBM;
+      const int n0 = (item % p.num_n_tiles) * BN + (int)cta_rank * (BN / 2);
+      for (int kc = 0; kc < num_kc; ++kc) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(stage), kPwATile + 2u * w_bytes);
+          tma_load_2d(a_hi(stage), &p.tmap_x, full_bar(stage), kc * kPwKC, m0);
+          tma_load_2d(w_hi(stage), &p.tmap_whi, full_bar(stage), kc * kPwKC, n0);
+          tma_load_2d(w_lo(stage), &p.tmap_wlo, full_bar(stage), kc * kPwKC, n0);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == kPwMmaWarp) {
+    // =========================== MMA issuer (leader CTA) ===========================
+    if (leader) {
+      const uint32_t idesc = make_idesc_tf32(2 * kPwBM, (uint32_t)BN);
+      constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      auto desc = [&](uint32_t addr) { return kDescHi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
+      int stage = 0;
+      uint32_t phase = 0, acc_iter = 0;
+      for (int item = item0; item < total_items; item += item_step, ++acc_iter) {
+        const uint32_t buf = acc_iter % nacc;
+        const uint32_t tmem_acc = tmem_base + buf * (uint32_t)BN;
+        mbar_wait(acc_empty_bar(buf), ((acc_iter / nacc) & 1u) ^ 1u);
+        tc_fence_after();
+        for (int kc = 0; kc < num_kc; ++kc) {
+          mbar_wait(conv_bar(stage), phase);   // both CTAs: A split (generic proxy + fence.proxy.async) and W halves landed
+          tc_fence_after();
+          if (elect_one()) {
+            const int ksteps = min(kPwKC, p.K - kc * kPwKC) >> 3;
+            const uint64_t ah = desc(a_hi(stage)), al = desc(a_lo(stage)), wh = desc(w_hi(stage)), wl = desc(w_lo(stage));
+            for (int k = 0; k < ksteps; ++k) {
+              umma_tf32_pair(tmem_acc, al + 2 * k, wh + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_tf32_pair(tmem_acc, ah + 2 * k, wl + 2 * k, idesc, 1u);
+              umma_tf32_pair(tmem_acc, ah + 2 * k, wh + 2 * k, idesc, 1u);
+            }
+            umma_commit_pair(empty_bar(stage), 0x3);
+            if (kc == num_kc - 1) umma_commit_pair(acc_full_bar(buf), 0x3);
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= kPwConvWarp0) {
+    // =========================== converter warps (both CTAs): own A rows -> (A * se) hi / lo ===========================
+    const int t = threadIdx.x - kPwConvWarp0 * 32;
+    const int cphys = t & 7;
+    const int rlow = (t >> 3) & 7;
+    const int clog = cphys ^ rlow;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = item0; item < total_items; item += item_step) {
+      const long long m0 = (long long)((item / p.num_n_tiles) * 2 + (int)cta_rank) * kPwBM;
+      const float* se_row = (p.se != nullptr && m0 < p.M) ? p.se + (m0 / p.hw) * p.K : nullptr;
+      for (int kc = 0; kc < num_kc; ++kc) {
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+        const int k = kc * kPwKC + clog * 4;
+        if (se_row != nullptr && k < p.K) sc = __ldg(reinterpret_cast<const float4*>(se_row + k));
+        mbar_wait(full_bar(stage), phase);
+        uint8_t* hi = smem_gen + (a_hi(stage) - smem_base);
+        uint8_t* lo = smem_gen + (a_lo(stage) - smem_base);
+        if (k < p.K) {
+          float4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(hi + (t + 128 * j) * 16);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float x[4] = {v[j].x * sc.x, v[j].y * sc.y, v[j].z * sc.z, v[j].w * sc.w};
+            float h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              h[e] = __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u);
+              l[e] = x[e] - h[e];
+            }
+            *reinterpret_cast<float4*>(hi + (t + 128 * j) * 16) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(lo + (t + 128 * j) * 16) = make_float4(l[0], l[1], l[2], l[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(conv_bar(stage), 0));
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // =========================== epilogue warps (both CTAs; same as the single-CTA kernel on the CTA's own 128 rows) ===========
+    const int q = warp & 3;
+    const int res = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint8_t* stg = smem_gen + stg_off + warp * kPwStgWarp;
+    const int rb_row = lane >> 2, rb_col = (lane & 3) * 4;
+    uint32_t acc_iter = 0;
+    for (int item = item0; item < total_items; item += item_step, ++acc_iter) {
+      const long long m0 = (long long)((item / p.num_n_tiles) * 2 + (int)cta_rank) * kPwBM;
+      const int n0 = (item % p.num_n_tiles) * BN;
+      const uint32_t buf = acc_iter % nacc;
+      const uint32_t acc_empty_remote = mapa_shared(acc_empty_bar(buf), 0);
+      const long long row_base = m0 + q * 32;
+      const int pieces = min(BN, p.N - n0 + 15) >> 4;
+      const int nmine = pieces > res ? (pieces - res + 3) >> 2 : 0;
+      const bool col_ok = n0 + res * 16 + rb_col < p.N;
+      float4 rs[4];
+      if (p.epi == kPwResidual && nmine > 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long row = row_base + 8 * i + rb_row;
+          rs[i] = (row < p.M && col_ok) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.N + n0 + res * 16 + rb_col))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      mbar_wait(acc_full_bar(buf), (acc_iter / nacc) & 1u);
+      tc_fence_after();
+      if (nmine == 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(acc_empty_remote);
+        continue;
+      }
+      for (int g = 0; g < nmine; ++g) {
+        const int pc = res + 4 * g;
+        const int c0 = n0 + pc * 16;
+        uint32_t tr[16];
+        tmem_ld_32x16(tmem_base + lane_base + buf * (uint32_t)BN + pc * 16, tr);
+        float4 b4[4];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4)
+          b4[i4] = c0 + i4 * 4 < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.epi == kPwResidual && g > 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const long long row = row_base + 8 * i + rb_row;
+            rs[i] = (row < p.M && c0 + rb_col < p.N) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.N + c0 + rb_col))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        tmem_wait_ld();
+        if (g == nmine - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(acc_empty_remote);
+        }
+        float f[16];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          f[i4 * 4 + 0] = __uint_as_float(tr[i4 * 4 + 0]) + b4[i4].x;
+          f[i4 * 4 + 1] = __uint_as_float(tr[i4 * 4 + 1]) + b4[i4].y;
+          f[i4 * 4 + 2] = __uint_as_float(tr[i4 * 4 + 2]) + b4[i4].z;
+          f[i4 * 4 + 3] = __uint_as_float(tr[i4 * 4 + 3]) + b4[i4].w;
+        }
+        if (p.epi == kPwSilu || p.epi == kPwSiluPool) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = pw_silu(f[i]);
+        }
+        if (p.epi == kPwSiluPool) {
+#pragma unroll
+          for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+            const bool up = (lane & bit) != 0;
+#pragma unroll
+            for (int i = 0; i < w; ++i) {
+              const float send = up ? f[i] : f[i + w];
+              const float keep = up ? f[i + w] : f[i];
+              f[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+            }
+          }
+          f[0] += __shfl_xor_sync(0xffffffffu, f[0], 1);
+          const int col = c0 + (lane >> 1);
+          if ((lane & 1) == 0 && col < p.N && row_base < p.M) atomicAdd(p.y + (row_base / p.hw) * p.N + col, f[0]);
+          continue;
+        }
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4)
+          *reinterpret_cast<float4*>(stg + lane * kPwStgStride + i4 * 16) = make_float4(f[i4 * 4], f[i4 * 4 + 1], f[i4 * 4 + 2], f[i4 * 4 + 3]);
+        __syncwarp();
+        float4 o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = *reinterpret_cast<const float4*>(stg + (8 * i + rb_row) * kPwStgStride + rb_col * 4);
+        float* yrow = p.y + (size_t)(row_base + rb_row) * p.N + c0 + rb_col;
+        const size_t ystep = (size_t)8 * p.N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (row_base + 8 * i + rb_row < p.M && c0 + rb_col < p.N) {
+            if (p.epi == kPwResidual) {
+              o[i].x += rs[i].x; o[i].y += rs[i].y; o[i].z += rs[i].z; o[i].w += rs[i].w;
+            }
+            *reinterpret_cast<float4*>(yrow + i * ystep) = o[i];
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA leaves while its pair may still read its shared memory or signal its barriers
+  if (warp == kPwMmaWarp) tmem_dealloc_pair(tmem_base, 512);
+}
+
+// AQ_PW_PAIR=0 keeps every layer on the single-CTA kernel (A/B measurements)
+static bool pw_pair_enabled() {
+  static const bool on = [] { const char* e = getenv("AQ_PW_PAIR"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 static int pick_pw_bn(int N) {
   const int n16 = (N + 15) / 16 * 16;
   if (n16 <= kPwMaxBN) return n16;
@@ -398,6 +686,31 @@ int launch_pointwise_tc(const PwTcArgs& a, cudaStream_t st) {
   const int w_tile_bytes = 2 * p.BN * 128;                                   // hi + lo of one k chunk
   const int fixed = kPwEpiWarps * kPwStgWarp + 512;
   p.w_resident = (p.num_n_tiles == 1 && p.num_kc * w_tile_bytes <= 96 * 1024) ? 1 : 0;
+  const int sms = sm_count();
+  if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
+  if (!p.w_resident && p.num_m_tiles >= 2 && pw_pair_enabled()) {
+    // CTA pairs: each CTA holds half of the W tile (see pointwise_tc_pair_kernel)
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+    uint64_t str[1] = {(uint64_t)a.K * 4};
+    uint32_t box[2] = {kPwKC, (uint32_t)(p.BN / 2)};
+    int rc = make_tmap(&p.tmap_whi, a.w_hi, 4, 2, dims, str, box, kSwz128);
+    if (rc) return rc;
+    rc = make_tmap(&p.tmap_wlo, a.w_lo, 4, 2, dims, str, box, kSwz128);
+    if (rc) return rc;
+    const int stage_bytes = 2 * kPwATile + w_tile_bytes / 2;
+    int stages = (kPwSmemBudget - fixed) / stage_bytes;
+    if (stages > 6) stages = 6;
+    AQ_REQUIRE(stages >= 2, AQ_ERR_BAD_SHAPE, "pointwise: column tile %d leaves no room for a pipeline", p.BN);
+    p.stages = stages;
+    const int smem = stages * stage_bytes + fixed + 1024;
+    const long long items = (long long)((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    const int slots = sms / 2;
+    const int grid = 2 * (int)(items < slots ? items : slots);
+    AQ_OPT_IN_SMEM((pointwise_tc_pair_kernel), 232448);
+    pointwise_tc_pair_kernel<<<grid, kPwThreads, smem, st>>>(p);
+    AQ_LAUNCHED();
+    return AQ_OK;
+  }
   const int wres_bytes = p.w_resident ? p.num_kc * w_tile_bytes : 0;
   const int stage_bytes = 2 * kPwATile + (p.w_resident ? 0 : w_tile_bytes);
   int stages = (kPwSmemBudget - fixed - wres_bytes) / stage_bytes;
@@ -405,8 +718,6 @@ int launch_pointwise_tc(const PwTcArgs& a, cudaStream_t st) {
   AQ_REQUIRE(stages >= 2, AQ_ERR_BAD_SHAPE, "pointwise: column tile %d leaves no room for a pipeline", p.BN);
   p.stages = stages;
   const int smem = wres_bytes + stages * stage_bytes + fixed + 1024;
-  const int sms = sm_count();
-  if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
   const long long items = (long long)p.num_m_tiles * p.num_n_tiles;
   const int grid = (int)(items < sms ? items : sms);
   AQ_OPT_IN_SMEM((pointwise_tc_kernel), 232448);
