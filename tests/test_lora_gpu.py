@@ -31,6 +31,18 @@ def _max_rel(got, want):
     return ((got.float().cpu() - want.cpu()).abs().max() / (want.abs().max() + 1e-12)).item()
 
 
+def _elem_err(got, want, rtol=2e-2, atol_rms=4e-2):
+    """Worst element of |got - want| / (rtol * |want| + atol_rms * rms(want)): < 1 means EVERY element is within 2 % of its own
+    magnitude plus 4 % of the tensor's rms.  (bf16 operands against the fp32 golden: each of the K products carries ~2^-8 of
+    relative rounding, so an output element is off by ~0.5 % of the output rms with random sign -- the absolute part is a > 5 sigma
+    allowance for elements near zero, the relative part covers the output's own bf16 rounding and large elements.  A bound
+    normalised by the tensor's MAXIMUM, as used before, let small elements be wrong by many times their value.)"""
+    want = want.float().cpu()
+    got = got.float().cpu()
+    rms = want.pow(2).mean().sqrt()
+    return ((got - want).abs() / (rtol * want.abs() + atol_rms * rms + 1e-30)).max().item()
+
+
 def _fro_rel(got, want):
     want = want.float().cpu()
     return ((got.float().cpu() - want).norm() / (want.norm() + 1e-12)).item()
@@ -71,9 +83,9 @@ def test_linear_golden_forward_backward(lm, cuda_device, golden_dir):
             scale = scale.to(dev).requires_grad_(True)
         y = lin(x, scale)
         assert y.dtype == torch.bfloat16 and tuple(y.shape) == tuple(c["y"].shape)
-        assert _max_rel(y, c["y"]) < BF16_TOL, c["kind"]
+        assert _elem_err(y, c["y"]) < 1.0, c["kind"]
         y.backward(c["gy"].to(dev, torch.bfloat16))
-        assert _max_rel(x.grad, c["gx"]) < BF16_TOL
+        assert _elem_err(x.grad, c["gx"]) < 1.0
         assert _fro_rel(lora.down.weight.grad, c["g_down"]) < BF16_TOL
         assert _fro_rel(lora.up.weight.grad, c["g_up"]) < BF16_TOL
         if isinstance(scale, torch.Tensor):
@@ -81,7 +93,7 @@ def test_linear_golden_forward_backward(lm, cuda_device, golden_dir):
         # lora_layer is None -> exact base op (utils/lora_modules.py:57-59)
         lin.set_lora_layer(None)
         yb = lin(x.detach(), 1.0)
-        assert _max_rel(yb, c["y_base"]) < BF16_TOL
+        assert _elem_err(yb, c["y_base"]) < 1.0
 
 
 def test_conv1x1_golden_forward_backward(lm, cuda_device, golden_dir):
@@ -100,9 +112,9 @@ def test_conv1x1_golden_forward_backward(lm, cuda_device, golden_dir):
         scale = c["scale"].to(dev).requires_grad_(True) if isinstance(c["scale"], torch.Tensor) else c["scale"]
         y = conv(x, scale)
         assert tuple(y.shape) == tuple(c["y"].shape)
-        assert _max_rel(y, c["y"]) < BF16_TOL
+        assert _elem_err(y, c["y"]) < 1.0
         y.backward(c["gy"].to(dev, torch.bfloat16))
-        assert _max_rel(x.grad, c["gx"]) < BF16_TOL
+        assert _elem_err(x.grad, c["gx"]) < 1.0
         assert _fro_rel(lora.down.weight.grad, c["g_down"]) < BF16_TOL
         assert _fro_rel(lora.up.weight.grad, c["g_up"]) < BF16_TOL
         if isinstance(scale, torch.Tensor):
@@ -142,8 +154,8 @@ def test_other_ranks_forward_backward(lm, cuda_device, r, B, N, din, dout, bias)
     sd = sc.to(dev).requires_grad_(True)
     y = lin(xd, sd)
     y.backward(gy.to(dev, torch.bfloat16))
-    assert _max_rel(y, want) < BF16_TOL
-    assert _max_rel(xd.grad, dx) < BF16_TOL
+    assert _elem_err(y, want) < 1.0
+    assert _elem_err(xd.grad, dx) < 1.0
     assert _fro_rel(lora.down.weight.grad, dd) < BF16_TOL and _fro_rel(lora.up.weight.grad, du) < BF16_TOL
     assert _fro_rel(sd.grad, ds) < BF16_TOL
     assert tuple(lora.down.weight.grad.shape) == (r, din) and tuple(sd.grad.shape) == (B, r)
@@ -177,7 +189,7 @@ def test_residual_rides_in_the_epilogue(lm, cuda_device, M, K, N, r, tok):
     if r > 64:
         want = (x.float() @ w.float().t() + b.float() + ((x.float() @ dn.float().t()).view(M // tok, tok, r) * sc[:, None, :]).view(M, r) @ up.float().t()
                 + res.float())
-        assert _max_rel(y_res, want) < BF16_TOL
+        assert _elem_err(y_res, want) < 1.0
     else:
         assert ((y_res.float() - want).abs() <= 2 ** -7 * (y_plain.float().abs() + want.abs()) + 1e-6).all()
     y0, _ = ops.lora_linear_fwd(x, w, None, None, None, None, tok, residual=res)          # plain projection + residual
@@ -228,7 +240,7 @@ def test_fp16_and_fp32_activations_cast_at_the_boundary(lm, cuda_device):
         xd = x.to(dev, dt).requires_grad_(True)
         y = lin(xd, sc.to(dev))
         assert y.dtype == dt
-        assert _max_rel(y, want) < BF16_TOL
+        assert _elem_err(y, want) < 1.0
         y.float().pow(2).sum().backward()
         assert xd.grad is not None and xd.grad.dtype == dt and torch.isfinite(xd.grad).all()
         assert lora.down.weight.grad is not None and torch.isfinite(lora.down.weight.grad).all()
@@ -247,7 +259,7 @@ def test_standalone_lora_layer_matches_oracle(lm, cuda_device):
         want = O.lora_linear_layer_forward(x.float(), lora.down.weight.data.bfloat16().float(), lora.up.weight.data.bfloat16().float(),
                                            scale.bfloat16().float() if isinstance(scale, torch.Tensor) else scale, 8.0, 16)
         got = lora.to(dev)(x.to(dev), scale.to(dev) if isinstance(scale, torch.Tensor) else scale)
-        assert _max_rel(got, want) < BF16_TOL
+        assert _elem_err(got, want) < 1.0
         lora = lora.cpu()
 
 
@@ -276,7 +288,7 @@ def test_forward_matches_autocast_oracle(cuda_device, M, K, N, r, tok):
     want, h_want = O.bf16_autocast_linear(x, w, b, dn, up, sc)
     y, h = ops.lora_linear_fwd(x.reshape(M, K).to(dev), w.to(dev), b.to(dev), dn.bfloat16().to(dev), up.bfloat16().to(dev),
                                sc.float().to(dev), tok, save_h=True)
-    assert _max_rel(y, want.reshape(M, N)) < BF16_TOL
+    assert _elem_err(y, want.reshape(M, N)) < 1.0
     # H is a single fp32-accumulated contraction rounded once: at most 1 bf16 ulp from the oracle's rounding
     assert _max_rel(h, h_want.reshape(M, r)) < 2 ** -7
 
@@ -360,7 +372,7 @@ def test_backward_matches_closed_form_oracle(cuda_device, M, K, N, r, tok, dx):
     gx = ops.lora_linear_bwd(gyd, xd, wd.t().contiguous() if dx else None, dnd.t().contiguous(), upd.t().contiguous(), scd, h,
                              g_dn, g_up, g_sc, tok)
     if dx:
-        assert _max_rel(gx, dxr.reshape(M, K)) < BF16_TOL
+        assert _elem_err(gx, dxr.reshape(M, K)) < 1.0
     else:
         assert gx is None
     assert _fro_rel(g_dn, ddr) < BF16_TOL and _fro_rel(g_up, dur) < BF16_TOL and _fro_rel(g_sc, dsr) < BF16_TOL
@@ -561,9 +573,9 @@ def test_grouped_projections_equal_separate_launches(lm, cuda_device, B, tok, di
         want = O.closed_form_linear(x0.float(), m.weight.float().cpu(), None if m.bias is None else m.bias.float().cpu(),
                                     m.lora_layer.down.weight.detach().bfloat16().float().cpu(),
                                     m.lora_layer.up.weight.detach().bfloat16().float().cpu(), s0.float())
-        assert _max_rel(yg, want) < BF16_TOL
+        assert _elem_err(yg, want) < 1.0
     if need_dx:
-        assert _max_rel(gx_g, gx_s) < BF16_TOL
+        assert _elem_err(gx_g, gx_s) < 1.0
     # d(scale) flows back through the reference's `.to(weight_dtype)` cast (utils/lora_modules.py:15-17): the grouped call rounds
     # the SUM over its projections to bf16 once, separate calls round each projection's term -> up to one bf16 ulp (2^-8) apart
     assert _fro_rel(gs_g, gs_s) < 2.0 ** -8
@@ -594,7 +606,7 @@ def test_grouped_plain_and_fallback(lm, cuda_device):
     for a, b, m in zip(got, want, mods):
         assert torch.equal(a, b)
         ref = torch.nn.functional.linear(x.float(), m.weight.float(), m.bias.float())
-        assert _max_rel(a, ref) < BF16_TOL
+        assert _elem_err(a, ref) < 1.0
     mods[1].set_lora_layer(None)
     with torch.no_grad():
         n0 = _launches()
