@@ -689,6 +689,12 @@ static int pick_group(int num_n_tiles, int num_m_pairs, int K, int BN, bool has_
   int best_g = 1;
   double best_cost = 1e30;
   const double kb = (double)((K + kBlockK - 1) / kBlockK);
+  // A [M, K] is streamed once per column-tile GROUP (the groups of a row block are num_m_pairs items apart, far beyond what the
+  // 126 MB L2 keeps when A is large): every extra group re-reads A from HBM.  In the cost unit below (one k-block of one column =
+  // 2 clocks of the pair's MMA rate) a byte costs 1.9e9 / 2 / 6.5e12 units.  Measured: (65 536, 1280 -> 320) without LoRA 69.8 us with
+  // one tile per item, 59.2 us with both tiles in one item (profiles/r02_gemm_sweep_all_plain.log).
+  const double a_bytes = (double)num_m_pairs * kPairM * (double)K * 2.0;
+  const double a_reread = a_bytes > 48e6 ? a_bytes * (1.9e9 / 2.0 / 6.5e12) : 0.0;
   for (int g = 1; g <= num_n_tiles; ++g) {
     const int groups = (num_n_tiles + g - 1) / g;
     const long long items = (long long)groups * num_m_pairs;
@@ -697,7 +703,7 @@ static int pick_group(int num_n_tiles, int num_m_pairs, int K, int BN, bool has_
     // item cannot hide the H -> Hs round trip behind the next tile's main loop
     const double bubble = has_lora ? (g == 1 ? 6.0 * BN : 1.0 * BN) : 0.0;
     const double item_cost = g * (kb + (has_lora ? 1.0 : 0.0)) * BN + (has_lora ? kb * kRankPad : 0.0) + bubble;
-    const double cost = (double)waves * item_cost;
+    const double cost = (double)waves * item_cost + (groups - 1) * a_reread;
     if (cost < best_cost - 1e-9) { best_cost = cost; best_g = g; }
   }
   return best_g;
