@@ -13,7 +13,7 @@
 //
 // One CTA per SM, persistent over (128-row tile, N tile <= 224) work items, 704 threads:
 //   warps 0-15   epilogue   TMEM lane quadrant = warp % 4, 16-column pieces pc = warp / 4 (mod 4):
-//                           TMEM -> +bias -> [SiLU] -> SMEM transpose -> coalesced 64 B row segments (+ residual) | SiLU + pooled sums
+//                           TMEM -> +bias -> [SiLU] [+ residual] -> staging tile (box of Y's tensor map) -> one bulk-tensor store | SiLU + pooled sums
 //   warps 16-19  converter  raw fp32 A tile (TMA, 128B swizzle) -> x * se -> hi (in place) / lo (second tile)
 //   warp 20      TMA producer (A raw, W_hi, W_lo per 32-wide k chunk)
 //   warp 21      TMEM allocator + MMA issuer (3 MMAs per 8-wide k step)
@@ -35,14 +35,14 @@ constexpr int kPwMaxBN = 224;                  // 2 pipeline stages + 16 epilogu
 constexpr int kPwBM = 128;
 constexpr int kPwKC = 32;                      // fp32 elements per k chunk = one 128-byte swizzle row
 constexpr int kPwATile = kPwBM * kPwKC * 4;    // 16 KiB
-constexpr int kPwStgStride = 80;               // 16 fp32 + 16 B pad: odd multiple of 16 B -> conflict-free 16 B accesses
-constexpr int kPwStgWarp = 32 * kPwStgStride;
+constexpr int kPwStgWarp = 32 * 64;             // per epilogue warp: one 32-row x 16-column fp32 piece = the box of Y's tensor map (64B swizzle)
 constexpr int kPwSmemBudget = 232448 - 1024;
 
 struct PwTcParams {
   CUtensorMap tmap_x;     // X    [M, K] fp32   box {32, 128}  swizzle 128B
   CUtensorMap tmap_whi;   // W_hi [N, K] fp32   box {32, BN}   swizzle 128B
   CUtensorMap tmap_wlo;   // W_lo [N, K]
+  CUtensorMap tmap_y;     // Y    [M, N] fp32   box {16, 32}   swizzle 64B (store; rows >= M / columns >= N are clipped)
   const float* bias;      // [N]
   const float* se;        // [M / hw, K] or null
   const float* residual;  // [M, N] or null
@@ -246,8 +246,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
     const int res = warp >> 2;     // this warp takes the 16-column pieces pc = res, res + 4, ...
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint8_t* stg = smem_gen + stg_off + warp * kPwStgWarp;
-    // read-back mapping of a 32 x 16 piece: instruction i covers rows 8 i ... 8 i + 7, 4 x 16 B per row
-    const int rb_row = lane >> 2, rb_col = (lane & 3) * 4;
+    const uint32_t stg_u32 = smem_base + stg_off + warp * kPwStgWarp;
     uint32_t acc_iter = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++acc_iter) {
       const long long m0 = (long long)(item / p.num_n_tiles) * kPwBM;
@@ -256,15 +255,15 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
       const long long row_base = m0 + q * 32;
       const int pieces = min(BN, p.N - n0 + 15) >> 4;                  // 16-column pieces that hold at least one valid column
       const int nmine = pieces > res ? (pieces - res + 3) >> 2 : 0;    // this warp's pieces
-      const bool col_ok = n0 + res * 16 + rb_col < p.N;                // (re-evaluated per piece below)
       float4 rs[4];
       if (p.epi == kPwResidual && nmine > 0) {
-        // residual of the first piece: requested before the accumulator wait so its DRAM latency hides behind the MMAs
+        // residual of the first piece (this lane's row, 64 bytes): requested before the accumulator wait so its DRAM latency
+        // hides behind the MMAs
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const long long row = row_base + 8 * i + rb_row;
-          rs[i] = (row < p.M && col_ok) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.N + n0 + res * 16 + rb_col))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int c = n0 + res * 16 + i4 * 4;
+          rs[i4] = (row_base + lane < p.M && c < p.N) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)(row_base + lane) * p.N + c))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       mbar_wait(acc_full_bar(buf), (acc_iter / nacc) & 1u);
@@ -286,11 +285,9 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
           b4[i4] = c0 + i4 * 4 < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.epi == kPwResidual && g > 0) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const long long row = row_base + 8 * i + rb_row;
-            rs[i] = (row < p.M && c0 + rb_col < p.N) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.N + c0 + rb_col))
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int i4 = 0; i4 < 4; ++i4)
+            rs[i4] = (row_base + lane < p.M && c0 + i4 * 4 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)(row_base + lane) * p.N + c0 + i4 * 4))
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         tmem_wait_ld();
         if (g == nmine - 1) {
@@ -327,28 +324,31 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
           if ((lane & 1) == 0 && col < p.N && row_base < p.M) atomicAdd(p.y + (row_base / p.hw) * p.N + col, f[0]);
           continue;
         }
+        if (p.epi == kPwResidual) {
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4)
-          *reinterpret_cast<float4*>(stg + lane * kPwStgStride + i4 * 16) = make_float4(f[i4 * 4], f[i4 * 4 + 1], f[i4 * 4 + 2], f[i4 * 4 + 3]);
-        __syncwarp();
-        // read back row-contiguous: 4 x 16 B per row -> 8 rows per instruction, 64 B runs in global memory
-        float4 o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = *reinterpret_cast<const float4*>(stg + (8 * i + rb_row) * kPwStgStride + rb_col * 4);
-        float* yrow = p.y + (size_t)(row_base + rb_row) * p.N + c0 + rb_col;
-        const size_t ystep = (size_t)8 * p.N;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (row_base + 8 * i + rb_row < p.M && c0 + rb_col < p.N) {
-            if (p.epi == kPwResidual) {
-              o[i].x += rs[i].x; o[i].y += rs[i].y; o[i].z += rs[i].z; o[i].w += rs[i].w;
-            }
-            *reinterpret_cast<float4*>(yrow + i * ystep) = o[i];
+          for (int i4 = 0; i4 < 4; ++i4) {
+            f[i4 * 4 + 0] += rs[i4].x; f[i4 * 4 + 1] += rs[i4].y; f[i4 * 4 + 2] += rs[i4].z; f[i4 * 4 + 3] += rs[i4].w;
           }
         }
+        // the piece goes out as ONE bulk-tensor store from the warp's staging tile (the box of Y's tensor map, 64B swizzle: lane =
+        // row, 16-byte chunk c at slot c ^ ((row >> 1) & 3) -> conflict-free); rows >= M and columns >= N are clipped by the map.
+        // Before: a padded transpose tile, 4 LDS.128 + 4 predicated STG.128 per lane and two warp barriers per piece -- the LSU
+        // data pipe was 65 % busy on the expand layers (ncu, profiles/r02_ncu_decoder_kernels_v10.txt).
+        if (lane == 0) tma_store_wait_read<0>();   // the previous piece's store has read the tile
         __syncwarp();
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4)
+          *reinterpret_cast<float4*>(stg + lane * 64 + ((i4 ^ ((lane >> 1) & 3)) << 4)) = make_float4(f[i4 * 4], f[i4 * 4 + 1], f[i4 * 4 + 2], f[i4 * 4 + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&p.tmap_y, stg_u32, c0, (int)row_base);
+          tma_store_commit();
+        }
       }
     }
+    if (lane == 0) tma_store_wait_read<0>();   // every bulk store has read its staging tile before the shared memory goes away
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -529,7 +529,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwThreads, 1) point
     const int res = warp >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint8_t* stg = smem_gen + stg_off + warp * kPwStgWarp;
-    const int rb_row = lane >> 2, rb_col = (lane & 3) * 4;
+    const uint32_t stg_u32 = smem_base + stg_off + warp * kPwStgWarp;
     uint32_t acc_iter = 0;
     for (int item = item0; item < total_items; item += item_step, ++acc_iter) {
       const long long m0 = (long long)((item / p.num_n_tiles) * 2 + (int)cta_rank) * kPwBM;
@@ -539,14 +539,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwThreads, 1) point
       const long long row_base = m0 + q * 32;
       const int pieces = min(BN, p.N - n0 + 15) >> 4;
       const int nmine = pieces > res ? (pieces - res + 3) >> 2 : 0;
-      const bool col_ok = n0 + res * 16 + rb_col < p.N;
       float4 rs[4];
       if (p.epi == kPwResidual && nmine > 0) {
+        // residual of the first piece (this lane's row, 64 bytes): requested before the accumulator wait so its DRAM latency
+        // hides behind the MMAs
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const long long row = row_base + 8 * i + rb_row;
-          rs[i] = (row < p.M && col_ok) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.N + n0 + res * 16 + rb_col))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int c = n0 + res * 16 + i4 * 4;
+          rs[i4] = (row_base + lane < p.M && c < p.N) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)(row_base + lane) * p.N + c))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       mbar_wait(acc_full_bar(buf), (acc_iter / nacc) & 1u);
@@ -568,11 +569,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwThreads, 1) point
           b4[i4] = c0 + i4 * 4 < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.epi == kPwResidual && g > 0) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const long long row = row_base + 8 * i + rb_row;
-            rs[i] = (row < p.M && c0 + rb_col < p.N) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.N + c0 + rb_col))
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int i4 = 0; i4 < 4; ++i4)
+            rs[i4] = (row_base + lane < p.M && c0 + i4 * 4 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)(row_base + lane) * p.N + c0 + i4 * 4))
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         tmem_wait_ld();
         if (g == nmine - 1) {
@@ -608,27 +607,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwThreads, 1) point
           if ((lane & 1) == 0 && col < p.N && row_base < p.M) atomicAdd(p.y + (row_base / p.hw) * p.N + col, f[0]);
           continue;
         }
+        if (p.epi == kPwResidual) {
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4)
-          *reinterpret_cast<float4*>(stg + lane * kPwStgStride + i4 * 16) = make_float4(f[i4 * 4], f[i4 * 4 + 1], f[i4 * 4 + 2], f[i4 * 4 + 3]);
-        __syncwarp();
-        float4 o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = *reinterpret_cast<const float4*>(stg + (8 * i + rb_row) * kPwStgStride + rb_col * 4);
-        float* yrow = p.y + (size_t)(row_base + rb_row) * p.N + c0 + rb_col;
-        const size_t ystep = (size_t)8 * p.N;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (row_base + 8 * i + rb_row < p.M && c0 + rb_col < p.N) {
-            if (p.epi == kPwResidual) {
-              o[i].x += rs[i].x; o[i].y += rs[i].y; o[i].z += rs[i].z; o[i].w += rs[i].w;
-            }
-            *reinterpret_cast<float4*>(yrow + i * ystep) = o[i];
+          for (int i4 = 0; i4 < 4; ++i4) {
+            f[i4 * 4 + 0] += rs[i4].x; f[i4 * 4 + 1] += rs[i4].y; f[i4 * 4 + 2] += rs[i4].z; f[i4 * 4 + 3] += rs[i4].w;
           }
         }
+        // the piece goes out as ONE bulk-tensor store from the warp's staging tile (the box of Y's tensor map, 64B swizzle: lane =
+        // row, 16-byte chunk c at slot c ^ ((row >> 1) & 3) -> conflict-free); rows >= M and columns >= N are clipped by the map.
+        // Before: a padded transpose tile, 4 LDS.128 + 4 predicated STG.128 per lane and two warp barriers per piece -- the LSU
+        // data pipe was 65 % busy on the expand layers (ncu, profiles/r02_ncu_decoder_kernels_v10.txt).
+        if (lane == 0) tma_store_wait_read<0>();   // the previous piece's store has read the tile
         __syncwarp();
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4)
+          *reinterpret_cast<float4*>(stg + lane * 64 + ((i4 ^ ((lane >> 1) & 3)) << 4)) = make_float4(f[i4 * 4], f[i4 * 4 + 1], f[i4 * 4 + 2], f[i4 * 4 + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&p.tmap_y, stg_u32, c0, (int)row_base);
+          tma_store_commit();
+        }
       }
     }
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -680,6 +683,14 @@ int launch_pointwise_tc(const PwTcArgs& a, cudaStream_t st) {
   }
   p.bias = a.bias; p.se = a.se; p.residual = a.residual; p.y = a.y;
   p.M = a.M; p.N = a.N; p.K = a.K; p.hw = a.hw; p.epi = a.epi;
+  if (a.epi != kPwSiluPool) {
+    AQ_REQUIRE((reinterpret_cast<uintptr_t>(a.y) & 15u) == 0, AQ_ERR_BAD_ALIGN, "pointwise: y must be 16-byte aligned");
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
+    uint64_t str[1] = {(uint64_t)a.N * 4};
+    uint32_t box[2] = {16, 32};
+    int rc = make_tmap(&p.tmap_y, a.y, 4, 2, dims, str, box, kSwz64);
+    if (rc) return rc;
+  }
   p.num_n_tiles = (a.N + p.BN - 1) / p.BN;
   p.num_m_tiles = (int)((a.M + kPwBM - 1) / kPwBM);
   p.num_kc = (a.K + kPwKC - 1) / kPwKC;
