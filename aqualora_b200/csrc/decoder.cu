@@ -615,14 +615,15 @@ static Buffers buffer_plan() {
   return bf;
 }
 
-// Which MBConv blocks run expand -> depthwise as one kernel (decoder_fused.cu).  Measured per 64 images (ncu launch list,
-// profiles/r02_decoder_launches_v12_fused_all.txt): 16 -> 96 k3 s2 at 256 x 256: 943 us fused vs 597 + 420 us unfused;
-// 24 -> 144 k3 s1 at 128 x 128: 625 vs 199 + 282 us; 24 -> 144 k5 s2: 846 vs 197 + 293 us -- the fused kernel removes the expanded
-// map's HBM round trip but pays the SiLU epilogue on the halo pixels too (1.2x ... 1.6x) at ~1.2 instructions per clock, so only
-// the first block (the largest map, stride 2: the output is 4x smaller than the expanded input) wins.  AQ_DEC_FUSED=0: never,
-// AQ_DEC_FUSED=2: every supported shape (A/B measurements, kernel tests); default: the winning shape only.
+// Which MBConv blocks run expand -> depthwise as one kernel (decoder_fused.cu).  Measured per 64 images (ncu launch lists,
+// profiles/r02_decoder_launches_v12_fused_all.txt, ..._v14_tma_store.txt): 16 -> 96 k3 s2 at 256 x 256: 938 us fused vs 433 + 419 us
+// unfused (597 + 420 before the pointwise kernel's TMA-store epilogue); 24 -> 144 k3 s1 at 128 x 128: 625 vs 152 + 283 us; 24 -> 144 k5
+// s2: 846 vs 152 + 293 us.  The fused kernel removes the expanded map's HBM round trip (DRAM traffic of the first block 3.9 -> 0.65 GB)
+// but pays the bias + SiLU epilogue on CUDA cores for the halo pixels too (1.2x ... 1.6x) at ~1.3 instructions per clock, and loses
+// to the tensor-core pair at every shape today -> opt-in.  AQ_DEC_FUSED=1: the first stage-2 block, =2: every supported shape
+// (A/B measurements; the kernel-level parity tests call aq_expand_dw_fused directly); default 0: never.
 static int fused_mode() {
-  static const int mode = [] { const char* e = getenv("AQ_DEC_FUSED"); return e == nullptr ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)); }();
+  static const int mode = [] { const char* e = getenv("AQ_DEC_FUSED"); return e == nullptr ? 0 : (e[0] == '1' ? 1 : (e[0] == '2' ? 2 : 0)); }();
   return mode;
 }
 static bool fused_enabled(int cin, int cexp, int k, int stride) {
