@@ -338,6 +338,59 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t m, uint32_
 // ----------------------------------------------------------------------------------------------
 // small numeric helpers
 // ----------------------------------------------------------------------------------------------
+// Packed fp32 FMA (FFMA2): (c0, c1) += (a0, a1) * (b0, b1), two independent IEEE fused multiply-adds in ONE issue slot.  The three
+// operand pairs must sit in aligned register pairs, which vector loads (float2 / float4) give for free.
+__device__ __forceinline__ void ffma2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+  asm("{\n"
+      ".reg .b64 ra, rb, rc;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "mov.b64 rc, {%0, %1};\n"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rc;\n"
+      "}"
+      : "+f"(c0), "+f"(c1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+// SiLU of two values with the SFU exponential / reciprocal and PACKED multiplies / add (FMUL2, FADD2): 7 issue slots per pair
+// instead of 10.  Same arithmetic as the scalar form x * rcp(1 + ex2(-x * log2 e)) (round-to-nearest multiplies, approx.ftz SFU ops;
+// ex2.approx.ftz saturates cleanly: x -> -inf gives e = inf, rcp = 0; x -> +inf gives e = 0).
+__device__ __forceinline__ void silu2(float& x0, float& x1) {
+  float t0, t1, e0, e1, r0, r1;
+  asm("{\n"
+      ".reg .b64 rx, rk, rt;\n"
+      "mov.b64 rx, {%2, %3};\n"
+      "mov.b64 rk, {%4, %4};\n"
+      "mul.rn.f32x2 rt, rx, rk;\n"
+      "mov.b64 {%0, %1}, rt;\n"
+      "}"
+      : "=f"(t0), "=f"(t1)
+      : "f"(x0), "f"(x1), "f"(-1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  asm("{\n"
+      ".reg .b64 re, ro, rs;\n"
+      "mov.b64 re, {%2, %3};\n"
+      "mov.b64 ro, {%4, %4};\n"
+      "add.rn.f32x2 rs, re, ro;\n"
+      "mov.b64 {%0, %1}, rs;\n"
+      "}"
+      : "=f"(e0), "=f"(e1)
+      : "f"(e0), "f"(e1), "f"(1.f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(e0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(e1));
+  asm("{\n"
+      ".reg .b64 rx, rr, ry;\n"
+      "mov.b64 rx, {%0, %1};\n"
+      "mov.b64 rr, {%2, %3};\n"
+      "mul.rn.f32x2 ry, rx, rr;\n"
+      "mov.b64 {%0, %1}, ry;\n"
+      "}"
+      : "+f"(x0), "+f"(x1)
+      : "f"(r0), "f"(r1));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -85,14 +85,11 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const float* __restr
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const float4 wv = wr[c4];
-            acc[0][4 * c4 + 0] = fmaf(v[kx], wv.x, acc[0][4 * c4 + 0]);
-            acc[0][4 * c4 + 1] = fmaf(v[kx], wv.y, acc[0][4 * c4 + 1]);
-            acc[0][4 * c4 + 2] = fmaf(v[kx], wv.z, acc[0][4 * c4 + 2]);
-            acc[0][4 * c4 + 3] = fmaf(v[kx], wv.w, acc[0][4 * c4 + 3]);
-            acc[1][4 * c4 + 0] = fmaf(v[kx + 2], wv.x, acc[1][4 * c4 + 0]);
-            acc[1][4 * c4 + 1] = fmaf(v[kx + 2], wv.y, acc[1][4 * c4 + 1]);
-            acc[1][4 * c4 + 2] = fmaf(v[kx + 2], wv.z, acc[1][4 * c4 + 2]);
-            acc[1][4 * c4 + 3] = fmaf(v[kx + 2], wv.w, acc[1][4 * c4 + 3]);
+            // packed FFMA2: 864 fused multiply-adds per pixel in 432 issue slots
+            ffma2(acc[0][4 * c4 + 0], acc[0][4 * c4 + 1], v[kx], v[kx], wv.x, wv.y);
+            ffma2(acc[0][4 * c4 + 2], acc[0][4 * c4 + 3], v[kx], v[kx], wv.z, wv.w);
+            ffma2(acc[1][4 * c4 + 0], acc[1][4 * c4 + 1], v[kx + 2], v[kx + 2], wv.x, wv.y);
+            ffma2(acc[1][4 * c4 + 2], acc[1][4 * c4 + 3], v[kx + 2], v[kx + 2], wv.z, wv.w);
           }
         }
       }
@@ -100,10 +97,12 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const float* __restr
   }
 #pragma unroll
   for (int c4 = 0; c4 < 8; ++c4) {
-    *reinterpret_cast<float4*>(&outs[2 * threadIdx.x][4 * c4]) =
-        make_float4(silu_fast(acc[0][4 * c4]), silu_fast(acc[0][4 * c4 + 1]), silu_fast(acc[0][4 * c4 + 2]), silu_fast(acc[0][4 * c4 + 3]));
-    *reinterpret_cast<float4*>(&outs[2 * threadIdx.x + 1][4 * c4]) =
-        make_float4(silu_fast(acc[1][4 * c4]), silu_fast(acc[1][4 * c4 + 1]), silu_fast(acc[1][4 * c4 + 2]), silu_fast(acc[1][4 * c4 + 3]));
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      silu2(acc[px][4 * c4], acc[px][4 * c4 + 1]);
+      silu2(acc[px][4 * c4 + 2], acc[px][4 * c4 + 3]);
+      *reinterpret_cast<float4*>(&outs[2 * threadIdx.x + px][4 * c4]) = make_float4(acc[px][4 * c4], acc[px][4 * c4 + 1], acc[px][4 * c4 + 2], acc[px][4 * c4 + 3]);
+    }
   }
   __syncthreads();
   // coalesced NHWC store: the tile is 256 pixels x 32 channels = 2048 contiguous float4
@@ -206,20 +205,31 @@ __global__ void __launch_bounds__(kDwThreads, 3) depthwise_kernel(const float* _
     const int yoff = ox * C;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      float acc[V];
+      float acc[V], acc2[V];   // even / odd taps: two independent FMA chains per channel (see depthwise_tma_kernel)
 #pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] = bias[v];
+      for (int v = 0; v < V; ++v) {
+        acc[v] = bias[v];
+        acc2[v] = 0.f;
+      }
 #pragma unroll
       for (int ky = 0; ky < KS; ++ky)
 #pragma unroll
         for (int kx = 0; kx < KS; ++kx)
 #pragma unroll
-          for (int v = 0; v < V; ++v) acc[v] = fmaf(win[r * S + ky][kx][v], wr[ky * KS + kx][v], acc[v]);
+          for (int v = 0; v < V; v += 2) {
+            if (((ky * KS + kx) & 1) == 0)
+              ffma2(acc[v], acc[v + 1], win[r * S + ky][kx][v], win[r * S + ky][kx][v + 1], wr[ky * KS + kx][v], wr[ky * KS + kx][v + 1]);
+            else
+              ffma2(acc2[v], acc2[v + 1], win[r * S + ky][kx][v], win[r * S + ky][kx][v + 1], wr[ky * KS + kx][v], wr[ky * KS + kx][v + 1]);
+          }
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] += acc2[v];
       if (oy0 + r < Ho) {
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          acc[v] = silu_fast(acc[v]);
+        for (int v = 0; v < V; v += 2) {
+          silu2(acc[v], acc[v + 1]);
           pool[v] += acc[v];
+          pool[v + 1] += acc[v + 1];
         }
         stv<V>(yn + (yoff + r * WoC), acc);
       }
@@ -258,6 +268,7 @@ struct DwTmaParams {
   CUtensorMap tmap_x;
   const float* w; const float* b; float* y; float* pooled;
   int B, H, W, C, tiles_x, tiles_y, cblocks, total_items, stages;
+  int direct_pool;   // 1: squeeze sums go out as per-warp global reductions (small maps), 0: shared-memory partials + one atomic per item
 };
 
 template <int KS, int TW, int CB>
@@ -374,20 +385,33 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
       for (int c = 0; c < CPW; ++c) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          float acc[V];
+          // two partial sums per channel (even / odd taps): a single accumulator is a chain of k*k dependent FMAs, and with 8 warps
+          // per SM and 2 - 4 chains per thread the 5 x 5 kernels ran at a quarter of the FMA issue rate
+          float acc[V], acc2[V];
 #pragma unroll
-          for (int v = 0; v < V; ++v) acc[v] = bias[v];
+          for (int v = 0; v < V; ++v) {
+            acc[v] = bias[v];
+            acc2[v] = 0.f;
+          }
 #pragma unroll
           for (int ky = 0; ky < KS; ++ky)
 #pragma unroll
             for (int kx = 0; kx < KS; ++kx)
 #pragma unroll
-              for (int v = 0; v < V; ++v) acc[v] = fmaf(win[r + ky][(kx + c) % KS][v], wr[ky * KS + kx][v], acc[v]);
+              for (int v = 0; v < V; v += 2) {   // packed FFMA2: the taps of a channel pair cost one issue slot each
+                if (((ky * KS + kx) & 1) == 0)
+                  ffma2(acc[v], acc[v + 1], win[r + ky][(kx + c) % KS][v], win[r + ky][(kx + c) % KS][v + 1], wr[ky * KS + kx][v], wr[ky * KS + kx][v + 1]);
+                else
+                  ffma2(acc2[v], acc2[v + 1], win[r + ky][(kx + c) % KS][v], win[r + ky][(kx + c) % KS][v + 1], wr[ky * KS + kx][v], wr[ky * KS + kx][v + 1]);
+              }
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] += acc2[v];
           if (ch_ok && oy0 + r < p.H && ox0 + c < p.W) {
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-              acc[v] = silu_fast(acc[v]);
+            for (int v = 0; v < V; v += 2) {
+              silu2(acc[v], acc[v + 1]);
               pool[v] += acc[v];
+              pool[v + 1] += acc[v + 1];
             }
             stv<V>(yb + ((size_t)r * p.W + c) * p.C, acc);
           }
@@ -401,25 +425,37 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar(stage));
       if (++stage == stages) { stage = 0; phase ^= 1u; }
-      // squeeze sums: shuffle-reduce over the workers of this warp (lanes with equal cv), per-warp partials in SMEM (no atomics:
-      // a contended shared fp32 atomicAdd is a CAS loop and cost 4 us per item), one global atomic per channel per item
+      // squeeze sums: shuffle-reduce over the workers of this warp (lanes with equal cv), then
+      //  * small maps (<= 16 tiles per image): one fire-and-forget global reduction per channel and warp.  No barrier: with 8
+      //    consumer warps per SM a 256-thread barrier per item left the tail of every item idle (5 x 5 layers at 64 x 64 and below:
+      //    -5 ... -9 %);
+      //  * large maps: per-warp partials in shared memory, a named barrier, ONE atomic per channel and item -- 8 reductions per
+      //    channel and item would put 2048 atomics on every address of a 256 x 256 map (measured: 3 x 3 layers +35 %).
 #pragma unroll
       for (int v = 0; v < V; ++v) {
 #pragma unroll
         for (int o = CV; o < 32; o <<= 1) pool[v] += __shfl_xor_sync(0xffffffffu, pool[v], o);
       }
-      float* part = pool_s + ((it & 1u) * 8 + (t >> 5)) * CB;
-      if (lane < CV) {
+      if (p.direct_pool) {
+        if (lane < CV && cb * CB + lane * V < p.C) {
+          float* dst = p.pooled + (size_t)n * p.C + cb * CB + lane * V;
 #pragma unroll
-        for (int v = 0; v < V; ++v) part[lane * V + v] = pool[v];
-      }
-      named_bar_sync(1, kDtConsumers);
-      if (t < CB) {
-        const float* base = pool_s + (it & 1u) * 8 * CB + t;
-        float sum = 0.f;
+          for (int v = 0; v < V; ++v) atomicAdd(dst + v, pool[v]);
+        }
+      } else {
+        float* part = pool_s + ((it & 1u) * 8 + (t >> 5)) * CB;
+        if (lane < CV) {
 #pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) sum += base[w8 * CB];
-        if (cb * CB + t < p.C) atomicAdd(p.pooled + (size_t)n * p.C + cb * CB + t, sum);
+          for (int v = 0; v < V; ++v) part[lane * V + v] = pool[v];
+        }
+        named_bar_sync(1, kDtConsumers);
+        if (t < CB) {
+          const float* base = pool_s + (it & 1u) * 8 * CB + t;
+          float sum = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) sum += base[w8 * CB];
+          if (cb * CB + t < p.C) atomicAdd(p.pooled + (size_t)n * p.C + cb * CB + t, sum);
+        }
       }
     }
   }
@@ -442,6 +478,7 @@ static int launch_depthwise_tma_t(const float* x, const float* w, const float* b
   p.tiles_x = (H + TW - 1) / TW;
   p.tiles_y = (H + kDtTH - 1) / kDtTH;
   p.cblocks = (C + CB - 1) / CB;
+  p.direct_pool = p.tiles_x * p.tiles_y <= 16 ? 1 : 0;
   const long long items = (long long)p.cblocks * B * p.tiles_x * p.tiles_y;
   AQ_REQUIRE(items < (1ll << 31), AQ_ERR_BAD_SHAPE, "depthwise: too many tiles");
   p.total_items = (int)items;

@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
         }
         if (p.epi == kPwSilu || p.epi == kPwSiluPool) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = pw_silu(f[i]);
+          for (int i = 0; i < 16; i += 2) silu2(f[i], f[i + 1]);
         }
         if (p.epi == kPwSiluPool) {
           // column sums over this warp's 32 rows (all inside one image: hw % 128 == 0), one atomic per column
@@ -589,7 +589,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwThreads, 1) point
         }
         if (p.epi == kPwSilu || p.epi == kPwSiluPool) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = pw_silu(f[i]);
+          for (int i = 0; i < 16; i += 2) silu2(f[i], f[i + 1]);
         }
         if (p.epi == kPwSiluPool) {
 #pragma unroll
