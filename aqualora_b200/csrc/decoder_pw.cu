@@ -11,12 +11,13 @@
 // pack time; activations are split by 4 converter warps inside shared memory (in place for the hi part), which is also where the
 // squeeze-excitation scale of the project convolutions is applied.
 //
-// One CTA per SM, persistent over (128-row tile, N tile <= 224) work items, 704 threads:
+// One CTA per SM, persistent over (128-row tile, N tile <= 224) work items, 832 threads:
 //   warps 0-15   epilogue   TMEM lane quadrant = warp % 4, 16-column pieces pc = warp / 4 (mod 4):
 //                           TMEM -> +bias -> [SiLU] [+ residual] -> staging tile (box of Y's tensor map) -> one bulk-tensor store | SiLU + pooled sums
-//   warps 16-19  converter  raw fp32 A tile (TMA, 128B swizzle) -> x * se -> hi (in place) / lo (second tile)
-//   warp 20      TMA producer (A raw, W_hi, W_lo per 32-wide k chunk)
-//   warp 21      TMEM allocator + MMA issuer (3 MMAs per 8-wide k step)
+//   warps 16-23  converter  raw fp32 A tile (TMA, 128B swizzle) -> x * se -> hi (in place) / lo (second tile); 8 warps since round 2:
+//                           with 4 the K-heavy, narrow project layers were bound by this stage
+//   warp 24      TMA producer (A raw, W_hi, W_lo per 32-wide k chunk)
+//   warp 25      TMEM allocator + MMA issuer (3 MMAs per 8-wide k step)
 // The expand convolutions (128 x 96 ... 240 outputs from a 16 ... 40-deep product) are bound by the epilogue's instruction issue
 // (ncu: ~0.75 instructions per output element, the 8 epilogue warps of the previous version busy 90 % of the time, tensor pipe
 // 4 % active), hence 16 epilogue warps -- 4 per scheduler -- an SFU SiLU and an accumulator ring of up to 8 tiles in TMEM.
@@ -28,9 +29,10 @@
 
 namespace aq {
 
-constexpr int kPwThreads = 704;
+constexpr int kPwThreads = 832;
 constexpr int kPwEpiWarps = 16;
-constexpr int kPwConvWarp0 = 16, kPwProducerWarp = 20, kPwMmaWarp = 21;
+constexpr int kPwConvWarp0 = 16, kPwConvWarps = 8, kPwProducerWarp = 24, kPwMmaWarp = 25;
+constexpr int kPwConvThreads = kPwConvWarps * 32, kPwConvIters = 1024 / kPwConvThreads;   // 1024 16-byte chunks per 128 x 32 fp32 tile
 constexpr int kPwMaxBN = 224;                  // 2 pipeline stages + 16 epilogue staging buffers must fit in 227 KiB
 constexpr int kPwBM = 128;
 constexpr int kPwKC = 32;                      // fp32 elements per k chunk = one 128-byte swizzle row
@@ -51,6 +53,7 @@ struct PwTcParams {
   int N, K, hw, epi;
   int BN, num_n_tiles, num_m_tiles, num_kc, stages;
   int w_resident;   // 1: all W chunks (hi + lo) stay in SMEM for the whole kernel (single N tile, small K): only A streams
+  int tile_par;     // 1: narrow outputs (<= 3 pieces): the four epilogue warps of a TMEM quadrant take WHOLE tiles in turn (single-CTA kernel)
 };
 
 // SiLU with the SFU exponential and reciprocal (relative error ~1e-6, far inside the decoder's 1e-4 logit tolerance)
@@ -106,12 +109,12 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(conv_bar(s), 4);
+      mbar_init(conv_bar(s), kPwConvWarps);
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 8; ++b) {
       mbar_init(acc_full_bar(b), 1);
-      mbar_init(acc_empty_bar(b), kPwEpiWarps);
+      mbar_init(acc_empty_bar(b), p.tile_par ? 4 : kPwEpiWarps);
     }
     mbar_init(w_full_bar, 1);
     fence_mbar_init();
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
     }
   } else if (warp >= kPwConvWarp0) {
     // =========================== converter warps: A -> (A * se) hi / lo ===========================
-    const int t = threadIdx.x - kPwConvWarp0 * 32;   // 0..127
+    const int t = threadIdx.x - kPwConvWarp0 * 32;   // 0 .. kPwConvThreads - 1
     const int cphys = t & 7;                  // 16-byte chunk inside the 128-byte row (physical, swizzled)
     const int rlow = (t >> 3) & 7;            // row & 7 of every row this thread touches (rows t/8 + 16 j)
     const int clog = cphys ^ rlow;            // logical chunk = k offset / 4 inside the chunk
@@ -218,11 +221,11 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
         // columns at or past K are never read by the MMAs (the k-step count stops at K): for the 16 / 24 / 40-deep expand
         // layers that is up to half of the chunk's shared-memory traffic (the LSU data pipe was 65 % busy there, ncu)
         if (k < p.K) {
-        float4 v[8];
+        float4 v[kPwConvIters];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(hi + (t + 128 * j) * 16);
+        for (int j = 0; j < kPwConvIters; ++j) v[j] = *reinterpret_cast<const float4*>(hi + (t + kPwConvThreads * j) * 16);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < kPwConvIters; ++j) {
           float x[4] = {v[j].x * sc.x, v[j].y * sc.y, v[j].z * sc.z, v[j].w * sc.w};
           float h[4], l[4];
 #pragma unroll
@@ -230,8 +233,8 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
             h[e] = __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u);
             l[e] = x[e] - h[e];
           }
-          *reinterpret_cast<float4*>(hi + (t + 128 * j) * 16) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(lo + (t + 128 * j) * 16) = make_float4(l[0], l[1], l[2], l[3]);
+          *reinterpret_cast<float4*>(hi + (t + kPwConvThreads * j) * 16) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(lo + (t + kPwConvThreads * j) * 16) = make_float4(l[0], l[1], l[2], l[3]);
         }
         }
         fence_proxy_async_smem();
@@ -243,25 +246,32 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
   } else {
     // =========================== epilogue warps ===========================
     const int q = warp & 3;        // TMEM lane quadrant
-    const int res = warp >> 2;     // this warp takes the 16-column pieces pc = res, res + 4, ...
+    const int res = warp >> 2;     // this warp takes the 16-column pieces pc = res, res + 4, ... of every tile -- or, for narrow
+                                   // outputs (tile_par: the 16 / 24 / 40-channel project layers, where 1 - 3 pieces would leave 12 - 4
+                                   // of the 16 epilogue warps idle on the layers with the most rows), every 4th tile as a whole.
+                                   // The accumulator ring then has 8 slots (a multiple of 4), so a slot always belongs to the
+                                   // same warp group and its full / empty phases are observed in order.
+    const bool tile_par = p.tile_par != 0;
+    const int pc_first = tile_par ? 0 : res, pc_step = tile_par ? 1 : 4;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint8_t* stg = smem_gen + stg_off + warp * kPwStgWarp;
     const uint32_t stg_u32 = smem_base + stg_off + warp * kPwStgWarp;
     uint32_t acc_iter = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++acc_iter) {
+      if (tile_par && (int)(acc_iter & 3u) != res) continue;
       const long long m0 = (long long)(item / p.num_n_tiles) * kPwBM;
       const int n0 = (item % p.num_n_tiles) * BN;
       const uint32_t buf = acc_iter % nacc;
       const long long row_base = m0 + q * 32;
       const int pieces = min(BN, p.N - n0 + 15) >> 4;                  // 16-column pieces that hold at least one valid column
-      const int nmine = pieces > res ? (pieces - res + 3) >> 2 : 0;    // this warp's pieces
+      const int nmine = tile_par ? pieces : (pieces > res ? (pieces - res + 3) >> 2 : 0);    // this warp's pieces
       float4 rs[4];
       if (p.epi == kPwResidual && nmine > 0) {
         // residual of the first piece (this lane's row, 64 bytes): requested before the accumulator wait so its DRAM latency
         // hides behind the MMAs
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
-          const int c = n0 + res * 16 + i4 * 4;
+          const int c = n0 + pc_first * 16 + i4 * 4;
           rs[i4] = (row_base + lane < p.M && c < p.N) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)(row_base + lane) * p.N + c))
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -275,7 +285,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
         continue;
       }
       for (int g = 0; g < nmine; ++g) {
-        const int pc = res + 4 * g;
+        const int pc = pc_first + pc_step * g;
         const int c0 = n0 + pc * 16;
         uint32_t tr[16];
         tmem_ld_32x16(tmem_base + lane_base + buf * (uint32_t)BN + pc * 16, tr);
@@ -407,7 +417,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwThreads, 1) point
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(conv_bar(s), 8);
+      mbar_init(conv_bar(s), 2 * kPwConvWarps);
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 8; ++b) {
@@ -501,11 +511,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwThreads, 1) point
         uint8_t* hi = smem_gen + (a_hi(stage) - smem_base);
         uint8_t* lo = smem_gen + (a_lo(stage) - smem_base);
         if (k < p.K) {
-          float4 v[8];
+          float4 v[kPwConvIters];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(hi + (t + 128 * j) * 16);
+          for (int j = 0; j < kPwConvIters; ++j) v[j] = *reinterpret_cast<const float4*>(hi + (t + kPwConvThreads * j) * 16);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < kPwConvIters; ++j) {
             float x[4] = {v[j].x * sc.x, v[j].y * sc.y, v[j].z * sc.z, v[j].w * sc.w};
             float h[4], l[4];
 #pragma unroll
@@ -513,8 +523,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwThreads, 1) point
               h[e] = __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u);
               l[e] = x[e] - h[e];
             }
-            *reinterpret_cast<float4*>(hi + (t + 128 * j) * 16) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(lo + (t + 128 * j) * 16) = make_float4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<float4*>(hi + (t + kPwConvThreads * j) * 16) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(lo + (t + kPwConvThreads * j) * 16) = make_float4(l[0], l[1], l[2], l[3]);
           }
         }
         fence_proxy_async_smem();
@@ -697,6 +707,7 @@ int launch_pointwise_tc(const PwTcArgs& a, cudaStream_t st) {
   const int w_tile_bytes = 2 * p.BN * 128;                                   // hi + lo of one k chunk
   const int fixed = kPwEpiWarps * kPwStgWarp + 512;
   p.w_resident = (p.num_n_tiles == 1 && p.num_kc * w_tile_bytes <= 96 * 1024) ? 1 : 0;
+  p.tile_par = (p.BN <= 48 && a.epi != kPwSiluPool) ? 1 : 0;   // 512 / BN >= 10 -> an 8-slot accumulator ring
   const int sms = sm_count();
   if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
   if (!p.w_resident && p.num_m_tiles >= 2 && pw_pair_enabled()) {
