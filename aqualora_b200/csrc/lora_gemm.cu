@@ -19,6 +19,7 @@
 //   warp 8     TMA producer      both CTAs: own A rows, own half of W / Dn / Up; bytes signalled on the LEADER's barrier
 //   warp 9     TMEM allocator; in the leader CTA one thread issues every tcgen05.mma of the pair
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "aq_ptx.cuh"
@@ -109,11 +110,13 @@ struct LoraGemmParams {
   LoraProblem prob[NP];
 };
 
-template <int BN>
+// DUAL: a pipeline stage carries the W tiles of TWO column tiles, so that one pass over A feeds both accumulators (K-heavy shapes:
+// the kernel is bound by operand traffic L2 -> SM there, and A is the larger part of it; see launch_bn)
+template <int BN, bool DUAL = false>
 struct SmemLayout {
   static constexpr int kNC = BN / 2;                         // accumulator columns per epilogue warp
   static constexpr int kWHalfBytes = (BN / 2) * kBlockK * 2;
-  static constexpr int kStageBytes = kATileBytes + kWHalfBytes + kDnHalfBytes;
+  static constexpr int kStageBytes = kATileBytes + (DUAL ? 2 : 1) * kWHalfBytes + kDnHalfBytes;
   // Output staging for the TMA-store epilogue: each epilogue warp owns two buffers of 32 rows x kPassCols bf16 in the layout of
   // the Y tensor map's box; a pass = convert kPassCols accumulator columns, st.shared, fence, one cp.async.bulk.tensor store.
   // 80-byte rows (BN = 160) are conflict-free as they are (8 consecutive lanes -> 8 distinct 16-byte bank groups); 64-byte rows
@@ -165,9 +168,9 @@ __device__ __forceinline__ void warp_colsum(float (&v)[N], int lane) {
 // footprint: ncu attributes a visible share of the epilogue warps' compute stalls to instruction fetch), and the projection /
 // launch parameters the epilogue loops need are read into registers once per item (a constant-bank read behind a uniform branch
 // inside an unrolled loop is a dependent LDCU -> compare -> branch chain per 8 columns).
-template <int BN, int NP, int MODE>
+template <int BN, int NP, int MODE, bool DUAL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_gemm_kernel(const __grid_constant__ LoraGemmParams<NP> p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, DUAL>;
   constexpr int kStages = L::kStages;
   constexpr int NC = L::kNC;
   extern __shared__ uint8_t smem_raw[];
@@ -194,7 +197,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
 
   auto a_tile = [&](int s) { return smem_base + s * L::kStageBytes; };
   auto w_tile = [&](int s) { return smem_base + s * L::kStageBytes + kATileBytes; };
-  auto dn_tile = [&](int s) { return smem_base + s * L::kStageBytes + kATileBytes + L::kWHalfBytes; };
+  auto w2_tile = [&](int s) { return smem_base + s * L::kStageBytes + kATileBytes + L::kWHalfBytes; };   // DUAL only
+  auto dn_tile = [&](int s) { return smem_base + s * L::kStageBytes + kATileBytes + (DUAL ? 2 : 1) * L::kWHalfBytes; };
   const uint32_t hs_tile = smem_base + L::kHsOff;
 
   if (warp == kProducerWarp && lane == 0) {
@@ -264,6 +268,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     };
+    // DUAL: one pass over A for the column tiles at n0 and n1
+    auto k_loads_dual = [&](const LoraProblem& q, int m0, int n0, int n1, bool first) {
+      const uint32_t bytes = 2u * (kATileBytes + 2u * L::kWHalfBytes + (first ? kDnHalfBytes : 0));
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t fb = mapa_shared(full_bar(stage), 0);
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), bytes);
+          tma_load_2d_pair(a_tile(stage), &p.tmap_a, fb, kb * kBlockK, m0);
+          tma_load_2d_pair(w_tile(stage), &q.tmap_w, fb, kb * kBlockK, n0 + w_row_off);
+          tma_load_2d_pair(w2_tile(stage), &q.tmap_w, fb, kb * kBlockK, n1 + w_row_off);
+          if (first) tma_load_2d_pair(dn_tile(stage), &q.tmap_dn, fb, kb * kBlockK, dn_row_off);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    };
     auto up_load = [&](const LoraProblem& q, int n0) {
       // the rank-r extra k-block: only the Up tile travels; its A operand (Hs) is produced on chip
       mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -287,6 +308,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
       const int nt_end = min(nt_begin + q.group_size, q.num_n_tiles);
       const bool fused = p.has_lora && p.has_main;
       AQ_TRACE(trace_iter, 0);
+      if constexpr (DUAL) {
+        // tiles in pairs (the host guarantees an even tile count per group, a main product and no rank-chunk continuation)
+        for (int nt = nt_begin; nt < nt_end; nt += 2) {
+          k_loads_dual(q, m0, nt * BN, (nt + 1) * BN, nt == nt_begin && p.has_lora);
+          if (fused) {
+            up_load(q, nt * BN);
+            up_load(q, (nt + 1) * BN);
+          }
+        }
+      } else
       if (fused && nt_end - nt_begin >= 2 && !p.skip_base) {
         // deferred order: the Hs.Up k-blocks of the first two tiles follow the second tile's main loop
         k_loads(q, m0, nt_begin * BN, true);
@@ -349,6 +380,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       };
+      // DUAL: both column tiles (and H on the first pair) from the same A stage
+      auto k_mmas_dual = [&](uint32_t acc_a, uint32_t acc_b, bool first) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = desc(a_tile(stage));
+            const uint64_t wd = desc(w_tile(stage));
+            const uint64_t w2d = desc(w2_tile(stage));
+            const uint64_t dd = desc(dn_tile(stage));
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint32_t acc_flag = (kb | k) != 0 ? 1u : 0u;
+              umma_f16_pair(acc_a, ad + 2 * k, wd + 2 * k, idesc_main, acc_flag);
+              umma_f16_pair(acc_b, ad + 2 * k, w2d + 2 * k, idesc_main, acc_flag);
+              if (first) umma_f16_pair(tmem_h, ad + 2 * k, dd + 2 * k, idesc_h, acc_flag);
+            }
+            umma_commit_pair(empty_bar(stage), kBothCtas);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      };
       using TrueC = BoolC<true>;
       using FalseC = BoolC<false>;
       const bool load_w = p.has_main && !p.skip_base;
@@ -378,6 +432,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) lora_ge
         const int nt_begin = grp * q.group_size;
         const int nt_end = min(nt_begin + q.group_size, q.num_n_tiles);
         const bool fused = p.has_lora && p.has_main;
+        if constexpr (DUAL) {
+          for (int nt = nt_begin; nt < nt_end; nt += 2) {
+            const bool first = nt == nt_begin && p.has_lora;
+            const uint32_t it0 = acc_iter, it1 = acc_iter + 1;
+            const uint32_t acc0 = tmem_base + (it0 & 1u) * BN, acc1 = tmem_base + (it1 & 1u) * BN;
+            acquire_acc(it0);
+            acquire_acc(it1);
+            k_mmas_dual(acc0, acc1, first);
+            if (first) {
+              commit(h_full_bar);
+              mbar_wait(hs_ready_bar, item_iter & 1u);
+              tc_fence_after();
+            }
+            if (fused) up_mmas(acc0);
+            commit(acc_full_bar(it0 & 1u));
+            if (fused) up_mmas(acc1);
+            commit(acc_full_bar(it1 & 1u));
+            acc_iter += 2;
+          }
+        } else
         if (fused && nt_end - nt_begin >= 2 && !p.skip_base) {
           const uint32_t it0 = acc_iter, it1 = acc_iter + 1;
           const uint32_t acc0 = tmem_base + (it0 & 1u) * BN, acc1 = tmem_base + (it1 & 1u) * BN;
@@ -710,9 +784,9 @@ static int pick_group(int num_n_tiles, int num_m_pairs, int K, int BN, bool has_
 }
 
 // `probs` are projections of the same A (same M, K, r, scale, tokens, mode); args[0] carries the shared operands.
-template <int BN, int NP, int MODE>
+template <int BN, int NP, int MODE, bool DUAL = false>
 static int launch_bn(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, DUAL>;
   const LoraGemmArgs& a = probs[0];
   static thread_local LoraGemmParams<NP> p;   // 14 KiB for NP = 32: kept off the stack
   memset(&p, 0, sizeof(p));
@@ -783,6 +857,10 @@ static int launch_bn(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) 
     if (a.force_group > 0) q.group_size = a.force_group;
     else if (nprob > 1) q.group_size = q.num_n_tiles < 2 ? q.num_n_tiles : 2;   // many projections fill the waves; 2 tiles hide the Hs bubble
     else q.group_size = pick_group(q.num_n_tiles, p.num_m_pairs, a.K, BN, has_lora != 0, slots);
+    if (DUAL) {
+      q.group_size = (q.group_size + 1) & ~1;   // tiles are processed in pairs
+      if (q.group_size > q.num_n_tiles) q.group_size = q.num_n_tiles;
+    }
     q.num_groups = (q.num_n_tiles + q.group_size - 1) / q.group_size;
     q.item_begin = (int)items;
     items += (long long)q.num_groups * p.num_m_pairs;
@@ -791,11 +869,17 @@ static int launch_bn(const LoraGemmArgs* probs, int nprob, cudaStream_t stream) 
   p.total_items = (int)items;
   const int grid = 2 * (int)(items < slots ? items : slots);
 
-  AQ_OPT_IN_SMEM((lora_gemm_kernel<BN, NP, MODE>), L::kTotal);
+  AQ_OPT_IN_SMEM((lora_gemm_kernel<BN, NP, MODE, DUAL>), L::kTotal);
   PdlLaunch launch(dim3(grid), dim3(kThreads), L::kTotal, stream);
-  AQ_CHECK_CUDA(cudaLaunchKernelEx(&launch.cfg, lora_gemm_kernel<BN, NP, MODE>, p));
+  AQ_CHECK_CUDA(cudaLaunchKernelEx(&launch.cfg, lora_gemm_kernel<BN, NP, MODE, DUAL>, p));
   AQ_LAUNCHED();
   return AQ_OK;
+}
+
+// AQ_GEMM_DUAL=0 disables the two-tiles-per-A-pass mode (A/B measurements)
+static bool dual_enabled() {
+  static const bool on = [] { const char* e = getenv("AQ_GEMM_DUAL"); return e == nullptr || e[0] != '0'; }();
+  return on;
 }
 
 static int pick_bn(int N) {
@@ -843,7 +927,14 @@ int launch_lora_gemm(const LoraGemmArgs& a, cudaStream_t stream) {
   switch (bn) {
     case 64: return a.mode ? launch_bn<64, 1, 1>(&a, 1, stream) : launch_bn<64, 1, 0>(&a, 1, stream);
     case 128: return a.mode ? launch_bn<128, 1, 1>(&a, 1, stream) : launch_bn<128, 1, 0>(&a, 1, stream);
-    case 160: return a.mode ? launch_bn<160, 1, 1>(&a, 1, stream) : launch_bn<160, 1, 0>(&a, 1, stream);
+    case 160:
+      // K-heavy projections with an even number of 160-column tiles (N = 320 / 640 / 1280 against K >= 1024: the feed-forward output
+      // projections, the dX of the feed-forward input projections): one pass over A feeds two column tiles -- 40 KB instead of 56 KB of
+      // operands per pair of k-blocks and CTA.  The price: both accumulators belong to one pass, so the tile epilogues no longer
+      // overlap the next pass; with >= 16 k-blocks per pass that is a few per cent against -29 % of L2 -> SM traffic.
+      if (dual_enabled() && a.has_main && !a.skip_base && a.K >= 1024 && ((a.N + 159) / 160) % 2 == 0 && (a.force_group == 0 || a.force_group % 2 == 0))
+        return a.mode ? launch_bn<160, 1, 1, true>(&a, 1, stream) : launch_bn<160, 1, 0, true>(&a, 1, stream);
+      return a.mode ? launch_bn<160, 1, 1>(&a, 1, stream) : launch_bn<160, 1, 0>(&a, 1, stream);
     case 192: return a.mode ? launch_bn<192, 1, 1>(&a, 1, stream) : launch_bn<192, 1, 0>(&a, 1, stream);
     default: return fail(AQ_ERR_BAD_SHAPE, "lora_gemm: unsupported column tile %d", bn);
   }
