@@ -267,20 +267,21 @@ constexpr int kDtConsumers = 256, kDtThreads = 288, kDtTH = 8, kDtCB = 32;
 struct DwTmaParams {
   CUtensorMap tmap_x;
   const float* w; const float* b; float* y; float* pooled;
-  int B, H, W, C, tiles_x, tiles_y, cblocks, total_items, stages;
+  int B, H, W, C, Ho, Wo, tiles_x, tiles_y, cblocks, total_items, stages;
   int direct_pool;   // 1: squeeze sums go out as per-warp global reductions (small maps), 0: shared-memory partials + one atomic per item
 };
 
-template <int KS, int TW, int CB>
+template <int KS, int TW, int CB, int S>
 __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __grid_constant__ DwTmaParams p) {
-  constexpr int P = (KS - 1) / 2, THin = kDtTH + KS - 1, TWin = TW + KS - 1;
+  // S = stride (1 or 2): output tile kDtTH x TW, input box ((kDtTH - 1) S + k) x ((TW - 1) S + k); p.H / p.W = INPUT size, p.Ho / p.Wo = output size
+  constexpr int P = (KS - 1) / 2, THin = (kDtTH - 1) * S + KS, TWin = (TW - 1) * S + KS;
   constexpr int V = KS == 3 ? 4 : 2;
   constexpr int CV = CB / V;                  // channel vectors per block
   constexpr int WORKERS = kDtConsumers / CV;     // 32 (k = 3) or 16 (k = 5)
   constexpr int WROWS = kDtTH / 2;               // 4 row pairs
   constexpr int WCOLS = WORKERS / WROWS;         // 8 or 4
   constexpr int CPW = TW / WCOLS;                // output columns per worker
-  constexpr int R = 2, NR = R + KS - 1;
+  constexpr int R = 2, NR = (R - 1) * S + KS;
   constexpr uint32_t kTileBytes = THin * TWin * CB * 4;
   constexpr uint32_t kTileStride = (kTileBytes + 127u) & ~127u;
   static_assert(CPW >= 1 && TW % WCOLS == 0, "tile width must split evenly over the workers");
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
       mbar_wait(empty_bar(stage), phase ^ 1u);
       if (elect_one()) {
         mbar_arrive_expect_tx(full_bar(stage), kTileBytes);
-        tma_load_4d(smem_base + (uint32_t)stage * kTileStride, &p.tmap_x, full_bar(stage), cb * CB, tx * TW - P, ty * kDtTH - P, n);
+        tma_load_4d(smem_base + (uint32_t)stage * kTileStride, &p.tmap_x, full_bar(stage), cb * CB, tx * TW * S - P, ty * kDtTH * S - P, n);
       }
       __syncwarp();
       if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -371,16 +372,17 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
         }
       };
       // window slot of logical column kx at unrolled output column c: (kx + c) % KS -- nothing is ever shifted
+      // input window of the worker: rows r0 S ..., columns (cbeg + c) S + kx; logical input column j lives in slot j % KS
       float win[NR][KS][V];
 #pragma unroll
       for (int kx = 0; kx < KS; ++kx)
 #pragma unroll
-        for (int r = 0; r < NR; ++r) lds(r0 + r, cbeg + kx, win[r][kx]);
+        for (int r = 0; r < NR; ++r) lds(r0 * S + r, cbeg * S + kx, win[r][kx]);
       float pool[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) pool[v] = 0.f;
       const int oy0 = ty * kDtTH + r0, ox0 = tx * TW + cbeg;
-      float* yb = p.y + (((size_t)n * p.H + oy0) * p.W + ox0) * p.C + c0;
+      float* yb = p.y + (((size_t)n * p.Ho + oy0) * p.Wo + ox0) * p.C + c0;
 #pragma unroll
       for (int c = 0; c < CPW; ++c) {
 #pragma unroll
@@ -400,25 +402,28 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
 #pragma unroll
               for (int v = 0; v < V; v += 2) {   // packed FFMA2: the taps of a channel pair cost one issue slot each
                 if (((ky * KS + kx) & 1) == 0)
-                  ffma2(acc[v], acc[v + 1], win[r + ky][(kx + c) % KS][v], win[r + ky][(kx + c) % KS][v + 1], wr[ky * KS + kx][v], wr[ky * KS + kx][v + 1]);
+                  ffma2(acc[v], acc[v + 1], win[r * S + ky][(kx + c * S) % KS][v], win[r * S + ky][(kx + c * S) % KS][v + 1], wr[ky * KS + kx][v], wr[ky * KS + kx][v + 1]);
                 else
-                  ffma2(acc2[v], acc2[v + 1], win[r + ky][(kx + c) % KS][v], win[r + ky][(kx + c) % KS][v + 1], wr[ky * KS + kx][v], wr[ky * KS + kx][v + 1]);
+                  ffma2(acc2[v], acc2[v + 1], win[r * S + ky][(kx + c * S) % KS][v], win[r * S + ky][(kx + c * S) % KS][v + 1], wr[ky * KS + kx][v], wr[ky * KS + kx][v + 1]);
               }
 #pragma unroll
           for (int v = 0; v < V; ++v) acc[v] += acc2[v];
-          if (ch_ok && oy0 + r < p.H && ox0 + c < p.W) {
+          if (ch_ok && oy0 + r < p.Ho && ox0 + c < p.Wo) {
 #pragma unroll
             for (int v = 0; v < V; v += 2) {
               silu2(acc[v], acc[v + 1]);
               pool[v] += acc[v];
               pool[v + 1] += acc[v + 1];
             }
-            stv<V>(yb + ((size_t)r * p.W + c) * p.C, acc);
+            stv<V>(yb + ((size_t)r * p.Wo + c) * p.C, acc);
           }
         }
         if (c + 1 < CPW) {
+          // the S input columns the next output column adds: logical columns c S + KS ... c S + KS + S - 1
 #pragma unroll
-          for (int r = 0; r < NR; ++r) lds(r0 + r, cbeg + c + KS, win[r][c % KS]);
+          for (int s2 = 0; s2 < S; ++s2)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) lds(r0 * S + r, cbeg * S + c * S + KS + s2, win[r][(c * S + KS + s2) % KS]);
         }
       }
       // this thread is done with the tile: hand the stage back to the producer
@@ -461,10 +466,11 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
   }
 }
 
-template <int KS, int TW, int CB>
+template <int KS, int TW, int CB, int S = 1>
 static int launch_depthwise_tma_t(const float* x, const float* w, const float* b, float* y, float* pooled, int B, int H, int C,
                                   cudaStream_t st) {
-  constexpr int THin = kDtTH + KS - 1, TWin = TW + KS - 1;
+  constexpr int THin = (kDtTH - 1) * S + KS, TWin = (TW - 1) * S + KS;
+  const int Ho = (H + 2 * ((KS - 1) / 2) - KS) / S + 1;
   constexpr int kTileStride = (THin * TWin * CB * 4 + 127) & ~127;
   DwTmaParams p;
   memset(&p, 0, sizeof(p));
@@ -474,9 +480,9 @@ static int launch_depthwise_tma_t(const float* x, const float* w, const float* b
   int rc = make_tmap(&p.tmap_x, x, 4, 4, dims, str, box, kSwzNone);
   if (rc) return rc;
   p.w = w; p.b = b; p.y = y; p.pooled = pooled;
-  p.B = B; p.H = H; p.W = H; p.C = C;
-  p.tiles_x = (H + TW - 1) / TW;
-  p.tiles_y = (H + kDtTH - 1) / kDtTH;
+  p.B = B; p.H = H; p.W = H; p.C = C; p.Ho = Ho; p.Wo = Ho;
+  p.tiles_x = (Ho + TW - 1) / TW;
+  p.tiles_y = (Ho + kDtTH - 1) / kDtTH;
   p.cblocks = (C + CB - 1) / CB;
   p.direct_pool = p.tiles_x * p.tiles_y <= 16 ? 1 : 0;
   const long long items = (long long)p.cblocks * B * p.tiles_x * p.tiles_y;
@@ -489,8 +495,8 @@ static int launch_depthwise_tma_t(const float* x, const float* w, const float* b
   const int sms = sm_count();
   if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
   const int grid = (int)(items < sms ? items : sms);
-  AQ_OPT_IN_SMEM((depthwise_tma_kernel<KS, TW, CB>), 227 * 1024);
-  depthwise_tma_kernel<KS, TW, CB><<<grid, kDtThreads, smem, st>>>(p);
+  AQ_OPT_IN_SMEM((depthwise_tma_kernel<KS, TW, CB, S>), 227 * 1024);
+  depthwise_tma_kernel<KS, TW, CB, S><<<grid, kDtThreads, smem, st>>>(p);
   AQ_LAUNCHED();
   return AQ_OK;
 }
@@ -670,11 +676,23 @@ static bool fused_enabled(int cin, int cexp, int k, int stride) {
   return cin == 16 && cexp == 96 && k == 3 && stride == 2;
 }
 
+// AQ_DW_S2_TMA=0 keeps the stride-2 layers on the register-window kernel (A/B measurements)
+static bool dw_s2_tma_enabled() {
+  static const bool on = [] { const char* e = getenv("AQ_DW_S2_TMA"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 static int launch_depthwise(const float* x, const float* w, const float* b, float* y, float* pooled, int B, int H, int C, int k,
                             int stride, int Ho, cudaStream_t st) {
   if (stride == 1 && C >= kDtCB && C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
     if (k == 3) return Ho >= 32 ? launch_depthwise_tma_t<3, 32, kDtCB>(x, w, b, y, pooled, B, H, C, st) : launch_depthwise_tma_t<3, 16, kDtCB>(x, w, b, y, pooled, B, H, C, st);
     if (k == 5) return Ho >= 32 ? launch_depthwise_tma_t<5, 32, kDtCB>(x, w, b, y, pooled, B, H, C, st) : launch_depthwise_tma_t<5, 16, kDtCB>(x, w, b, y, pooled, B, H, C, st);
+  }
+  // stride 2 through the same TMA-staged kernel (input boxes of 17 x 33 / 19 x 35 pixels for 8 x 16 outputs): the register-window
+  // kernel below kept ~24 KiB of loads in flight per SM and ran the 5 x 5 stride-2 layers at 2.3 - 2.8 TB/s
+  if (stride == 2 && C >= kDtCB && C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && dw_s2_tma_enabled()) {
+    if (k == 3) return launch_depthwise_tma_t<3, 16, kDtCB, 2>(x, w, b, y, pooled, B, H, C, st);
+    if (k == 5) return launch_depthwise_tma_t<5, 16, kDtCB, 2>(x, w, b, y, pooled, B, H, C, st);
   }
   // the 16-channel depthwise of the second stage-1 block (256 x 256 maps): same kernel with a 16-channel block
   if (stride == 1 && C == 16 && k == 3 && Ho >= 32 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0)
