@@ -676,6 +676,11 @@ static bool fused_enabled(int cin, int cexp, int k, int stride) {
   return cin == 16 && cexp == 96 && k == 3 && stride == 2;
 }
 
+static bool dw_tw16() {
+  static const bool on = [] { const char* e = getenv("AQ_DW_TW16"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+
 // AQ_DW_S2_TMA=0 keeps the stride-2 layers on the register-window kernel (A/B measurements)
 static bool dw_s2_tma_enabled() {
   static const bool on = [] { const char* e = getenv("AQ_DW_S2_TMA"); return e == nullptr || e[0] != '0'; }();
@@ -685,8 +690,9 @@ static bool dw_s2_tma_enabled() {
 static int launch_depthwise(const float* x, const float* w, const float* b, float* y, float* pooled, int B, int H, int C, int k,
                             int stride, int Ho, cudaStream_t st) {
   if (stride == 1 && C >= kDtCB && C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
-    if (k == 3) return Ho >= 32 ? launch_depthwise_tma_t<3, 32, kDtCB>(x, w, b, y, pooled, B, H, C, st) : launch_depthwise_tma_t<3, 16, kDtCB>(x, w, b, y, pooled, B, H, C, st);
-    if (k == 5) return Ho >= 32 ? launch_depthwise_tma_t<5, 32, kDtCB>(x, w, b, y, pooled, B, H, C, st) : launch_depthwise_tma_t<5, 16, kDtCB>(x, w, b, y, pooled, B, H, C, st);
+    const bool wide = Ho >= 32 && !dw_tw16();
+    if (k == 3) return wide ? launch_depthwise_tma_t<3, 32, kDtCB>(x, w, b, y, pooled, B, H, C, st) : launch_depthwise_tma_t<3, 16, kDtCB>(x, w, b, y, pooled, B, H, C, st);
+    if (k == 5) return wide ? launch_depthwise_tma_t<5, 32, kDtCB>(x, w, b, y, pooled, B, H, C, st) : launch_depthwise_tma_t<5, 16, kDtCB>(x, w, b, y, pooled, B, H, C, st);
   }
   // stride 2 through the same TMA-staged kernel (input boxes of 17 x 33 / 19 x 35 pixels for 8 x 16 outputs): the register-window
   // kernel below kept ~24 KiB of loads in flight per SM and ran the 5 x 5 stride-2 layers at 2.3 - 2.8 TB/s
