@@ -43,26 +43,38 @@ __device__ __forceinline__ float silu_fast(float v) {
 // ---------------------------------------------------------------------------------------------------------------
 // stem: [B, 3, 512, 512] NCHW -> [B, 256, 256, 32] NHWC.  w [27][32] ((ky, kx, ci) major), b [32]
 // ---------------------------------------------------------------------------------------------------------------
-// One thread = TWO adjacent output pixels x 32 channels: the 27 x 32 weights come from shared memory once per pixel pair
-// (216 LDS.128 for 1728 FMAs; one pixel per thread was bound by instruction issue and the LSU pipe at 75 % each, ncu
-// profiles/r02_ncu_decoder_kernels_v10.txt), the 3 x 5 input window per channel is one aligned float4 + one scalar per row.
+// One thread = FOUR adjacent output pixels x 16 channels (warps 0-1: channels 0-15, warps 2-3: channels 16-31).  The kernel is bound
+// by the LSU pipe, not by FMA issue: every weight vector is a warp-wide LDS.128 broadcast that still occupies the pipe for 4 cycles
+// (32 lanes x 16 bytes of register write-back).  One pixel x 32 channels per thread: 216 LDS per pixel (LSU and issue both at 75 %,
+// ncu profiles/r02_ncu_decoder_kernels_v10.txt); two pixels: 108 per pixel (394 -> 289 us per 64 images); four pixels x 16
+// channels: 27 LDS per pixel and channel half = 54 per pixel, the same 64 accumulators per thread.  The 3 x 9 input window per
+// channel is two aligned float4 + one scalar per row (both channel halves load it: L1 hits).
 constexpr int kStemThreads = 128;
-constexpr int kStemTile = 2 * kStemThreads;   // output pixels (one row segment) per block
+constexpr int kStemPx = 4;                                  // output pixels per thread
+constexpr int kStemTile = kStemPx * (kStemThreads / 2);     // 256 output pixels (one row segment) per block
 
 __global__ void __launch_bounds__(kStemThreads) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                               const float* __restrict__ b, float* __restrict__ y, int H, int W,
                                                               int Ho, int Wo) {
   __shared__ __align__(16) float ws[27 * 32 + 32];
-  __shared__ __align__(16) float outs[kStemTile][36];   // 144-byte rows: float4-aligned, 8 consecutive lanes cover all 32 banks
+  // output tile [256 pixels][8 chunks of 4 channels], chunk c of pixel px stored at slot c ^ ((px >> 2) & 7): the 8 lanes of a
+  // quarter warp own pixels 4 lanes apart (128-byte rows, same banks) and land in 8 different slots
+  __shared__ __align__(16) float outs[kStemTile * 32];
   for (int i = threadIdx.x; i < 27 * 32 + 32; i += blockDim.x) ws[i] = i < 27 * 32 ? w[i] : b[i - 27 * 32];
   __syncthreads();
-  const int ox0 = blockIdx.x * kStemTile + 2 * threadIdx.x, oy = blockIdx.y, n = blockIdx.z;
-  float acc[2][32];
+  const int half = threadIdx.x / (kStemThreads / 2);        // warp-uniform
+  const int pg = threadIdx.x % (kStemThreads / 2);
+  const int ox0 = blockIdx.x * kStemTile + kStemPx * pg, oy = blockIdx.y, n = blockIdx.z;
+  float acc[kStemPx][16];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) acc[0][c] = acc[1][c] = ws[27 * 32 + c];
+  for (int c = 0; c < 16; ++c) {
+    const float bv = ws[27 * 32 + half * 16 + c];
+#pragma unroll
+    for (int px = 0; px < kStemPx; ++px) acc[px][c] = bv;
+  }
   if (ox0 < Wo) {
     const float* xn = x + (size_t)n * 3 * H * W;
-    const int ix0 = 2 * ox0;   // input columns ix0 - 1 ... ix0 + 3 (ix0 is a multiple of 4: the float4 below is aligned)
+    const int ix0 = 2 * ox0;   // input columns ix0 - 1 ... ix0 + 7 (ix0 is a multiple of 8: the float4 loads below are aligned)
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = oy * 2 - 1 + ky;
@@ -70,47 +82,53 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const float* __restr
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
         const float* row = xn + ((size_t)ci * H + iy) * W;
-        float v[5];
+        float v[2 * kStemPx + 1];
         v[0] = ix0 > 0 ? __ldg(row + ix0 - 1) : 0.f;
-        if (ix0 + 3 < W) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(row + ix0));
-          v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w;
+        if (ix0 + 7 < W) {
+          const float4 q0 = __ldg(reinterpret_cast<const float4*>(row + ix0));
+          const float4 q1 = __ldg(reinterpret_cast<const float4*>(row + ix0 + 4));
+          v[1] = q0.x; v[2] = q0.y; v[3] = q0.z; v[4] = q0.w;
+          v[5] = q1.x; v[6] = q1.y; v[7] = q1.z; v[8] = q1.w;
         } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[1 + j] = ix0 + j < W ? __ldg(row + ix0 + j) : 0.f;
+          for (int j = 0; j < 8; ++j) v[1 + j] = ix0 + j < W ? __ldg(row + ix0 + j) : 0.f;
         }
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + ci) * 32);
+          const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + ci) * 32 + half * 16);
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
+          for (int c4 = 0; c4 < 4; ++c4) {
             const float4 wv = wr[c4];
             // packed FFMA2: 864 fused multiply-adds per pixel in 432 issue slots
-            ffma2(acc[0][4 * c4 + 0], acc[0][4 * c4 + 1], v[kx], v[kx], wv.x, wv.y);
-            ffma2(acc[0][4 * c4 + 2], acc[0][4 * c4 + 3], v[kx], v[kx], wv.z, wv.w);
-            ffma2(acc[1][4 * c4 + 0], acc[1][4 * c4 + 1], v[kx + 2], v[kx + 2], wv.x, wv.y);
-            ffma2(acc[1][4 * c4 + 2], acc[1][4 * c4 + 3], v[kx + 2], v[kx + 2], wv.z, wv.w);
+#pragma unroll
+            for (int px = 0; px < kStemPx; ++px) {
+              ffma2(acc[px][4 * c4 + 0], acc[px][4 * c4 + 1], v[2 * px + kx], v[2 * px + kx], wv.x, wv.y);
+              ffma2(acc[px][4 * c4 + 2], acc[px][4 * c4 + 3], v[2 * px + kx], v[2 * px + kx], wv.z, wv.w);
+            }
           }
         }
       }
     }
   }
 #pragma unroll
-  for (int c4 = 0; c4 < 8; ++c4) {
+  for (int px = 0; px < kStemPx; ++px) {
 #pragma unroll
-    for (int px = 0; px < 2; ++px) {
+    for (int c4 = 0; c4 < 4; ++c4) {
       silu2(acc[px][4 * c4], acc[px][4 * c4 + 1]);
       silu2(acc[px][4 * c4 + 2], acc[px][4 * c4 + 3]);
-      *reinterpret_cast<float4*>(&outs[2 * threadIdx.x + px][4 * c4]) = make_float4(acc[px][4 * c4], acc[px][4 * c4 + 1], acc[px][4 * c4 + 2], acc[px][4 * c4 + 3]);
+      const int slot = (half * 4 + c4) ^ (pg & 7);
+      *reinterpret_cast<float4*>(&outs[(kStemPx * pg + px) * 32 + slot * 4]) =
+          make_float4(acc[px][4 * c4], acc[px][4 * c4 + 1], acc[px][4 * c4 + 2], acc[px][4 * c4 + 3]);
     }
   }
   __syncthreads();
-  // coalesced NHWC store: the tile is 256 pixels x 32 channels = 2048 contiguous float4
+  // coalesced NHWC store: the tile is 256 pixels x 32 channels = 2048 contiguous float4 (slot i & 7 of pixel i >> 3 holds chunk
+  // (i & 7) ^ ((i >> 5) & 7); the 8 lanes of a pixel still write its whole 128-byte line)
   float4* dst = reinterpret_cast<float4*>(y + (((size_t)n * Ho + oy) * Wo + (size_t)blockIdx.x * kStemTile) * 32);
   const int valid4 = min(kStemTile, Wo - blockIdx.x * kStemTile) * 8;
 #pragma unroll 4
   for (int i = threadIdx.x; i < kStemTile * 8; i += kStemThreads)
-    if (i < valid4) dst[i] = *reinterpret_cast<const float4*>(&outs[i >> 3][(i & 7) * 4]);
+    if (i < valid4) dst[(i & ~7) | ((i & 7) ^ ((i >> 5) & 7))] = *reinterpret_cast<const float4*>(&outs[i * 4]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -127,6 +145,16 @@ __device__ __forceinline__ void ldv(const float* p, float (&d)[V]) {
     d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
   } else {
     const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    d[0] = t.x; d[1] = t.y;
+  }
+}
+template <int V>
+__device__ __forceinline__ void ldsv(const float* p, float (&d)[V]) {   // plain (shared-memory) vector load
+  if constexpr (V == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+  } else {
+    const float2 t = *reinterpret_cast<const float2*>(p);
     d[0] = t.x; d[1] = t.y;
   }
 }
@@ -266,6 +294,8 @@ constexpr int kDtConsumers = 256, kDtThreads = 288, kDtTH = 8, kDtCB = 32;
 
 struct DwTmaParams {
   CUtensorMap tmap_x;
+  CUtensorMap tmap_w;   // weights as {C, k*k}, box {CB, k*k}
+  CUtensorMap tmap_b;   // bias as {C, 1}, box {CB, 1}
   const float* w; const float* b; float* y; float* pooled;
   int B, H, W, C, Ho, Wo, tiles_x, tiles_y, cblocks, total_items, stages;
   int direct_pool;   // 1: squeeze sums go out as per-warp global reductions (small maps), 0: shared-memory partials + one atomic per item
@@ -282,8 +312,14 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
   constexpr int WCOLS = WORKERS / WROWS;         // 8 or 4
   constexpr int CPW = TW / WCOLS;                // output columns per worker
   constexpr int R = 2, NR = (R - 1) * S + KS;
+  // a stage = input box | the channel block's k*k weight rows | its bias row, all brought by the producer's bulk-tensor loads: with
+  // the channel block as the fastest item index a CTA changes block every item, and fetching the 25 + 1 weight vectors through LDG
+  // cost ~250 instructions of 64-bit address arithmetic per item and thread (a quarter of the 5 x 5 loop body)
   constexpr uint32_t kTileBytes = THin * TWin * CB * 4;
-  constexpr uint32_t kTileStride = (kTileBytes + 127u) & ~127u;
+  constexpr uint32_t kWBytes = KS * KS * CB * 4, kBBytes = CB * 4;
+  constexpr uint32_t kWOff = (kTileBytes + 127u) & ~127u;
+  constexpr uint32_t kBOff = (kWOff + kWBytes + 127u) & ~127u;
+  constexpr uint32_t kTileStride = (kBOff + kBBytes + 127u) & ~127u;
   static_assert(CPW >= 1 && TW % WCOLS == 0, "tile width must split evenly over the workers");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -308,7 +344,11 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
 
   if (warp == kDtConsumers / 32) {
     // =========================== TMA producer ===========================
-    if (lane == 0) tma_prefetch_desc(&p.tmap_x);
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tmap_x);
+      tma_prefetch_desc(&p.tmap_w);
+      tma_prefetch_desc(&p.tmap_b);
+    }
     int stage = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -320,8 +360,11 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
       const int ty = t2 / p.tiles_x, tx = t2 % p.tiles_x;
       mbar_wait(empty_bar(stage), phase ^ 1u);
       if (elect_one()) {
-        mbar_arrive_expect_tx(full_bar(stage), kTileBytes);
-        tma_load_4d(smem_base + (uint32_t)stage * kTileStride, &p.tmap_x, full_bar(stage), cb * CB, tx * TW * S - P, ty * kDtTH * S - P, n);
+        mbar_arrive_expect_tx(full_bar(stage), kTileBytes + kWBytes + kBBytes);
+        const uint32_t dst = smem_base + (uint32_t)stage * kTileStride;
+        tma_load_2d(dst + kWOff, &p.tmap_w, full_bar(stage), cb * CB, 0);
+        tma_load_2d(dst + kBOff, &p.tmap_b, full_bar(stage), cb * CB, 0);
+        tma_load_4d(dst, &p.tmap_x, full_bar(stage), cb * CB, tx * TW * S - P, ty * kDtTH * S - P, n);
       }
       __syncwarp();
       if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -333,7 +376,6 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
     const int wy = worker / WCOLS, wx = worker % WCOLS;
     const int r0 = 2 * wy, cbeg = wx * CPW;
     float wr[KS * KS][V], bias[V];
-    int cur_cb = -1;
     int stage = 0;
     uint32_t phase = 0, it = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
@@ -342,25 +384,12 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
       const int n = rem / tiles_per_img, t2 = rem % tiles_per_img;
       const int ty = t2 / p.tiles_x, tx = t2 % p.tiles_x;
       const int c0 = cb * CB + cv * V;
-      const bool ch_ok = c0 < p.C;
-      if (cb != cur_cb) {
-        cur_cb = cb;
-#pragma unroll
-        for (int i = 0; i < KS * KS; ++i) {
-          if (ch_ok) ldv<V>(p.w + i * p.C + c0, wr[i]);
-          else {
-#pragma unroll
-            for (int v = 0; v < V; ++v) wr[i][v] = 0.f;
-          }
-        }
-        if (ch_ok) ldv<V>(p.b + c0, bias);
-        else {
-#pragma unroll
-          for (int v = 0; v < V; ++v) bias[v] = 0.f;
-        }
-      }
+      const bool ch_ok = c0 < p.C;     // channels past C: zero-filled input, weights and bias; nothing is stored for them
       mbar_wait(full_bar(stage), phase);
       const float* tile = reinterpret_cast<const float*>(smem_gen + (uint32_t)stage * kTileStride) + cv * V;
+#pragma unroll
+      for (int i = 0; i < KS * KS; ++i) ldsv<V>(tile + kWOff / 4 + i * CB, wr[i]);
+      ldsv<V>(tile + kBOff / 4, bias);
       auto lds = [&](int row, int col, float (&d)[V]) {
         const float* q = tile + (row * TWin + col) * CB;
         if constexpr (V == 4) {
@@ -382,7 +411,16 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
 #pragma unroll
       for (int v = 0; v < V; ++v) pool[v] = 0.f;
       const int oy0 = ty * kDtTH + r0, ox0 = tx * TW + cbeg;
-      float* yb = p.y + (((size_t)n * p.Ho + oy0) * p.Wo + ox0) * p.C + c0;
+      // one 64-bit base per output row, 32-bit element offsets per column: the full (r Wo + c) C product in 64 bits cost ~10 integer
+      // instructions per store (16 stores per item in the 5 x 5 kernels)
+      float* yrow[R];
+      bool row_ok[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        yrow[r] = p.y + (((size_t)n * p.Ho + oy0 + r) * p.Wo + ox0) * p.C + c0;
+        row_ok[r] = ch_ok && oy0 + r < p.Ho;
+      }
+      const int pix = p.C;
 #pragma unroll
       for (int c = 0; c < CPW; ++c) {
 #pragma unroll
@@ -408,15 +446,17 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
               }
 #pragma unroll
           for (int v = 0; v < V; ++v) acc[v] += acc2[v];
-          if (ch_ok && oy0 + r < p.Ho && ox0 + c < p.Wo) {
+          // SiLU outside the bounds test: inside it every output was its own branch region with the serial chain FMUL2 -> MUFU.EX2 ->
+          // FADD2 -> MUFU.RCP -> FMUL2 -> STG exposed (16 regions per item in the 5 x 5 kernel, ~60 cycles each, two warps per
+          // scheduler to hide them); unconditional, ptxas interleaves the SFU work with the FFMA2 stream of the next outputs.  The
+          // squeeze sum takes the value times 1.0 / 0.0 (an exact add) and the store is a single predicated instruction.
 #pragma unroll
-            for (int v = 0; v < V; v += 2) {
-              silu2(acc[v], acc[v + 1]);
-              pool[v] += acc[v];
-              pool[v + 1] += acc[v + 1];
-            }
-            stv<V>(yb + ((size_t)r * p.Wo + c) * p.C, acc);
-          }
+          for (int v = 0; v < V; v += 2) silu2(acc[v], acc[v + 1]);
+          const bool ok = row_ok[r] && ox0 + c < p.Wo;
+          const float keep = ok ? 1.f : 0.f;
+#pragma unroll
+          for (int v = 0; v < V; ++v) pool[v] = fmaf(acc[v], keep, pool[v]);
+          if (ok) stv<V>(yrow[r] + c * pix, acc);
         }
         if (c + 1 < CPW) {
           // the S input columns the next output column adds: logical columns c S + KS ... c S + KS + S - 1
@@ -471,7 +511,9 @@ static int launch_depthwise_tma_t(const float* x, const float* w, const float* b
                                   cudaStream_t st) {
   constexpr int THin = (kDtTH - 1) * S + KS, TWin = (TW - 1) * S + KS;
   const int Ho = (H + 2 * ((KS - 1) / 2) - KS) / S + 1;
-  constexpr int kTileStride = (THin * TWin * CB * 4 + 127) & ~127;
+  constexpr int kWOff = (THin * TWin * CB * 4 + 127) & ~127;
+  constexpr int kBOff = (kWOff + KS * KS * CB * 4 + 127) & ~127;
+  constexpr int kTileStride = (kBOff + CB * 4 + 127) & ~127;     // the kernel's stage layout: input box | weights | bias
   DwTmaParams p;
   memset(&p, 0, sizeof(p));
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)H, (uint64_t)H, (uint64_t)B};
@@ -479,6 +521,17 @@ static int launch_depthwise_tma_t(const float* x, const float* w, const float* b
   uint32_t box[4] = {CB, TWin, THin, 1};
   int rc = make_tmap(&p.tmap_x, x, 4, 4, dims, str, box, kSwzNone);
   if (rc) return rc;
+  {
+    uint64_t wd[2] = {(uint64_t)C, (uint64_t)(KS * KS)};
+    uint64_t ws[1] = {(uint64_t)C * 4};
+    uint32_t wb[2] = {CB, KS * KS};
+    rc = make_tmap(&p.tmap_w, w, 4, 2, wd, ws, wb, kSwzNone);
+    if (rc) return rc;
+    uint64_t bd[2] = {(uint64_t)C, 1};
+    uint32_t bb[2] = {CB, 1};
+    rc = make_tmap(&p.tmap_b, b, 4, 2, bd, ws, bb, kSwzNone);
+    if (rc) return rc;
+  }
   p.w = w; p.b = b; p.y = y; p.pooled = pooled;
   p.B = B; p.H = H; p.W = H; p.C = C; p.Ho = Ho; p.Wo = Ho;
   p.tiles_x = (Ho + TW - 1) / TW;

@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
   const uint32_t tmem_slot = bar_base + 8u * 41;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * 41);
   // accumulator ring in TMEM: narrow layers (BN = 16 ... 64) keep up to 8 tiles in flight between the MMA thread and the epilogue
-  const uint32_t nacc = min(8u, 512u / (uint32_t)BN);
+  // tile_par needs a ring size that is a multiple of 4 (a slot always belongs to the same epilogue warp group)
+  const uint32_t nacc = p.tile_par ? (BN <= 64 ? 8u : 4u) : min(8u, 512u / (uint32_t)BN);
 
   auto a_hi = [&](int s) { return smem_base + ring_off + (uint32_t)s * stage_bytes; };
   auto a_lo = [&](int s) { return smem_base + ring_off + (uint32_t)s * stage_bytes + kPwATile; };
@@ -707,7 +708,8 @@ int launch_pointwise_tc(const PwTcArgs& a, cudaStream_t st) {
   const int w_tile_bytes = 2 * p.BN * 128;                                   // hi + lo of one k chunk
   const int fixed = kPwEpiWarps * kPwStgWarp + 512;
   p.w_resident = (p.num_n_tiles == 1 && p.num_kc * w_tile_bytes <= 96 * 1024) ? 1 : 0;
-  p.tile_par = (p.BN <= 48 && a.epi != kPwSiluPool) ? 1 : 0;   // 512 / BN >= 10 -> an 8-slot accumulator ring
+  // narrow outputs (<= 3 pieces: 8-slot ring) and the 96-wide expand (6 pieces over 4 warp groups = 2, 2, 1, 1 per tile; 4-slot ring)
+  p.tile_par = ((p.BN <= 48 || p.BN == 96) && a.epi != kPwSiluPool) ? 1 : 0;
   const int sms = sm_count();
   if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
   if (!p.w_resident && p.num_m_tiles >= 2 && pw_pair_enabled()) {
