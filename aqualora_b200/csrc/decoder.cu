@@ -52,19 +52,52 @@ __device__ __forceinline__ float silu_fast(float v) {
 constexpr int kStemThreads = 128;
 constexpr int kStemPx = 4;                                  // output pixels per thread
 constexpr int kStemTile = kStemPx * (kStemThreads / 2);     // 256 output pixels (one row segment) per block
+constexpr int kStemInW = 2 * kStemTile;                     // 512 input columns per block (+ 1 halo column on the left)
+constexpr int kStemRow = kStemInW + 8;                      // staged input row: [3] = halo column, [4 ... 4 + 512) = the segment
 
+// The 9 input rows (3 ky x 3 channels) of the block are staged in shared memory first: each thread issues its 9 independent 16-byte
+// loads back to back (one exposed DRAM latency per block).  Loading a row right before the FMA block that consumes it -- the form
+// ptxas produces when the loads sit in the ky / ci loops behind the bounds branches -- exposed that latency nine times per thread
+// (ncu: long-scoreboard 3.6 warps per issue, 41 % issue utilisation at 16 warps per SM).
 __global__ void __launch_bounds__(kStemThreads) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                               const float* __restrict__ b, float* __restrict__ y, int H, int W,
                                                               int Ho, int Wo) {
   __shared__ __align__(16) float ws[27 * 32 + 32];
   // output tile [256 pixels][8 chunks of 4 channels], chunk c of pixel px stored at slot c ^ ((px >> 2) & 7): the 8 lanes of a
-  // quarter warp own pixels 4 lanes apart (128-byte rows, same banks) and land in 8 different slots
+  // quarter warp own pixels 4 lanes apart (128-byte rows, same banks) and land in 8 different slots.  The staged input rows
+  // (9 x 520 floats) live in the same 32 KiB: they are dead once every thread has finished its FMAs (barrier below).
   __shared__ __align__(16) float outs[kStemTile * 32];
+  static_assert(9 * kStemRow <= kStemTile * 32, "the staged input must fit in the output tile");
+  float* xs = outs;
+  const int oy = blockIdx.y, n = blockIdx.z;
+  const int ixb = blockIdx.x * kStemInW;                    // first input column of the segment (a multiple of 512)
+  {
+    const float* xn = x + (size_t)n * 3 * H * W;
+    float4 q[9];
+    float hv = 0.f;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {                           // r = ky * 3 + ci
+      const int iy = oy * 2 - 1 + r / 3;
+      const float* row = xn + ((size_t)(r % 3) * H + iy) * W;
+      const int ix = ixb + 4 * threadIdx.x;
+      const bool rok = iy >= 0 && iy < H;
+      q[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rok && ix + 3 < W) q[r] = __ldg(reinterpret_cast<const float4*>(row + ix));
+      else if (rok) {
+        if (ix < W) q[r].x = __ldg(row + ix);
+        if (ix + 1 < W) q[r].y = __ldg(row + ix + 1);
+        if (ix + 2 < W) q[r].z = __ldg(row + ix + 2);
+      }
+      if ((int)threadIdx.x == r && rok && ixb > 0) hv = __ldg(row + ixb - 1);
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) *reinterpret_cast<float4*>(&xs[r * kStemRow + 4 + 4 * threadIdx.x]) = q[r];
+    if (threadIdx.x < 9) xs[threadIdx.x * kStemRow + 3] = hv;
+  }
   for (int i = threadIdx.x; i < 27 * 32 + 32; i += blockDim.x) ws[i] = i < 27 * 32 ? w[i] : b[i - 27 * 32];
   __syncthreads();
   const int half = threadIdx.x / (kStemThreads / 2);        // warp-uniform
   const int pg = threadIdx.x % (kStemThreads / 2);
-  const int ox0 = blockIdx.x * kStemTile + kStemPx * pg, oy = blockIdx.y, n = blockIdx.z;
   float acc[kStemPx][16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
@@ -72,40 +105,27 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const float* __restr
 #pragma unroll
     for (int px = 0; px < kStemPx; ++px) acc[px][c] = bv;
   }
-  if (ox0 < Wo) {
-    const float* xn = x + (size_t)n * 3 * H * W;
-    const int ix0 = 2 * ox0;   // input columns ix0 - 1 ... ix0 + 7 (ix0 is a multiple of 8: the float4 loads below are aligned)
+  // rows above / below the image and columns past W are staged as zeros: their taps add 0 * w (exact), like the padding they are
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = oy * 2 - 1 + ky;
-      if (iy < 0 || iy >= H) continue;
+  for (int r = 0; r < 9; ++r) {
+    const float* xr = xs + r * kStemRow + 4 + 8 * pg;       // input columns 8 pg - 1 ... 8 pg + 7 of the segment
+    float v[2 * kStemPx + 1];
+    v[0] = xr[-1];
+    const float4 q0 = *reinterpret_cast<const float4*>(xr);
+    const float4 q1 = *reinterpret_cast<const float4*>(xr + 4);
+    v[1] = q0.x; v[2] = q0.y; v[3] = q0.z; v[4] = q0.w;
+    v[5] = q1.x; v[6] = q1.y; v[7] = q1.z; v[8] = q1.w;
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        const float* row = xn + ((size_t)ci * H + iy) * W;
-        float v[2 * kStemPx + 1];
-        v[0] = ix0 > 0 ? __ldg(row + ix0 - 1) : 0.f;
-        if (ix0 + 7 < W) {
-          const float4 q0 = __ldg(reinterpret_cast<const float4*>(row + ix0));
-          const float4 q1 = __ldg(reinterpret_cast<const float4*>(row + ix0 + 4));
-          v[1] = q0.x; v[2] = q0.y; v[3] = q0.z; v[4] = q0.w;
-          v[5] = q1.x; v[6] = q1.y; v[7] = q1.z; v[8] = q1.w;
-        } else {
+    for (int kx = 0; kx < 3; ++kx) {
+      const float4* wr = reinterpret_cast<const float4*>(ws + (((r / 3) * 3 + kx) * 3 + (r % 3)) * 32 + half * 16);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[1 + j] = ix0 + j < W ? __ldg(row + ix0 + j) : 0.f;
-        }
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 wv = wr[c4];
+        // packed FFMA2: 864 fused multiply-adds per pixel in 432 issue slots
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + ci) * 32 + half * 16);
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const float4 wv = wr[c4];
-            // packed FFMA2: 864 fused multiply-adds per pixel in 432 issue slots
-#pragma unroll
-            for (int px = 0; px < kStemPx; ++px) {
-              ffma2(acc[px][4 * c4 + 0], acc[px][4 * c4 + 1], v[2 * px + kx], v[2 * px + kx], wv.x, wv.y);
-              ffma2(acc[px][4 * c4 + 2], acc[px][4 * c4 + 3], v[2 * px + kx], v[2 * px + kx], wv.z, wv.w);
-            }
-          }
+        for (int px = 0; px < kStemPx; ++px) {
+          ffma2(acc[px][4 * c4 + 0], acc[px][4 * c4 + 1], v[2 * px + kx], v[2 * px + kx], wv.x, wv.y);
+          ffma2(acc[px][4 * c4 + 2], acc[px][4 * c4 + 3], v[2 * px + kx], v[2 * px + kx], wv.z, wv.w);
         }
       }
     }
@@ -116,6 +136,13 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const float* __restr
     for (int c4 = 0; c4 < 4; ++c4) {
       silu2(acc[px][4 * c4], acc[px][4 * c4 + 1]);
       silu2(acc[px][4 * c4 + 2], acc[px][4 * c4 + 3]);
+    }
+  }
+  __syncthreads();   // every thread is done reading the staged input: the buffer becomes the output tile
+#pragma unroll
+  for (int px = 0; px < kStemPx; ++px) {
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
       const int slot = (half * 4 + c4) ^ (pg & 7);
       *reinterpret_cast<float4*>(&outs[(kStemPx * pg + px) * 32 + slot * 4]) =
           make_float4(acc[px][4 * c4], acc[px][4 * c4 + 1], acc[px][4 * c4 + 2], acc[px][4 * c4 + 3]);
@@ -755,7 +782,8 @@ static int launch_depthwise(const float* x, const float* w, const float* b, floa
   }
   // the 16-channel depthwise of the second stage-1 block (256 x 256 maps): same kernel with a 16-channel block
   if (stride == 1 && C == 16 && k == 3 && Ho >= 32 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0)
-    return launch_depthwise_tma_t<3, 32, 16>(x, w, b, y, pooled, B, H, C, st);
+    return Ho >= 64 ? launch_depthwise_tma_t<3, 64, 16>(x, w, b, y, pooled, B, H, C, st)    // 4 output columns per worker instead of 2
+                    : launch_depthwise_tma_t<3, 32, 16>(x, w, b, y, pooled, B, H, C, st);
   const int R = 2;   // output rows per thread
   const int TW = Ho >= 64 ? 32 : 16;
   const int V = k == 3 ? 4 : 2;

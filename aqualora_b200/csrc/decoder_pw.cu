@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
                                    // The accumulator ring then has 8 slots (a multiple of 4), so a slot always belongs to the
                                    // same warp group and its full / empty phases are observed in order.
     const bool tile_par = p.tile_par != 0;
-    const int pc_first = tile_par ? 0 : res, pc_step = tile_par ? 1 : 4;
+    const int pc_step = tile_par ? 1 : 4;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint8_t* stg = smem_gen + stg_off + warp * kPwStgWarp;
     const uint32_t stg_u32 = smem_base + stg_off + warp * kPwStgWarp;
@@ -265,7 +265,11 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
       const uint32_t buf = acc_iter % nacc;
       const long long row_base = m0 + q * 32;
       const int pieces = min(BN, p.N - n0 + 15) >> 4;                  // 16-column pieces that hold at least one valid column
-      const int nmine = tile_par ? pieces : (pieces > res ? (pieces - res + 3) >> 2 : 0);    // this warp's pieces
+      // the first piece of a warp group rotates with the tile: with 9 pieces (the 144-wide expand layers) a fixed assignment gives
+      // group 0 three pieces of EVERY tile and the others two (the tile is released when the slowest group is done); rotating, every
+      // group carries the extra piece every fourth tile and the 3-slot accumulator ring absorbs the difference
+      const int pc_first = tile_par ? 0 : (int)((res + acc_iter) & 3u);
+      const int nmine = tile_par ? pieces : (pieces > pc_first ? (pieces - pc_first + 3) >> 2 : 0);    // this warp's pieces
       float4 rs[4];
       if (p.epi == kPwResidual && nmine > 0) {
         // residual of the first piece (this lane's row, 64 bytes): requested before the accumulator wait so its DRAM latency
