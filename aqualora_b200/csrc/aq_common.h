@@ -51,8 +51,9 @@ enum TmaSwizzle { kSwzNone = 0, kSwz32 = 1, kSwz64 = 2, kSwz128 = 3 };
 
 // Encode a tiled bf16 / fp32 tensor map (rank 2 or 3).  dims/box are innermost-first; strides are in
 // BYTES for dims 1..rank-1.  Returns AQ_OK or an error code (aq_last_error() explains).
+// l2_promotion: bytes an L2 miss of the map's loads is widened to (0 = none, 128, 256)
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box, TmaSwizzle swz);
+              const uint64_t* strides_bytes, const uint32_t* box, TmaSwizzle swz, int l2_promotion = 256);
 
 // Launch configuration with the programmatic-dependent-launch attribute (opt-in: AQ_PDL=1 in the environment): the kernel's
 // prologue (barrier init, TMEM allocation, descriptor prefetch) and its launch latency overlap the tail of the previous kernel in

@@ -47,7 +47,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box, TmaSwizzle swz) {
+              const uint64_t* strides_bytes, const uint32_t* box, TmaSwizzle swz, int l2_promotion) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return fail(AQ_ERR_LAUNCH, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0)
@@ -71,7 +71,10 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
                           : swz == kSwz32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                           : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  l2_promotion >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                  : l2_promotion >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                        : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(AQ_ERR_LAUNCH, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu x %llu box %u x %u)", (int)r, rank,
                 (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 1), box[0], rank > 1 ? box[1] : 1u);

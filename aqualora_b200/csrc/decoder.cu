@@ -309,124 +309,139 @@ __global__ void __launch_bounds__(kDwThreads, 3) depthwise_kernel(const float* _
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// depthwise k x k STRIDE 1 with TMA-staged input tiles (the 19 stride-1 launches carry 80 % of the depthwise bytes).
+// depthwise k x k (stride 1 and 2) with TMA-staged input tiles.
 // The register-window kernel above keeps only ~24 KiB of loads in flight per SM (12 warps x a handful of LDGs) and sat at
-// 1 - 2.6 TB/s; here a producer warp streams (8 + k - 1) x (TW + k - 1) x 32-channel input boxes through a 3 - 4 stage mbarrier
-// ring with cp.async.bulk.tensor.4d (zero-filled halo = the convolution's padding, no bounds checks in the math), so 100+ KiB
-// are in flight per SM and the 8 consumer warps run the same sliding window out of shared memory.
-//   x as a 4-D tensor {C, W, H, B}; box {32, TW + k - 1, 8 + k - 1, 1}; work item = (channel block, image, tile y, tile x)
+// 1 - 2.6 TB/s; here a producer warp streams ((8 - 1) S + k) x ((TW - 1) S + k) x 32-channel input boxes through a 3 - 6 stage
+// mbarrier ring with cp.async.bulk.tensor.4d (zero-filled halo = the convolution's padding, no bounds checks in the math), so
+// 100+ KiB are in flight per SM and the 8 consumer warps run the same sliding window out of shared memory.
+//   x as a 4-D tensor {C, W, H, B}; box {32, TWin, THin, 1}
 //   consumer thread = (V channels, worker); worker = 2 output rows x TW / WCOLS output columns
+// Work distribution: CTA b owns ONE channel block (b % cblocks) and a CONTIGUOUS range of the spatial tiles (image, tile x,
+// tile y; y fastest) -- group g = b / cblocks of G = SMs / cblocks takes tiles [g T / G, (g + 1) T / G).  The cblocks CTAs of a group walk the
+// same tiles at the same time, so all channel blocks of a pixel (which share 128 B lines / 256 B L2 promotions when 4 C is not
+// a multiple of 128) are still fetched together, and per CTA
+//   * the k*k weights and the bias are loaded once (before: every item, the channel block was the fastest item index),
+//   * the tile coordinates advance by increments (before: three integer divisions per item and thread),
+//   * the squeeze sums stay in registers until the image changes (before: per item a shuffle reduction, shared-memory partials,
+//     a 256-thread named barrier and an atomic per channel -- the barrier kept the 8 warps in lock step, i.e. no warp could hide
+//     another's SFU / shared-memory latency across items; ncu: 37 % issue utilisation at 2 warps per scheduler).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kDtConsumers = 256, kDtThreads = 288, kDtTH = 8, kDtCB = 32;
+constexpr int kDtTH = 8, kDtCB = 32;
 
 struct DwTmaParams {
   CUtensorMap tmap_x;
-  CUtensorMap tmap_w;   // weights as {C, k*k}, box {CB, k*k}
-  CUtensorMap tmap_b;   // bias as {C, 1}, box {CB, 1}
   const float* w; const float* b; float* y; float* pooled;
-  int B, H, W, C, Ho, Wo, tiles_x, tiles_y, cblocks, total_items, stages;
-  int direct_pool;   // 1: squeeze sums go out as per-warp global reductions (small maps), 0: shared-memory partials + one atomic per item
+  int B, H, W, C, Ho, Wo, tiles_x, tiles_y, cblocks, groups, total_tiles, stages;
 };
 
-template <int KS, int TW, int CB, int S>
-__global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __grid_constant__ DwTmaParams p) {
+// V = channels per thread, NCONS = consumer threads: 3 x 3 runs V = 2 with 16 consumer warps (<= 120 registers), 5 x 5 (50 weight
+// + 60 window registers at V = 2) stays at 8 warps
+template <int KS, int TW, int CB, int S, int V, int NCONS>
+__global__ void __launch_bounds__(NCONS + 32, 1) depthwise_tma_kernel(const __grid_constant__ DwTmaParams p) {
   // S = stride (1 or 2): output tile kDtTH x TW, input box ((kDtTH - 1) S + k) x ((TW - 1) S + k); p.H / p.W = INPUT size, p.Ho / p.Wo = output size
   constexpr int P = (KS - 1) / 2, THin = (kDtTH - 1) * S + KS, TWin = (TW - 1) * S + KS;
-  constexpr int V = KS == 3 ? 4 : 2;
   constexpr int CV = CB / V;                  // channel vectors per block
-  constexpr int WORKERS = kDtConsumers / CV;     // 32 (k = 3) or 16 (k = 5)
+  constexpr int WORKERS = NCONS / CV;
   constexpr int WROWS = kDtTH / 2;               // 4 row pairs
   constexpr int WCOLS = WORKERS / WROWS;         // 8 or 4
   constexpr int CPW = TW / WCOLS;                // output columns per worker
   constexpr int R = 2, NR = (R - 1) * S + KS;
-  // a stage = input box | the channel block's k*k weight rows | its bias row, all brought by the producer's bulk-tensor loads: with
-  // the channel block as the fastest item index a CTA changes block every item, and fetching the 25 + 1 weight vectors through LDG
-  // cost ~250 instructions of 64-bit address arithmetic per item and thread (a quarter of the 5 x 5 loop body)
   constexpr uint32_t kTileBytes = THin * TWin * CB * 4;
-  constexpr uint32_t kWBytes = KS * KS * CB * 4, kBBytes = CB * 4;
-  constexpr uint32_t kWOff = (kTileBytes + 127u) & ~127u;
-  constexpr uint32_t kBOff = (kWOff + kWBytes + 127u) & ~127u;
-  constexpr uint32_t kTileStride = (kBOff + kBBytes + 127u) & ~127u;
+  constexpr uint32_t kTileStride = (kTileBytes + 127u) & ~127u;
   static_assert(CPW >= 1 && TW % WCOLS == 0, "tile width must split evenly over the workers");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stages = p.stages;
-  const uint32_t pool_off = (uint32_t)stages * kTileStride;            // float pool_s[2][8 warps][32]: per-warp partial squeeze sums
-  const uint32_t bar_off = pool_off + 2 * 8 * CB * 4;
+  const uint32_t bar_off = (uint32_t)stages * kTileStride;
   auto full_bar = [&](int s) { return smem_base + bar_off + 8u * s; };
   auto empty_bar = [&](int s) { return smem_base + bar_off + 8u * (8 + s); };
-  float* pool_s = reinterpret_cast<float*>(smem_gen + pool_off);
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), kDtConsumers / 32);
+      mbar_init(empty_bar(s), NCONS / 32);
     }
     fence_mbar_init();
   }
   __syncthreads();
+  // this CTA's channel block and tile range; (n, ty, tx) of the first tile by division, then by increments
+  const int cb = (int)blockIdx.x % p.cblocks, grp = (int)blockIdx.x / p.cblocks;
+  const int t_begin = (int)((long long)grp * p.total_tiles / p.groups);
+  const int t_end = (int)((long long)(grp + 1) * p.total_tiles / p.groups);
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  int n = t_begin / tiles_per_img;
+  // tile y is the fastest index: the two halo rows a tile shares with the tile below are re-read by the very next item (L2 hit).
+  // With tile x fastest the re-read came tiles_x items later and missed: DRAM reads of the 144-channel layers 604 -> 767 MB.
+  int tx = (t_begin % tiles_per_img) / p.tiles_y, ty = (t_begin % tiles_per_img) % p.tiles_y;
 
-  if (warp == kDtConsumers / 32) {
+  if (warp == NCONS / 32) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
-      tma_prefetch_desc(&p.tmap_x);
-      tma_prefetch_desc(&p.tmap_w);
-      tma_prefetch_desc(&p.tmap_b);
-    }
+    if (lane == 0) tma_prefetch_desc(&p.tmap_x);
     int stage = 0;
     uint32_t phase = 0;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      // channel block fastest: the blocks of one spatial tile are fetched by neighbouring CTAs at the same time (a pixel's
-      // channels share 128 B lines / 256 B L2 promotions when C * 4 is not a multiple of 128)
-      const int cb = item % p.cblocks;
-      const int rem = item / p.cblocks;
-      const int n = rem / tiles_per_img, t2 = rem % tiles_per_img;
-      const int ty = t2 / p.tiles_x, tx = t2 % p.tiles_x;
+    for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(empty_bar(stage), phase ^ 1u);
       if (elect_one()) {
-        mbar_arrive_expect_tx(full_bar(stage), kTileBytes + kWBytes + kBBytes);
-        const uint32_t dst = smem_base + (uint32_t)stage * kTileStride;
-        tma_load_2d(dst + kWOff, &p.tmap_w, full_bar(stage), cb * CB, 0);
-        tma_load_2d(dst + kBOff, &p.tmap_b, full_bar(stage), cb * CB, 0);
-        tma_load_4d(dst, &p.tmap_x, full_bar(stage), cb * CB, tx * TW * S - P, ty * kDtTH * S - P, n);
+        mbar_arrive_expect_tx(full_bar(stage), kTileBytes);
+        tma_load_4d(smem_base + (uint32_t)stage * kTileStride, &p.tmap_x, full_bar(stage), cb * CB, tx * TW * S - P, ty * kDtTH * S - P, n);
       }
       __syncwarp();
       if (++stage == stages) { stage = 0; phase ^= 1u; }
+      if (++ty == p.tiles_y) {
+        ty = 0;
+        if (++tx == p.tiles_x) { tx = 0; ++n; }
+      }
     }
   } else {
     // =========================== consumers ===========================
-    const int t = threadIdx.x;
-    const int cv = t % CV, worker = t / CV;
+    const int tid = threadIdx.x;
+    const int cv = tid % CV, worker = tid / CV;
     const int wy = worker / WCOLS, wx = worker % WCOLS;
     const int r0 = 2 * wy, cbeg = wx * CPW;
+    const int c0 = cb * CB + cv * V;
+    const bool ch_ok = c0 < p.C;       // channels past C: zero-filled input, zero weights; nothing is stored or summed for them
     float wr[KS * KS][V], bias[V];
+#pragma unroll
+    for (int i = 0; i < KS * KS; ++i) {
+      if (ch_ok) ldv<V>(p.w + i * p.C + c0, wr[i]);
+      else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) wr[i][v] = 0.f;
+      }
+    }
+    if (ch_ok) ldv<V>(p.b + c0, bias);
+    else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) bias[v] = 0.f;
+    }
+    float pool[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) pool[v] = 0.f;
+    // squeeze sums of image `img`: shuffle-reduce over the workers of this warp (lanes with equal cv), one fire-and-forget global
+    // reduction per channel and warp -- once per image and CTA, not per item
+    auto flush_pool = [&](int img) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+#pragma unroll
+        for (int o = CV; o < 32; o <<= 1) pool[v] += __shfl_xor_sync(0xffffffffu, pool[v], o);
+      }
+      if (lane < CV && cb * CB + lane * V < p.C) {
+        float* dst = p.pooled + (size_t)img * p.C + cb * CB + lane * V;
+#pragma unroll
+        for (int v = 0; v < V; ++v) atomicAdd(dst + v, pool[v]);
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) pool[v] = 0.f;
+    };
+    const int pix = p.C;
     int stage = 0;
-    uint32_t phase = 0, it = 0;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
-      const int cb = item % p.cblocks;
-      const int rem = item / p.cblocks;
-      const int n = rem / tiles_per_img, t2 = rem % tiles_per_img;
-      const int ty = t2 / p.tiles_x, tx = t2 % p.tiles_x;
-      const int c0 = cb * CB + cv * V;
-      const bool ch_ok = c0 < p.C;     // channels past C: zero-filled input, weights and bias; nothing is stored for them
+    uint32_t phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(full_bar(stage), phase);
       const float* tile = reinterpret_cast<const float*>(smem_gen + (uint32_t)stage * kTileStride) + cv * V;
-#pragma unroll
-      for (int i = 0; i < KS * KS; ++i) ldsv<V>(tile + kWOff / 4 + i * CB, wr[i]);
-      ldsv<V>(tile + kBOff / 4, bias);
-      auto lds = [&](int row, int col, float (&d)[V]) {
-        const float* q = tile + (row * TWin + col) * CB;
-        if constexpr (V == 4) {
-          const float4 v4 = *reinterpret_cast<const float4*>(q);
-          d[0] = v4.x; d[1] = v4.y; d[2] = v4.z; d[3] = v4.w;
-        } else {
-          const float2 v2 = *reinterpret_cast<const float2*>(q);
-          d[0] = v2.x; d[1] = v2.y;
-        }
-      };
+      auto lds = [&](int row, int col, float (&d)[V]) { ldsv<V>(tile + (row * TWin + col) * CB, d); };
       // window slot of logical column kx at unrolled output column c: (kx + c) % KS -- nothing is ever shifted
       // input window of the worker: rows r0 S ..., columns (cbeg + c) S + kx; logical input column j lives in slot j % KS
       float win[NR][KS][V];
@@ -434,9 +449,6 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
       for (int kx = 0; kx < KS; ++kx)
 #pragma unroll
         for (int r = 0; r < NR; ++r) lds(r0 * S + r, cbeg * S + kx, win[r][kx]);
-      float pool[V];
-#pragma unroll
-      for (int v = 0; v < V; ++v) pool[v] = 0.f;
       const int oy0 = ty * kDtTH + r0, ox0 = tx * TW + cbeg;
       // one 64-bit base per output row, 32-bit element offsets per column: the full (r Wo + c) C product in 64 bits cost ~10 integer
       // instructions per store (16 stores per item in the 5 x 5 kernels)
@@ -447,7 +459,6 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
         yrow[r] = p.y + (((size_t)n * p.Ho + oy0 + r) * p.Wo + ox0) * p.C + c0;
         row_ok[r] = ch_ok && oy0 + r < p.Ho;
       }
-      const int pix = p.C;
 #pragma unroll
       for (int c = 0; c < CPW; ++c) {
 #pragma unroll
@@ -497,88 +508,79 @@ __global__ void __launch_bounds__(kDtThreads, 1) depthwise_tma_kernel(const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar(stage));
       if (++stage == stages) { stage = 0; phase ^= 1u; }
-      // squeeze sums: shuffle-reduce over the workers of this warp (lanes with equal cv), then
-      //  * small maps (<= 16 tiles per image): one fire-and-forget global reduction per channel and warp.  No barrier: with 8
-      //    consumer warps per SM a 256-thread barrier per item left the tail of every item idle (5 x 5 layers at 64 x 64 and below:
-      //    -5 ... -9 %);
-      //  * large maps: per-warp partials in shared memory, a named barrier, ONE atomic per channel and item -- 8 reductions per
-      //    channel and item would put 2048 atomics on every address of a 256 x 256 map (measured: 3 x 3 layers +35 %).
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-#pragma unroll
-        for (int o = CV; o < 32; o <<= 1) pool[v] += __shfl_xor_sync(0xffffffffu, pool[v], o);
-      }
-      if (p.direct_pool) {
-        if (lane < CV && cb * CB + lane * V < p.C) {
-          float* dst = p.pooled + (size_t)n * p.C + cb * CB + lane * V;
-#pragma unroll
-          for (int v = 0; v < V; ++v) atomicAdd(dst + v, pool[v]);
-        }
-      } else {
-        float* part = pool_s + ((it & 1u) * 8 + (t >> 5)) * CB;
-        if (lane < CV) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) part[lane * V + v] = pool[v];
-        }
-        named_bar_sync(1, kDtConsumers);
-        if (t < CB) {
-          const float* base = pool_s + (it & 1u) * 8 * CB + t;
-          float sum = 0.f;
-#pragma unroll
-          for (int w8 = 0; w8 < 8; ++w8) sum += base[w8 * CB];
-          if (cb * CB + t < p.C) atomicAdd(p.pooled + (size_t)n * p.C + cb * CB + t, sum);
+      if (++ty == p.tiles_y) {
+        ty = 0;
+        if (++tx == p.tiles_x) {
+          tx = 0;
+          flush_pool(n);     // last tile of image n in this CTA's range
+          ++n;
         }
       }
     }
+    if (tx != 0 || ty != 0) flush_pool(n);   // the range ended inside an image
   }
 }
 
-template <int KS, int TW, int CB, int S = 1>
-static int launch_depthwise_tma_t(const float* x, const float* w, const float* b, float* y, float* pooled, int B, int H, int C,
+// AQ_DW_PROMO = 0 / 128 / 256: L2 promotion of the depthwise input map (A/B measurements)
+static int dw_l2_promotion() {
+  static const int v = [] { const char* e = getenv("AQ_DW_PROMO"); return e == nullptr ? 256 : atoi(e); }();
+  return v;
+}
+
+template <int KS, int TW, int CB, int S, int V, int NCONS>
+static int launch_depthwise_tma_v(const float* x, const float* w, const float* b, float* y, float* pooled, int B, int H, int C,
                                   cudaStream_t st) {
   constexpr int THin = (kDtTH - 1) * S + KS, TWin = (TW - 1) * S + KS;
   const int Ho = (H + 2 * ((KS - 1) / 2) - KS) / S + 1;
-  constexpr int kWOff = (THin * TWin * CB * 4 + 127) & ~127;
-  constexpr int kBOff = (kWOff + KS * KS * CB * 4 + 127) & ~127;
-  constexpr int kTileStride = (kBOff + CB * 4 + 127) & ~127;     // the kernel's stage layout: input box | weights | bias
+  constexpr int kTileStride = (THin * TWin * CB * 4 + 127) & ~127;
   DwTmaParams p;
   memset(&p, 0, sizeof(p));
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)H, (uint64_t)H, (uint64_t)B};
   uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)H * C * 4, (uint64_t)H * H * C * 4};
   uint32_t box[4] = {CB, TWin, THin, 1};
-  int rc = make_tmap(&p.tmap_x, x, 4, 4, dims, str, box, kSwzNone);
+  int rc = make_tmap(&p.tmap_x, x, 4, 4, dims, str, box, kSwzNone, dw_l2_promotion());
   if (rc) return rc;
-  {
-    uint64_t wd[2] = {(uint64_t)C, (uint64_t)(KS * KS)};
-    uint64_t ws[1] = {(uint64_t)C * 4};
-    uint32_t wb[2] = {CB, KS * KS};
-    rc = make_tmap(&p.tmap_w, w, 4, 2, wd, ws, wb, kSwzNone);
-    if (rc) return rc;
-    uint64_t bd[2] = {(uint64_t)C, 1};
-    uint32_t bb[2] = {CB, 1};
-    rc = make_tmap(&p.tmap_b, b, 4, 2, bd, ws, bb, kSwzNone);
-    if (rc) return rc;
-  }
   p.w = w; p.b = b; p.y = y; p.pooled = pooled;
   p.B = B; p.H = H; p.W = H; p.C = C; p.Ho = Ho; p.Wo = Ho;
   p.tiles_x = (Ho + TW - 1) / TW;
   p.tiles_y = (Ho + kDtTH - 1) / kDtTH;
   p.cblocks = (C + CB - 1) / CB;
-  p.direct_pool = p.tiles_x * p.tiles_y <= 16 ? 1 : 0;
-  const long long items = (long long)p.cblocks * B * p.tiles_x * p.tiles_y;
-  AQ_REQUIRE(items < (1ll << 31), AQ_ERR_BAD_SHAPE, "depthwise: too many tiles");
-  p.total_items = (int)items;
+  const long long tiles = (long long)B * p.tiles_x * p.tiles_y;
+  AQ_REQUIRE(tiles < (1ll << 31), AQ_ERR_BAD_SHAPE, "depthwise: too many tiles");
+  p.total_tiles = (int)tiles;
   int stages = (200 * 1024) / kTileStride;
   if (stages > 6) stages = 6;
   p.stages = stages;
-  const int smem = stages * kTileStride + 2 * 8 * CB * 4 + 16 * 8 + 128;
+  const int smem = stages * kTileStride + 16 * 8 + 128;
   const int sms = sm_count();
   if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
-  const int grid = (int)(items < sms ? items : sms);
-  AQ_OPT_IN_SMEM((depthwise_tma_kernel<KS, TW, CB, S>), 227 * 1024);
-  depthwise_tma_kernel<KS, TW, CB, S><<<grid, kDtThreads, smem, st>>>(p);
+  // G groups of cblocks CTAs; a group never gets less than one tile
+  int groups = sms / p.cblocks;
+  if (groups < 1) groups = 1;
+  if (groups > p.total_tiles) groups = p.total_tiles;
+  p.groups = groups;
+  const int grid = groups * p.cblocks;
+  AQ_OPT_IN_SMEM((depthwise_tma_kernel<KS, TW, CB, S, V, NCONS>), 227 * 1024);
+  depthwise_tma_kernel<KS, TW, CB, S, V, NCONS><<<grid, NCONS + 32, smem, st>>>(p);
   AQ_LAUNCHED();
   return AQ_OK;
+}
+
+// AQ_DW_V4=1: the 3 x 3 layers on 4 channels per thread and 8 consumer warps (the layout before the 16-warp version; A/B measurements)
+static bool dw_v4() {
+  static const bool on = [] { const char* e = getenv("AQ_DW_V4"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+
+template <int KS, int TW, int CB, int S = 1>
+static int launch_depthwise_tma_t(const float* x, const float* w, const float* b, float* y, float* pooled, int B, int H, int C,
+                                  cudaStream_t st) {
+  if constexpr (KS == 3) {
+    if (dw_v4()) return launch_depthwise_tma_v<KS, TW, CB, S, 4, 256>(x, w, b, y, pooled, B, H, C, st);
+    return launch_depthwise_tma_v<KS, TW, CB, S, 2, 512>(x, w, b, y, pooled, B, H, C, st);
+  } else {
+    return launch_depthwise_tma_v<KS, TW, CB, S, 2, 256>(x, w, b, y, pooled, B, H, C, st);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -654,20 +656,32 @@ se_kernel(const float* __restrict__ pooled, const float* __restrict__ w1, const 
 // ---------------------------------------------------------------------------------------------------------------
 // classifier: logits[n, o] = b[o] + sum_c w[o, c] * pooled_sum[n, c] / hw ;  bits[n, i] = argmax(logits[n, 2i], logits[n, 2i+1])
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ pooled, const float* __restrict__ w,
+// 32 warps per image, 3 outputs each, 10 independent 16-byte weight loads per lane and output: with 8 warps x 12 outputs and a scalar
+// load per step the kernel was one L2 latency chain (53 us for 7.9 MFLOP)
+__global__ void __launch_bounds__(1024) fc_kernel(const float* __restrict__ pooled, const float* __restrict__ w,
                                                   const float* __restrict__ b, float* __restrict__ logits,
                                                   unsigned char* __restrict__ bits, int C, int O, float inv_hw) {
-  extern __shared__ float sm[];   // mean [C], out [O]
+  extern __shared__ __align__(16) float sm[];   // mean [C], out [O]
   float* mean = sm;
   float* out = sm + C;
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pooled[(size_t)n * C + c] * inv_hw;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int o = warp; o < O; o += 8) {
-    const float* wr = w + (size_t)o * C;
+  const int nwarps = blockDim.x >> 5;
+  for (int o = warp; o < O; o += nwarps) {
+    const float4* wr4 = reinterpret_cast<const float4*>(w + (size_t)o * C);       // C % 4 == 0, rows 16-byte aligned (host checks)
+    const float4* mean4 = reinterpret_cast<const float4*>(mean);
     float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(wr + c), mean[c], acc);
+#pragma unroll 10
+    for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
+      const float4 wv = __ldg(wr4 + c4);
+      const float4 mv = mean4[c4];
+      acc = fmaf(wv.x, mv.x, acc);
+      acc = fmaf(wv.y, mv.y, acc);
+      acc = fmaf(wv.z, mv.z, acc);
+      acc = fmaf(wv.w, mv.w, acc);
+    }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
     if (lane == 0) {
@@ -914,7 +928,7 @@ int aq_effnetb1_fwd(const float* x, const float* packed, float* logits, unsigned
   {
     const float* w = wk.take((size_t)out_features * kHeadC);
     const float* b = wk.take(out_features);
-    fc_kernel<<<B, 256, (kHeadC + out_features) * sizeof(float), st>>>(head_pool, w, b, logits, bits, kHeadC, out_features, 1.f / (float)(h * h));
+    fc_kernel<<<B, 1024, (kHeadC + out_features) * sizeof(float), st>>>(head_pool, w, b, logits, bits, kHeadC, out_features, 1.f / (float)(h * h));
     AQ_LAUNCHED();
   }
   return AQ_OK;

@@ -54,6 +54,7 @@ struct PwTcParams {
   int BN, num_n_tiles, num_m_tiles, num_kc, stages;
   int w_resident;   // 1: all W chunks (hi + lo) stay in SMEM for the whole kernel (single N tile, small K): only A streams
   int tile_par;     // 1: narrow outputs (<= 3 pieces): the four epilogue warps of a TMEM quadrant take WHOLE tiles in turn (single-CTA kernel)
+  int stack;        // 1: W_hi and W_lo form ONE B operand of 2 BN rows (single-CTA kernel): a_hi is read from shared memory once per k step
 };
 
 // SiLU with the SFU exponential and reciprocal (relative error ~1e-6, far inside the decoder's 1e-4 logit tolerance)
@@ -94,7 +95,13 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * 41);
   // accumulator ring in TMEM: narrow layers (BN = 16 ... 64) keep up to 8 tiles in flight between the MMA thread and the epilogue
   // tile_par needs a ring size that is a multiple of 4 (a slot always belongs to the same epilogue warp group)
-  const uint32_t nacc = p.tile_par ? (BN <= 64 ? 8u : 4u) : min(8u, 512u / (uint32_t)BN);
+  // stack: the accumulator of a tile is [a_hi w_hi + a_lo w_hi | a_hi w_lo] (2 BN columns, summed by the epilogue).  The narrow project
+  // layers are bound by shared-memory bandwidth (per 128 x 160 A tile: 80 KB TMA write, 80 KB converter read, 160 KB hi / lo write,
+  // 3 x 80 KB operand reads by the MMAs -- the 16-cycle MMA of a 32-column tile waits for its 4 KB A read); one stacked MMA reads a_hi
+  // once instead of twice
+  const bool stack = p.stack != 0;
+  const uint32_t acc_cols = stack ? 2u * (uint32_t)BN : (uint32_t)BN;
+  const uint32_t nacc = p.tile_par ? (acc_cols <= 64 ? 8u : 4u) : min(8u, 512u / acc_cols);
 
   auto a_hi = [&](int s) { return smem_base + ring_off + (uint32_t)s * stage_bytes; };
   auto a_lo = [&](int s) { return smem_base + ring_off + (uint32_t)s * stage_bytes + kPwATile; };
@@ -168,6 +175,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
   } else if (warp == kPwMmaWarp) {
     // =========================== MMA issuer ===========================
     const uint32_t idesc = make_idesc_tf32(kPwBM, (uint32_t)BN);
+    const uint32_t idesc2 = make_idesc_tf32(kPwBM, 2u * (uint32_t)BN);   // stacked [W_hi ; W_lo] (contiguous in shared memory)
     constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
     auto desc = [&](uint32_t addr) { return kDescHi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
     int stage = 0;
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
     }
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++acc_iter) {
       const uint32_t buf = acc_iter % nacc;
-      const uint32_t tmem_acc = tmem_base + buf * (uint32_t)BN;
+      const uint32_t tmem_acc = tmem_base + buf * acc_cols;
       mbar_wait(acc_empty_bar(buf), ((acc_iter / nacc) & 1u) ^ 1u);
       tc_fence_after();
       for (int kc = 0; kc < num_kc; ++kc) {
@@ -188,11 +196,18 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
         if (elect_one()) {
           const int ksteps = min(kPwKC, p.K - kc * kPwKC) >> 3;   // 8 tf32 per MMA; the zero-filled tail is skipped
           const uint64_t ah = desc(a_hi(stage)), al = desc(a_lo(stage)), wh = desc(w_hi(stage, kc)), wl = desc(w_lo(stage, kc));
-          for (int k = 0; k < ksteps; ++k) {
-            // small terms first, the dominant hi * hi product last
-            umma_tf32(tmem_acc, al + 2 * k, wh + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
-            umma_tf32(tmem_acc, ah + 2 * k, wl + 2 * k, idesc, 1u);
-            umma_tf32(tmem_acc, ah + 2 * k, wh + 2 * k, idesc, 1u);
+          if (stack) {
+            for (int k = 0; k < ksteps; ++k) {
+              umma_tf32(tmem_acc, ah + 2 * k, wh + 2 * k, idesc2, (kc | k) != 0 ? 1u : 0u);   // [a_hi w_hi | a_hi w_lo]
+              umma_tf32(tmem_acc, al + 2 * k, wh + 2 * k, idesc, 1u);                          // first half += a_lo w_hi
+            }
+          } else {
+            for (int k = 0; k < ksteps; ++k) {
+              // small terms first, the dominant hi * hi product last
+              umma_tf32(tmem_acc, al + 2 * k, wh + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_tf32(tmem_acc, ah + 2 * k, wl + 2 * k, idesc, 1u);
+              umma_tf32(tmem_acc, ah + 2 * k, wh + 2 * k, idesc, 1u);
+            }
           }
           umma_commit(empty_bar(stage));
           if (kc == num_kc - 1) umma_commit(acc_full_bar(buf));
@@ -293,11 +308,29 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
         const int pc = pc_first + pc_step * g;
         const int c0 = n0 + pc * 16;
         uint32_t tr[16];
-        tmem_ld_32x16(tmem_base + lane_base + buf * (uint32_t)BN + pc * 16, tr);
+        tmem_ld_32x16(tmem_base + lane_base + buf * acc_cols + pc * 16, tr);
         float4 b4[4];
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4)
           b4[i4] = c0 + i4 * 4 < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (stack) {
+          // the a_hi w_lo half of the stacked accumulator: bias joins the first half while the second is in flight, then the second
+          // half takes the bias slot of the sum below
+          tmem_wait_ld();
+          uint32_t t2[16];
+          tmem_ld_32x16(tmem_base + lane_base + buf * acc_cols + (uint32_t)BN + pc * 16, t2);
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            tr[i4 * 4 + 0] = __float_as_uint(__uint_as_float(tr[i4 * 4 + 0]) + b4[i4].x);
+            tr[i4 * 4 + 1] = __float_as_uint(__uint_as_float(tr[i4 * 4 + 1]) + b4[i4].y);
+            tr[i4 * 4 + 2] = __float_as_uint(__uint_as_float(tr[i4 * 4 + 2]) + b4[i4].z);
+            tr[i4 * 4 + 3] = __float_as_uint(__uint_as_float(tr[i4 * 4 + 3]) + b4[i4].w);
+          }
+          tmem_wait_ld();
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4)
+            b4[i4] = make_float4(__uint_as_float(t2[i4 * 4]), __uint_as_float(t2[i4 * 4 + 1]), __uint_as_float(t2[i4 * 4 + 2]), __uint_as_float(t2[i4 * 4 + 3]));
+        }
         if (p.epi == kPwResidual && g > 0) {
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4)
@@ -661,6 +694,12 @@ static bool pw_pair_enabled() {
   return on;
 }
 
+// AQ_PW_STACK=0: three separate MMAs per k step everywhere (A/B measurements)
+static bool pw_stack_enabled() {
+  static const bool on = [] { const char* e = getenv("AQ_PW_STACK"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 static int pick_pw_bn(int N) {
   const int n16 = (N + 15) / 16 * 16;
   if (n16 <= kPwMaxBN) return n16;
@@ -714,6 +753,8 @@ int launch_pointwise_tc(const PwTcArgs& a, cudaStream_t st) {
   p.w_resident = (p.num_n_tiles == 1 && p.num_kc * w_tile_bytes <= 96 * 1024) ? 1 : 0;
   // narrow outputs (<= 3 pieces: 8-slot ring) and the 96-wide expand (6 pieces over 4 warp groups = 2, 2, 1, 1 per tile; 4-slot ring)
   p.tile_par = ((p.BN <= 48 || p.BN == 96) && a.epi != kPwSiluPool) ? 1 : 0;
+  // stacked B operand for the narrow layers with a deep product (the project convolutions): 2 BN <= 96 accumulator columns x 4 - 8 slots
+  p.stack = (p.tile_par && p.BN <= 48 && a.K >= 32 && p.num_n_tiles == 1 && pw_stack_enabled()) ? 1 : 0;
   const int sms = sm_count();
   if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
   if (!p.w_resident && p.num_m_tiles >= 2 && pw_pair_enabled()) {
