@@ -72,23 +72,25 @@ __global__ void __launch_bounds__(kStemThreads) stem_kernel(const float* __restr
   const int oy = blockIdx.y, n = blockIdx.z;
   const int ixb = blockIdx.x * kStemInW;                    // first input column of the segment (a multiple of 512)
   {
+    // W % 4 == 0 (host check): a float4 either lies inside the row or starts past it.  All nine loads are predicated, not branched,
+    // and leave back to back; the halo column is ONE load of the threads 0 ... 8 (inside the row loop it shared a destination
+    // register across the unrolled iterations and serialised the nine loads: 38 % of the kernel's stall samples)
     const float* xn = x + (size_t)n * 3 * H * W;
+    const int ix = ixb + 4 * (int)threadIdx.x;
     float4 q[9];
-    float hv = 0.f;
 #pragma unroll
     for (int r = 0; r < 9; ++r) {                           // r = ky * 3 + ci
       const int iy = oy * 2 - 1 + r / 3;
-      const float* row = xn + ((size_t)(r % 3) * H + iy) * W;
-      const int ix = ixb + 4 * threadIdx.x;
-      const bool rok = iy >= 0 && iy < H;
-      q[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rok && ix + 3 < W) q[r] = __ldg(reinterpret_cast<const float4*>(row + ix));
-      else if (rok) {
-        if (ix < W) q[r].x = __ldg(row + ix);
-        if (ix + 1 < W) q[r].y = __ldg(row + ix + 1);
-        if (ix + 2 < W) q[r].z = __ldg(row + ix + 2);
-      }
-      if ((int)threadIdx.x == r && rok && ixb > 0) hv = __ldg(row + ixb - 1);
+      const bool ok = iy >= 0 && iy < H && ix < W;
+      const float* row = xn + ((size_t)(r % 3) * H + (ok ? iy : 0)) * W + (ok ? ix : 0);
+      q[r] = __ldg(reinterpret_cast<const float4*>(row));
+      if (!ok) q[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float hv = 0.f;
+    if (threadIdx.x < 9) {
+      const int r = threadIdx.x;
+      const int iy = oy * 2 - 1 + r / 3;
+      if (iy >= 0 && iy < H && ixb > 0) hv = __ldg(xn + ((size_t)(r % 3) * H + iy) * W + ixb - 1);
     }
 #pragma unroll
     for (int r = 0; r < 9; ++r) *reinterpret_cast<float4*>(&xs[r * kStemRow + 4 + 4 * threadIdx.x]) = q[r];
@@ -854,6 +856,7 @@ int aq_effnetb1_fwd(const float* x, const float* packed, float* logits, unsigned
   {
     const float* w = wk.take(27 * 32);
     const float* b = wk.take(32);
+    static_assert(kImg % 4 == 0, "stem_kernel loads the input rows as float4");
     dim3 grid((h + kStemTile - 1) / kStemTile, h, B);
     stem_kernel<<<grid, kStemThreads, 0, st>>>(x, w, b, act[0], kImg, kImg, h, h);
     AQ_LAUNCHED();
