@@ -97,6 +97,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* t, 
       "l"(t), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// the same load with an L2 cache policy (createpolicy encodings as CUTLASS's TMA::CacheHintSm90: evict_first 0x12F0..., evict_last 0x14F0...)
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull, kL2EvictFirst = 0x12F0000000000000ull, kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap* t, uint32_t bar, int c0, int c1, int c2, int c3, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+      "l"(t), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* t, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(t),
                "r"(src), "r"(c0), "r"(c1)

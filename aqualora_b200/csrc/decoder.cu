@@ -333,7 +333,8 @@ constexpr int kDtTH = 8, kDtCB = 32;
 struct DwTmaParams {
   CUtensorMap tmap_x;
   const float* w; const float* b; float* y; float* pooled;
-  int B, H, W, C, Ho, Wo, tiles_x, tiles_y, cblocks, groups, total_tiles, stages;
+  int B, H, W, C, Ho, Wo, tiles_x, tiles_y, cblocks, groups, ychunks, round_robin, stages;
+  int l2_hint;   // L2 policy of the input loads: 0 default, 1 evict_last, 2 evict_first
 };
 
 // V = channels per thread, NCONS = consumer threads: 3 x 3 runs V = 2 with 16 consumer warps (<= 120 registers), 5 x 5 (50 weight
@@ -368,33 +369,56 @@ __global__ void __launch_bounds__(NCONS + 32, 1) depthwise_tma_kernel(const __gr
     fence_mbar_init();
   }
   __syncthreads();
-  // this CTA's channel block and tile range; (n, ty, tx) of the first tile by division, then by increments
+  // this CTA's channel block and group; a group walks UNITS = (image, tile column, chunk of `ulen` consecutive tile rows), unit u of
+  // group g: u = g, g + G, ... -- the groups work on neighbouring tile columns at the same time (the horizontal halo of a column is
+  // fetched by the neighbour group within the same microseconds) and a CTA walks DOWN its column (the two halo rows it shares with
+  // the next tile are in L2).  Contiguous per-group ranges (groups 2+ images apart) read 28 % more DRAM bytes than the tensor holds
+  // on the 144-channel maps (profiles/r02_decoder_launches_v22_final.txt).
+  // Small maps (tile columns of < 16 tiles) keep CONTIGUOUS unit ranges per group instead (p.round_robin = 0): there the interleaved
+  // walk changes image every 1 - 2 tiles and measured 8 - 12 % slower, while their DRAM reads are at the algorithmic minimum anyway.
   const int cb = (int)blockIdx.x % p.cblocks, grp = (int)blockIdx.x / p.cblocks;
-  const int t_begin = (int)((long long)grp * p.total_tiles / p.groups);
-  const int t_end = (int)((long long)(grp + 1) * p.total_tiles / p.groups);
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
-  int n = t_begin / tiles_per_img;
-  // tile y is the fastest index: the two halo rows a tile shares with the tile below are re-read by the very next item (L2 hit).
-  // With tile x fastest the re-read came tiles_x items later and missed: DRAM reads of the 144-channel layers 604 -> 767 MB.
-  int tx = (t_begin % tiles_per_img) / p.tiles_y, ty = (t_begin % tiles_per_img) % p.tiles_y;
+  const int units = p.B * p.tiles_x * p.ychunks, ulen = p.tiles_y / p.ychunks;
+  const int u_begin = p.round_robin ? grp : (int)((long long)grp * units / p.groups);
+  const int u_end = p.round_robin ? units : (int)((long long)(grp + 1) * units / p.groups);
+  const int u_step = p.round_robin ? p.groups : 1;
+  // (image, tile column, chunk) of the current unit: by division at the start and per round-robin step (units are long there), by
+  // increments in the contiguous walk
+  int chunk = u_begin % p.ychunks, n = (u_begin / p.ychunks) / p.tiles_x, tx = (u_begin / p.ychunks) % p.tiles_x;
+  auto next_unit = [&](int u) {
+    if (u_step == 1) {
+      if (++chunk == p.ychunks) {
+        chunk = 0;
+        if (++tx == p.tiles_x) { tx = 0; ++n; }
+      }
+    } else {
+      const int un = u + u_step, strip = un / p.ychunks;
+      chunk = un % p.ychunks;
+      n = strip / p.tiles_x;
+      tx = strip % p.tiles_x;
+    }
+  };
 
   if (warp == NCONS / 32) {
     // =========================== TMA producer ===========================
     if (lane == 0) tma_prefetch_desc(&p.tmap_x);
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = t_begin; t < t_end; ++t) {
-      mbar_wait(empty_bar(stage), phase ^ 1u);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(full_bar(stage), kTileBytes);
-        tma_load_4d(smem_base + (uint32_t)stage * kTileStride, &p.tmap_x, full_bar(stage), cb * CB, tx * TW * S - P, ty * kDtTH * S - P, n);
+    for (int u = u_begin; u < u_end; u += u_step) {
+      const int ty0 = chunk * ulen;
+      for (int ty = ty0; ty < ty0 + ulen; ++ty) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(stage), kTileBytes);
+          if (p.l2_hint != 0)
+            tma_load_4d_hint(smem_base + (uint32_t)stage * kTileStride, &p.tmap_x, full_bar(stage), cb * CB, tx * TW * S - P, ty * kDtTH * S - P, n,
+                             p.l2_hint == 1 ? kL2EvictLast : kL2EvictFirst);
+          else
+            tma_load_4d(smem_base + (uint32_t)stage * kTileStride, &p.tmap_x, full_bar(stage), cb * CB, tx * TW * S - P, ty * kDtTH * S - P, n);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
-      if (++stage == stages) { stage = 0; phase ^= 1u; }
-      if (++ty == p.tiles_y) {
-        ty = 0;
-        if (++tx == p.tiles_x) { tx = 0; ++n; }
-      }
+      next_unit(u);
     }
   } else {
     // =========================== consumers ===========================
@@ -438,9 +462,15 @@ __global__ void __launch_bounds__(NCONS + 32, 1) depthwise_tma_kernel(const __gr
       for (int v = 0; v < V; ++v) pool[v] = 0.f;
     };
     const int pix = p.C;
-    int stage = 0;
+    int stage = 0, cur_n = -1;
     uint32_t phase = 0;
-    for (int t = t_begin; t < t_end; ++t) {
+    for (int u = u_begin; u < u_end; u += u_step) {
+      const int ty0 = chunk * ulen;
+      if (n != cur_n) {
+        if (cur_n >= 0) flush_pool(cur_n);     // the squeeze sums of the previous image leave when the image changes
+        cur_n = n;
+      }
+      for (int ty = ty0; ty < ty0 + ulen; ++ty) {
       mbar_wait(full_bar(stage), phase);
       const float* tile = reinterpret_cast<const float*>(smem_gen + (uint32_t)stage * kTileStride) + cv * V;
       auto lds = [&](int row, int col, float (&d)[V]) { ldsv<V>(tile + (row * TWin + col) * CB, d); };
@@ -510,22 +540,22 @@ __global__ void __launch_bounds__(NCONS + 32, 1) depthwise_tma_kernel(const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar(stage));
       if (++stage == stages) { stage = 0; phase ^= 1u; }
-      if (++ty == p.tiles_y) {
-        ty = 0;
-        if (++tx == p.tiles_x) {
-          tx = 0;
-          flush_pool(n);     // last tile of image n in this CTA's range
-          ++n;
-        }
       }
+      next_unit(u);
     }
-    if (tx != 0 || ty != 0) flush_pool(n);   // the range ended inside an image
+    if (cur_n >= 0) flush_pool(cur_n);
   }
 }
 
 // AQ_DW_PROMO = 0 / 128 / 256: L2 promotion of the depthwise input map (A/B measurements)
 static int dw_l2_promotion() {
   static const int v = [] { const char* e = getenv("AQ_DW_PROMO"); return e == nullptr ? 256 : atoi(e); }();
+  return v;
+}
+
+// AQ_DW_L2HINT = 0 / 1 / 2: L2 policy of the depthwise input loads (default, evict_last, evict_first; A/B measurements)
+static int dw_l2_hint() {
+  static const int v = [] { const char* e = getenv("AQ_DW_L2HINT"); return e == nullptr ? 0 : atoi(e); }();
   return v;
 }
 
@@ -547,20 +577,44 @@ static int launch_depthwise_tma_v(const float* x, const float* w, const float* b
   p.tiles_x = (Ho + TW - 1) / TW;
   p.tiles_y = (Ho + kDtTH - 1) / kDtTH;
   p.cblocks = (C + CB - 1) / CB;
-  const long long tiles = (long long)B * p.tiles_x * p.tiles_y;
-  AQ_REQUIRE(tiles < (1ll << 31), AQ_ERR_BAD_SHAPE, "depthwise: too many tiles");
-  p.total_tiles = (int)tiles;
+  const long long strips = (long long)B * p.tiles_x;
+  AQ_REQUIRE(strips * p.tiles_y < (1ll << 31), AQ_ERR_BAD_SHAPE, "depthwise: too many tiles");
   int stages = (200 * 1024) / kTileStride;
   if (stages > 6) stages = 6;
   p.stages = stages;
   const int smem = stages * kTileStride + 16 * 8 + 128;
   const int sms = sm_count();
   if (sms <= 0) return fail(AQ_ERR_LAUNCH, "no CUDA device");
-  // G groups of cblocks CTAs; a group never gets less than one tile
+  // G groups of cblocks CTAs.  Large maps (tile columns of >= 16 tiles): units dealt round-robin, a unit = a tile column or 1 / 2,
+  // 1 / 4, 1 / 8 of one -- the coarsest split within 2 % of the best last-round occupancy.  Small maps: contiguous ranges of units of
+  // <= 2 tiles (balance within one unit).  AQ_DW_RR=0 / 1 forces one of the walks (A/B measurements).
   int groups = sms / p.cblocks;
   if (groups < 1) groups = 1;
-  if (groups > p.total_tiles) groups = p.total_tiles;
+  static const int rr_env = [] { const char* e = getenv("AQ_DW_RR"); return e == nullptr ? -1 : atoi(e); }();
+  p.round_robin = rr_env >= 0 ? (rr_env != 0) : (p.tiles_y >= 16 ? 1 : 0);
+  if (p.round_robin) {
+    int best_chunks = 1;
+    double best_eff = 0.0;
+    for (int ch = 1; ch <= 8 && ch <= p.tiles_y; ch *= 2) {
+      if (p.tiles_y % ch != 0) break;
+      const long long units = strips * ch;
+      const long long g = groups < units ? groups : units;
+      const double eff = (double)units / (double)(((units + g - 1) / g) * g);
+      if (eff > best_eff + 0.02) {
+        best_eff = eff;
+        best_chunks = ch;
+      }
+    }
+    p.ychunks = best_chunks;
+  } else {
+    static const int ulen_env = [] { const char* e = getenv("AQ_DW_ULEN"); return e == nullptr ? 2 : atoi(e); }();
+    const int ulen = (ulen_env >= 1 && p.tiles_y % ulen_env == 0) ? ulen_env : 1;     // tiles per unit (AQ_DW_ULEN, default 2)
+    p.ychunks = p.tiles_y / ulen;
+    if (p.ychunks < 1) p.ychunks = 1;
+  }
+  if ((long long)groups > strips * p.ychunks) groups = (int)(strips * p.ychunks);
   p.groups = groups;
+  p.l2_hint = dw_l2_hint();
   const int grid = groups * p.cblocks;
   AQ_OPT_IN_SMEM((depthwise_tma_kernel<KS, TW, CB, S, V, NCONS>), 227 * 1024);
   depthwise_tma_kernel<KS, TW, CB, S, V, NCONS><<<grid, NCONS + 32, smem, st>>>(p);
@@ -785,6 +839,12 @@ static bool dw_s2_tma_enabled() {
 
 static int launch_depthwise(const float* x, const float* w, const float* b, float* y, float* pooled, int B, int H, int C, int k,
                             int stride, int Ho, cudaStream_t st) {
+  // AQ_DW_CB16=1 (A/B measurement): channel counts that are an odd multiple of 16 (144 = 9 x 16) in 16-channel blocks -- no half-empty
+  // last block, every box row is a whole 64-byte-aligned piece of the pixel -- instead of 32-channel blocks with a 64-byte-misaligned
+  // 128-byte row on every other pixel
+  static const bool cb16 = [] { const char* e = getenv("AQ_DW_CB16"); return e != nullptr && e[0] == '1'; }();
+  if (cb16 && stride == 1 && k == 3 && C % 32 == 16 && C > 16 && Ho >= 64 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0)
+    return launch_depthwise_tma_t<3, 64, 16>(x, w, b, y, pooled, B, H, C, st);
   if (stride == 1 && C >= kDtCB && C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
     const bool wide = Ho >= 32 && !dw_tw16();
     if (k == 3) return wide ? launch_depthwise_tma_t<3, 32, kDtCB>(x, w, b, y, pooled, B, H, C, st) : launch_depthwise_tma_t<3, 16, kDtCB>(x, w, b, y, pooled, B, H, C, st);
