@@ -399,6 +399,31 @@ __device__ __forceinline__ void silu2(float& x0, float& x1) {
       : "f"(r0), "f"(r1));
 }
 
+// SiLU of two values with ONE SFU operation per element: the exponential stays on the SFU, the reciprocal of d = 1 + e runs on the FMA
+// pipe -- seed r0 = bits(0x7EF311C7 - bits(d)) (12 % off at worst) and three Newton steps r <- r + r (1 - d r) (error 0.12 -> 1.4e-2
+// -> 2e-4 -> 4e-8, i.e. fp32 round-off).  silu2() costs 7 issue slots and 4 SFU operations per pair; the SFU delivers 16 results per
+// clock and SM, so an epilogue of 16 warps that is nothing but SiLU is SFU-bound at 32 cycles per pair and warp.  This form: 15 issue
+// slots (packed FFMA2) and 2 SFU operations = 16 SFU cycles.  The exponent is clamped at 2^126 so that d stays finite (x < -87: the
+// result is -0 / denormal either way).
+__device__ __forceinline__ void silu2_nr(float& x0, float& x1) {
+  float t0 = fminf(x0 * -1.4426950408889634f, 126.f), t1 = fminf(x1 * -1.4426950408889634f, 126.f);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  float nd0 = -1.f, nd1 = -1.f;                       // nd = -(1 + e)
+  ffma2(nd0, nd1, e0, e1, -1.f, -1.f);
+  // bits(d) = bits(nd) - 0x80000000, so 0x7EF311C7 - bits(d) = 0xFEF311C7 - bits(nd) (mod 2^32)
+  float r0 = __uint_as_float(0xFEF311C7u - __float_as_uint(nd0)), r1 = __uint_as_float(0xFEF311C7u - __float_as_uint(nd1));
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    float u0 = 1.f, u1 = 1.f;
+    ffma2(u0, u1, nd0, nd1, r0, r1);                  // u = 1 - d r
+    ffma2(r0, r1, r0, r1, u0, u1);                    // r = r + r u
+  }
+  x0 *= r0;
+  x1 *= r1;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -54,6 +54,7 @@ struct PwTcParams {
   int BN, num_n_tiles, num_m_tiles, num_kc, stages;
   int w_resident;   // 1: all W chunks (hi + lo) stay in SMEM for the whole kernel (single N tile, small K): only A streams
   int tile_par;     // 1: narrow outputs (<= 3 pieces): the four epilogue warps of a TMEM quadrant take WHOLE tiles in turn (single-CTA kernel)
+  int silu_nr;      // 1: SiLU with the reciprocal on the FMA pipe (silu2_nr: one SFU operation per element instead of two)
   int stack;        // 1: W_hi and W_lo form ONE B operand of 2 BN rows (single-CTA kernel): a_hi is read from shared memory once per k step
 };
 
@@ -353,7 +354,10 @@ __global__ void __launch_bounds__(kPwThreads, 1) pointwise_tc_kernel(const __gri
         }
         if (p.epi == kPwSilu || p.epi == kPwSiluPool) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) silu2(f[i], f[i + 1]);
+          for (int i = 0; i < 16; i += 2) {
+            if (p.silu_nr) silu2_nr(f[i], f[i + 1]);
+            else silu2(f[i], f[i + 1]);
+          }
         }
         if (p.epi == kPwSiluPool) {
           // column sums over this warp's 32 rows (all inside one image: hw % 128 == 0), one atomic per column
@@ -637,7 +641,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwThreads, 1) point
         }
         if (p.epi == kPwSilu || p.epi == kPwSiluPool) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) silu2(f[i], f[i + 1]);
+          for (int i = 0; i < 16; i += 2) {
+            if (p.silu_nr) silu2_nr(f[i], f[i + 1]);
+            else silu2(f[i], f[i + 1]);
+          }
         }
         if (p.epi == kPwSiluPool) {
 #pragma unroll
@@ -700,6 +707,12 @@ static bool pw_stack_enabled() {
   return on;
 }
 
+// AQ_SILU_NR=0 / 1: SiLU epilogues with two SFU operations per element / with the Newton reciprocal (A/B measurements)
+static bool pw_silu_nr() {
+  static const bool on = [] { const char* e = getenv("AQ_SILU_NR"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+
 static int pick_pw_bn(int N) {
   const int n16 = (N + 15) / 16 * 16;
   if (n16 <= kPwMaxBN) return n16;
@@ -753,6 +766,7 @@ int launch_pointwise_tc(const PwTcArgs& a, cudaStream_t st) {
   p.w_resident = (p.num_n_tiles == 1 && p.num_kc * w_tile_bytes <= 96 * 1024) ? 1 : 0;
   // narrow outputs (<= 3 pieces: 8-slot ring) and the 96-wide expand (6 pieces over 4 warp groups = 2, 2, 1, 1 per tile; 4-slot ring)
   p.tile_par = ((p.BN <= 48 || p.BN == 96) && a.epi != kPwSiluPool) ? 1 : 0;
+  p.silu_nr = pw_silu_nr() ? 1 : 0;
   // stacked B operand for the narrow layers with a deep product (the project convolutions): 2 BN <= 96 accumulator columns x 4 - 8 slots
   p.stack = (p.tile_par && p.BN <= 48 && a.K >= 32 && p.num_n_tiles == 1 && pw_stack_enabled()) ? 1 : 0;
   const int sms = sm_count();
