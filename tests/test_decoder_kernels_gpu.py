@@ -70,7 +70,11 @@ def test_conv1x1_tf32x3_matches_float64(cuda_device, M, K, N, hw, epi, use_se):
 
 
 @pytest.mark.parametrize("B,H,C,k,stride", [(2, 64, 32, 3, 1), (2, 64, 96, 3, 2), (1, 32, 144, 5, 2), (3, 16, 480, 5, 1),
-                                            (2, 16, 1152, 3, 1), (1, 33, 16, 3, 1), (1, 20, 672, 5, 2)])
+                                            (2, 16, 1152, 3, 1), (1, 33, 16, 3, 1), (1, 20, 672, 5, 2),
+                                            # large maps = the round-robin unit walk: 144 channels (half-empty last block, groups not a
+                                            # divisor of the units), 16 channels on 64-wide tiles with a partial tile column, a single
+                                            # image whose tile columns are split into chunks (fewer units than groups)
+                                            (3, 128, 144, 3, 1), (2, 72, 16, 3, 1), (1, 256, 32, 3, 1), (2, 136, 96, 5, 1)])
 def test_depthwise_silu_matches_float64(cuda_device, B, H, C, k, stride):
     from aqualora_b200 import ops
 
