@@ -713,8 +713,8 @@ NOISE_P = [0.4, 0.1, 0.2, 0.05, 0.1, 0.15]
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum over the 93 decoder launches of one 64-image batch (ncu launch list
-# profiles/r01_decoder_launches_v9.txt: 13.51 GB read + 9.74 GB written), per image
-DECODE_DRAM_TRAFFIC_PER_IMAGE = (13.511e9 + 9.737e9) / 64
+# profiles/r02_decoder_launches_v23.txt: 13.77 GB read + 9.73 GB written), per image
+DECODE_DRAM_TRAFFIC_PER_IMAGE = (13.767e9 + 9.729e9) / 64
 
 
 def run_decode(args):
@@ -874,7 +874,7 @@ def measure_decode(images, cpu_check=True, device_index=0, shard=0, check_all=Tr
                                                                "cuda_path_vs_cpu_oracle_bits": [s_agree, s_total]}},
             "roofline": {"bound": "hbm", "kernel": "decoder chain (csrc/decoder.cu), decoder-only loop", "achieved": round(DECODE_BYTES_PER_IMAGE_FP32 * dec_rate / 1e9, 1),
                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(DECODE_BYTES_PER_IMAGE_FP32 * dec_rate / 1e9 / pk["hbm_gbs"], 4),
-                         "traffic": round(DECODE_DRAM_TRAFFIC_PER_IMAGE), "traffic_note": "DRAM bytes per image, ncu launch list of one 64-image batch",
+                         "traffic": round(DECODE_DRAM_TRAFFIC_PER_IMAGE), "traffic_note": "DRAM bytes per image, ncu launch list of one 64-image batch (profiles/r02_decoder_launches_v23.txt)",
                          "decoder_images_per_sec": round(dec_rate, 1),
                          "algorithmic_bytes_per_image": DECODE_BYTES_PER_IMAGE_FP32},
             "cpu_baseline": {"value": round(48 / t_cpu, 3), "unit": "images/s", "cores": cores, "kind": "port",
