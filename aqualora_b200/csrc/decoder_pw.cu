@@ -39,6 +39,7 @@ constexpr int kPwKC = 32;                      // fp32 elements per k chunk = on
 constexpr int kPwATile = kPwBM * kPwKC * 4;    // 16 KiB
 constexpr int kPwStgWarp = 32 * 64;             // per epilogue warp: one 32-row x 16-column fp32 piece = the box of Y's tensor map (64B swizzle)
 constexpr int kPwSmemBudget = 232448 - 1024;
+constexpr int kPwResidentMax = 120 * 1024;     // resident W of a single > 224-column tile: leaves two 32 KB stages beside the 32 KB of staging
 
 struct PwTcParams {
   CUtensorMap tmap_x;     // X    [M, K] fp32   box {32, 128}  swizzle 128B
@@ -713,6 +714,12 @@ static bool pw_silu_nr() {
   return on;
 }
 
+// AQ_PW_WIDE_RES=0: N = 240 layers as two tiles on the CTA-pair kernel (A/B measurements)
+static bool pw_wide_resident() {
+  static const bool on = [] { const char* e = getenv("AQ_PW_WIDE_RES"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 static int pick_pw_bn(int N) {
   const int n16 = (N + 15) / 16 * 16;
   if (n16 <= kPwMaxBN) return n16;
@@ -732,6 +739,12 @@ int launch_pointwise_tc(const PwTcArgs& a, cudaStream_t st) {
   PwTcParams p;
   memset(&p, 0, sizeof(p));
   p.BN = pick_pw_bn(a.N);
+  {
+    // wide but shallow layers (40 -> 240): ONE column tile whose weights stay in shared memory (120 KB of W hi / lo + 2 stages of A)
+    // instead of two 128-column tiles on the CTA-pair kernel, which re-streamed 122 KB of W per 256-row item against 64 KB of A
+    const int n16 = (a.N + 15) / 16 * 16, kc = (a.K + kPwKC - 1) / kPwKC;
+    if (n16 > kPwMaxBN && n16 <= 256 && kc * 2 * n16 * 128 <= kPwResidentMax && a.epi != kPwSiluPool && pw_wide_resident()) p.BN = n16;
+  }
   {
     uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
     uint64_t str[1] = {(uint64_t)a.K * 4};
@@ -763,7 +776,7 @@ int launch_pointwise_tc(const PwTcArgs& a, cudaStream_t st) {
   p.num_kc = (a.K + kPwKC - 1) / kPwKC;
   const int w_tile_bytes = 2 * p.BN * 128;                                   // hi + lo of one k chunk
   const int fixed = kPwEpiWarps * kPwStgWarp + 512;
-  p.w_resident = (p.num_n_tiles == 1 && p.num_kc * w_tile_bytes <= 96 * 1024) ? 1 : 0;
+  p.w_resident = (p.num_n_tiles == 1 && p.num_kc * w_tile_bytes <= (p.BN > kPwMaxBN ? kPwResidentMax : 96 * 1024)) ? 1 : 0;
   // narrow outputs (<= 3 pieces: 8-slot ring) and the 96-wide expand (6 pieces over 4 warp groups = 2, 2, 1, 1 per tile; 4-slot ring)
   p.tile_par = ((p.BN <= 48 || p.BN == 96) && a.epi != kPwSiluPool) ? 1 : 0;
   p.silu_nr = pw_silu_nr() ? 1 : 0;
