@@ -18,6 +18,12 @@
 //                           with 4 the K-heavy, narrow project layers were bound by this stage
 //   warp 24      TMA producer (A raw, W_hi, W_lo per 32-wide k chunk)
 //   warp 25      TMEM allocator + MMA issuer (3 MMAs per 8-wide k step)
+// Variations chosen per layer by launch_pointwise_tc (all measured, profiles/r02_decoder_launches_v19 ... v24):
+//   tile_par   narrow outputs (N <= 48) and the 96-wide expand: a warp group takes WHOLE tiles in turn (4 / 8-slot accumulator ring)
+//   rotation   otherwise the first 16-column piece of a warp group rotates with the tile (9 pieces = 3 + 2 + 2 + 2 per tile)
+//   stack      N <= 48, K >= 32: [W_hi ; W_lo] as ONE B operand of 2 BN rows, 2 MMAs per k step, the epilogue adds the two halves
+//   resident W single column tile with <= 96 KB of W hi / lo (<= 120 KB for the one 240-column tile): only A streams
+//   CTA pairs  everything whose W is not resident (pointwise_tc_pair_kernel below)
 // The expand convolutions (128 x 96 ... 240 outputs from a 16 ... 40-deep product) are bound by the epilogue's instruction issue
 // (ncu: ~0.75 instructions per output element, the 8 epilogue warps of the previous version busy 90 % of the time, tensor pipe
 // 4 % active), hence 16 epilogue warps -- 4 per scheduler -- an SFU SiLU and an accumulator ring of up to 8 tiles in TMEM.
